@@ -1,0 +1,117 @@
+/* lamp_b200 -- C ABI of the B200-native label-graph attention path of LaMP.
+ *
+ * The reference (QData/LaMP) is pure Python/PyTorch and defines no FFI; its seam for this path is the Python
+ * class API.  This header is the native boundary underneath that seam: every entry
+ * point cites the reference function (file:line under the reference checkout) whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller, row-major, 16-byte aligned; the library never
+ *    allocates or frees device memory and keeps no state besides per-process one-time kernel attributes;
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *  - return value: 0 on success, a negative LAMP_E* code otherwise; lamp_last_error() gives a thread-local
+ *    human-readable message.  Nothing throws, nothing calls exit();
+ *  - re-entrant / thread-safe: one process per GPU or several host threads may call concurrently.
+ *
+ * Number formats
+ *  - LAMP_PREC_FP32 : fp32 in / fp32 out; contractions run on the tcgen05 tensor cores as 3-term split-bf16
+ *                     products (hi*hi + hi*lo + lo*hi, fp32 accumulate), ~2^-16 relative per product;
+ *  - LAMP_PREC_BF16 : operands rounded to bf16 once (1-term), fp32 accumulate / softmax / LayerNorm.
+ *  - "planes": an fp32 matrix carried as two bf16 matrices (hi = bf16(x), lo = bf16(x - hi)) with a common
+ *    leading dimension; `lo` may be NULL for LAMP_PREC_BF16.  Intermediate activations stay in this form between
+ *    the kernels of a layer so that every HBM byte moved is a byte a tensor core consumes.
+ */
+#ifndef LAMP_B200_H_
+#define LAMP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAMP_OK 0
+#define LAMP_EINVAL (-1)     /* bad shape, stride or alignment                       */
+#define LAMP_ECUDA (-2)      /* CUDA runtime / driver error                          */
+#define LAMP_EARCH (-3)      /* current device is not compute capability 10.x        */
+#define LAMP_EWORKSPACE (-4) /* workspace too small                                  */
+
+#define LAMP_PREC_FP32 0
+#define LAMP_PREC_BF16 1
+
+int lamp_version(void);
+const char* lamp_last_error(void);
+/* 0 if the CURRENT device can run the library (sm_100), LAMP_EARCH otherwise. */
+int lamp_device_check(void);
+int lamp_sm_count(void);
+
+/* ---------------------------------------------------------------- level 1: kernels ------------------------ */
+
+/* x[rows, cols] fp32 (leading dim ld) -> planes (leading dim ldp).  cols % 4 == 0. */
+int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* hi, void* lo, int64_t ldp,
+                      void* stream);
+
+/* C[M,N] = A[M,K] * W[N,K]^T, then (+bias[N]) (ReLU) (+residual[row % resid_mod or row, :]) and store as fp32
+ * and/or planes.  Replaces the nn.Linear / Conv1d(k=1) contractions of lamp/SubLayers.py:91-93 (w_qs,w_ks,w_vs),
+ * :110 (fc) and :133 (w_1, w_2).  K % 8 == 0, N % 8 == 0. */
+int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                     int64_t ldw, int M, int N, int K, int precision, const float* bias, int relu,
+                     const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
+                     void* out_lo, int64_t ldp, void* stream);
+
+/* Masked softmax attention over label nodes for B samples x H heads (lamp/SubLayers.py:27-43 with the head
+ * split/merge of :96-107 folded into the addressing).  Q planes: [B*Lq (or Lq if q_bcast), ldq], head h at
+ * columns q_col0 + h*d; K/V planes: [B*Lk, ldkv] at k_col0 / v_col0 + h*d.  mask: NULL or bytes (non-zero =
+ * masked) addressed as mask[b*msb + i*msq + j*msk] (strides may be 0: [L,L] label mask -> msb = 0; [B,Lk]
+ * key padding -> msq = 0).  Outputs: planes and/or fp32 [B*Lq, ld], head h at columns h*d.  If `probs` is not
+ * NULL it receives the attention probabilities [H*B, Lq, Lk] (head-major batch index h*B + b, as
+ * lamp/SubLayers.py:96-98,121) and row_max/row_sum ([H*B*Lq] floats each) must be provided as scratch.
+ * d % 16 == 0, d <= 128.  A fully masked row yields NaN exactly like the reference's softmax over all -inf. */
+int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                          const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
+                          int Lq, int Lk, int d, float temperature, int precision, const uint8_t* mask,
+                          int64_t msb, int64_t msq, int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
+                          int64_t ldof, float* row_max, float* row_sum, float* probs, void* stream);
+
+/* out = LayerNorm(y (+ add[row % add_mod or row])) * gamma + beta  (torch.nn.LayerNorm semantics, eps inside the
+ * sqrt; lamp/SubLayers.py:117,141).  Writes fp32 and/or planes (any may be NULL).  D % 4 == 0, D <= 4096. */
+int lamp_layernorm(const float* y, const float* add, int add_mod, const float* gamma, const float* beta, float eps,
+                   int64_t rows, int D, float* out, void* out_hi, void* out_lo, void* stream);
+
+/* out[r,:] = word_emb[seq[r],:] (+ pos_emb[pos[r],:])  (lamp/Encoders.py:66,75). seq/pos are int64. */
+int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, const float* pos_emb, int64_t rows,
+               int D, float* out, void* out_hi, void* out_lo, void* stream);
+
+/* logits[b,l] = <x[b,l,:], W[l,:]> (+bias[l]) : the diagonal of the [B,L,L] projection, lamp/Models.py:124-126. */
+int lamp_diag_proj(const float* x, const float* W, const float* bias, int64_t B, int L, int D, float* logits,
+                   void* stream);
+
+/* ---------------------------------------------------------------- level 2: reference-shaped ops ----------- */
+
+/* ScaledDotProductAttention.forward (lamp/SubLayers.py:27-43), eval mode.
+ * q [N,Lq,d], k,v [N,Lk,d] fp32; mask as above with N in place of B; out [N,Lq,d]; attn [N,Lq,Lk] or NULL. */
+size_t lamp_sdpa_workspace_bytes(int N, int Lq, int Lk, int d);
+int lamp_sdpa_fwd(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
+                  int64_t msk, float* out, float* attn, int N, int Lq, int Lk, int d, float temperature,
+                  int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* MultiHeadAttention.forward (lamp/SubLayers.py:77-121), eval mode (dropout = identity).
+ * q [B,Lq,D]; kv [B,Lk,D] or NULL for self-attention (k = v = q); Wq,Wk,Wv [H*d, D]; Wfc [D, H*d] or NULL iff
+ * H == 1 (:72-74); out = LayerNorm(fc(concat heads) + q) [B,Lq,D]; attn [H*B,Lq,Lk] head-major or NULL. */
+size_t lamp_mha_workspace_bytes(int B, int Lq, int Lk, int D, int H, int d, int self_attn, int want_attn);
+int lamp_mha_fwd(const float* q, const float* kv, const float* Wq, const float* Wk, const float* Wv,
+                 const float* Wfc, const float* ln_w, const float* ln_b, const uint8_t* mask, int64_t msb,
+                 int64_t msq, int64_t msk, float* out, float* attn, int B, int Lq, int Lk, int D, int H, int d,
+                 int precision, float ln_eps, void* workspace, size_t workspace_bytes, void* stream);
+
+/* PositionwiseFeedForward.forward (lamp/SubLayers.py:135-142), eval mode.
+ * x [rows, D]; W1 [d_inner, D] (Conv1d weight [d_inner, D, 1]); b1 [d_inner]; W2 [D, d_inner]; b2 [D]. */
+size_t lamp_ffn_workspace_bytes(int64_t rows, int D, int d_inner);
+int lamp_ffn_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                 const float* ln_w, const float* ln_b, float* out, int64_t rows, int D, int d_inner, int precision,
+                 float ln_eps, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAMP_B200_H_ */

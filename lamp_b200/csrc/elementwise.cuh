@@ -1,0 +1,143 @@
+// HBM-bound row kernels around the tensor-core stages: plane split, (add +) LayerNorm, embedding gather,
+// diagonal label projection.  All are one-pass, 128-bit vectorised, one warp per row where a row reduction exists.
+#pragma once
+#include "sm100_primitives.cuh"
+
+namespace lamp {
+
+// fp32 [rows, cols] (leading dim ld) -> hi/lo bf16 planes (leading dim ldp).  cols % 4 == 0.
+__global__ void split_planes_kernel(const float* __restrict__ x, long long rows, int cols, long long ld,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldp) {
+  const int c4 = cols >> 2;
+  const long long total = rows * c4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / c4;
+    const int c = static_cast<int>(i % c4) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi + r * ldp + c) = h;
+    if (lo != nullptr) *reinterpret_cast<uint2*>(lo + r * ldp + c) = l;
+  }
+}
+
+// out = LayerNorm(y (+ add)) * gamma + beta  (biased variance, eps inside the sqrt: torch.nn.LayerNorm, used at
+// lamp/SubLayers.py:117,141).  One warp per row, the row lives in registers (D <= 32*4*MAXV), two-pass variance.
+// `add` rows are indexed modulo add_mod when add_mod > 0 (label embeddings shared by every sample).
+template <int MAXV>
+__global__ void layernorm_kernel(const float* __restrict__ y, const float* __restrict__ add, int add_mod,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 long long rows, int D, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                 __nv_bfloat16* __restrict__ out_lo) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int d4 = D >> 2;
+  const float4* yr = reinterpret_cast<const float4*>(y + row * D);
+  const float4* ar = nullptr;
+  if (add != nullptr) ar = reinterpret_cast<const float4*>(add + (add_mod ? row % add_mod : row) * D);
+  float4 v[MAXV];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < d4) {
+      v[i] = yr[idx];
+      if (ar != nullptr) {
+        const float4 a = ar[idx];
+        v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  const float mean = s / D;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < d4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+  const float rstd = rsqrtf(q / D + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < d4) {
+      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out != nullptr) reinterpret_cast<float4*>(out + row * D)[idx] = o;
+      if (out_hi != nullptr) {
+        uint2 h, l;
+        split_bf16x2(o.x, o.y, h.x, l.x);
+        split_bf16x2(o.z, o.w, h.y, l.y);
+        reinterpret_cast<uint2*>(out_hi + row * D)[idx] = h;
+        if (out_lo != nullptr) reinterpret_cast<uint2*>(out_lo + row * D)[idx] = l;
+      }
+    }
+  }
+}
+
+// enc_input[r, :] = word_emb[src_seq[r], :] (+ pos_emb[src_pos[r], :])   -- lamp/Encoders.py:66,75.
+// Writes fp32 and/or planes.  One warp per token row.
+__global__ void embed_kernel(const long long* __restrict__ seq, const long long* __restrict__ pos,
+                             const float* __restrict__ word_emb, const float* __restrict__ pos_emb, long long rows,
+                             int D, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                             __nv_bfloat16* __restrict__ out_lo) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* w = reinterpret_cast<const float4*>(word_emb + seq[row] * D);
+  const float4* q = pos_emb ? reinterpret_cast<const float4*>(pos_emb + pos[row] * D) : nullptr;
+  for (int idx = lane; idx < (D >> 2); idx += 32) {
+    float4 v = __ldg(w + idx);
+    if (q != nullptr) {
+      const float4 a = __ldg(q + idx);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (out != nullptr) reinterpret_cast<float4*>(out + row * D)[idx] = v;
+    if (out_hi != nullptr) {
+      uint2 h, l;
+      split_bf16x2(v.x, v.y, h.x, l.x);
+      split_bf16x2(v.z, v.w, h.y, l.y);
+      reinterpret_cast<uint2*>(out_hi + row * D)[idx] = h;
+      if (out_lo != nullptr) reinterpret_cast<uint2*>(out_lo + row * D)[idx] = l;
+    }
+  }
+}
+
+// logits[b, l] = <x[b, l, :], W[l, :]> (+ bias[l])  -- the diagonal of the reference's [B, L, L] projection
+// (lamp/Models.py:124-126) without the L-fold redundant work.  One warp per (b, l), fp32 FMA.
+__global__ void diag_proj_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                 const float* __restrict__ bias, long long rows, int L, int D,
+                                 float* __restrict__ logits) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int l = static_cast<int>(row % L);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const float4* wr = reinterpret_cast<const float4*>(W + static_cast<long long>(l) * D);
+  float s = 0.0f;
+  for (int idx = lane; idx < (D >> 2); idx += 32) {
+    const float4 a = xr[idx], b = __ldg(wr + idx);
+    s += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) logits[row] = s + (bias ? bias[l] : 0.0f);
+}
+
+}  // namespace lamp

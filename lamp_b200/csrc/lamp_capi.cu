@@ -1,0 +1,502 @@
+// C ABI of lamp_b200 (see include/lamp_b200.h).  Host-side validation, TMA descriptor construction and launches.
+#include "../../include/lamp_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "attn_core.cuh"
+#include "elementwise.cuh"
+#include "gemm_planes.cuh"
+
+using namespace lamp;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) return fail(LAMP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_));    \
+  } while (0)
+
+#define REQUIRE(cond, ...)                              \
+  do {                                                  \
+    if (!(cond)) return fail(LAMP_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- driver entry point for TMA descriptor encoding (no link-time libcuda dependency)
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static std::atomic<EncodeTiledFn> cached{nullptr};
+  EncodeTiledFn f = cached.load(std::memory_order_acquire);
+  if (f) return f;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  f = reinterpret_cast<EncodeTiledFn>(sym);
+  cached.store(f, std::memory_order_release);
+  return f;
+}
+
+// bf16 matrix viewed as {cols, rows[, batch]}; box = {64 cols (128 B), box_rows[, 1]}, 128B swizzle, zero OOB fill.
+int make_tmap(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+              uint32_t box_rows, bool three_d) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!aligned16(base)) return fail(LAMP_EINVAL, "TMA base pointer not 16-byte aligned");
+  if ((ld_elems * 2) % 16 != 0) return fail(LAMP_EINVAL, "leading dimension %llu not a multiple of 8 elements",
+                                            (unsigned long long)ld_elems);
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld_elems * 2, rows * ld_elems * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, three_d ? 3 : 2, const_cast<void*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return LAMP_OK;
+}
+
+int sm_count_cached() {
+  static std::atomic<int> n{0};
+  int v = n.load();
+  if (v) return v;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  n.store(v);
+  return v;
+}
+
+int arch_check() {
+  static std::atomic<int> ok{0};  // 0 unknown, 1 ok, -1 bad
+  int v = ok.load();
+  if (v == 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+      return fail(LAMP_ECUDA, "no CUDA device");
+    v = (major == 10) ? 1 : -1;
+    ok.store(v);
+  }
+  if (v < 0) return fail(LAMP_EARCH, "lamp_b200 kernels are built for sm_100a only");
+  return LAMP_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, uint32_t bytes) {
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return LAMP_OK;
+}
+
+int launch_check() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LAMP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+  return LAMP_OK;
+}
+
+template <int BLOCK_N, int NTERMS>
+int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BLOCK_N, NTERMS>;
+  static std::once_flag once;
+  static int once_rc = LAMP_OK;
+  std::call_once(once, [] { once_rc = set_smem(gemm_planes_kernel<BLOCK_N, NTERMS>, Cfg::SMEM_BYTES); });
+  if (once_rc != LAMP_OK) return once_rc;
+  const int tiles = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
+  gemm_planes_kernel<BLOCK_N, NTERMS><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  return launch_check();
+}
+
+template <int BLOCK_KV, bool ALIAS, int NTERMS>
+int launch_attn(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi, const CUtensorMap& kv_lo,
+                const AttnParams& p, cudaStream_t st) {
+  using SM = AttnSmem<BLOCK_KV, ALIAS, NTERMS>;
+  static std::once_flag once;
+  static int once_rc = LAMP_OK;
+  // <128,false> is only dispatched for d <= 64 (one 64-column block); the other two variants carry d <= 128.
+  constexpr int MAX_KB64 = (BLOCK_KV == 128 && !ALIAS) ? 1 : 2;
+  std::call_once(once, [] { once_rc = set_smem(attn_core_kernel<BLOCK_KV, ALIAS, NTERMS>, SM::total(MAX_KB64)); });
+  if (once_rc != LAMP_OK) return once_rc;
+  const int kb64 = (p.d + 63) / 64;
+  const int items = p.B * p.H * ((p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M);
+  const int grid = items < sm_count_cached() ? items : sm_count_cached();
+  attn_core_kernel<BLOCK_KV, ALIAS, NTERMS><<<grid, ATTN_THREADS, SM::total(kb64), st>>>(q_hi, q_lo, kv_hi, kv_lo, p);
+  return launch_check();
+}
+
+inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<uint8_t*>(b)) {}
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += align_up(bytes);
+    return p;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int lamp_version(void) { return 100; }
+const char* lamp_last_error(void) { return g_err; }
+int lamp_device_check(void) { return arch_check(); }
+int lamp_sm_count(void) { return sm_count_cached(); }
+
+int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* hi, void* lo, int64_t ldp,
+                      void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(x && hi, "split_planes: null pointer");
+  REQUIRE(cols % 4 == 0 && ld % 4 == 0 && ldp % 4 == 0, "split_planes: cols/ld/ldp must be multiples of 4");
+  REQUIRE(aligned16(x) && (reinterpret_cast<uintptr_t>(hi) % 8 == 0), "split_planes: alignment");
+  if (rows == 0 || cols == 0) return LAMP_OK;
+  const long long total = rows * (cols / 4);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 32LL * sm_count_cached();
+  if (blocks > cap) blocks = cap;
+  split_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      x, rows, cols, ld, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ldp);
+  return launch_check();
+}
+
+int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                     int64_t ldw, int M, int N, int K, int precision, const float* bias, int relu,
+                     const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
+                     void* out_lo, int64_t ldp, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  REQUIRE(K % 8 == 0 && N % 8 == 0, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
+  REQUIRE(a_hi && w_hi, "gemm: null operand");
+  const bool three = (precision == LAMP_PREC_FP32);
+  REQUIRE(precision == LAMP_PREC_FP32 || precision == LAMP_PREC_BF16, "gemm: unknown precision %d", precision);
+  REQUIRE(!three || (a_lo && w_lo), "gemm: LAMP_PREC_FP32 needs lo planes");
+  REQUIRE(out_f32 || out_hi, "gemm: no output");
+  REQUIRE(!out_f32 || (aligned16(out_f32) && ldo % 4 == 0), "gemm: out_f32 alignment");
+  REQUIRE(!out_hi || (aligned16(out_hi) && ldp % 8 == 0 && (!out_lo || aligned16(out_lo))), "gemm: plane alignment");
+  REQUIRE(!residual || (aligned16(residual) && ldr % 4 == 0), "gemm: residual alignment");
+  REQUIRE(!bias || aligned16(bias), "gemm: bias alignment");
+  if (M == 0) return LAMP_OK;
+  const bool wide = (N > 128);
+  const uint32_t box_n = wide ? 256 : 128;
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  if (int rc = make_tmap(&ta_hi, a_hi, K, M, 1, lda, GEMM_BLOCK_M, false)) return rc;
+  if (int rc = make_tmap(&tw_hi, w_hi, K, N, 1, ldw, box_n, false)) return rc;
+  if (three) {
+    if (int rc = make_tmap(&ta_lo, a_lo, K, M, 1, lda, GEMM_BLOCK_M, false)) return rc;
+    if (int rc = make_tmap(&tw_lo, w_lo, K, N, 1, ldw, box_n, false)) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tw_lo = tw_hi;
+  }
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.residual = residual; p.ldr = (int)ldr; p.resid_mod = resid_mod; p.relu = relu;
+  p.out_f32 = out_f32; p.ldo = (int)ldo;
+  p.out_hi = static_cast<__nv_bfloat16*>(out_hi);
+  p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+  p.ldp = (int)ldp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (three) return wide ? launch_gemm<256, 3>(ta_hi, ta_lo, tw_hi, tw_lo, p, st) : launch_gemm<128, 3>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);
+  return wide ? launch_gemm<256, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st) : launch_gemm<128, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);
+}
+
+int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                          const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
+                          int Lq, int Lk, int d, float temperature, int precision, const uint8_t* mask,
+                          int64_t msb, int64_t msq, int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
+                          int64_t ldof, float* row_max, float* row_sum, float* probs, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "attn: bad shape B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+  REQUIRE(d % 16 == 0 && d >= 16 && d <= 128, "attn: head width %d must be a multiple of 16 in [16,128]", d);
+  REQUIRE(precision == LAMP_PREC_FP32 || precision == LAMP_PREC_BF16, "attn: unknown precision %d", precision);
+  const bool three = (precision == LAMP_PREC_FP32);
+  REQUIRE(q_hi && kv_hi && (!three || (q_lo && kv_lo)), "attn: null operand planes");
+  REQUIRE(o_hi || o_f32, "attn: no output");
+  REQUIRE(!o_hi || (aligned16(o_hi) && ldo % 8 == 0 && (!o_lo || aligned16(o_lo))), "attn: output plane alignment");
+  REQUIRE(!o_f32 || (aligned16(o_f32) && ldof % 4 == 0), "attn: o_f32 alignment");
+  REQUIRE(!probs || (row_max && row_sum), "attn: probs need row_max/row_sum scratch");
+  REQUIRE(temperature > 0.0f, "attn: temperature must be positive");
+  REQUIRE(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "attn: column offsets must be multiples of 8");
+  if (B == 0) return LAMP_OK;
+  const bool multi = Lk > 128;
+  const int block_kv = (d > 64 && multi) ? 64 : 128;
+  CUtensorMap tq_hi, tq_lo, tkv_hi, tkv_lo;
+  if (int rc = make_tmap(&tq_hi, q_hi, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, ATTN_BLOCK_M, true)) return rc;
+  if (int rc = make_tmap(&tkv_hi, kv_hi, (uint64_t)ldkv, Lk, B, ldkv, block_kv, true)) return rc;
+  if (three) {
+    if (int rc = make_tmap(&tq_lo, q_lo, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, ATTN_BLOCK_M, true)) return rc;
+    if (int rc = make_tmap(&tkv_lo, kv_lo, (uint64_t)ldkv, Lk, B, ldkv, block_kv, true)) return rc;
+  } else {
+    tq_lo = tq_hi;
+    tkv_lo = tkv_hi;
+  }
+  AttnParams p;
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.d = d;
+  p.scale_log2 = 1.4426950408889634f / temperature;
+  p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.q_bcast = q_bcast;
+  p.mask = mask; p.msb = msb; p.msq = msq; p.msk = msk;
+  p.o_hi = static_cast<__nv_bfloat16*>(o_hi);
+  p.o_lo = static_cast<__nv_bfloat16*>(o_lo);
+  p.ldo = (int)ldo; p.o_f32 = o_f32; p.ldof = (int)ldof;
+  p.row_max = row_max; p.row_sum = row_sum;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (d <= 64) {
+    rc = three ? launch_attn<128, false, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
+               : launch_attn<128, false, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
+  } else if (!multi) {
+    rc = three ? launch_attn<128, true, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
+               : launch_attn<128, true, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
+  } else {
+    rc = three ? launch_attn<64, false, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
+               : launch_attn<64, false, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
+  }
+  if (rc != LAMP_OK) return rc;
+  if (probs) {
+    ProbsParams pp;
+    pp.B = B; pp.H = H; pp.Lq = Lq; pp.Lk = Lk; pp.d = d; pp.scale_log2 = p.scale_log2;
+    pp.q_hi = static_cast<const __nv_bfloat16*>(q_hi);
+    pp.q_lo = three ? static_cast<const __nv_bfloat16*>(q_lo) : nullptr;
+    pp.kv_hi = static_cast<const __nv_bfloat16*>(kv_hi);
+    pp.kv_lo = three ? static_cast<const __nv_bfloat16*>(kv_lo) : nullptr;
+    pp.ldq = (int)ldq; pp.ldkv = (int)ldkv; pp.q_col0 = q_col0; pp.k_col0 = k_col0; pp.q_bcast = q_bcast;
+    pp.mask = mask; pp.msb = msb; pp.msq = msq; pp.msk = msk;
+    pp.row_max = row_max; pp.row_sum = row_sum; pp.probs = probs;
+    const long long nrows = (long long)H * B * Lq;
+    const long long blocks = (nrows * 32 + 255) / 256;
+    attn_probs_kernel<<<(unsigned)blocks, 256, 0, st>>>(pp);
+    rc = launch_check();
+  }
+  return rc;
+}
+
+int lamp_layernorm(const float* y, const float* add, int add_mod, const float* gamma, const float* beta, float eps,
+                   int64_t rows, int D, float* out, void* out_hi, void* out_lo, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(y && gamma && beta && (out || out_hi), "layernorm: null pointer");
+  REQUIRE(D % 4 == 0 && D > 0 && D <= 4096, "layernorm: D=%d must be a multiple of 4, <= 4096", D);
+  REQUIRE(aligned16(y) && (!add || aligned16(add)) && aligned16(gamma) && aligned16(beta), "layernorm: alignment");
+  if (rows == 0) return LAMP_OK;
+  const long long blocks = (rows * 32 + 255) / 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(out_hi);
+  __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(out_lo);
+  if (D <= 512)
+    layernorm_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo);
+  else if (D <= 1024)
+    layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo);
+  else
+    layernorm_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo);
+  return launch_check();
+}
+
+int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, const float* pos_emb, int64_t rows,
+               int D, float* out, void* out_hi, void* out_lo, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(seq && word_emb && (out || out_hi), "embed: null pointer");
+  REQUIRE(!pos_emb || pos, "embed: pos_emb without pos ids");
+  REQUIRE(D % 4 == 0, "embed: D must be a multiple of 4");
+  if (rows == 0) return LAMP_OK;
+  const long long blocks = (rows * 32 + 255) / 256;
+  embed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(seq), reinterpret_cast<const long long*>(pos), word_emb, pos_emb, rows, D,
+      out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo));
+  return launch_check();
+}
+
+int lamp_diag_proj(const float* x, const float* W, const float* bias, int64_t B, int L, int D, float* logits,
+                   void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(x && W && logits, "diag_proj: null pointer");
+  REQUIRE(D % 4 == 0 && aligned16(x) && aligned16(W), "diag_proj: D multiple of 4 and 16-byte alignment required");
+  const long long rows = B * L;
+  if (rows == 0) return LAMP_OK;
+  const long long blocks = (rows * 32 + 255) / 256;
+  diag_proj_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, W, bias, rows, L, D, logits);
+  return launch_check();
+}
+
+// ------------------------------------------------------------------------------------ level 2
+
+size_t lamp_sdpa_workspace_bytes(int N, int Lq, int Lk, int d) {
+  Carver c(nullptr);
+  c.take((size_t)N * Lq * d * 4);      // Q planes
+  c.take((size_t)N * Lk * 2 * d * 4);  // [K | V] planes
+  c.take((size_t)N * Lq * 8);          // row statistics
+  return c.off;
+}
+
+int lamp_sdpa_fwd(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
+                  int64_t msk, float* out, float* attn, int N, int Lq, int Lk, int d, float temperature,
+                  int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  REQUIRE(q && k && v && out, "sdpa: null pointer");
+  REQUIRE(N >= 0 && Lq > 0 && Lk > 0 && d > 0, "sdpa: bad shape");
+  if (!workspace || workspace_bytes < lamp_sdpa_workspace_bytes(N, Lq, Lk, d))
+    return fail(LAMP_EWORKSPACE, "sdpa: workspace too small");
+  const bool three = precision == LAMP_PREC_FP32;
+  Carver c(workspace);
+  const size_t qn = (size_t)N * Lq * d, kvn = (size_t)N * Lk * 2 * d;
+  __nv_bfloat16* qp = static_cast<__nv_bfloat16*>(c.take(qn * 4));
+  __nv_bfloat16* kvp = static_cast<__nv_bfloat16*>(c.take(kvn * 4));
+  float* stats = static_cast<float*>(c.take((size_t)N * Lq * 8));
+  __nv_bfloat16* qlo = three ? qp + qn : nullptr;
+  __nv_bfloat16* kvlo = three ? kvp + kvn : nullptr;
+  if (int rc = lamp_split_planes(q, (int64_t)N * Lq, d, d, qp, qlo, d, stream)) return rc;
+  // K and V side by side in one [N*Lk, 2d] matrix so that a single tensor map serves both operands
+  if (int rc = lamp_split_planes(k, (int64_t)N * Lk, d, d, kvp, kvlo, 2 * d, stream)) return rc;
+  if (int rc = lamp_split_planes(v, (int64_t)N * Lk, d, d, kvp + d, three ? kvlo + d : nullptr, 2 * d, stream)) return rc;
+  return lamp_attn_core_planes(qp, qlo, d, 0, 0, kvp, kvlo, 2 * d, 0, d, N, 1, Lq, Lk, d, temperature, precision, mask,
+                               msb, msq, msk, nullptr, nullptr, 0, out, d, stats, stats + (size_t)N * Lq, attn, stream);
+}
+
+namespace {
+struct MhaPlan {
+  size_t xq, xkv, wqkv, wfc, qkv, kv, o, y, stats, total;
+};
+MhaPlan mha_plan(int B, int Lq, int Lk, int D, int H, int d, int self_attn, int want_attn) {
+  const size_t hd = (size_t)H * d, mq = (size_t)B * Lq, mk = (size_t)B * Lk;
+  Carver c(nullptr);
+  MhaPlan p{};
+  p.xq = c.off;   c.take(mq * D * 4);
+  p.xkv = c.off;  c.take(self_attn ? 0 : mk * D * 4);
+  p.wqkv = c.off; c.take(3 * hd * D * 4);
+  p.wfc = c.off;  c.take(H > 1 ? hd * D * 4 : 0);
+  p.qkv = c.off;  c.take(self_attn ? mq * 3 * hd * 4 : mq * hd * 4);
+  p.kv = c.off;   c.take(self_attn ? 0 : mk * 2 * hd * 4);
+  p.o = c.off;    c.take(mq * hd * 4);
+  p.y = c.off;    c.take(mq * (size_t)(D > (int)hd ? D : hd) * 4);
+  p.stats = c.off; c.take(want_attn ? (size_t)H * mq * 8 : 0);
+  p.total = c.off;
+  return p;
+}
+}  // namespace
+
+size_t lamp_mha_workspace_bytes(int B, int Lq, int Lk, int D, int H, int d, int self_attn, int want_attn) {
+  return mha_plan(B, Lq, Lk, D, H, d, self_attn, want_attn).total;
+}
+
+int lamp_mha_fwd(const float* q, const float* kv, const float* Wq, const float* Wk, const float* Wv,
+                 const float* Wfc, const float* ln_w, const float* ln_b, const uint8_t* mask, int64_t msb,
+                 int64_t msq, int64_t msk, float* out, float* attn, int B, int Lq, int Lk, int D, int H, int d,
+                 int precision, float ln_eps, void* workspace, size_t workspace_bytes, void* stream) {
+  REQUIRE(q && Wq && Wk && Wv && ln_w && ln_b && out, "mha: null pointer");
+  REQUIRE((H > 1) == (Wfc != nullptr), "mha: fc weight must be given iff n_head > 1 (lamp/SubLayers.py:72-74)");
+  REQUIRE(H == 1 ? d == D : true, "mha: with n_head == 1 the head width must equal d_model (no fc)");
+  REQUIRE(D % 8 == 0, "mha: d_model must be a multiple of 8");
+  const int self_attn = (kv == nullptr || kv == q);
+  REQUIRE(!self_attn || Lq == Lk, "mha: self-attention needs Lq == Lk");
+  const MhaPlan pl = mha_plan(B, Lq, Lk, D, H, d, self_attn, attn != nullptr);
+  if (!workspace || workspace_bytes < pl.total) return fail(LAMP_EWORKSPACE, "mha: workspace too small");
+  const bool three = precision == LAMP_PREC_FP32;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t hd = (size_t)H * d, mq = (size_t)B * Lq, mk = (size_t)B * Lk;
+  auto hi = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  auto lo = [&](size_t off, size_t n) { return three ? reinterpret_cast<__nv_bfloat16*>(ws + off) + n : nullptr; };
+  // 1. operand planes: activations and (stateless API) weights
+  if (int rc = lamp_split_planes(q, mq, D, D, hi(pl.xq), lo(pl.xq, mq * D), D, stream)) return rc;
+  if (!self_attn)
+    if (int rc = lamp_split_planes(kv, mk, D, D, hi(pl.xkv), lo(pl.xkv, mk * D), D, stream)) return rc;
+  const float* ws_in[3] = {Wq, Wk, Wv};
+  for (int i = 0; i < 3; ++i)
+    if (int rc = lamp_split_planes(ws_in[i], hd, D, D, hi(pl.wqkv) + i * hd * D, three ? lo(pl.wqkv, 3 * hd * D) + i * hd * D : nullptr, D, stream)) return rc;
+  if (H > 1)
+    if (int rc = lamp_split_planes(Wfc, D, (int)hd, hd, hi(pl.wfc), lo(pl.wfc, hd * D), hd, stream)) return rc;
+  // 2. projections (lamp/SubLayers.py:91-93) -> planes
+  const __nv_bfloat16 *qh, *ql, *kvh, *kvl;
+  int64_t ldq, ldkv;
+  int k_col0, v_col0;
+  if (self_attn) {
+    if (int rc = lamp_gemm_planes(hi(pl.xq), lo(pl.xq, mq * D), D, hi(pl.wqkv), lo(pl.wqkv, 3 * hd * D), D, (int)mq, (int)(3 * hd), D, precision,
+                                  nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.qkv), lo(pl.qkv, mq * 3 * hd), 3 * hd, stream)) return rc;
+    qh = kvh = hi(pl.qkv); ql = kvl = lo(pl.qkv, mq * 3 * hd);
+    ldq = ldkv = 3 * hd; k_col0 = (int)hd; v_col0 = (int)(2 * hd);
+  } else {
+    if (int rc = lamp_gemm_planes(hi(pl.xq), lo(pl.xq, mq * D), D, hi(pl.wqkv), lo(pl.wqkv, 3 * hd * D), D, (int)mq, (int)hd, D, precision,
+                                  nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.qkv), lo(pl.qkv, mq * hd), hd, stream)) return rc;
+    if (int rc = lamp_gemm_planes(hi(pl.xkv), lo(pl.xkv, mk * D), D, hi(pl.wqkv) + hd * D, three ? lo(pl.wqkv, 3 * hd * D) + hd * D : nullptr, D,
+                                  (int)mk, (int)(2 * hd), D, precision, nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.kv), lo(pl.kv, mk * 2 * hd), 2 * hd, stream)) return rc;
+    qh = hi(pl.qkv); ql = lo(pl.qkv, mq * hd); kvh = hi(pl.kv); kvl = lo(pl.kv, mk * 2 * hd);
+    ldq = hd; ldkv = 2 * hd; k_col0 = 0; v_col0 = (int)hd;
+  }
+  // 3. masked softmax attention (lamp/SubLayers.py:104 -> :27-43), temperature sqrt(d_k) (:63/:65)
+  float* y = reinterpret_cast<float*>(ws + pl.y);
+  float* stats = attn ? reinterpret_cast<float*>(ws + pl.stats) : nullptr;
+  const float temperature = sqrtf((float)d);
+  if (int rc = lamp_attn_core_planes(qh, ql, ldq, 0, 0, kvh, kvl, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature, precision, mask, msb,
+                                     msq, msk, H > 1 ? hi(pl.o) : nullptr, H > 1 ? lo(pl.o, mq * hd) : nullptr, hd, H > 1 ? nullptr : y, hd,
+                                     stats, stats ? stats + (size_t)H * mq : nullptr, attn, stream)) return rc;
+  // 4. fc + residual (:110,:117) then LayerNorm
+  if (H > 1) {
+    if (int rc = lamp_gemm_planes(hi(pl.o), lo(pl.o, mq * hd), hd, hi(pl.wfc), lo(pl.wfc, hd * D), hd, (int)mq, D, (int)hd, precision, nullptr, 0,
+                                  q, D, 0, y, D, nullptr, nullptr, 0, stream)) return rc;
+    return lamp_layernorm(y, nullptr, 0, ln_w, ln_b, ln_eps, mq, D, out, nullptr, nullptr, stream);
+  }
+  return lamp_layernorm(y, q, 0, ln_w, ln_b, ln_eps, mq, D, out, nullptr, nullptr, stream);
+}
+
+size_t lamp_ffn_workspace_bytes(int64_t rows, int D, int d_inner) {
+  Carver c(nullptr);
+  c.take((size_t)rows * D * 4);        // x planes
+  c.take((size_t)d_inner * D * 4);     // W1 planes
+  c.take((size_t)d_inner * D * 4);     // W2 planes
+  c.take((size_t)rows * d_inner * 4);  // hidden planes
+  c.take((size_t)rows * D * 4);        // pre-LN fp32
+  return c.off;
+}
+
+int lamp_ffn_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                 const float* ln_w, const float* ln_b, float* out, int64_t rows, int D, int d_inner, int precision,
+                 float ln_eps, void* workspace, size_t workspace_bytes, void* stream) {
+  REQUIRE(x && W1 && b1 && W2 && b2 && ln_w && ln_b && out, "ffn: null pointer");
+  REQUIRE(D % 8 == 0 && d_inner % 8 == 0, "ffn: D and d_inner must be multiples of 8");
+  if (!workspace || workspace_bytes < lamp_ffn_workspace_bytes(rows, D, d_inner))
+    return fail(LAMP_EWORKSPACE, "ffn: workspace too small");
+  const bool three = precision == LAMP_PREC_FP32;
+  Carver c(workspace);
+  const size_t nx = (size_t)rows * D, nw = (size_t)d_inner * D, nh = (size_t)rows * d_inner;
+  __nv_bfloat16* xp = static_cast<__nv_bfloat16*>(c.take(nx * 4));
+  __nv_bfloat16* w1p = static_cast<__nv_bfloat16*>(c.take(nw * 4));
+  __nv_bfloat16* w2p = static_cast<__nv_bfloat16*>(c.take(nw * 4));
+  __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(c.take(nh * 4));
+  float* y = static_cast<float*>(c.take(nx * 4));
+  auto lo = [&](__nv_bfloat16* p, size_t n) { return three ? p + n : nullptr; };
+  if (int rc = lamp_split_planes(x, rows, D, D, xp, lo(xp, nx), D, stream)) return rc;
+  if (int rc = lamp_split_planes(W1, d_inner, D, D, w1p, lo(w1p, nw), D, stream)) return rc;
+  if (int rc = lamp_split_planes(W2, D, d_inner, d_inner, w2p, lo(w2p, nw), d_inner, stream)) return rc;
+  // w_1 + ReLU (lamp/SubLayers.py:138), hidden kept as planes only
+  if (int rc = lamp_gemm_planes(xp, lo(xp, nx), D, w1p, lo(w1p, nw), D, (int)rows, d_inner, D, precision, b1, 1, nullptr, 0, 0, nullptr, 0, hp,
+                                lo(hp, nh), d_inner, stream)) return rc;
+  // w_2 + residual (:138-141)
+  if (int rc = lamp_gemm_planes(hp, lo(hp, nh), d_inner, w2p, lo(w2p, nw), d_inner, (int)rows, D, d_inner, precision, b2, 0, x, D, 0, y, D, nullptr,
+                                nullptr, 0, stream)) return rc;
+  return lamp_layernorm(y, nullptr, 0, ln_w, ln_b, ln_eps, rows, D, out, nullptr, nullptr, stream);
+}
+
+}  // extern "C"
