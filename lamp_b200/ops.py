@@ -1,0 +1,233 @@
+"""Host-side orchestration of the native kernels (level-1 C ABI) for the label-graph path.
+
+Activations travel between kernels as :class:`Act`: an fp32 matrix ``[rows, D]`` (residual / API tensor) plus
+its split-bf16 planes (tensor-core operand form).  Producers (LayerNorm, embedding, GEMM epilogues) emit the planes
+directly, so no separate conversion pass runs inside a layer.  Weights are split once and cached per parameter
+version.  Everything is enqueued on torch's current CUDA stream; torch only provides memory and streams.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _native as nat
+
+_DEFAULT_PRECISION = nat.PREC_FP32
+
+
+def set_default_precision(name: str) -> None:
+    """'fp32' (3-term split-bf16 tensor-core products; meets the 1e-3 fp32 tolerance) or 'bf16'."""
+    global _DEFAULT_PRECISION
+    _DEFAULT_PRECISION = {'fp32': nat.PREC_FP32, 'bf16': nat.PREC_BF16}[name]
+
+
+def default_precision() -> int:
+    return _DEFAULT_PRECISION
+
+
+@dataclass
+class Act:
+    """fp32 activation ``[rows, cols]`` and/or its planes.  ``bcast``: logical row count when the ``rows``
+    physical rows are shared by every sample (label embeddings: rows = L, logical rows = B*L)."""
+    f32: Optional[torch.Tensor]
+    hi: Optional[torch.Tensor]
+    lo: Optional[torch.Tensor]
+    rows: int
+    cols: int
+    bcast_rows: int = 0
+
+    @property
+    def has_planes(self) -> bool:
+        return self.hi is not None
+
+
+def _empty_planes(rows: int, cols: int, prec: int, device) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=device)
+    lo = torch.empty((rows, cols), dtype=torch.bfloat16, device=device) if prec == nat.PREC_FP32 else None
+    return hi, lo
+
+
+def split(x: torch.Tensor, prec: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """fp32 ``[..., cols]`` (contiguous) -> planes ``[rows, cols]``."""
+    nat.require_cuda(x)
+    x = x.contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    hi, lo = _empty_planes(rows, cols, prec, x.device)
+    nat.check(nat.lib().lamp_split_planes(x.data_ptr(), rows, cols, cols, hi.data_ptr(), nat.ptr(lo), cols,
+                                          nat.stream()), 'lamp_split_planes')
+    return hi, lo
+
+
+def act_from_tensor(x: torch.Tensor, prec: int) -> Act:
+    """Wrap an fp32 tensor ``[..., D]``; reuse planes stashed on the tensor by the producing module if still valid."""
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    stash = getattr(x, '_lamp_planes', None)
+    if stash is not None:
+        hi, lo, ver, sprec = stash
+        if ver == x._version and sprec == prec and hi.shape == (rows, cols):
+            return Act(x.view(rows, cols), hi, lo, rows, cols)
+    hi, lo = split(x, prec)
+    return Act(x.view(rows, cols), hi, lo, rows, cols)
+
+
+def stash_planes(x: torch.Tensor, act: Act, prec: int) -> torch.Tensor:
+    """Attach the planes to the API tensor so that the next lamp_b200 module can skip the split pass."""
+    if act.has_planes:
+        x._lamp_planes = (act.hi, act.lo, x._version, prec)
+    return x
+
+
+class WeightPlanes:
+    """Split-bf16 planes of (a concatenation of) 2-D weights, cached against the parameters' versions."""
+
+    def __init__(self):
+        self._cache: Dict[tuple, tuple] = {}
+
+    def get(self, key: str, params, prec: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        sig = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params) + (prec,)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            mats = [p.detach().reshape(p.shape[0], -1).float() for p in params]  # Conv1d [out,in,1] -> [out,in]
+            w = mats[0] if len(mats) == 1 else torch.cat(mats, dim=0)
+            hi, lo = split(w, prec)
+        self._cache[key] = (sig, hi, lo)
+        return hi, lo
+
+
+def gemm(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, prec: int, *, bias=None, relu=False,
+         residual=None, ldr: int = 0, resid_mod: int = 0, out_f32=None, ldo: int = 0, out_hi=None, out_lo=None,
+         ldp: int = 0) -> None:
+    nat.check(nat.lib().lamp_gemm_planes(
+        nat.ptr(a_hi), nat.ptr(a_lo), lda, nat.ptr(w_hi), nat.ptr(w_lo), ldw, M, N, K, prec, nat.ptr(bias), int(relu),
+        nat.ptr(residual), ldr, resid_mod, nat.ptr(out_f32), ldo, nat.ptr(out_hi), nat.ptr(out_lo), ldp,
+        nat.stream()), 'lamp_gemm_planes')
+
+
+def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=False) -> Act:
+    """planes(x) @ W^T (+bias)(ReLU) -> planes only (operand for the next tensor-core stage)."""
+    hi, lo = _empty_planes(x.rows, N, prec, x.hi.device)
+    gemm(x.hi, x.lo, x.cols, w_hi, w_lo, x.cols, x.rows, N, x.cols, prec, bias=bias, relu=relu, out_hi=hi, out_lo=lo,
+         ldp=N)
+    return Act(None, hi, lo, x.rows, N, x.bcast_rows)
+
+
+def linear_residual_f32(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, *, bias=None) -> torch.Tensor:
+    """planes(x) @ W^T (+bias) + residual -> fp32 [rows, N] (pre-LayerNorm)."""
+    y = torch.empty((x.rows, N), dtype=torch.float32, device=x.hi.device)
+    mod = residual.rows if residual.bcast_rows else 0
+    gemm(x.hi, x.lo, x.cols, w_hi, w_lo, x.cols, x.rows, N, x.cols, prec, bias=bias, residual=residual.f32,
+         ldr=residual.cols, resid_mod=mod, out_f32=y, ldo=N)
+    return y
+
+
+def layernorm(y: torch.Tensor, gamma, beta, eps: float, prec: int, *, add: Optional[Act] = None,
+              want_planes: bool = True) -> Act:
+    rows, D = y.shape
+    out = torch.empty_like(y)
+    hi, lo = _empty_planes(rows, D, prec, y.device) if want_planes else (None, None)
+    add_t, add_mod = (None, 0)
+    if add is not None:
+        add_t, add_mod = add.f32, (add.rows if add.bcast_rows else 0)
+    nat.check(nat.lib().lamp_layernorm(y.data_ptr(), nat.ptr(add_t), add_mod, gamma.data_ptr(), beta.data_ptr(),
+                                       float(eps), rows, D, out.data_ptr(), nat.ptr(hi), nat.ptr(lo), nat.stream()),
+              'lamp_layernorm')
+    return Act(out, hi, lo, rows, D)
+
+
+def mask_args(mask: Optional[torch.Tensor], B: int, Lq: int, Lk: int):
+    """Bool/uint8 mask broadcastable to [B, Lq, Lk] -> (keepalive tensor, ptr, stride_b, stride_q, stride_k).
+    Expanded (stride-0) views are passed through untouched: the kernel never needs the tiled copy."""
+    if mask is None:
+        return None, None, 0, 0, 0
+    nat.require_cuda(mask)
+    if mask.dim() == 2:
+        mask = mask.unsqueeze(0)
+    if mask.dtype == torch.bool:
+        m8 = mask.view(torch.uint8) if mask.is_contiguous() or True else mask
+    elif mask.dtype == torch.uint8:
+        m8 = mask
+    else:
+        m8 = (mask != 0).view(torch.uint8)
+    m8 = m8.expand(B, Lq, Lk)
+    sb, sq, sk = m8.stride()
+    return m8, m8.data_ptr(), sb, sq, sk
+
+
+def attention(q: Act, q_col0: int, kv: Act, k_col0: int, v_col0: int, B: int, H: int, Lq: int, Lk: int, d: int,
+              prec: int, mask: Optional[torch.Tensor], want_probs: bool, out_f32: bool = False):
+    """-> (O as Act [B*Lq, H*d] (planes, or fp32 when out_f32), probs [H*B, Lq, Lk] or None)."""
+    dev = q.hi.device
+    hd = H * d
+    o_hi = o_lo = o32 = None
+    if out_f32:
+        o32 = torch.empty((B * Lq, hd), dtype=torch.float32, device=dev)
+    else:
+        o_hi, o_lo = _empty_planes(B * Lq, hd, prec, dev)
+    probs = rmax = rsum = None
+    if want_probs:
+        probs = torch.empty((H * B, Lq, Lk), dtype=torch.float32, device=dev)
+        rmax = torch.empty((H * B * Lq,), dtype=torch.float32, device=dev)
+        rsum = torch.empty_like(rmax)
+    keep, mptr, sb, sq, sk = mask_args(mask, B, Lq, Lk)
+    nat.check(nat.lib().lamp_attn_core_planes(
+        q.hi.data_ptr(), nat.ptr(q.lo), q.cols, q_col0, 1 if q.bcast_rows else 0,
+        kv.hi.data_ptr(), nat.ptr(kv.lo), kv.cols, k_col0, v_col0, B, H, Lq, Lk, d, float(math.sqrt(d)), prec,
+        mptr, sb, sq, sk, nat.ptr(o_hi), nat.ptr(o_lo), hd, nat.ptr(o32), hd, nat.ptr(rmax), nat.ptr(rsum),
+        nat.ptr(probs), nat.stream()), 'lamp_attn_core_planes')
+    del keep
+    return Act(o32, o_hi, o_lo, B * Lq, hd), probs
+
+
+def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask, temperature: float, prec: int, want_attn=True):
+    """ScaledDotProductAttention on head-major fp32 tensors through the level-2 entry point."""
+    nat.require_cuda(q, k, v)
+    q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+    N, Lq, d = q.shape
+    Lk = k.shape[1]
+    L = nat.lib()
+    out = torch.empty((N, Lq, d), dtype=torch.float32, device=q.device)
+    attn = torch.empty((N, Lq, Lk), dtype=torch.float32, device=q.device) if want_attn else None
+    ws = torch.empty((max(L.lamp_sdpa_workspace_bytes(N, Lq, Lk, d), 16),), dtype=torch.uint8, device=q.device)
+    keep, mptr, sb, sq, sk = mask_args(mask, N, Lq, Lk)
+    nat.check(L.lamp_sdpa_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), mptr, sb, sq, sk, out.data_ptr(), nat.ptr(attn),
+                              N, Lq, Lk, d, float(temperature), prec, ws.data_ptr(), ws.numel(), nat.stream()),
+              'lamp_sdpa_fwd')
+    del keep
+    return out, attn
+
+
+def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor, pos_emb: Optional[torch.Tensor],
+          prec: int) -> Act:
+    nat.require_cuda(seq, word_emb)
+    seq = seq.contiguous().long()
+    rows = seq.numel()
+    D = word_emb.shape[1]
+    out = torch.empty((rows, D), dtype=torch.float32, device=seq.device)
+    hi, lo = _empty_planes(rows, D, prec, seq.device)
+    if pos_emb is not None:
+        pos = pos.contiguous().long()
+    nat.check(nat.lib().lamp_embed(seq.data_ptr(), nat.ptr(pos) if pos_emb is not None else None,
+                                   word_emb.data_ptr(), nat.ptr(pos_emb), rows, D, out.data_ptr(), hi.data_ptr(),
+                                   nat.ptr(lo), nat.stream()), 'lamp_embed')
+    return Act(out, hi, lo, rows, D)
+
+
+def diag_proj(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """x [B, L, D], W [L, D] -> logits [B, L]."""
+    nat.require_cuda(x, W)
+    B, L, D = x.shape
+    x = x.contiguous()
+    out = torch.empty((B, L), dtype=torch.float32, device=x.device)
+    nat.check(nat.lib().lamp_diag_proj(x.data_ptr(), W.data_ptr(), nat.ptr(bias), B, L, D, out.data_ptr(),
+                                       nat.stream()), 'lamp_diag_proj')
+    return out
