@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""Benchmark of the label-graph forward (BASELINE.json metric: "label-graph forward samples/sec at L=103
+d_model=512; HBM GB/s vs roofline").
+
+A *step* is one ``LAMP.forward`` (graph encoder -> GraphDecoder label message passing -> diagonal label
+projection; lamp/Models.py:110-137) in eval mode over one batch of synthetic documents at BASELINE cfg-1/2 dims:
+L=103 labels, T=300 tokens, d_model=512, n_head=4, 2+2 layers, d_inner=512, prior label mask, fp32 in/out
+(LAMP_PREC_FP32: 3-term split-bf16 tensor-core products, parity-checked at 1e-3 against the reference).
+
+  value : samples/s, whole job, token ids already resident in HBM, CUDA-event timed, max over ranks
+  e2e   : same metric through the public API with HOST (pinned) token ids: H2D copy + forward + D2H of the logits
+          inside the timed region
+  roofline      : dominant kernel (projection GEMM, tensor-bound) -- algorithmic FLOPs / measured kernel time
+  roofline_attn : masked attention core kernel (HBM-bound)        -- algorithmic bytes / measured kernel time
+  cpu_baseline  : the CPU oracle (oracle/lamp_oracle.py, a torch-CPU port of the reference incl. its discarded
+                  encoder self-attention) timed on the host cores on a bounded sample
+  --impl reference : only the CPU port, same config, "impl": "reference"
+
+Launch: ``python bench.py --gpus N --steps K --warmup W`` (N > 1 under torchrun, one rank per GPU; the batch is
+sharded, the label graph and weights replicated, no forward collective -> "scaling": "weak").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(L=103, T=300, V=20000, D=512, d_inner=512, H=4, n_enc=2, n_dec=2, mask='prior', seed=0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=1024, help='samples per GPU per step')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--cpu-batch', type=int, default=32)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p['hbm_gbs'], tensor=p.get('bf16_tflops_sustained', p['bf16_tflops']), src='measured')
+    return dict(hbm=6650.0, tensor=1400.0, src='fallback')
+
+
+def synth(batch, seed):
+    from lamp_b200 import synthetic as syn
+    c = CFG
+    params = syn.lamp_params(c['V'] + 4, c['L'], c['T'], c['D'], c['d_inner'], c['H'], c['n_enc'], c['n_dec'],
+                             seed=c['seed'])
+    adj = syn.prior_adjacency(syn.make_label_sets(c['L'], seed=c['seed']), c['L'])
+    src_seq, src_pos = syn.make_tokens(batch, c['T'], c['V'], seed)
+    return params, adj, src_seq, src_pos
+
+
+def cpu_reference_throughput(steps, warmup, batch):
+    """The reference algorithm on the host cores: oracle port, all threads, eval, fp32."""
+    from oracle import lamp_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    params, adj, src_seq, src_pos = synth(batch, 1234)
+    lm = orc.label_mask_from(CFG['L'], adj, 'prior')
+    cfg = dict(n_layers_enc=CFG['n_enc'], n_layers_dec=CFG['n_dec'], n_head=CFG['H'], n_head2=CFG['H'])
+    with torch.no_grad():
+        for _ in range(warmup):
+            orc.lamp_forward(params, cfg, src_seq, src_pos, lm, compute_dead_attention=True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.lamp_forward(params, cfg, src_seq, src_pos, lm, compute_dead_attention=True)
+        dt = time.perf_counter() - t0
+    return steps * batch / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.rows:
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = max(smax, float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=smax or None, reasons=[], samples=0)
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    config = dict(workload='LAMP.forward eval, synthetic cfg-1/2 dims: L=103 T=300 d_model=512 n_head=4 '
+                           'n_layers 2+2 d_inner=512 prior label mask, fp32 I/O',
+                  batch_per_gpu=args.batch, global_batch=args.batch * world, seq_len=CFG['T'], n_labels=CFG['L'],
+                  precision=args.precision, parallelism=f'batch-sharded x{world}, replicated label graph',
+                  l2='activations per step (GBs) exceed the 126 MB L2; no explicit flush')
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        v, ms, cores = cpu_reference_throughput(args.steps, max(args.warmup, 1), args.cpu_batch)
+        config['batch_per_gpu'] = config['global_batch'] = args.cpu_batch
+        print(json.dumps(dict(
+            metric='label-graph forward samples/sec at L=103 d_model=512', value=v, unit='samples/s', n_gpus=0,
+            steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak',
+            vs_baseline=None, dtype='f32', data='synthetic', impl='reference', config=config,
+            cpu_baseline=dict(value=v, unit='samples/s', cores=cores, kind='port',
+                              sample=f'{args.steps} x LAMP.forward on B={args.cpu_batch} synthetic documents, '
+                                     'oracle port of the reference (torch CPU, MKL), all host threads'),
+            e2e=dict(value=v, unit='samples/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    import lamp_b200
+    from lamp_b200 import ops
+    from lamp_b200.Models import LAMP
+    lamp_b200.set_default_precision(args.precision)
+    dev = torch.device('cuda', local_rank)
+
+    params, adj, src_seq, src_pos = synth(args.batch, 100 + rank)
+    c = CFG
+    d = c['D'] // c['H']
+    model = LAMP(c['V'] + 4, c['L'], c['T'], c['L'], n_layers_enc=c['n_enc'], n_layers_dec=c['n_dec'], n_head=c['H'],
+                 n_head2=c['H'], d_word_vec=c['D'], d_model=c['D'], d_inner_hid=c['d_inner'], d_k=d, d_v=d,
+                 dropout=0.2, dec_dropout=0.2, dec_dropout2=False, proj_share_weight=True, encoder='graph',
+                 decoder='graph', label_adj_matrix=adj, label_mask='prior')
+    model.load_state_dict(params, strict=True)
+    model = model.to(dev).eval()
+    seq_d, pos_d = src_seq.to(dev), src_pos.to(dev)
+    seq_h, pos_h = src_seq.pin_memory(), src_pos.pin_memory()
+    logits_h = torch.empty((args.batch, c['L']), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            model((seq_d, pos_d), None, None, None)
+        # ---------------- device-resident throughput, with per-kernel CUDA events inside the timed region
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ops.STATS.reset()
+        t_wall0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ops.STATS.timed():
+            e0.record()
+            for _ in range(args.steps):
+                logits, _, _ = model((seq_d, pos_d), None, None, None)
+            e1.record()
+            barrier()
+            per_kernel = ops.STATS.stop_timing()
+        t_wall1 = time.perf_counter()
+        launches = ops.STATS.launches
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        # ---------------- end to end: pinned host ids -> H2D -> forward -> D2H logits, every step
+        for _ in range(2):
+            model((seq_h.to(dev, non_blocking=True), pos_h.to(dev, non_blocking=True)), None, None, None)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s_d = seq_h.to(dev, non_blocking=True)
+            p_d = pos_h.to(dev, non_blocking=True)
+            lg, _, _ = model((s_d, p_d), None, None, None)
+            logits_h.copy_(lg, non_blocking=True)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    total_samples = args.batch * world * args.steps
+    value = total_samples / (ms_total * 1e-3)
+    e2e_value = total_samples / e2e_s
+    pk = peaks()
+
+    def roof(name, bound):
+        k = per_kernel.get(name)
+        if not k or k['ms'] <= 0:
+            return None
+        sec = k['ms'] * 1e-3
+        if bound == 'tensor':
+            ach, peak, unit = k['flops'] / sec / 1e12, pk['tensor'], 'TFLOP/s'
+        else:
+            ach, peak, unit = k['bytes'] / sec / 1e9, pk['hbm'], 'GB/s'
+        return dict(kernel=name, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+                    peak_source=pk['src'], launches=k['calls'], avg_launch_ms=k['ms'] / k['calls'],
+                    share_of_step=k['ms'] / sum(v['ms'] for v in per_kernel.values()),
+                    alg_gbs=k['bytes'] / sec / 1e9, alg_tflops=k['flops'] / sec / 1e12)
+
+    out = dict(
+        metric='label-graph forward samples/sec at L=103 d_model=512', value=value, unit='samples/s', n_gpus=world,
+        steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True,
+        scaling='weak', vs_baseline=None, dtype='f32' if args.precision == 'fp32' else 'bf16', data='synthetic',
+        config=config,
+        e2e=dict(value=e2e_value, unit='samples/s',
+                 h2d_bytes_per_step=int(seq_h.numel() * 8 + pos_h.numel() * 8) * world,
+                 d2h_bytes_per_step=int(logits_h.numel() * 4) * world),
+        gpu_launches=launches, clocks=clocks,
+        roofline=roof('gemm_planes', 'tensor'), roofline_attn=roof('attn_core', 'hbm'),
+        kernels={k: dict(calls=v['calls'], ms=round(v['ms'], 3)) for k, v in per_kernel.items()})
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms, cores = cpu_reference_throughput(10, 2, args.cpu_batch)
+            out['cpu_baseline'] = dict(value=v, unit='samples/s', cores=cores, kind='port',
+                                       sample=f'10 x LAMP.forward on B={args.cpu_batch} synthetic documents '
+                                              f'({ms:.0f} ms each), oracle port of the reference, all host threads')
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

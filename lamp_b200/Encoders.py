@@ -1,0 +1,115 @@
+"""Drop-in replacement for ``lamp/Encoders.py:GraphEncoder``."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import Constants
+from . import _native as nat
+from . import ops
+from . import utils
+from .Layers import EncoderLayer
+from .SubLayers import _needs_autograd
+
+
+class GraphEncoder(nn.Module):
+    """lamp/Encoders.py:31-110: word (+ frozen sinusoid position) embeddings, ``n_layers`` x ``EncoderLayer``,
+    optional pooling (``enc_transform``).
+
+    Fused path: one gather kernel writes ``emb + pos`` as fp32 and as tensor-core operand planes; each layer is the
+    fused FFN (the token self-attention of the reference does not influence ``enc_output`` -- see
+    ``Layers.EncoderLayer`` -- and is evaluated only for ``return_attns=True``).  The genomics front-end
+    (``onehot=True``) and the per-sample ``adj`` masks of the ``sider`` dataset are outside the label-graph path and
+    run on the composed torch path.
+    """
+
+    def __init__(self, n_src_vocab, n_max_seq, n_layers=6, n_head=8, d_k=64, d_v=64,
+                 d_word_vec=512, d_model=512, d_inner_hid=1024, onehot=False, enc_transform='',
+                 dropout=0.1, no_enc_pos_embedding=False):
+        super().__init__()
+        n_position = n_max_seq + 1
+        self.n_max_seq = n_max_seq
+        self.d_model = d_model
+        self.onehot = onehot
+        self.enc_transform = enc_transform
+        self.dropout = nn.Dropout(dropout)
+        if onehot:
+            self.src_word_emb = nn.Embedding(n_src_vocab, n_src_vocab, padding_idx=Constants.PAD)
+            with torch.no_grad():
+                self.src_word_emb.weight.zero_()
+                self.src_word_emb.weight[1:, 1:] = torch.eye(n_src_vocab - 1)
+            self.conv1 = nn.Conv1d(9, d_model, 16, stride=1, padding=8)
+            self.conv2 = nn.Conv1d(d_model, d_model, 16, stride=1, padding=8)
+        else:
+            self.src_word_emb = nn.Embedding(n_src_vocab, d_word_vec, padding_idx=Constants.PAD)
+        if no_enc_pos_embedding is False:
+            self.position_enc = nn.Embedding(n_position, d_word_vec, padding_idx=Constants.PAD)
+            self.position_enc.weight.data = utils.position_encoding_init(n_position, d_word_vec)
+        self.layer_stack = nn.ModuleList([
+            EncoderLayer(d_model, d_inner_hid, n_head, d_k, d_v, dropout=dropout) for _ in range(n_layers)])
+
+    def fused_ok(self, adj) -> bool:
+        return (not self.onehot and not adj and len(self.layer_stack) > 0 and self.d_model % 8 == 0
+                and all(l.pos_ffn.fused_ok() and l.slf_attn.fused_ok() for l in self.layer_stack))
+
+    def _pool(self, enc_output, src_seq, batch_size):
+        t = self.enc_transform
+        if t == '':
+            return enc_output
+        if t == 'max':
+            pooled = enc_output.max(dim=1).values  # (the reference's 'max' branch references an undefined name)
+        elif t == 'sum':
+            pooled = enc_output.sum(1)
+        elif t == 'mean':
+            pooled = enc_output.sum(1) / ((src_seq > 0).sum(dim=1).float().view(-1, 1))
+        elif t == 'flatten':
+            pooled = enc_output.reshape(batch_size, -1).float()
+        else:
+            raise NotImplementedError(t)
+        return pooled.view(batch_size, 1, -1)
+
+    def _forward_composed(self, src_seq, adj, src_pos, return_attns):
+        enc_input = self.src_word_emb(src_seq)
+        if self.onehot:
+            x = F.relu(self.dropout(self.conv1(enc_input.transpose(1, 2))))[:, :, 0:-1]
+            x = F.max_pool1d(x, 2, 2)
+            enc_input = F.relu(self.conv2(x).transpose(1, 2))[:, 0:-1, :]
+            enc_input = enc_input + self.position_enc(src_pos[:, 0:enc_input.size(1)])
+            src_seq = src_seq[:, 0:enc_input.size(1)]
+        elif hasattr(self, 'position_enc'):
+            enc_input = enc_input + self.position_enc(src_pos)
+        mask = utils.get_attn_padding_mask(src_seq, src_seq)
+        if adj:
+            mask = mask.clone()
+            for i, a in enumerate(adj):
+                n = a.size(0)
+                mask[i, 0:n, 0:n] = (a == 0)
+        attns = []
+        out = enc_input
+        for layer in self.layer_stack:
+            out, attn = layer(out, slf_attn_mask=mask)
+            attns.append(attn)
+        return self._pool(out, src_seq, src_seq.size(0)), attns
+
+    def _forward_fused(self, src_seq, src_pos, return_attns):
+        B, T = src_seq.shape
+        prec = ops.default_precision() if self.layer_stack[0].pos_ffn.precision is None \
+            else self.layer_stack[0].pos_ffn.precision
+        pos_w = self.position_enc.weight if hasattr(self, 'position_enc') else None
+        x = ops.embed(src_seq, src_pos, self.src_word_emb.weight, pos_w, prec)
+        mask = src_seq.eq(Constants.PAD).unsqueeze(1) if return_attns else None  # [B, 1, T]
+        attns = []
+        for layer in self.layer_stack:
+            x, attn = layer.forward_act(x, B, T, mask, return_attns)
+            attns.append(attn)
+        out = x.f32.view(B, T, self.d_model)
+        if self.enc_transform == '':
+            ops.stash_planes(out, x, prec)
+        return self._pool(out, src_seq, B), attns
+
+    def forward(self, src_seq, adj, src_pos, return_attns=False):
+        nat.require_cuda(src_seq, src_pos)
+        if _needs_autograd(self) or not self.fused_ok(adj):
+            out, attns = self._forward_composed(src_seq, adj, src_pos, return_attns)
+        else:
+            out, attns = self._forward_fused(src_seq, src_pos, return_attns)
+        return (out, attns) if return_attns else (out, None)

@@ -1,0 +1,93 @@
+"""Drop-in replacement for ``lamp/Models.py:LAMP`` (graph encoder + graph decoder configurations)."""
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+from . import ops
+from .Decoders import GraphDecoder
+from .Encoders import GraphEncoder
+from .SubLayers import XavierLinear, _needs_autograd
+
+
+class LAMP(nn.Module):
+    """Same 30-keyword constructor, ``forward`` signature / return tuples, ``get_trainable_parameters`` and
+    ``state_dict`` keys as lamp/Models.py:18-137.  ``encoder`` must be ``'graph'`` and ``decoder`` ``'graph'``:
+    the MLP / RNN baselines are not part of the label-graph attention path."""
+
+    def __init__(self, n_src_vocab, n_tgt_vocab, n_max_seq_e, n_max_seq_d, n_layers_enc=6, n_layers_dec=6,
+                 n_head=8, n_head2=8, d_word_vec=512, d_model=512, d_inner_hid=1024, d_k=64, d_v=64,
+                 dropout=0.1, dec_dropout=0.1, dec_dropout2=0.1, proj_share_weight=True, embs_share_weight=True,
+                 encoder='selfatt', decoder='sa_m', enc_transform='', onehot=False, no_enc_pos_embedding=False,
+                 no_dec_self_att=False, loss='ce', label_adj_matrix=None, label_mask=None, matching_mlp=False,
+                 graph_conv=False, attn_type='softmax', int_preds=False):
+        super().__init__()
+        self.decoder_type = decoder
+        self.onehot = onehot
+        self.loss = loss
+        self.enc_vec = (encoder == 'mlp' or enc_transform != '')
+        if encoder != 'graph':
+            raise NotImplementedError(f"lamp_b200 implements the label-graph path only: encoder='{encoder}' "
+                                      "is a reference baseline outside it (use -encoder graph)")
+        if decoder != 'graph':
+            raise NotImplementedError(f"lamp_b200 implements the label-graph path only: decoder='{decoder}' "
+                                      "is a reference baseline outside it (use -decoder graph)")
+        self.encoder = GraphEncoder(
+            n_src_vocab, n_max_seq_e, n_layers=n_layers_enc, n_head=n_head, d_word_vec=d_word_vec, d_model=d_model,
+            d_k=d_k, d_v=d_v, d_inner_hid=d_inner_hid, onehot=onehot, dropout=dropout,
+            no_enc_pos_embedding=no_enc_pos_embedding, enc_transform=enc_transform)
+        self.decoder = GraphDecoder(
+            n_tgt_vocab, n_max_seq_d, n_layers=n_layers_dec, n_head=n_head, n_head2=n_head2, d_word_vec=d_word_vec,
+            d_model=d_model, d_k=d_k, d_v=d_v, d_inner_hid=d_inner_hid, dropout=dec_dropout, dropout2=dec_dropout2,
+            no_dec_self_att=no_dec_self_att, label_adj_matrix=label_adj_matrix, label_mask=label_mask,
+            enc_vec=self.enc_vec, graph_conv=graph_conv, attn_type=attn_type)
+        bias = not proj_share_weight  # lamp/Models.py:79-81 (graph decoder)
+        assert d_model == d_word_vec
+        self.proj_share_weight = proj_share_weight
+        if proj_share_weight:
+            self.tgt_word_proj = XavierLinear(d_model, n_tgt_vocab, bias=bias)
+            # As in the reference (:89) this registers an extra, unused alias parameter `tgt_word_proj.weight`;
+            # forward() uses `tgt_word_proj.linear.weight`.  Kept so reference checkpoints load strictly.
+            self.tgt_word_proj.weight = self.decoder.tgt_word_emb.weight
+        else:
+            self.tgt_word_proj = XavierLinear(d_model, 1, bias=bias)
+        if int_preds:
+            self.tgt_word_proj_copy = XavierLinear(d_model, n_tgt_vocab, bias=bias)
+
+    def get_trainable_parameters(self):
+        """Everything except the frozen sinusoid table (and the one-hot table) -- lamp/Models.py:97-107."""
+        frozen = set()
+        if hasattr(self.encoder, 'position_enc'):
+            frozen |= set(map(id, self.encoder.position_enc.parameters()))
+        if self.onehot:
+            frozen |= set(map(id, self.encoder.src_word_emb.parameters()))
+        return (p for p in self.parameters() if id(p) not in frozen)
+
+    def _project(self, x, fused):
+        """[B, L, D] -> [B, L]: diagonal of the label projection (lamp/Models.py:124-126)."""
+        lin = self.tgt_word_proj.linear
+        if fused and self.proj_share_weight:
+            return ops.diag_proj(x, lin.weight, lin.bias)
+        return torch.diagonal(self.tgt_word_proj(x), 0, 1, 2)
+
+    def forward(self, src, adj, tgt_seq, binary_tgt, return_attns=False, int_preds=False):
+        src_seq, src_pos = src
+        nat.require_cuda(src_seq, src_pos)
+        batch_size = src_seq.size(0)
+        fused = not _needs_autograd(self)
+        enc_output, *enc_self_attns = self.encoder(src_seq, adj, src_pos, return_attns=return_attns)
+        dec_output, *dec_output2 = self.decoder(tgt_seq, src_seq, enc_output, return_attns=return_attns,
+                                                int_preds=int_preds)
+        seq_logit = self._project(dec_output, fused)
+        seq_logit = seq_logit.reshape(-1, seq_logit.size(-1))
+        if int_preds:
+            w = self.tgt_word_proj.linear.weight.detach()
+            intermediate = []
+            for int_out in dec_output2[0][:-1]:
+                if fused and self.proj_share_weight:
+                    intermediate.append(ops.diag_proj(int_out, w, None))
+                else:
+                    intermediate.append(torch.einsum('bld,ld->bl', int_out, w))
+            return seq_logit, enc_output, intermediate
+        if return_attns:
+            return seq_logit, enc_output, enc_self_attns, dec_output2
+        return seq_logit, enc_output, None

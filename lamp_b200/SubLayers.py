@@ -1,0 +1,232 @@
+"""Drop-in replacements for ``lamp/SubLayers.py`` -- same class names, constructor signatures, ``forward``
+signatures / return tuples and ``state_dict`` keys -- with the arithmetic executed by the sm_100a kernels.
+
+* inference (``torch.no_grad()`` or ``module.eval()``): the fused kernel path
+  (``lamp_b200.ops`` -> ``liblamp_b200.so``);
+* training (``module.train()`` with grad enabled): a differentiable composition of torch CUDA ops with identical semantics
+  (dropout included); fusing the backward is listed as "next" in DESIGN.md.
+
+There is no CPU path: CPU tensors raise.  Reference rough edges fixed at the boundary: masks may be
+``bool`` or ``uint8``; nothing calls ``.cuda()`` unconditionally.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.nn.init as init
+
+from . import _native as nat
+from . import ops
+
+
+def _needs_autograd(module: nn.Module, *tensors) -> bool:
+    """The fused kernels are forward-only.  They serve every call made under ``torch.no_grad()`` or in ``eval()``
+    mode (outputs are then not attached to the autograd graph); a module in ``train()`` mode with grad enabled takes
+    the differentiable composed path (which also applies dropout)."""
+    return torch.is_grad_enabled() and module.training
+
+
+class XavierLinear(nn.Module):
+    """``nn.Linear`` with xavier-normal weights (lamp/SubLayers.py:7-13); keeps the ``.linear.weight`` key."""
+
+    def __init__(self, d_in, d_out, bias=True):
+        super().__init__()
+        self.linear = nn.Linear(d_in, d_out, bias=bias)
+        init.xavier_normal_(self.linear.weight)
+
+    def forward(self, x):
+        return self.linear(x)
+
+
+class ScaledDotProductAttention(nn.Module):
+    """softmax(mask(q k^T / temperature)) v  -- lamp/SubLayers.py:16-43.
+
+    q ``[N, Lq, d]``, k/v ``[N, Lk, d]``, attn_mask ``[N, Lq, Lk]`` (True / non-zero = masked).  Returns
+    ``(output, attn)``.  ``attn_type='sigmoid'`` (unreachable from the reference's layers) and autograd runs use
+    the composed torch path.
+    """
+
+    def __init__(self, temperature, dropout=0.1, attn_type='softmax'):
+        super().__init__()
+        self.temperature = float(temperature)
+        self.dropout = nn.Dropout(dropout)
+        self.attn_kind = attn_type
+        self.precision = None  # None -> ops.default_precision()
+
+    def _composed(self, q, k, v, attn_mask):
+        attn = torch.bmm(q, k.transpose(1, 2)) / self.temperature
+        if attn_mask is not None:
+            attn = attn.masked_fill(attn_mask.bool(), float('-inf'))
+        attn = torch.softmax(attn, dim=2) if self.attn_kind == 'softmax' else torch.sigmoid(attn)
+        attn = self.dropout(attn)
+        return torch.bmm(attn, v), attn
+
+    def forward(self, q, k, v, attn_mask=None, stop_sig=False):
+        nat.require_cuda(q, k, v, attn_mask)
+        d = q.shape[-1]
+        fused_ok = (self.attn_kind == 'softmax' and d % 16 == 0 and d <= 128 and k.shape[-1] == d
+                    and v.shape[-1] == d)
+        if _needs_autograd(self, q, k, v) or not fused_ok:
+            return self._composed(q, k, v, attn_mask)
+        prec = ops.default_precision() if self.precision is None else self.precision
+        return ops.sdpa(q, k, v, attn_mask, self.temperature, prec, want_attn=True)
+
+
+class MultiHeadAttention(nn.Module):
+    """Masked multi-head attention over label nodes -- lamp/SubLayers.py:46-121.
+
+    ``forward(q, k, v, attn_mask=None, dec_self=False) -> (LayerNorm(fc(heads) + q), attn [H*B, Lq, Lk])``.
+    The fused path runs: one projection GEMM (Q|K|V concatenated for self-attention, Q and K|V for
+    label<-input attention) -> masked softmax attention kernel (mask read in place, never tiled per head) ->
+    fc GEMM with the residual added in its epilogue -> LayerNorm that also emits the operand planes of the
+    next layer.  ``return_attn=False`` (internal callers) skips the probability output.
+    """
+
+    def __init__(self, n_head, d_model, d_k, d_v, dropout=0.1, dropout2=False, attn_type='softmax'):
+        super().__init__()
+        self.n_head = n_head
+        self.d_k = d_k
+        self.d_v = d_v
+        self.d_model = d_model
+        self.w_qs = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_ks = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_vs = nn.Linear(d_model, n_head * d_v, bias=False)
+        nn.init.normal_(self.w_qs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
+        nn.init.normal_(self.w_ks.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
+        nn.init.normal_(self.w_vs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_v)))
+        # lamp/SubLayers.py:61-65: `dropout2` (when truthy) replaces the attention-probability dropout rate
+        self.attention = ScaledDotProductAttention(temperature=np.power(d_k, 0.5), attn_type=attn_type,
+                                                   dropout=dropout2 if dropout2 else dropout)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(d_model)
+        if n_head > 1:
+            self.fc = nn.Linear(n_head * d_v, d_model, bias=False)
+            nn.init.xavier_normal_(self.fc.weight)
+        self.attn_kind = attn_type
+        self.precision = None
+        self._wp = ops.WeightPlanes()
+
+    # ------------------------------------------------------------------ composed (autograd) path
+    def _composed(self, q, k, v, attn_mask):
+        d_k, d_v, n_head = self.d_k, self.d_v, self.n_head
+        sz_b, len_q, _ = q.size()
+        len_k, len_v = k.size(1), v.size(1)
+        residual = q
+        qh = self.w_qs(q).view(sz_b, len_q, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_q, d_k)
+        kh = self.w_ks(k).view(sz_b, len_k, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_k, d_k)
+        vh = self.w_vs(v).view(sz_b, len_v, n_head, d_v).permute(2, 0, 1, 3).reshape(-1, len_v, d_v)
+        if attn_mask is not None:
+            attn_mask = attn_mask.bool().repeat(n_head, 1, 1)
+        out, attn = self.attention._composed(qh, kh, vh, attn_mask)
+        out = out.view(n_head, sz_b, len_q, d_v).permute(1, 2, 0, 3).reshape(sz_b, len_q, -1)
+        if hasattr(self, 'fc'):
+            out = self.fc(out)
+        out = self.dropout(out)
+        return self.layer_norm(out + residual), attn
+
+    # ------------------------------------------------------------------ fused path on Act objects
+    def fused_ok(self) -> bool:
+        d = self.d_k
+        return (self.attn_kind == 'softmax' and self.d_k == self.d_v and d % 16 == 0 and d <= 128
+                and self.d_model % 8 == 0 and (self.n_head > 1 or d == self.d_model))
+
+    def _prec(self) -> int:
+        return ops.default_precision() if self.precision is None else self.precision
+
+    def forward_act(self, q: ops.Act, kv, B: int, Lq: int, Lk: int, attn_mask, want_attn: bool,
+                    kv_proj=None):
+        """q: Act [B*Lq (or Lq, broadcast), D]; kv: None (self-attention) or Act [B*Lk, D].
+        ``kv_proj``: optional precomputed ``(Act [B*Lk, ld], k_col0, v_col0)`` K|V projection (GraphDecoder batches
+        the label<-input K|V projections of all its layers into one GEMM).  -> (Act out, probs or None)."""
+        prec = self._prec()
+        H, d, D = self.n_head, self.d_k, self.d_model
+        hd = H * d
+        if kv is None and kv_proj is None:
+            w_hi, w_lo = self._wp.get('qkv', (self.w_qs.weight, self.w_ks.weight, self.w_vs.weight), prec)
+            qkv = ops.linear_planes(q, w_hi, w_lo, 3 * hd, prec)
+            qp, q_col0, kvp, k_col0, v_col0 = qkv, 0, qkv, hd, 2 * hd
+        else:
+            w_hi, w_lo = self._wp.get('q', (self.w_qs.weight,), prec)
+            qp, q_col0 = ops.linear_planes(q, w_hi, w_lo, hd, prec), 0
+            if kv_proj is not None:
+                kvp, k_col0, v_col0 = kv_proj
+            else:
+                w_hi, w_lo = self._wp.get('kv', (self.w_ks.weight, self.w_vs.weight), prec)
+                kvp, k_col0, v_col0 = ops.linear_planes(kv, w_hi, w_lo, 2 * hd, prec), 0, hd
+        o, probs = ops.attention(qp, q_col0, kvp, k_col0, v_col0, B, H, Lq, Lk, d, prec, attn_mask, want_attn,
+                                 out_f32=(H == 1))
+        ln = self.layer_norm
+        if H > 1:
+            f_hi, f_lo = self._wp.get('fc', (self.fc.weight,), prec)
+            y = ops.linear_residual_f32(o, f_hi, f_lo, D, prec, residual=q)
+            out = ops.layernorm(y, ln.weight, ln.bias, ln.eps, prec)
+        else:
+            out = ops.layernorm(o.f32, ln.weight, ln.bias, ln.eps, prec, add=q)
+        return out, probs
+
+    def forward(self, q, k, v, attn_mask=None, dec_self=False, return_attn=True):
+        nat.require_cuda(q, k, v, attn_mask)
+        if _needs_autograd(self, q, k, v) or not self.fused_ok():
+            return self._composed(q, k, v, attn_mask)
+        B, Lq, D = q.shape
+        Lk = k.shape[1]
+        prec = self._prec()
+        qa = ops.act_from_tensor(q, prec)
+        if k is v:
+            kva = None if (k is q) else ops.act_from_tensor(k, prec)
+            out, probs = self.forward_act(qa, kva, B, Lq, Lk, attn_mask, return_attn)
+        else:
+            # distinct key / value sources (never produced by the reference's layers): project each into one [K|V] buffer
+            hd = self.n_head * self.d_k
+            ka, va = ops.act_from_tensor(k, prec), ops.act_from_tensor(v, prec)
+            hi, lo = ops._empty_planes(B * Lk, 2 * hd, prec, q.device)
+            for src, w, off in ((ka, self.w_ks.weight, 0), (va, self.w_vs.weight, hd)):
+                w_hi, w_lo = self._wp.get('k' if off == 0 else 'v', (w,), prec)
+                ops.gemm(src.hi, src.lo, D, w_hi, w_lo, D, B * Lk, hd, D, prec, out_hi=hi[:, off:],
+                         out_lo=None if lo is None else lo[:, off:], ldp=2 * hd)
+            out, probs = self.forward_act(qa, None, B, Lq, Lk, attn_mask, return_attn,
+                                          kv_proj=(ops.Act(None, hi, lo, B * Lk, 2 * hd), 0, hd))
+        res = out.f32.view(B, Lq, D)
+        ops.stash_planes(res, out, prec)
+        return res, probs
+
+
+class PositionwiseFeedForward(nn.Module):
+    """Conv1d(k=1) -> ReLU -> Conv1d(k=1) -> dropout -> +residual -> LayerNorm  -- lamp/SubLayers.py:125-142.
+    Fused path: GEMM(+bias, ReLU, planes out) -> GEMM(+bias, +residual) -> LayerNorm(+planes)."""
+
+    def __init__(self, d_in, d_hid, dropout=0.1):
+        super().__init__()
+        self.w_1 = nn.Conv1d(d_in, d_hid, 1)
+        self.w_2 = nn.Conv1d(d_hid, d_in, 1)
+        self.layer_norm = nn.LayerNorm(d_in)
+        self.dropout = nn.Dropout(dropout)
+        self.precision = None
+        self._wp = ops.WeightPlanes()
+
+    def _composed(self, x):
+        out = self.w_2(F.relu(self.w_1(x.transpose(1, 2)))).transpose(1, 2)
+        return self.layer_norm(self.dropout(out) + x)
+
+    def fused_ok(self) -> bool:
+        return self.w_1.in_channels % 8 == 0 and self.w_1.out_channels % 8 == 0
+
+    def forward_act(self, x: ops.Act, want_planes: bool = True) -> ops.Act:
+        prec = ops.default_precision() if self.precision is None else self.precision
+        D, dh = self.w_1.in_channels, self.w_1.out_channels
+        w1_hi, w1_lo = self._wp.get('w1', (self.w_1.weight,), prec)
+        w2_hi, w2_lo = self._wp.get('w2', (self.w_2.weight,), prec)
+        h = ops.linear_planes(x, w1_hi, w1_lo, dh, prec, bias=self.w_1.bias, relu=True)
+        y = ops.linear_residual_f32(h, w2_hi, w2_lo, D, prec, residual=x, bias=self.w_2.bias)
+        ln = self.layer_norm
+        return ops.layernorm(y, ln.weight, ln.bias, ln.eps, prec, want_planes=want_planes)
+
+    def forward(self, x):
+        nat.require_cuda(x)
+        if _needs_autograd(self, x) or not self.fused_ok():
+            return self._composed(x)
+        prec = ops.default_precision() if self.precision is None else self.precision
+        out = self.forward_act(ops.act_from_tensor(x, prec))
+        res = out.f32.view(x.shape)
+        ops.stash_planes(res, out, prec)
+        return res

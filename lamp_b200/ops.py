@@ -28,6 +28,60 @@ def default_precision() -> int:
     return _DEFAULT_PRECISION
 
 
+class LaunchStats:
+    """Kernel-launch accounting (always on, a counter per entry point) and optional CUDA-event timing of every
+    native call (``with ops.STATS.timed(): ...``), used by bench.py for the per-kernel roofline numbers."""
+
+    def __init__(self):
+        self.launches = 0
+        self.by_kernel: Dict[str, int] = {}
+        self._events = None
+
+    def reset(self):
+        self.launches = 0
+        self.by_kernel = {}
+
+    def timed(self):
+        stats = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                stats._events = []
+                return stats
+
+            def __exit__(self_inner, *exc):
+                return False
+        return _Ctx()
+
+    def stop_timing(self):
+        """-> {kernel: dict(calls, ms, flops, bytes)}; synchronises."""
+        ev, self._events = self._events or [], None
+        torch.cuda.synchronize()
+        out: Dict[str, dict] = {}
+        for name, e0, e1, flops, nbytes in ev:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            d['calls'] += 1
+            d['ms'] += e0.elapsed_time(e1)
+            d['flops'] += flops
+            d['bytes'] += nbytes
+        return out
+
+    def call(self, name: str, n_kernels: int, fn, args, flops: float = 0.0, nbytes: float = 0.0):
+        self.launches += n_kernels
+        self.by_kernel[name] = self.by_kernel.get(name, 0) + n_kernels
+        if self._events is None:
+            nat.check(fn(*args), name)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nat.check(fn(*args), name)
+        e1.record()
+        self._events.append((name, e0, e1, flops, nbytes))
+
+
+STATS = LaunchStats()
+
+
 @dataclass
 class Act:
     """fp32 activation ``[rows, cols]`` and/or its planes.  ``bcast``: logical row count when the ``rows``
@@ -57,8 +111,9 @@ def split(x: torch.Tensor, prec: int) -> Tuple[torch.Tensor, Optional[torch.Tens
     cols = x.shape[-1]
     rows = x.numel() // cols
     hi, lo = _empty_planes(rows, cols, prec, x.device)
-    nat.check(nat.lib().lamp_split_planes(x.data_ptr(), rows, cols, cols, hi.data_ptr(), nat.ptr(lo), cols,
-                                          nat.stream()), 'lamp_split_planes')
+    STATS.call('split_planes', 1, nat.lib().lamp_split_planes,
+               (x.data_ptr(), rows, cols, cols, hi.data_ptr(), nat.ptr(lo), cols, nat.stream()),
+               nbytes=rows * cols * (4 + (4 if lo is not None else 2)))
     return hi, lo
 
 
@@ -107,10 +162,13 @@ class WeightPlanes:
 def gemm(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, prec: int, *, bias=None, relu=False,
          residual=None, ldr: int = 0, resid_mod: int = 0, out_f32=None, ldo: int = 0, out_hi=None, out_lo=None,
          ldp: int = 0) -> None:
-    nat.check(nat.lib().lamp_gemm_planes(
-        nat.ptr(a_hi), nat.ptr(a_lo), lda, nat.ptr(w_hi), nat.ptr(w_lo), ldw, M, N, K, prec, nat.ptr(bias), int(relu),
-        nat.ptr(residual), ldr, resid_mod, nat.ptr(out_f32), ldo, nat.ptr(out_hi), nat.ptr(out_lo), ldp,
-        nat.stream()), 'lamp_gemm_planes')
+    pl = 4 if prec == nat.PREC_FP32 else 2  # bytes per element of a plane pair
+    nbytes = M * K * pl + N * K * pl + (M * N * 4 if out_f32 is not None else 0) + \
+        (M * N * pl if out_hi is not None else 0) + (M * N * 4 if residual is not None and not resid_mod else 0)
+    STATS.call('gemm_planes', 1, nat.lib().lamp_gemm_planes,
+               (nat.ptr(a_hi), nat.ptr(a_lo), lda, nat.ptr(w_hi), nat.ptr(w_lo), ldw, M, N, K, prec, nat.ptr(bias),
+                int(relu), nat.ptr(residual), ldr, resid_mod, nat.ptr(out_f32), ldo, nat.ptr(out_hi), nat.ptr(out_lo),
+                ldp, nat.stream()), flops=2.0 * M * N * K, nbytes=nbytes)
 
 
 def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=False) -> Act:
@@ -138,9 +196,10 @@ def layernorm(y: torch.Tensor, gamma, beta, eps: float, prec: int, *, add: Optio
     add_t, add_mod = (None, 0)
     if add is not None:
         add_t, add_mod = add.f32, (add.rows if add.bcast_rows else 0)
-    nat.check(nat.lib().lamp_layernorm(y.data_ptr(), nat.ptr(add_t), add_mod, gamma.data_ptr(), beta.data_ptr(),
-                                       float(eps), rows, D, out.data_ptr(), nat.ptr(hi), nat.ptr(lo), nat.stream()),
-              'lamp_layernorm')
+    STATS.call('layernorm', 1, nat.lib().lamp_layernorm,
+               (y.data_ptr(), nat.ptr(add_t), add_mod, gamma.data_ptr(), beta.data_ptr(), float(eps), rows, D,
+                out.data_ptr(), nat.ptr(hi), nat.ptr(lo), nat.stream()),
+               nbytes=rows * D * (8 + (0 if hi is None else (4 if lo is not None else 2))))
     return Act(out, hi, lo, rows, D)
 
 
@@ -153,7 +212,7 @@ def mask_args(mask: Optional[torch.Tensor], B: int, Lq: int, Lk: int):
     if mask.dim() == 2:
         mask = mask.unsqueeze(0)
     if mask.dtype == torch.bool:
-        m8 = mask.view(torch.uint8) if mask.is_contiguous() or True else mask
+        m8 = mask.view(torch.uint8)
     elif mask.dtype == torch.uint8:
         m8 = mask
     else:
@@ -179,11 +238,15 @@ def attention(q: Act, q_col0: int, kv: Act, k_col0: int, v_col0: int, B: int, H:
         rmax = torch.empty((H * B * Lq,), dtype=torch.float32, device=dev)
         rsum = torch.empty_like(rmax)
     keep, mptr, sb, sq, sk = mask_args(mask, B, Lq, Lk)
-    nat.check(nat.lib().lamp_attn_core_planes(
-        q.hi.data_ptr(), nat.ptr(q.lo), q.cols, q_col0, 1 if q.bcast_rows else 0,
-        kv.hi.data_ptr(), nat.ptr(kv.lo), kv.cols, k_col0, v_col0, B, H, Lq, Lk, d, float(math.sqrt(d)), prec,
-        mptr, sb, sq, sk, nat.ptr(o_hi), nat.ptr(o_lo), hd, nat.ptr(o32), hd, nat.ptr(rmax), nat.ptr(rsum),
-        nat.ptr(probs), nat.stream()), 'lamp_attn_core_planes')
+    pl = 4 if prec == nat.PREC_FP32 else 2
+    # algorithmic bytes of the attention core: Q + K + V read, O written, 4 B (fp32-equivalent
+    # plane pair) or 2 B (bf16) per element; a broadcast Q is read once.
+    nbytes = ((1 if q.bcast_rows else B) * Lq * hd + 2 * B * Lk * hd) * pl + B * Lq * hd * (4 if out_f32 else pl)
+    STATS.call('attn_core', 2 if want_probs else 1, nat.lib().lamp_attn_core_planes,
+               (q.hi.data_ptr(), nat.ptr(q.lo), q.cols, q_col0, 1 if q.bcast_rows else 0,
+                kv.hi.data_ptr(), nat.ptr(kv.lo), kv.cols, k_col0, v_col0, B, H, Lq, Lk, d, float(math.sqrt(d)), prec,
+                mptr, sb, sq, sk, nat.ptr(o_hi), nat.ptr(o_lo), hd, nat.ptr(o32), hd, nat.ptr(rmax), nat.ptr(rsum),
+                nat.ptr(probs), nat.stream()), flops=4.0 * B * H * Lq * Lk * d, nbytes=nbytes)
     del keep
     return Act(o32, o_hi, o_lo, B * Lq, hd), probs
 
@@ -199,9 +262,9 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask, temperature: f
     attn = torch.empty((N, Lq, Lk), dtype=torch.float32, device=q.device) if want_attn else None
     ws = torch.empty((max(L.lamp_sdpa_workspace_bytes(N, Lq, Lk, d), 16),), dtype=torch.uint8, device=q.device)
     keep, mptr, sb, sq, sk = mask_args(mask, N, Lq, Lk)
-    nat.check(L.lamp_sdpa_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), mptr, sb, sq, sk, out.data_ptr(), nat.ptr(attn),
-                              N, Lq, Lk, d, float(temperature), prec, ws.data_ptr(), ws.numel(), nat.stream()),
-              'lamp_sdpa_fwd')
+    STATS.call('sdpa_fwd', 5 if want_attn else 4, L.lamp_sdpa_fwd,
+               (q.data_ptr(), k.data_ptr(), v.data_ptr(), mptr, sb, sq, sk, out.data_ptr(), nat.ptr(attn), N, Lq, Lk, d,
+                float(temperature), prec, ws.data_ptr(), ws.numel(), nat.stream()), flops=4.0 * N * Lq * Lk * d)
     del keep
     return out, attn
 
@@ -216,9 +279,10 @@ def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor
     hi, lo = _empty_planes(rows, D, prec, seq.device)
     if pos_emb is not None:
         pos = pos.contiguous().long()
-    nat.check(nat.lib().lamp_embed(seq.data_ptr(), nat.ptr(pos) if pos_emb is not None else None,
-                                   word_emb.data_ptr(), nat.ptr(pos_emb), rows, D, out.data_ptr(), hi.data_ptr(),
-                                   nat.ptr(lo), nat.stream()), 'lamp_embed')
+    STATS.call('embed', 1, nat.lib().lamp_embed,
+               (seq.data_ptr(), nat.ptr(pos) if pos_emb is not None else None, word_emb.data_ptr(), nat.ptr(pos_emb),
+                rows, D, out.data_ptr(), hi.data_ptr(), nat.ptr(lo), nat.stream()),
+               nbytes=rows * D * (4 + 4 + (4 if lo is not None else 2)))
     return Act(out, hi, lo, rows, D)
 
 
@@ -228,6 +292,7 @@ def diag_proj(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) ->
     B, L, D = x.shape
     x = x.contiguous()
     out = torch.empty((B, L), dtype=torch.float32, device=x.device)
-    nat.check(nat.lib().lamp_diag_proj(x.data_ptr(), W.data_ptr(), nat.ptr(bias), B, L, D, out.data_ptr(),
-                                       nat.stream()), 'lamp_diag_proj')
+    STATS.call('diag_proj', 1, nat.lib().lamp_diag_proj,
+               (x.data_ptr(), W.data_ptr(), nat.ptr(bias), B, L, D, out.data_ptr(), nat.stream()),
+               flops=2.0 * B * L * D, nbytes=B * L * D * 4)
     return out

@@ -1,0 +1,216 @@
+"""GPU parity of the drop-in modules (lamp_b200.SubLayers / Layers / Decoders / Encoders / Models) against the
+reference-generated fixtures and the CPU oracle.  Tolerance: 1e-3 relative (north_star), fp32 path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import lamp_b200
+from lamp_b200.Models import LAMP
+from lamp_b200.SubLayers import MultiHeadAttention, PositionwiseFeedForward, ScaledDotProductAttention
+from lamp_b200.Layers import DecoderLayer, EncoderLayer
+from oracle import lamp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+DEV = 'cuda'
+TOL = 1e-3
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def load(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLD, name + '.npz')).items()}
+
+
+def build_model(c, p, adj):
+    d = c['D'] // c['H']
+    m = LAMP(c['V'] + 4, c['L'], c['T'], c['L'], n_layers_enc=c['n_enc'], n_layers_dec=c['n_dec'], n_head=c['H'],
+             n_head2=c['H'], d_word_vec=c['D'], d_model=c['D'], d_inner_hid=c['d_inner'], d_k=d, d_v=d, dropout=0.2,
+             dec_dropout=0.2, dec_dropout2=False, proj_share_weight=True, encoder='graph', decoder='graph',
+             enc_transform=c.get('enc_transform', ''), no_enc_pos_embedding=not c.get('pos_enc', True),
+             label_adj_matrix=adj, label_mask=c['mask'])
+    m.load_state_dict(p, strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize('name', list(cases.MODEL_CASES))
+def test_lamp_forward_golden(name):
+    c = cases.MODEL_CASES[name]
+    g = load('model_' + name)
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    adj_before = None if adj is None else adj.clone()
+    model = build_model(c, p, adj)
+    assert adj is None or torch.equal(adj, adj_before)  # caller's adjacency is not mutated
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+    with torch.no_grad():
+        logits, enc_out, none = model(src, None, None, None)
+    assert none is None and logits.shape == (c['B'], c['L'])
+    e = rel_err(logits, g['logits'])
+    e_enc = rel_err(enc_out[:, ::7], g['enc_output'])
+    print(f'{name}: logits vs reference {e:.2e}, enc_output {e_enc:.2e}')
+    assert e < TOL and e_enc < TOL
+    # attention maps: layout [H*B, Lq, Lk] head-major, returned as in the reference
+    with torch.no_grad():
+        logits2, _, enc_attns, dec_rest = model(src, None, None, None, return_attns=True)
+    dec_slf, dec_enc = dec_rest
+    assert rel_err(logits2, g['logits']) < TOL
+    assert rel_err(dec_slf[0], g['dec_slf_attn0']) < TOL
+    assert rel_err(dec_enc[-1][:, ::5], g['dec_enc_attn_last']) < TOL
+    assert rel_err(enc_attns[0][0][:, ::11, ::3], g['enc_slf_attn0']) < TOL
+    with torch.no_grad():
+        logits3, _, int_preds = model(src, None, None, None, int_preds=True)
+    assert len(int_preds) == int(g['n_int_preds'])
+    assert rel_err(int_preds[0], g['int_pred0']) < TOL
+    assert rel_err(logits3, g['logits']) < TOL
+
+
+def test_eval_mode_without_no_grad_uses_fused_path_and_matches():
+    c = cases.MODEL_CASES['lamp_L37_none']
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    model = build_model(c, p, adj)
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+    logits, _, _ = model(src, None, None, None)  # grad enabled, eval mode
+    assert not logits.requires_grad
+    g = load('model_lamp_L37_none')
+    assert rel_err(logits, g['logits']) < TOL
+
+
+def test_training_path_is_differentiable_and_matches_oracle_without_dropout():
+    c = dict(cases.MODEL_CASES['lamp_L37_inveye'])
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    model = build_model(c, p, adj)
+    model.train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+    logits, _, _ = model(src, None, None, None)
+    assert logits.requires_grad
+    lm = orc.label_mask_from(c['L'], adj, c['mask'])
+    ref, _ = orc.lamp_forward(p, cfg, src_seq, src_pos, lm)
+    assert rel_err(logits, ref) < TOL
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, torch.zeros_like(logits))
+    loss.backward()
+    got = [n for n, q in model.named_parameters() if q.grad is not None]
+    dead = [n for n, q in model.named_parameters() if q.grad is None and q.requires_grad]
+    assert any('decoder.layer_stack.0.slf_attn.w_qs' in n for n in got)
+    # the encoder self-attention never receives gradients (lamp/Layers.py:16-18), nor does the alias / pos table
+    assert all(('encoder.layer_stack' in n and 'slf_attn' in n) or n == 'encoder.position_enc.weight' for n in dead), dead
+
+
+@pytest.mark.parametrize('name', ['self_L103_H4_prior', 'enc_L103_T300_H4_pad', 'self_L40_H1_nofc',
+                                  'self_L983_H4_prior'])
+def test_mha_module(name):
+    c = cases.MHA_CASES[name]
+    g = load('mha_' + name)
+    p, q, kv, mask = cases.mha_inputs(c)
+    d = c['D'] // c['H']
+    m = MultiHeadAttention(c['H'], c['D'], d, d, dropout=0.1)
+    m.load_state_dict(p, strict=True)
+    m = m.to(DEV).eval()
+    qd = q.to(DEV)
+    kvd = qd if kv is q else kv.to(DEV)
+    md = None if mask is None else mask.to(DEV)
+    with torch.no_grad():
+        out, attn = m(qd, kvd, kvd, attn_mask=md)
+    assert attn.shape == (c['H'] * c['B'], c['Lq'], c['Lk'])
+    assert rel_err(out[:, ::c.get('row_stride', 1)], g['out']) < TOL
+    # uint8 masks (the reference's .byte()) are accepted too
+    if md is not None:
+        with torch.no_grad():
+            out2, _ = m(qd, kvd, kvd, attn_mask=md.contiguous().to(torch.uint8), return_attn=False)
+        assert torch.equal(out, out2)
+    # distinct k / v tensors
+    with torch.no_grad():
+        out3, _ = m(qd, kvd, kvd.clone(), attn_mask=md, return_attn=False)
+    assert rel_err(out3, out) < 1e-5
+
+
+def test_sdpa_module_and_layers():
+    rs = np.random.RandomState(0)
+    q = torch.from_numpy(rs.standard_normal((6, 50, 64)).astype(np.float32))
+    k = torch.from_numpy(rs.standard_normal((6, 70, 64)).astype(np.float32))
+    v = torch.from_numpy(rs.standard_normal((6, 70, 64)).astype(np.float32))
+    mask = torch.from_numpy(rs.rand(6, 50, 70) < 0.5)
+    mask[:, :, 3] = False
+    sd = ScaledDotProductAttention(8.0).to(DEV).eval()
+    with torch.no_grad():
+        out, attn = sd(q.to(DEV), k.to(DEV), v.to(DEV), attn_mask=mask.to(DEV))
+    ro, ra = orc.sdpa(q, k, v, mask, 8.0)
+    assert rel_err(out, ro) < TOL and rel_err(attn, ra) < TOL
+    # DecoderLayer / EncoderLayer / FFN modules against the oracle
+    from lamp_b200 import synthetic as syn
+    D, H, dh, B, L, T = 128, 4, 256, 3, 37, 50
+    p = {}
+    p.update(syn.mha_params(rs, 'enc_attn.', H, D, D // H, D // H, True))
+    p.update(syn.ffn_params(rs, 'pos_ffn1.', D, dh, True))
+    p.update(syn.mha_params(rs, 'slf_attn.', H, D, D // H, D // H, True))
+    p.update(syn.ffn_params(rs, 'pos_ffn2.', D, dh, True))
+    layer = DecoderLayer(D, dh, H, H, D // H, D // H)
+    layer.load_state_dict(p, strict=True)
+    layer = layer.to(DEV).eval()
+    x = torch.from_numpy(rs.standard_normal((B, L, D)).astype(np.float32))
+    enc = torch.from_numpy(rs.standard_normal((B, T, D)).astype(np.float32))
+    lm = torch.from_numpy(rs.rand(L, L) < 0.6)
+    lm[torch.arange(L), torch.arange(L)] = False
+    slf = lm.unsqueeze(0).expand(B, L, L)
+    with torch.no_grad():
+        out, out_int, sa, ea = layer(x.to(DEV), enc.to(DEV), slf_attn_mask=slf.to(DEV))
+    r_out, r_int, r_sa, r_ea = orc.decoder_layer(p, '', x, enc, slf, None, H, H)
+    for a, b in ((out, r_out), (out_int, r_int), (sa, r_sa), (ea, r_ea)):
+        assert rel_err(a, b) < TOL
+    pe = {}
+    pe.update(syn.mha_params(rs, 'slf_attn.', H, D, D // H, D // H, True))
+    pe.update(syn.ffn_params(rs, 'pos_ffn.', D, dh, True))
+    el = EncoderLayer(D, dh, H, D // H, D // H)
+    el.load_state_dict(pe, strict=True)
+    el = el.to(DEV).eval()
+    with torch.no_grad():
+        eo, eattn = el(enc.to(DEV))
+    r_eo, r_eattn = orc.encoder_layer(pe, '', enc, None, H)
+    assert rel_err(eo, r_eo) < TOL and rel_err(eattn, r_eattn) < TOL
+    ff = PositionwiseFeedForward(D, dh)
+    ff.load_state_dict({k[len('pos_ffn.'):]: v for k, v in pe.items() if k.startswith('pos_ffn.')})
+    ff = ff.to(DEV).eval()
+    with torch.no_grad():
+        fo = ff(enc.to(DEV))
+    assert rel_err(fo, orc.ffn(pe, 'pos_ffn.', enc)) < TOL
+
+
+def test_cpu_tensors_raise():
+    m = MultiHeadAttention(2, 32, 16, 16).eval()
+    x = torch.zeros(1, 4, 32)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m(x, x, x)
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg-2 shape at a bench-size batch, through size-independent properties: batch-permutation
+    equivariance, independence of samples from one another, probabilities sum to one."""
+    c = cases.MHA_CASES['self_L103_H4_prior']
+    p, q, kv, mask = cases.mha_inputs(c)
+    d = c['D'] // c['H']
+    m = MultiHeadAttention(c['H'], c['D'], d, d)
+    m.load_state_dict(p, strict=True)
+    m = m.to(DEV).eval()
+    B = 1024
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(B, 103, 512, device=DEV, generator=g)
+    md = mask[:1].to(DEV).expand(B, 103, 103)
+    with torch.no_grad():
+        out, _ = m(x, x, x, attn_mask=md, return_attn=False)
+        perm = torch.randperm(B, device=DEV, generator=g)
+        out_p, _ = m(x[perm], x[perm], x[perm], attn_mask=md, return_attn=False)
+        out_s, attn_s = m(x[:3], x[:3], x[:3], attn_mask=md[:3])
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[perm], out_p)            # deterministic, sample-independent
+    assert torch.equal(out[:3], out_s)
+    assert rel_err(attn_s.sum(-1), torch.ones_like(attn_s.sum(-1))) < 1e-5
+    ref, _ = orc.mha(p, '', x[:2].cpu(), x[:2].cpu(), x[:2].cpu(), mask[:2], c['H'])
+    assert rel_err(out[:2], ref) < TOL
