@@ -44,6 +44,9 @@ const char* lamp_last_error(void);
 /* 0 if the CURRENT device can run the library (sm_100), LAMP_EARCH otherwise. */
 int lamp_device_check(void);
 int lamp_sm_count(void);
+/* Process-wide tuning knobs (benchmarking aid; results are identical for every setting). */
+#define LAMP_TUNE_GEMM_BLOCK_K 1 /* 32 (default: 64B-swizzle, deeper TMA ring) or 64 (128B swizzle) */
+int lamp_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------- level 1: kernels ------------------------ */
 

@@ -27,6 +27,7 @@ _SIGNATURES = {
     'lamp_last_error': ([], C.c_char_p),
     'lamp_device_check': ([], _i),
     'lamp_sm_count': ([], _i),
+    'lamp_set_tuning': ([_i, _i], _i),
     'lamp_split_planes': ([_vp, _i64, _i, _i64, _vp, _vp, _i64, _vp], _i),
     'lamp_gemm_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp,
                           _i64, _vp], _i),

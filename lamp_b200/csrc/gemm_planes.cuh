@@ -3,14 +3,17 @@
 // Operands are "split-bf16 planes" (see sm100_primitives.cuh): each fp32 matrix is carried as a hi and a lo
 // bf16 matrix.  With NTERMS == 3 every K-slice issues three tcgen05.mma (hi*hi + hi*lo + lo*hi, fp32
 // accumulation in TMEM), which reproduces an fp32 GEMM to ~2^-16 relative -- this is the path that meets the
-// reference's 1e-3 fp32 tolerance with >30x margin.  NTERMS == 1 uses the hi planes only (plain bf16 GEMM).
+// reference's 1e-3 fp32 tolerance with >100x margin.  NTERMS == 1 uses the hi planes only (plain bf16 GEMM).
 //
 // Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0   : TMA producer   -- cp.async.bulk.tensor 2D, 128B-swizzled [rows x 64] bf16 boxes, STAGES-deep ring
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor 2D, swizzled [rows x BLOCK_K] bf16 boxes, STAGES-deep ring.
+//                                BLOCK_K = 32 (64 B rows, 64B swizzle) keeps 4 stages of 48 KB in flight for the
+//                                3-term 128x256 tile; BLOCK_K = 64 (128B swizzle) is kept for comparison.
 //   warp 1   : MMA issuer     -- one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into a double-buffered
 //                                TMEM accumulator (2 x BLOCK_N columns); tcgen05.commit releases smem stages
-//   warps 2-5: epilogue       -- tcgen05.ld (lane == output row), bias / ReLU / residual, then fp32 and/or
-//                                split-bf16 stores; overlaps with the next tile's main loop
+//   warps 2-5: epilogue       -- tcgen05.ld (lane == output row) -> per-warp XOR-swizzled smem transpose -> every
+//                                global access (residual read, fp32 / plane stores) is a full 128 B row segment
+//                                per 8 lanes; overlaps with the next tile's main loop
 // Used for: Q/K/V projections, fc (+residual), both FFN layers (lamp/SubLayers.py:91-93,110,133).
 #pragma once
 #include "sm100_primitives.cuh"
@@ -32,33 +35,39 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
+constexpr uint32_t GEMM_EPI_STAGING = 4 * 32 * 128;  // 4 epilogue warps x (32 rows x 128 B)
 
-template <int BLOCK_N, int NTERMS>
+template <int BLOCK_N, int NTERMS, int BLOCK_K>
 struct GemmCfg {
+  static_assert(BLOCK_K == 32 || BLOCK_K == 64, "BLOCK_K selects the 64B / 128B swizzle");
   static constexpr int NPL = (NTERMS == 3) ? 2 : 1;
-  static constexpr uint32_t A_TILE = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  static constexpr uint32_t W_TILE = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr uint32_t ROW_BYTES = BLOCK_K * 2;
+  static constexpr uint32_t A_TILE = GEMM_BLOCK_M * ROW_BYTES;
+  static constexpr uint32_t W_TILE = BLOCK_N * ROW_BYTES;
   static constexpr uint32_t STAGE_BYTES = NPL * (A_TILE + W_TILE);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_STAGING + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint64_t LAYOUT = (BLOCK_K == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;  // 8-row core-matrix group
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
 };
 
-template <int BLOCK_N, int NTERMS>
+template <int BLOCK_N, int NTERMS, int BLOCK_K>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                    const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, NTERMS>;
+  using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NPL = Cfg::NPL;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_STAGING);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -96,7 +105,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
   const int num_m = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_k = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_tiles = num_m * num_n;
 
   auto stage_ptr = [&](int s, int which) -> uint8_t* {
@@ -121,7 +130,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          const int k0 = kb * GEMM_BLOCK_K;
+          const int k0 = kb * BLOCK_K;
           tma_load_2d(stage_ptr(stage, 0), &tmA_hi, &full_bar[stage], k0, m0);
           tma_load_2d(stage_ptr(stage, 1), &tmW_hi, &full_bar[stage], k0, n0);
           if (NPL == 2) {
@@ -152,14 +161,14 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           const uint32_t a_lo = smem_u32(stage_ptr(stage, 2));
           const uint32_t w_lo = smem_u32(stage_ptr(stage, 3));
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the 128 B swizzle row
-            const uint64_t da_hi = umma_smem_desc(a_hi + koff, 16, 1024);
-            const uint64_t dw_hi = umma_smem_desc(w_hi + koff, 16, 1024);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the swizzled row
+            const uint64_t da_hi = umma_smem_desc(a_hi + koff, 16, Cfg::SBO, Cfg::LAYOUT);
+            const uint64_t dw_hi = umma_smem_desc(w_hi + koff, 16, Cfg::SBO, Cfg::LAYOUT);
             umma_bf16_ss(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (NTERMS == 3) {
-              const uint64_t da_lo = umma_smem_desc(a_lo + koff, 16, 1024);
-              const uint64_t dw_lo = umma_smem_desc(w_lo + koff, 16, 1024);
+              const uint64_t da_lo = umma_smem_desc(a_lo + koff, 16, Cfg::SBO, Cfg::LAYOUT);
+              const uint64_t dw_lo = umma_smem_desc(w_lo + koff, 16, Cfg::SBO, Cfg::LAYOUT);
               umma_bf16_ss(d_tmem, da_hi, dw_lo, idesc, 1u);
               umma_bf16_ss(d_tmem, da_lo, dw_hi, idesc, 1u);
             }
@@ -174,68 +183,72 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* stg = staging + wq * (32 * 128);
+    const int sub_r = lane >> 3;  // coalesced phase: 8 lanes per row, 4 rows per pass
+    const int sub_c = lane & 7;   // 16-byte chunk (4 fp32) inside the 128 B row segment
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * GEMM_BLOCK_M;
+      const int m0 = (tile / num_n) * GEMM_BLOCK_M + wq * 32;
       const int n0 = (tile % num_n) * BLOCK_N;
-      const int row = m0 + wq * 32 + lane;
-      const bool row_ok = row < p.M;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
-      const float* res_row = nullptr;
-      if (p.residual != nullptr && row_ok) {
-        const int rr = p.resid_mod ? (row % p.resid_mod) : row;
-        res_row = p.residual + static_cast<size_t>(rr) * p.ldr;
-      }
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_row + c0, r);
         tmem_wait_ld();
-        if (row_ok) {
+        if (n0 + c0 >= p.N) continue;  // warp-uniform: whole 32-column chunk out of range
+        // registers (lane == row) -> swizzled staging: chunk c of row `lane` lives at chunk (c ^ (lane & 7))
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = n0 + c0 + j;
-            if (col < p.N) {  // N % 8 == 0 is enforced by the host wrapper
-              float v[8];
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        __syncwarp();
+        const int col = n0 + c0 + sub_c * 4;
+        const bool col_ok = col < p.N;  // N % 8 == 0 (host-checked) -> the 4 columns are all in or all out
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        // residual rows first (8 independent 128-bit loads in flight), then the staged accumulators
+        float4 resv[8];
+        if (p.residual != nullptr) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-              }
-              if (res_row != nullptr) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(res_row + col));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(res_row + col + 4));
-                v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w;
-                v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
-              }
-              if (p.out_f32 != nullptr) {
-                float4* o = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * p.ldo + col);
-                o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                o[1] = make_float4(v[4], v[5], v[6], v[7]);
-              }
-              if (p.out_hi != nullptr) {
-                uint4 hi, lo;
-                split_bf16x2(v[0], v[1], hi.x, lo.x);
-                split_bf16x2(v[2], v[3], hi.y, lo.y);
-                split_bf16x2(v[4], v[5], hi.z, lo.z);
-                split_bf16x2(v[6], v[7], hi.w, lo.w);
-                const size_t off = static_cast<size_t>(row) * p.ldp + col;
-                *reinterpret_cast<uint4*>(p.out_hi + off) = hi;
-                if (p.out_lo != nullptr) *reinterpret_cast<uint4*>(p.out_lo + off) = lo;
-              }
+          for (int i = 0; i < 8; ++i) {
+            const int row = m0 + i * 4 + sub_r;
+            resv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < p.M && col_ok) {
+              const int rres = p.resid_mod ? (row % p.resid_mod) : row;
+              resv[i] = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rres) * p.ldr + col));
             }
           }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub_r;
+          const int row = m0 + rr;
+          float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((sub_c ^ (rr & 7)) << 4));
+          if (row < p.M && col_ok) {
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (p.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if (p.residual != nullptr) {
+              v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w;
+            }
+            if (p.out_f32 != nullptr)
+              *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * p.ldo + col) = v;
+            if (p.out_hi != nullptr) {
+              uint2 hi, lo;
+              split_bf16x2(v.x, v.y, hi.x, lo.x);
+              split_bf16x2(v.z, v.w, hi.y, lo.y);
+              const size_t off = static_cast<size_t>(row) * p.ldp + col;
+              *reinterpret_cast<uint2*>(p.out_hi + off) = hi;
+              if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + off) = lo;
+            }
+          }
+        }
+        __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);

@@ -63,7 +63,7 @@ EncodeTiledFn encode_fn() {
 
 // bf16 matrix viewed as {cols, rows[, batch]}; box = {64 cols (128 B), box_rows[, 1]}, 128B swizzle, zero OOB fill.
 int make_tmap(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
-              uint32_t box_rows, bool three_d) {
+              uint32_t box_rows, bool three_d, uint32_t box_cols = 64) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (!aligned16(base)) return fail(LAMP_EINVAL, "TMA base pointer not 16-byte aligned");
@@ -71,10 +71,11 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, ui
                                             (unsigned long long)ld_elems);
   cuuint64_t dims[3] = {cols, rows, batch};
   cuuint64_t strides[2] = {ld_elems * 2, rows * ld_elems * 2};
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  const CUtensorMapSwizzle swz = (box_cols == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, three_d ? 3 : 2, const_cast<void*>(base), dims, strides, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return LAMP_OK;
@@ -117,19 +118,21 @@ int launch_check() {
   return LAMP_OK;
 }
 
-template <int BLOCK_N, int NTERMS>
+template <int BLOCK_N, int NTERMS, int BLOCK_K>
 int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                 const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BLOCK_N, NTERMS>;
+  using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K>;
   static std::once_flag once;
   static int once_rc = LAMP_OK;
-  std::call_once(once, [] { once_rc = set_smem(gemm_planes_kernel<BLOCK_N, NTERMS>, Cfg::SMEM_BYTES); });
+  std::call_once(once, [] { once_rc = set_smem(gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K>, Cfg::SMEM_BYTES); });
   if (once_rc != LAMP_OK) return once_rc;
   const int tiles = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
-  gemm_planes_kernel<BLOCK_N, NTERMS><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, p);
   return launch_check();
 }
+
+std::atomic<int> g_gemm_block_k{32};  // tuning knob (lamp_set_tuning): 32 -> 64B swizzle / deep ring, 64 -> 128B swizzle
 
 template <int BLOCK_KV, bool ALIAS, int NTERMS>
 int launch_attn(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi, const CUtensorMap& kv_lo,
@@ -170,6 +173,14 @@ const char* lamp_last_error(void) { return g_err; }
 int lamp_device_check(void) { return arch_check(); }
 int lamp_sm_count(void) { return sm_count_cached(); }
 
+int lamp_set_tuning(int key, int value) {
+  if (key == LAMP_TUNE_GEMM_BLOCK_K && (value == 32 || value == 64)) {
+    g_gemm_block_k.store(value);
+    return LAMP_OK;
+  }
+  return fail(LAMP_EINVAL, "set_tuning: unknown key/value %d/%d", key, value);
+}
+
 int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* hi, void* lo, int64_t ldp,
                       void* stream) {
   if (int rc = arch_check()) return rc;
@@ -206,11 +217,12 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
   const bool wide = (N > 128);
   const uint32_t box_n = wide ? 256 : 128;
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
-  if (int rc = make_tmap(&ta_hi, a_hi, K, M, 1, lda, GEMM_BLOCK_M, false)) return rc;
-  if (int rc = make_tmap(&tw_hi, w_hi, K, N, 1, ldw, box_n, false)) return rc;
+  const int bk = g_gemm_block_k.load();
+  if (int rc = make_tmap(&ta_hi, a_hi, K, M, 1, lda, GEMM_BLOCK_M, false, bk)) return rc;
+  if (int rc = make_tmap(&tw_hi, w_hi, K, N, 1, ldw, box_n, false, bk)) return rc;
   if (three) {
-    if (int rc = make_tmap(&ta_lo, a_lo, K, M, 1, lda, GEMM_BLOCK_M, false)) return rc;
-    if (int rc = make_tmap(&tw_lo, w_lo, K, N, 1, ldw, box_n, false)) return rc;
+    if (int rc = make_tmap(&ta_lo, a_lo, K, M, 1, lda, GEMM_BLOCK_M, false, bk)) return rc;
+    if (int rc = make_tmap(&tw_lo, w_lo, K, N, 1, ldw, box_n, false, bk)) return rc;
   } else {
     ta_lo = ta_hi;
     tw_lo = tw_hi;
@@ -223,8 +235,16 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
   p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.ldp = (int)ldp;
   cudaStream_t st = (cudaStream_t)stream;
-  if (three) return wide ? launch_gemm<256, 3>(ta_hi, ta_lo, tw_hi, tw_lo, p, st) : launch_gemm<128, 3>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);
-  return wide ? launch_gemm<256, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st) : launch_gemm<128, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);
+#define LAMP_GEMM_DISPATCH(BK)                                                                                      \
+  do {                                                                                                             \
+    if (three) return wide ? launch_gemm<256, 3, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st)                            \
+                           : launch_gemm<128, 3, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                           \
+    return wide ? launch_gemm<256, 1, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st)                                       \
+                : launch_gemm<128, 1, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                                      \
+  } while (0)
+  if (bk == 64) LAMP_GEMM_DISPATCH(64);
+  LAMP_GEMM_DISPATCH(32);
+#undef LAMP_GEMM_DISPATCH
 }
 
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,

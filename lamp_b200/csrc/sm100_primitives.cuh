@@ -106,13 +106,15 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //   [46,48) version = 1 | [49,52) base offset | [61,64) layout: 0 none, 2 = 128B, 4 = 64B, 6 = 32B swizzle
 constexpr uint64_t UMMA_LAYOUT_SW128 = 2;
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+constexpr uint64_t UMMA_LAYOUT_SW64 = 4;
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint64_t layout = UMMA_LAYOUT_SW128) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= UMMA_LAYOUT_SW128 << 61;
+  d |= layout << 61;
   return d;
 }
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32:
