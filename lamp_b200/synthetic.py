@@ -141,3 +141,29 @@ def lamp_params(n_src_vocab: int, n_labels: int, n_max_seq: int, d_model: int, d
     p['tgt_word_proj.weight'] = p['decoder.tgt_word_emb.weight']  # alias, unused by forward (Models.py:88-90)
     p['tgt_word_proj.linear.weight'] = _normal(rs, (n_labels, d_model), math.sqrt(2.0 / (d_model + n_labels)))
     return p
+
+
+def make_dataset_dict(n_labels: int, vocab: int, n_train: int, n_valid: int, n_test: int, max_len: int = 40,
+                      seed: int = 0):
+    """A ``train_valid_test.pt``-style dict in the reference's on-disk format (utils/preprocess.py:200-232):
+    word/label <-> index dicts with the 4 special tokens first, ``src`` rows ``[BOS, w..., EOS]`` and ``tgt`` rows
+    ``[BOS, l..., EOS]``; every label occurs in ``train`` (required by utils/data_loader.py:60-73)."""
+    import argparse
+    rs = np.random.RandomState(seed)
+    special = {'<blank>': PAD, '<unk>': UNK, '<s>': BOS, '</s>': EOS}
+    src_dict = dict(special)
+    src_dict.update({f'w{i}': i + 4 for i in range(vocab)})
+    tgt_dict = dict(special)
+    tgt_dict.update({f'l{i}': i + 4 for i in range(n_labels)})
+
+    def split(n, s):
+        tg = make_label_sets(n_labels, n_docs=n, seed=s)
+        src = []
+        for _ in range(n):
+            ln = rs.randint(5, max_len + 1)
+            src.append([BOS] + rs.randint(4, vocab + 4, size=ln).tolist() + [EOS])
+        return {'src': src, 'tgt': tg}
+    settings = argparse.Namespace(max_seq_len=max_len + 2, max_tgt_len=n_labels)
+    return {'settings': settings, 'dict': {'src': src_dict, 'tgt': tgt_dict},
+            'train': split(max(n_train, n_labels), seed + 1), 'valid': split(n_valid, seed + 2),
+            'test': split(n_test, seed + 3)}
