@@ -1,19 +1,24 @@
 // Masked attention core over label nodes:   O = softmax(mask(Q K^T / temperature)) V      (per sample, per head)
 // Reference: lamp/SubLayers.py:27-43 (ScaledDotProductAttention.forward), called from :104.
 //
-// One persistent CTA per SM loops over work items (b, h, q-tile of 128 label rows) and, inside, over KV tiles:
+// One persistent CTA per SM walks a sequence of "units" = (work item (b, h, 128-row q tile), KV tile j):
 //   warp 0   : TMA producer -- 3D tensor maps {cols, L, B}: rows >= L are zero-filled by the hardware, so ragged
 //              label counts (L = 103, 159, 983 ...) need no padding in HBM.  Q/K/V arrive as 128B-swizzled
-//              [rows x 64] bf16 boxes of the split-bf16 planes written by the projection GEMM.
-//   warp 1   : MMA issuer   -- S = Q K^T  (A, B K-major) and O (+)= P V  (B = V is MN-major: V is consumed in its
-//              natural [keys x d] layout, no transpose pass); 3-term split-bf16 products, fp32 accumulators in TMEM.
-//   warps 2-5: softmax      -- TMEM lane == query row, so each thread owns a whole score row: mask + running
-//              max/sum (online softmax across KV tiles) + exp2 + hi/lo split; P goes back to smem as the A operand
-//              of the PV product; O is rescaled in TMEM when the running max moves; final 1/sum folded into the
-//              epilogue which writes the head's slice of the concatenated output (no permute / contiguous copies).
-// The label mask is read from its single [Lq, Lk] (or [B, Lk] key-padding) byte copy with arbitrary strides and
-// turned into per-row bit words with warp ballots -- it is never tiled per head or per sample
-// (the reference materialises H*B*Lq*Lk bytes, lamp/SubLayers.py:102 / lamp/Decoders.py:141).
+//              [rows x 64] bf16 boxes of the split-bf16 planes written by the projection GEMM.  Q, K and V have
+//              independent buffers/barriers, so the next unit's operands stream in while the current one computes.
+//   warp 1   : MMA issuer   -- S = Q K^T (A, B from smem, K-major) into one of TWO TMEM score buffers, issued one
+//              unit ahead of the softmax; O (+)= P V with P read from TENSOR MEMORY (TS form) and V consumed
+//              MN-major straight from its natural [keys x d] layout (no transpose pass); 3-term split-bf16 products.
+//   warps 2.. : softmax     -- 4 * (BLOCK_KV/32) warps: TMEM lane == query row and every warp owns one 32-column
+//              chunk of the rows of its lane quarter (4 warps per scheduler hide the ALU/MUFU latency of the
+//              exp2 / split chain).  Strided byte mask -> bit words via warp ballots, row max exchanged through
+//              2 KB of smem, online max/sum across KV tiles, ex2, hi/lo split, P written back to TMEM (never to
+//              shared or global memory); O rescaled in TMEM when the running max moves.  The epilogue of the
+//              PREVIOUS item (1/sum, hi/lo split, stores into the head's column slice of the concatenated output)
+//              runs after the current unit's softmax, hiding the PV latency.
+// TMEM columns: S0 [0,128) | S1 [128,256) | P hi/lo [256,384) | O [384,512).
+// The label mask is read from its single [Lq, Lk] (or [B, Lk] key-padding) copy -- it is never tiled per head or
+// per sample (the reference materialises H*B*Lq*Lk bytes, lamp/SubLayers.py:102 / lamp/Decoders.py:141).
 #pragma once
 #include "sm100_primitives.cuh"
 
@@ -36,57 +41,66 @@ struct AttnParams {
 };
 
 constexpr int ATTN_BLOCK_M = 128;
-constexpr int ATTN_THREADS = 192;
-constexpr uint32_t ATTN_TMEM_COLS = 256;  // S: [0,128)   O: [128,256)
+constexpr uint32_t ATTN_TMEM_COLS = 512;
+constexpr uint32_t ATTN_TMEM_S = 0, ATTN_TMEM_P = 256, ATTN_TMEM_O = 384;
+// row-statistics exchange between the column-warps of a row: max [2 units][NW][128] + sum [2 items][NW][128] floats
+constexpr uint32_t ATTN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
+__host__ __device__ constexpr int attn_threads(int block_kv) { return 64 + 128 * (block_kv / 32); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Shared-memory plan (bytes).  kb64 = ceil(d / 64) column blocks of 64 bf16 (= one 128 B swizzle row each).
-template <int BLOCK_KV, bool ALIAS_PQ, int NTERMS>
+template <int BLOCK_KV, int KV_STAGES, int NTERMS>
 struct AttnSmem {
   static constexpr int NPL = (NTERMS == 3) ? 2 : 1;
   __host__ __device__ static constexpr uint32_t q_bytes(int kb64) { return NPL * kb64 * ATTN_BLOCK_M * 128; }
   __host__ __device__ static constexpr uint32_t kv_bytes(int kb64) { return NPL * kb64 * BLOCK_KV * 128; }
-  __host__ __device__ static constexpr uint32_t p_bytes() { return NPL * (BLOCK_KV / 64) * ATTN_BLOCK_M * 128; }
   __host__ __device__ static constexpr uint32_t total(int kb64) {
-    const uint32_t qp = ALIAS_PQ ? (q_bytes(kb64) > p_bytes() ? q_bytes(kb64) : p_bytes()) : q_bytes(kb64) + p_bytes();
-    return qp + 2 * kv_bytes(kb64) + 1024 /*align*/ + 256 /*barriers*/;
+    return q_bytes(kb64) + 2 * KV_STAGES * kv_bytes(kb64) + ATTN_RED_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   }
 };
 
-template <int BLOCK_KV, bool ALIAS_PQ, int NTERMS>
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+template <int BLOCK_KV, int KV_STAGES, int NTERMS>
+__global__ void __launch_bounds__(attn_threads(BLOCK_KV), 1)
 attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
                  const __grid_constant__ CUtensorMap tmKV_hi, const __grid_constant__ CUtensorMap tmKV_lo,
                  const AttnParams p) {
-  using SM = AttnSmem<BLOCK_KV, ALIAS_PQ, NTERMS>;
+  using SM = AttnSmem<BLOCK_KV, KV_STAGES, NTERMS>;
   constexpr int NPL = SM::NPL;
-  constexpr int NW = BLOCK_KV / 32;  // mask words per row
+  constexpr int NW = BLOCK_KV / 32;        // 32-column score chunks per row == softmax warps per lane quarter
+  constexpr int NSW = 4 * NW * 32;         // softmax threads
+  constexpr uint32_t P_LO = BLOCK_KV / 2;  // TMEM column offset of the lo plane inside the P region
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kb64 = (p.d + 63) >> 6;
-  const uint32_t q_bytes = SM::q_bytes(kb64), kv_bytes = SM::kv_bytes(kb64), p_bytes = SM::p_bytes();
+  const uint32_t q_bytes = SM::q_bytes(kb64), kv_bytes = SM::kv_bytes(kb64);
   uint8_t* sQ = smem;
-  uint8_t* sP = ALIAS_PQ ? smem : smem + q_bytes;
-  const uint32_t qp_bytes = ALIAS_PQ ? (q_bytes > p_bytes ? q_bytes : p_bytes) : q_bytes + p_bytes;
-  uint8_t* sK = smem + qp_bytes;
-  uint8_t* sV = sK + kv_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kv_bytes);
+  uint8_t* sK = sQ + q_bytes;                   // KV_STAGES buffers
+  uint8_t* sV = sK + KV_STAGES * kv_bytes;      // KV_STAGES buffers
+  float* red_max = reinterpret_cast<float*>(sV + KV_STAGES * kv_bytes);  // [2][4][128]
+  float* red_l = red_max + 2 * 4 * 128;                                  // [2][4][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_max) + ATTN_RED_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;
-  uint64_t* k_empty = bars + 3;
-  uint64_t* v_full = bars + 4;
-  uint64_t* v_empty = bars + 5;
-  uint64_t* s_full = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* o_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* p_full = bars + 2;   // count NSW
+  uint64_t* o_done = bars + 3;
+  uint64_t* s_full = bars + 4;   // [2]
+  uint64_t* s_free = bars + 6;   // [2], count NSW
+  uint64_t* k_full = bars + 8;   // [KV_STAGES]
+  uint64_t* k_empty = bars + 8 + KV_STAGES;
+  uint64_t* v_full = bars + 8 + 2 * KV_STAGES;
+  uint64_t* v_empty = bars + 8 + 3 * KV_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 4 * KV_STAGES);
 
   // plane pl (0 = hi, 1 = lo), 64-column block kb
   auto q_tile = [&](int pl, int kb) { return sQ + (pl * kb64 + kb) * (ATTN_BLOCK_M * 128); };
-  auto k_tile = [&](int pl, int kb) { return sK + (pl * kb64 + kb) * (BLOCK_KV * 128); };
-  auto v_tile = [&](int pl, int kb) { return sV + (pl * kb64 + kb) * (BLOCK_KV * 128); };
-  auto p_tile = [&](int pl, int kb) { return sP + (pl * (BLOCK_KV / 64) + kb) * (ATTN_BLOCK_M * 128); };
+  auto k_tile = [&](int st, int pl, int kb) { return sK + st * kv_bytes + (pl * kb64 + kb) * (BLOCK_KV * 128); };
+  auto v_tile = [&](int st, int pl, int kb) { return sV + st * kv_bytes + (pl * kb64 + kb) * (BLOCK_KV * 128); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,7 +112,20 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       tma_prefetch_desc(&tmQ_lo);
       tma_prefetch_desc(&tmKV_lo);
     }
-    for (int i = 0; i < 9; ++i) mbar_init(&bars[i], i == 7 ? 128u : 1u);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(p_full, NSW);
+    mbar_init(o_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], NSW);
+    }
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -109,8 +136,6 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
 
   const int num_qt = (p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M;
   const int num_kv = (p.Lk + BLOCK_KV - 1) / BLOCK_KV;
@@ -120,17 +145,20 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      uint32_t it = 0, kvc = 0;  // per-CTA counters -> barrier parities
+      uint32_t it = 0, u = 0;  // per-CTA item / unit counters -> barrier stages and parities
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int qt = item % num_qt;
         const int h = (item / num_qt) % p.H;
         const int b = item / (num_qt * p.H);
-        for (int j = 0; j < num_kv; ++j, ++kvc) {
-          mbar_wait(k_empty, (kvc & 1) ^ 1);
-          mbar_arrive_expect_tx(k_full, kv_bytes);
+        for (int j = 0; j < num_kv; ++j, ++u) {
+          const int st = u % KV_STAGES;
+          const uint32_t par = (u / KV_STAGES) & 1;
+          mbar_wait(&k_empty[st], par ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], kv_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(k_tile(0, kb), &tmKV_hi, k_full, p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
-            if (NPL == 2) tma_load_3d(k_tile(1, kb), &tmKV_lo, k_full, p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            tma_load_3d(k_tile(st, 0, kb), &tmKV_hi, &k_full[st], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            if (NPL == 2)
+              tma_load_3d(k_tile(st, 1, kb), &tmKV_lo, &k_full[st], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
           }
           if (j == 0) {
             mbar_wait(q_empty, (it & 1) ^ 1);
@@ -142,11 +170,12 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 tma_load_3d(q_tile(1, kb), &tmQ_lo, q_full, p.q_col0 + h * p.d + kb * 64, qt * ATTN_BLOCK_M, bq);
             }
           }
-          mbar_wait(v_empty, (kvc & 1) ^ 1);
-          mbar_arrive_expect_tx(v_full, kv_bytes);
+          mbar_wait(&v_empty[st], par ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], kv_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(v_tile(0, kb), &tmKV_hi, v_full, p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
-            if (NPL == 2) tma_load_3d(v_tile(1, kb), &tmKV_lo, v_full, p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            tma_load_3d(v_tile(st, 0, kb), &tmKV_hi, &v_full[st], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            if (NPL == 2)
+              tma_load_3d(v_tile(st, 1, kb), &tmKV_lo, &v_full[st], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
           }
         }
       }
@@ -155,210 +184,240 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(ATTN_BLOCK_M, BLOCK_KV, 0, 0);
-      const uint32_t idesc_o = umma_idesc_bf16(ATTN_BLOCK_M, p.d, 0, 1);  // B = V is MN-major
-      uint32_t it = 0, kvc = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        for (int j = 0; j < num_kv; ++j, ++kvc) {
-          const bool last = (j == num_kv - 1);
-          if (j == 0) mbar_wait(q_full, it & 1);
-          mbar_wait(k_full, kvc & 1);
-          tcgen05_fence_after();
-          // S = Q K^T : both operands K-major (d contiguous), SBO = 8 rows * 128 B
-          for (int t = 0; t < ksteps_d; ++t) {
-            const int kb = t >> 2;
-            const uint32_t koff = (t & 3) * 32;
-            const uint64_t dq_hi = umma_smem_desc(smem_u32(q_tile(0, kb)) + koff, 16, 1024);
-            const uint64_t dk_hi = umma_smem_desc(smem_u32(k_tile(0, kb)) + koff, 16, 1024);
-            umma_bf16_ss(tmem_S, dq_hi, dk_hi, idesc_s, t != 0 ? 1u : 0u);
-            if (NTERMS == 3) {
-              const uint64_t dq_lo = umma_smem_desc(smem_u32(q_tile(1, kb)) + koff, 16, 1024);
-              const uint64_t dk_lo = umma_smem_desc(smem_u32(k_tile(1, kb)) + koff, 16, 1024);
-              umma_bf16_ss(tmem_S, dq_hi, dk_lo, idesc_s, 1u);
-              umma_bf16_ss(tmem_S, dq_lo, dk_hi, idesc_s, 1u);
-            }
+      const uint32_t idesc_o = umma_idesc_bf16(ATTN_BLOCK_M, p.d, 0, 1);  // A = P from TMEM, B = V MN-major
+      const int my_items = (num_items > static_cast<int>(blockIdx.x))
+                               ? (num_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+      const uint32_t total_units = static_cast<uint32_t>(my_items) * num_kv;
+
+      // S(u) = Q K_u^T into score buffer u & 1
+      auto issue_s = [&](uint32_t u) {
+        const uint32_t it = u / num_kv;
+        const int j = static_cast<int>(u % num_kv);
+        const int st = u % KV_STAGES;
+        const uint32_t par = (u / KV_STAGES) & 1;
+        const uint32_t sb = u & 1;
+        if (j == 0) mbar_wait(q_full, it & 1);
+        mbar_wait(&k_full[st], par);
+        mbar_wait(&s_free[sb], ((u >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128;
+        for (int t = 0; t < ksteps_d; ++t) {
+          const int kb = t >> 2;
+          const uint32_t koff = (t & 3) * 32;
+          const uint64_t dq_hi = umma_smem_desc(smem_u32(q_tile(0, kb)) + koff, 16, 1024);
+          const uint64_t dk_hi = umma_smem_desc(smem_u32(k_tile(st, 0, kb)) + koff, 16, 1024);
+          umma_bf16_ss(tS, dq_hi, dk_hi, idesc_s, t != 0 ? 1u : 0u);
+          if (NTERMS == 3) {
+            const uint64_t dq_lo = umma_smem_desc(smem_u32(q_tile(1, kb)) + koff, 16, 1024);
+            const uint64_t dk_lo = umma_smem_desc(smem_u32(k_tile(st, 1, kb)) + koff, 16, 1024);
+            umma_bf16_ss(tS, dq_hi, dk_lo, idesc_s, 1u);
+            umma_bf16_ss(tS, dq_lo, dk_hi, idesc_s, 1u);
           }
-          umma_commit(s_full);
-          umma_commit(k_empty);
-          if (last && !ALIAS_PQ) umma_commit(q_empty);
-          // O (+)= P V_j
-          mbar_wait(p_full, kvc & 1);
-          mbar_wait(v_full, kvc & 1);
-          tcgen05_fence_after();
-          const int kv_valid = min(BLOCK_KV, p.Lk - j * BLOCK_KV);
-          const int ksteps_kv = (kv_valid + 15) >> 4;
-          for (int t = 0; t < ksteps_kv; ++t) {
-            // A = P: K-major, 64-column blocks; B = V: MN-major, K (= key index) advances by 16 rows of 128 B,
-            // LBO = distance between the 64-wide d blocks, SBO = 8 key rows.
-            const uint32_t pa = (t & 3) * 32;
-            const uint64_t dp_hi = umma_smem_desc(smem_u32(p_tile(0, t >> 2)) + pa, 16, 1024);
-            const uint64_t dv_hi = umma_smem_desc(smem_u32(v_tile(0, 0)) + t * 2048, BLOCK_KV * 128, 1024);
-            const uint32_t accum = (j != 0 || t != 0) ? 1u : 0u;
-            umma_bf16_ss(tmem_O, dp_hi, dv_hi, idesc_o, accum);
-            if (NTERMS == 3) {
-              const uint64_t dp_lo = umma_smem_desc(smem_u32(p_tile(1, t >> 2)) + pa, 16, 1024);
-              const uint64_t dv_lo = umma_smem_desc(smem_u32(v_tile(1, 0)) + t * 2048, BLOCK_KV * 128, 1024);
-              umma_bf16_ss(tmem_O, dp_hi, dv_lo, idesc_o, 1u);
-              umma_bf16_ss(tmem_O, dp_lo, dv_hi, idesc_o, 1u);
-            }
-          }
-          umma_commit(o_done);
-          umma_commit(v_empty);
-          if (last && ALIAS_PQ) umma_commit(q_empty);
         }
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[st]);
+        if (j == num_kv - 1) umma_commit(q_empty);
+      };
+
+      if (total_units > 0) issue_s(0);
+      for (uint32_t u = 0; u < total_units; ++u) {
+        if (u + 1 < total_units) issue_s(u + 1);  // one unit ahead: overlaps the softmax of unit u
+        const int j = static_cast<int>(u % num_kv);
+        const int st = u % KV_STAGES;
+        const uint32_t par = (u / KV_STAGES) & 1;
+        mbar_wait(p_full, u & 1);
+        mbar_wait(&v_full[st], par);
+        tcgen05_fence_after();
+        const int kv_valid = min(BLOCK_KV, p.Lk - j * BLOCK_KV);
+        const int ksteps_kv = (kv_valid + 15) >> 4;
+        const uint32_t tO = tmem_base + ATTN_TMEM_O;
+        const uint32_t tP = tmem_base + ATTN_TMEM_P;
+        for (int t = 0; t < ksteps_kv; ++t) {
+          // A = P from TMEM: 16 bf16 (8 columns) per K-step.  B = V MN-major: K (= key index) advances by 16 rows of
+          // 128 B, LBO = distance between the 64-wide d blocks, SBO = 8 key rows.
+          const uint64_t dv_hi = umma_smem_desc(smem_u32(v_tile(st, 0, 0)) + t * 2048, BLOCK_KV * 128, 1024);
+          const uint32_t accum = (j != 0 || t != 0) ? 1u : 0u;
+          umma_bf16_ts(tO, tP + 8 * t, dv_hi, idesc_o, accum);
+          if (NTERMS == 3) {
+            const uint64_t dv_lo = umma_smem_desc(smem_u32(v_tile(st, 1, 0)) + t * 2048, BLOCK_KV * 128, 1024);
+            umma_bf16_ts(tO, tP + 8 * t, dv_lo, idesc_o, 1u);
+            umma_bf16_ts(tO, tP + P_LO + 8 * t, dv_hi, idesc_o, 1u);
+          }
+        }
+        umma_commit(o_done);
+        umma_commit(&v_empty[st]);
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax + epilogue (warps 2..5)
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;  // row inside the q tile == TMEM lane
+    // ---------------------------------------------------------------- softmax + epilogue (warps 2 .. 2+4*NW)
+    const int wq = warp & 3;           // TMEM lane quarter (hardware rule: warp_id % 4)
+    const int cw = (warp - 2) >> 2;    // 32-column chunk of the score tile owned by this warp
+    const int row = wq * 32 + lane;    // row inside the q tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
-    uint32_t mw[NW];  // mask words of this thread's row (bit set = masked)
-    long long mkey = -1;  // (b, qt, j) combination the words were built for
-    uint32_t kvc = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int qt = item % num_qt;
-      const int h = (item / num_qt) % p.H;
-      const int b = item / (num_qt * p.H);
+    const uint32_t tO = tmem_base + ATTN_TMEM_O + lane_sel;
+    const uint32_t tP = tmem_base + ATTN_TMEM_P + lane_sel;
+    const int ngroups = p.d >> 4;      // 16-column groups of O; group g belongs to column-warp g % NW
+    uint32_t mw = 0;                   // mask bits of (row, this warp's 32 columns); bit set = masked
+    long long mkey = -1;               // (b, qt, j) combination the word was built for
+
+    // O / l -> this head's column slice of the concatenated output.  Each thread writes full 32 B sectors.
+    auto epilogue = [&](int b, int h, int qt, int par, float m_run) {
+      float l_tot = 0.0f;
+#pragma unroll
+      for (int c = 0; c < NW; ++c) l_tot += red_l[(par * 4 + c) * 128 + row];
+      const float inv = 1.0f / l_tot;  // l == 0 (row fully masked) -> inf -> NaN, as the reference's softmax of all -inf
       const int qrow = qt * ATTN_BLOCK_M + row;
-      float m_run = -INFINITY, l_run = 0.0f;
-      for (int j = 0; j < num_kv; ++j, ++kvc) {
-        const int k0 = j * BLOCK_KV;
-        // ---- mask words for (row, this KV tile); cached while the addressed mask region is unchanged
-        {
-          const long long key = (p.mask == nullptr)
-                                    ? static_cast<long long>(j)
-                                    : ((p.msb ? static_cast<long long>(b) : 0) * num_qt + (p.msq ? qt : 0)) * num_kv + j;
-          if (key != mkey) {
-            mkey = key;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-              const int rem = p.Lk - (k0 + 32 * w);  // valid columns in this word
-              mw[w] = rem >= 32 ? 0u : (rem <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << rem));
-            }
-            if (p.mask != nullptr) {
-              const uint8_t* mb = p.mask + static_cast<long long>(b) * p.msb;
-              const int nrows = p.msq ? 32 : 1;
-              for (int rr = 0; rr < nrows; ++rr) {
-                const int qr = qt * ATTN_BLOCK_M + wq * 32 + rr;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                  const int kc = k0 + 32 * w + lane;
-                  uint32_t byte = 0;
-                  if (kc < p.Lk && qr < p.Lq) byte = mb[static_cast<long long>(qr) * p.msq + static_cast<long long>(kc) * p.msk];
-                  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, byte != 0);
-                  if (!p.msq || lane == rr) mw[w] |= bal;
-                }
-              }
-            }
-          }
-        }
-        mbar_wait(s_full, kvc & 1);
-        tcgen05_fence_after();
-        // ---- pass 1: row maximum of the masked scores (raw, unscaled; scale > 0)
-        float mx = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_sel + 32 * w, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (!((mw[w] >> e) & 1u)) mx = fmaxf(mx, __uint_as_float(r[e]));
-        }
-        const float m_new = fmaxf(m_run, mx);
-        const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-        const float alpha = (m_new == -INFINITY) ? 1.0f : exp2f((m_run - m_new) * p.scale_log2);
-        // ---- rescale the running output when the maximum moved (needs PV of the previous tile retired)
-        if (j > 0) {
-          mbar_wait(o_done, (kvc - 1) & 1);
-          tcgen05_fence_after();
-          for (int c = 0; c < p.d; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_O + lane_sel + c, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-            tmem_st16(tmem_O + lane_sel + c, r);
-          }
-          tmem_wait_st();
-        }
-        // ---- pass 2: P = exp2((s - m) * scale), hi/lo split, swizzled K-major store for the PV product
-        float sum = 0.0f;
-        const float mb2 = m_use * p.scale_log2;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t r[32];
-          tmem_ld32(tmem_S + lane_sel + 32 * w, r);
-          tmem_wait_ld();
-          float pv[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float x = exp2f(__uint_as_float(r[e]) * p.scale_log2 - mb2);
-            pv[e] = ((mw[w] >> e) & 1u) ? 0.0f : x;
-            sum += pv[e];
-          }
-          // columns [32w, 32w+32) -> 64-column block (w>>1), 16-byte chunks (4*(w&1) .. +4), XOR-swizzled by row
-          uint8_t* ph = p_tile(0, w >> 1) + row * 128;
-          uint8_t* pl = p_tile(1, w >> 1) + row * 128;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 hi, lo;
-            split_bf16x2(pv[8 * c + 0], pv[8 * c + 1], hi.x, lo.x);
-            split_bf16x2(pv[8 * c + 2], pv[8 * c + 3], hi.y, lo.y);
-            split_bf16x2(pv[8 * c + 4], pv[8 * c + 5], hi.z, lo.z);
-            split_bf16x2(pv[8 * c + 6], pv[8 * c + 7], hi.w, lo.w);
-            const uint32_t chunk = static_cast<uint32_t>((4 * (w & 1) + c) ^ (row & 7)) << 4;
-            *reinterpret_cast<uint4*>(ph + chunk) = hi;
-            if (NPL == 2) *reinterpret_cast<uint4*>(pl + chunk) = lo;
-          }
-        }
-        l_run = l_run * alpha + sum;
-        m_run = m_new;
-        fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core
-        tcgen05_fence_before();
-        mbar_arrive(p_full);
-      }
-      // ---- epilogue: O / l -> this head's column slice of the concatenated output
-      mbar_wait(o_done, (kvc - 1) & 1);
-      tcgen05_fence_after();
-      const float inv = 1.0f / l_run;  // l == 0 (row fully masked) -> inf -> NaN, as the reference's softmax of all -inf
       const bool row_ok = qrow < p.Lq;
       const size_t grow = static_cast<size_t>(b) * p.Lq + qrow;
-      for (int c = 0; c < p.d; c += 16) {
+      for (int g = cw; g < ngroups; g += NW) {
         uint32_t r[16];
-        tmem_ld16(tmem_O + lane_sel + c, r);
+        tmem_ld16(tO + 16 * g, r);
         tmem_wait_ld();
         if (row_ok) {
           float v[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) * inv;
-          const int col = h * p.d + c;
+          const int col = h * p.d + 16 * g;
           if (p.o_f32 != nullptr) {
             float4* o = reinterpret_cast<float4*>(p.o_f32 + grow * p.ldof + col);
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
           }
           if (p.o_hi != nullptr) {
+            uint4 hi[2], lo[2];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              uint4 hi, lo;
-              split_bf16x2(v[8 * g + 0], v[8 * g + 1], hi.x, lo.x);
-              split_bf16x2(v[8 * g + 2], v[8 * g + 3], hi.y, lo.y);
-              split_bf16x2(v[8 * g + 4], v[8 * g + 5], hi.z, lo.z);
-              split_bf16x2(v[8 * g + 6], v[8 * g + 7], hi.w, lo.w);
-              const size_t off = grow * p.ldo + col + 8 * g;
-              *reinterpret_cast<uint4*>(p.o_hi + off) = hi;
-              if (p.o_lo != nullptr) *reinterpret_cast<uint4*>(p.o_lo + off) = lo;
+            for (int q2 = 0; q2 < 2; ++q2) {
+              split_bf16x2(v[8 * q2 + 0], v[8 * q2 + 1], hi[q2].x, lo[q2].x);
+              split_bf16x2(v[8 * q2 + 2], v[8 * q2 + 3], hi[q2].y, lo[q2].y);
+              split_bf16x2(v[8 * q2 + 4], v[8 * q2 + 5], hi[q2].z, lo[q2].z);
+              split_bf16x2(v[8 * q2 + 6], v[8 * q2 + 7], hi[q2].w, lo[q2].w);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(p.o_hi + grow * p.ldo + col);
+            oh[0] = hi[0];
+            oh[1] = hi[1];
+            if (p.o_lo != nullptr) {
+              uint4* ol = reinterpret_cast<uint4*>(p.o_lo + grow * p.ldo + col);
+              ol[0] = lo[0];
+              ol[1] = lo[1];
             }
           }
         }
       }
-      if (row_ok && p.row_sum != nullptr) {
+      if (cw == 0 && row_ok && p.row_sum != nullptr) {
         const size_t si = (static_cast<size_t>(h) * p.B + b) * p.Lq + qrow;
         p.row_max[si] = ((m_run == -INFINITY) ? 0.0f : m_run) * p.scale_log2;
-        p.row_sum[si] = l_run;
+        p.row_sum[si] = l_tot;
       }
-      tcgen05_fence_before();  // O reads retired before the next item's PV (ordered through p_full)
+    };
+
+    uint32_t u = 0, it = 0;
+    bool have_prev = false;
+    int pb = 0, ph = 0, pqt = 0;
+    float pm = 0.0f;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int qt = item % num_qt;
+      const int h = (item / num_qt) % p.H;
+      const int b = item / (num_qt * p.H);
+      float m_run = -INFINITY, l_part = 0.0f;
+      for (int j = 0; j < num_kv; ++j, ++u) {
+        const int k0 = j * BLOCK_KV + 32 * cw;  // first key column of this warp's chunk
+        const uint32_t sb = u & 1;
+        const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128 + lane_sel + 32 * cw;
+        // ---- mask word for (row, this chunk); cached while the addressed mask region is unchanged
+        {
+          const long long key = (p.mask == nullptr)
+                                    ? static_cast<long long>(j)
+                                    : ((p.msb ? static_cast<long long>(b) : 0) * num_qt + (p.msq ? qt : 0)) * num_kv + j;
+          if (key != mkey) {
+            mkey = key;
+            const int rem = p.Lk - k0;  // valid columns in this chunk
+            mw = rem >= 32 ? 0u : (rem <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << rem));
+            if (p.mask != nullptr) {
+              const uint8_t* mb = p.mask + static_cast<long long>(b) * p.msb;
+              const int nrows = p.msq ? 32 : 1;
+              const int kc = k0 + lane;
+              for (int rr = 0; rr < nrows; ++rr) {
+                const int qr = qt * ATTN_BLOCK_M + wq * 32 + rr;
+                uint32_t byte = 0;
+                if (kc < p.Lk && (qr < p.Lq || !p.msq))
+                  byte = mb[static_cast<long long>(qr) * p.msq + static_cast<long long>(kc) * p.msk];
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, byte != 0);
+                if (!p.msq || lane == rr) mw |= bal;
+              }
+            }
+          }
+        }
+        mbar_wait(&s_full[sb], (u >> 1) & 1);
+        tcgen05_fence_after();
+        // ---- pass 1: masked scores of this chunk stay in registers; chunk max -> smem -> row max
+        uint32_t r[32];
+        tmem_ld32(tS, r);
+        tmem_wait_ld();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float sv = ((mw >> e) & 1u) ? -INFINITY : __uint_as_float(r[e]);
+          r[e] = __float_as_uint(sv);
+          mx = fmaxf(mx, sv);
+        }
+        float* rm = red_max + (u & 1) * (4 * 128);
+        rm[cw * 128 + row] = mx;
+        named_bar_sync(1, NSW);
+#pragma unroll
+        for (int c = 0; c < NW; ++c) mx = fmaxf(mx, rm[c * 128 + row]);
+        const float m_new = fmaxf(m_run, mx);
+        const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_run - m_new) * p.scale_log2);
+        // ---- the previous PV must have retired before P is overwritten / O is rescaled
+        if (u > 0) {
+          mbar_wait(o_done, (u - 1) & 1);
+          tcgen05_fence_after();
+        }
+        if (j > 0) {  // running maximum moved: rescale the partial output in TMEM (this warp's column groups)
+          for (int g = cw; g < ngroups; g += NW) {
+            uint32_t o[16];
+            tmem_ld16(tO + 16 * g, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st16(tO + 16 * g, o);
+          }
+        }
+        // ---- pass 2: P = 2^((s - m) * scale) -> hi/lo bf16 planes in TMEM (A operand of the PV product)
+        float sum = 0.0f;
+        const float mb2 = m_use * p.scale_log2;
+        uint32_t ph_[16], pl_[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float x0 = ex2_approx(fmaf(__uint_as_float(r[e]), p.scale_log2, -mb2));      // 2^(-inf) = 0 for masked
+          const float x1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), p.scale_log2, -mb2));
+          sum += x0 + x1;
+          split_bf16x2(x0, x1, ph_[e >> 1], pl_[e >> 1]);
+        }
+        tmem_st16(tP + 16 * cw, ph_);
+        if (NPL == 2) tmem_st16(tP + P_LO + 16 * cw, pl_);
+        l_part = l_part * alpha + sum;
+        m_run = m_new;
+        if (j == num_kv - 1) red_l[((it & 1) * 4 + cw) * 128 + row] = l_part;  // read after the next unit's barrier
+        tmem_wait_st();
+        tcgen05_fence_before();
+        mbar_arrive(&s_free[sb]);  // score buffer consumed
+        // ---- deferred epilogue of the previous item: its O is complete (o_done above) and is only overwritten by
+        //      the PV of THIS unit, which cannot start before the p_full arrival below
+        if (j == 0 && have_prev) {
+          epilogue(pb, ph, pqt, (it & 1) ^ 1, pm);
+          tcgen05_fence_before();
+        }
+        mbar_arrive(p_full);
+      }
+      have_prev = true;
+      pb = b; ph = h; pqt = qt; pm = m_run;
+    }
+    if (have_prev) {
+      named_bar_sync(1, NSW);  // make the last item's row sums visible
+      mbar_wait(o_done, (u - 1) & 1);
+      tcgen05_fence_after();
+      epilogue(pb, ph, pqt, (it & 1) ^ 1, pm);
     }
   }
 

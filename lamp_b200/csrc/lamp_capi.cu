@@ -134,20 +134,20 @@ int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
 
 std::atomic<int> g_gemm_block_k{32};  // tuning knob (lamp_set_tuning): 32 -> 64B swizzle / deep ring, 64 -> 128B swizzle
 
-template <int BLOCK_KV, bool ALIAS, int NTERMS>
+template <int BLOCK_KV, int KV_STAGES, int NTERMS>
 int launch_attn(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi, const CUtensorMap& kv_lo,
                 const AttnParams& p, cudaStream_t st) {
-  using SM = AttnSmem<BLOCK_KV, ALIAS, NTERMS>;
+  using SM = AttnSmem<BLOCK_KV, KV_STAGES, NTERMS>;
   static std::once_flag once;
   static int once_rc = LAMP_OK;
-  // <128,false> is only dispatched for d <= 64 (one 64-column block); the other two variants carry d <= 128.
-  constexpr int MAX_KB64 = (BLOCK_KV == 128 && !ALIAS) ? 1 : 2;
-  std::call_once(once, [] { once_rc = set_smem(attn_core_kernel<BLOCK_KV, ALIAS, NTERMS>, SM::total(MAX_KB64)); });
+  // <128,2> is only dispatched for d <= 64 (one 64-column block); the other two variants carry d <= 128.
+  constexpr int MAX_KB64 = (BLOCK_KV == 128 && KV_STAGES == 2) ? 1 : 2;
+  std::call_once(once, [] { once_rc = set_smem(attn_core_kernel<BLOCK_KV, KV_STAGES, NTERMS>, SM::total(MAX_KB64)); });
   if (once_rc != LAMP_OK) return once_rc;
   const int kb64 = (p.d + 63) / 64;
   const int items = p.B * p.H * ((p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M);
   const int grid = items < sm_count_cached() ? items : sm_count_cached();
-  attn_core_kernel<BLOCK_KV, ALIAS, NTERMS><<<grid, ATTN_THREADS, SM::total(kb64), st>>>(q_hi, q_lo, kv_hi, kv_lo, p);
+  attn_core_kernel<BLOCK_KV, KV_STAGES, NTERMS><<<grid, attn_threads(BLOCK_KV), SM::total(kb64), st>>>(q_hi, q_lo, kv_hi, kv_lo, p);
   return launch_check();
 }
 
@@ -289,14 +289,14 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (d <= 64) {
-    rc = three ? launch_attn<128, false, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
-               : launch_attn<128, false, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
+    rc = three ? launch_attn<128, 2, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
+               : launch_attn<128, 2, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
   } else if (!multi) {
-    rc = three ? launch_attn<128, true, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
-               : launch_attn<128, true, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
+    rc = three ? launch_attn<128, 1, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
+               : launch_attn<128, 1, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
   } else {
-    rc = three ? launch_attn<64, false, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
-               : launch_attn<64, false, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
+    rc = three ? launch_attn<64, 2, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
+               : launch_attn<64, 2, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
   }
   if (rc != LAMP_OK) return rc;
   if (probs) {
