@@ -11,9 +11,10 @@
 //                                3-term 128x256 tile; BLOCK_K = 64 (128B swizzle) is kept for comparison.
 //   warp 1   : MMA issuer     -- one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into a double-buffered
 //                                TMEM accumulator (2 x BLOCK_N columns); tcgen05.commit releases smem stages
-//   warps 2-5: epilogue       -- tcgen05.ld (lane == output row) -> per-warp XOR-swizzled smem transpose -> every
-//                                global access (residual read, fp32 / plane stores) is a full 128 B row segment
-//                                per 8 lanes; overlaps with the next tile's main loop
+//   warps 2-9: epilogue       -- 8 warps (two per TMEM lane quarter, alternating 32-column chunks, i.e. two per
+//                                scheduler to hide latencies): tcgen05.ld (lane == output row) -> per-warp
+//                                XOR-swizzled smem transpose -> every global access (residual read, fp32 / plane
+//                                stores) is a full 128 B row segment per 8 lanes; overlaps the next tile's main loop
 // Used for: Q/K/V projections, fc (+residual), both FFN layers (lamp/SubLayers.py:91-93,110,133).
 #pragma once
 #include "sm100_primitives.cuh"
@@ -35,8 +36,13 @@ struct GemmParams {
 };
 
 constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_THREADS = 192;
-constexpr uint32_t GEMM_EPI_STAGING = 4 * 32 * 128;  // 4 epilogue warps x (32 rows x 128 B)
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+constexpr uint32_t GEMM_EPI_STAGING = GEMM_EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 128 B
+// epilogue flavours (compile-time, so the per-element code carries no dead branches)
+constexpr int EPI_PLANES = 0;  // (+bias)(ReLU) -> hi/lo planes
+constexpr int EPI_F32 = 1;     // (+bias)(+residual) -> fp32
+constexpr int EPI_ANY = 2;     // everything, selected at run time (tests / rare combinations)
 
 template <int BLOCK_N, int NTERMS, int BLOCK_K>
 struct GemmCfg {
@@ -46,7 +52,7 @@ struct GemmCfg {
   static constexpr uint32_t A_TILE = GEMM_BLOCK_M * ROW_BYTES;
   static constexpr uint32_t W_TILE = BLOCK_N * ROW_BYTES;
   static constexpr uint32_t STAGE_BYTES = NPL * (A_TILE + W_TILE);
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_EPI_STAGING + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint64_t LAYOUT = (BLOCK_K == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
@@ -54,7 +60,7 @@ struct GemmCfg {
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
 };
 
-template <int BLOCK_N, int NTERMS, int BLOCK_K>
+template <int BLOCK_N, int NTERMS, int BLOCK_K, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -90,7 +96,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 32 * GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -181,11 +187,18 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int wq = warp & 3;  // TMEM lane quarter this warp may access
-    uint8_t* stg = staging + wq * (32 * 128);
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int wq = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2; // which of the two warps of this quarter: handles chunks half, half+2, ...
+    uint8_t* stg = staging + (warp - 2) * (32 * 128);
     const int sub_r = lane >> 3;  // coalesced phase: 8 lanes per row, 4 rows per pass
     const int sub_c = lane & 7;   // 16-byte chunk (4 fp32) inside the 128 B row segment
+    const bool want_f32 = (EPI == EPI_F32) || (EPI == EPI_ANY && p.out_f32 != nullptr);
+    const bool want_pl = (EPI == EPI_PLANES) || (EPI == EPI_ANY && p.out_hi != nullptr);
+    const bool want_lo = want_pl && p.out_lo != nullptr;
+    const bool has_res = (EPI != EPI_PLANES) && p.residual != nullptr;
+    const bool has_bias = p.bias != nullptr;
+    const bool relu = (EPI != EPI_F32) && p.relu;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -194,8 +207,9 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
+      const int rows_left = p.M - m0 - sub_r;  // row (m0 + sub_r + 4 i) is valid iff 4 i < rows_left
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(t_row + c0, r);
         tmem_wait_ld();
@@ -209,42 +223,40 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const int col = n0 + c0 + sub_c * 4;
         const bool col_ok = col < p.N;  // N % 8 == 0 (host-checked) -> the 4 columns are all in or all out
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         // residual rows first (8 independent 128-bit loads in flight), then the staged accumulators
         float4 resv[8];
-        if (p.residual != nullptr) {
+        if (has_res) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = m0 + i * 4 + sub_r;
             resv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < p.M && col_ok) {
+            if (4 * i < rows_left && col_ok) {
+              const int row = m0 + i * 4 + sub_r;
               const int rres = p.resid_mod ? (row % p.resid_mod) : row;
               resv[i] = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rres) * p.ldr + col));
             }
           }
         }
+        float* of = want_f32 ? p.out_f32 + static_cast<size_t>(m0 + sub_r) * p.ldo + col : nullptr;
+        const size_t poff = static_cast<size_t>(m0 + sub_r) * p.ldp + col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub_r;
-          const int row = m0 + rr;
           float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((sub_c ^ (rr & 7)) << 4));
-          if (row < p.M && col_ok) {
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if (p.relu) {
+          if (4 * i < rows_left && col_ok) {
+            if (has_bias) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+            if (relu) {
               v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
             }
-            if (p.residual != nullptr) {
-              v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w;
-            }
-            if (p.out_f32 != nullptr)
-              *reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(row) * p.ldo + col) = v;
-            if (p.out_hi != nullptr) {
+            if (has_res) { v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w; }
+            if (want_f32) *reinterpret_cast<float4*>(of + static_cast<size_t>(4 * i) * p.ldo) = v;
+            if (want_pl) {
               uint2 hi, lo;
               split_bf16x2(v.x, v.y, hi.x, lo.x);
               split_bf16x2(v.z, v.w, hi.y, lo.y);
-              const size_t off = static_cast<size_t>(row) * p.ldp + col;
+              const size_t off = poff + static_cast<size_t>(4 * i) * p.ldp;
               *reinterpret_cast<uint2*>(p.out_hi + off) = hi;
-              if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + off) = lo;
+              if (want_lo) *reinterpret_cast<uint2*>(p.out_lo + off) = lo;
             }
           }
         }

@@ -118,18 +118,28 @@ int launch_check() {
   return LAMP_OK;
 }
 
-template <int BLOCK_N, int NTERMS, int BLOCK_K>
-int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
-                const GemmParams& p, cudaStream_t st) {
+template <int BLOCK_N, int NTERMS, int BLOCK_K, int EPI>
+int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                    const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K>;
   static std::once_flag once;
   static int once_rc = LAMP_OK;
-  std::call_once(once, [] { once_rc = set_smem(gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K>, Cfg::SMEM_BYTES); });
+  std::call_once(once, [] { once_rc = set_smem(gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K, EPI>, Cfg::SMEM_BYTES); });
   if (once_rc != LAMP_OK) return once_rc;
   const int tiles = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
-  gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, p);
   return launch_check();
+}
+
+template <int BLOCK_N, int NTERMS, int BLOCK_K>
+int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
+                const GemmParams& p, cudaStream_t st) {
+  if (p.out_hi != nullptr && p.out_f32 == nullptr && p.residual == nullptr)
+    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_PLANES>(a_hi, a_lo, w_hi, w_lo, p, st);
+  if (p.out_hi == nullptr && !p.relu)
+    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_F32>(a_hi, a_lo, w_hi, w_lo, p, st);
+  return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_ANY>(a_hi, a_lo, w_hi, w_lo, p, st);
 }
 
 std::atomic<int> g_gemm_block_k{32};  // tuning knob (lamp_set_tuning): 32 -> 64B swizzle / deep ring, 64 -> 128B swizzle

@@ -195,12 +195,14 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 // Pack two floats' hi (or lo) parts into one 32-bit word: element 0 in the low half.
+// cvt.rn.bf16x2.f32 packs both hi parts in one instruction; the bf16 -> fp32 expansion is a shift / mask.
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 h0, l0, h1, l1;
-  split_bf16(x0, h0, l0);
-  split_bf16(x1, h1, l1);
-  hi = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-  lo = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);  // .x = x0 (low half), .y = x1
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float r0 = x0 - __uint_as_float(hi << 16);
+  const float r1 = x1 - __uint_as_float(hi & 0xFFFF0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // Named barrier among a subset of warps (id 1..15; 0 is __syncthreads).
