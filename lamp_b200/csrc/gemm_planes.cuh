@@ -44,13 +44,15 @@ constexpr int EPI_PLANES = 0;  // (+bias)(ReLU) -> hi/lo planes
 constexpr int EPI_F32 = 1;     // (+bias)(+residual) -> fp32
 constexpr int EPI_ANY = 2;     // everything, selected at run time (tests / rare combinations)
 
-template <int BLOCK_N, int NTERMS, int BLOCK_K>
+template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP = 1>
 struct GemmCfg {
   static_assert(BLOCK_K == 32 || BLOCK_K == 64, "BLOCK_K selects the 64B / 128B swizzle");
+  static_assert(CTA_GROUP == 1 || CTA_GROUP == 2, "one CTA or a CTA pair");
   static constexpr int NPL = (NTERMS == 3) ? 2 : 1;
   static constexpr uint32_t ROW_BYTES = BLOCK_K * 2;
+  static constexpr int W_ROWS = BLOCK_N / CTA_GROUP;  // rows of W staged by ONE CTA (a pair splits N between its CTAs)
   static constexpr uint32_t A_TILE = GEMM_BLOCK_M * ROW_BYTES;
-  static constexpr uint32_t W_TILE = BLOCK_N * ROW_BYTES;
+  static constexpr uint32_t W_TILE = W_ROWS * ROW_BYTES;
   static constexpr uint32_t STAGE_BYTES = NPL * (A_TILE + W_TILE);
   static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -60,28 +62,35 @@ struct GemmCfg {
   static_assert(STAGES >= 2, "need at least a double-buffered ring");
 };
 
-template <int BLOCK_N, int NTERMS, int BLOCK_K, int EPI>
+// CTA_GROUP == 2: the two CTAs of a cluster form an MMA pair (tcgen05 cta_group::2, M = 256): each CTA stages its own
+// 128 rows of A and only HALF of the W tile, the leader issues one MMA for both, and each CTA keeps the accumulator
+// of its own 128 rows.  Per output tile every SM ingests 1/3 fewer operand bytes than with two independent CTAs --
+// the operand stream from L2 (~31 B/clk/SM measured) is what bounds this kernel, not the tensor pipe.
+template <int BLOCK_N, int NTERMS, int BLOCK_K, int EPI, int CTA_GROUP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                    const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K>;
+  using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K, CTA_GROUP>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NPL = Cfg::NPL;
+  constexpr bool PAIR = (CTA_GROUP == 2);
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_STAGING);
-  uint64_t* full_bar = bars;
+  uint64_t* full_bar = bars;                    // PAIR: only the leader's copies are used
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // PAIR: only the leader's copies are used
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
@@ -96,23 +105,30 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 32 * GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty[a], 32 * GEMM_EPI_WARPS * CTA_GROUP);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_m = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int num_m = (p.M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP);
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_tiles = num_m * num_n;
+  const int tile0 = static_cast<int>(blockIdx.x) / CTA_GROUP;
+  const int tile_step = static_cast<int>(gridDim.x) / CTA_GROUP;
 
   auto stage_ptr = [&](int s, int which) -> uint8_t* {
     // which: 0 = A_hi, 1 = W_hi, 2 = A_lo, 3 = W_lo
@@ -126,36 +142,48 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (every CTA loads its own slices)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * GEMM_BLOCK_M;
-        const int n0 = (tile % num_n) * BLOCK_N;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile / num_n) * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M;
+        const int n0 = (tile % num_n) * BLOCK_N + static_cast<int>(rank) * Cfg::W_ROWS;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int k0 = kb * BLOCK_K;
-          tma_load_2d(stage_ptr(stage, 0), &tmA_hi, &full_bar[stage], k0, m0);
-          tma_load_2d(stage_ptr(stage, 1), &tmW_hi, &full_bar[stage], k0, n0);
-          if (NPL == 2) {
-            tma_load_2d(stage_ptr(stage, 2), &tmA_lo, &full_bar[stage], k0, m0);
-            tma_load_2d(stage_ptr(stage, 3), &tmW_lo, &full_bar[stage], k0, n0);
+          if (PAIR) {
+            // both CTAs' bytes complete on the leader's barrier; the leader posts the expected total
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t fb = mapa_shared(&full_bar[stage], 0);
+            tma_load_2d_cg2(stage_ptr(stage, 0), &tmA_hi, fb, k0, m0);
+            tma_load_2d_cg2(stage_ptr(stage, 1), &tmW_hi, fb, k0, n0);
+            if (NPL == 2) {
+              tma_load_2d_cg2(stage_ptr(stage, 2), &tmA_lo, fb, k0, m0);
+              tma_load_2d_cg2(stage_ptr(stage, 3), &tmW_lo, fb, k0, n0);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(stage_ptr(stage, 0), &tmA_hi, &full_bar[stage], k0, m0);
+            tma_load_2d(stage_ptr(stage, 1), &tmW_hi, &full_bar[stage], k0, n0);
+            if (NPL == 2) {
+              tma_load_2d(stage_ptr(stage, 2), &tmA_lo, &full_bar[stage], k0, m0);
+              tma_load_2d(stage_ptr(stage, 3), &tmW_lo, &full_bar[stage], k0, n0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
+    // ------------------------------------------------------------ MMA issuer (leader CTA only for a pair)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M * CTA_GROUP, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -171,18 +199,26 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const uint32_t koff = k * 32;  // 16 bf16 = 32 B inside the swizzled row
             const uint64_t da_hi = umma_smem_desc(a_hi + koff, 16, Cfg::SBO, Cfg::LAYOUT);
             const uint64_t dw_hi = umma_smem_desc(w_hi + koff, 16, Cfg::SBO, Cfg::LAYOUT);
-            umma_bf16_ss(d_tmem, da_hi, dw_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+            if (PAIR) umma_bf16_ss_cg2(d_tmem, da_hi, dw_hi, idesc, first); else umma_bf16_ss(d_tmem, da_hi, dw_hi, idesc, first);
             if (NTERMS == 3) {
               const uint64_t da_lo = umma_smem_desc(a_lo + koff, 16, Cfg::SBO, Cfg::LAYOUT);
               const uint64_t dw_lo = umma_smem_desc(w_lo + koff, 16, Cfg::SBO, Cfg::LAYOUT);
-              umma_bf16_ss(d_tmem, da_hi, dw_lo, idesc, 1u);
-              umma_bf16_ss(d_tmem, da_lo, dw_hi, idesc, 1u);
+              if (PAIR) {
+                umma_bf16_ss_cg2(d_tmem, da_hi, dw_lo, idesc, 1u);
+                umma_bf16_ss_cg2(d_tmem, da_lo, dw_hi, idesc, 1u);
+              } else {
+                umma_bf16_ss(d_tmem, da_hi, dw_lo, idesc, 1u);
+                umma_bf16_ss(d_tmem, da_lo, dw_hi, idesc, 1u);
+              }
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+          if (PAIR) umma_commit_cg2_mc(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (PAIR) umma_commit_cg2_mc(&tmem_full[acc], 0x3); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -201,8 +237,9 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const bool relu = (EPI != EPI_F32) && p.relu;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * GEMM_BLOCK_M + wq * 32;
+    const uint32_t te_addr[2] = {mapa_shared(&tmem_empty[0], 0), mapa_shared(&tmem_empty[1], 0)};  // leader's copies
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m0 = (tile / num_n) * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
       const int n0 = (tile % num_n) * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -263,16 +300,16 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         __syncwarp();
       }
       tcgen05_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if (PAIR) mbar_arrive_cluster(te_addr[acc]); else mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // a pair must not tear down while the peer may still signal it
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -118,31 +118,48 @@ int launch_check() {
   return LAMP_OK;
 }
 
-template <int BLOCK_N, int NTERMS, int BLOCK_K, int EPI>
+template <int BLOCK_N, int NTERMS, int BLOCK_K, int EPI, int CTA_GROUP>
 int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                     const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K>;
+  using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K, CTA_GROUP>;
+  auto kernel = gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K, EPI, CTA_GROUP>;
   static std::once_flag once;
   static int once_rc = LAMP_OK;
-  std::call_once(once, [] { once_rc = set_smem(gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K, EPI>, Cfg::SMEM_BYTES); });
+  std::call_once(once, [kernel] { once_rc = set_smem(kernel, Cfg::SMEM_BYTES); });
   if (once_rc != LAMP_OK) return once_rc;
-  const int tiles = ((p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = tiles < sm_count_cached() ? tiles : sm_count_cached();
-  gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, w_hi, w_lo, p);
+  const int tiles = ((p.M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP)) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int max_groups = sm_count_cached() / CTA_GROUP;
+  const int groups = tiles < max_groups ? tiles : max_groups;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * CTA_GROUP);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA_GROUP;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a_hi, a_lo, w_hi, w_lo, p);
+  if (e != cudaSuccess) return fail(LAMP_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
   return launch_check();
 }
 
-template <int BLOCK_N, int NTERMS, int BLOCK_K>
+template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP>
 int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                 const GemmParams& p, cudaStream_t st) {
   if (p.out_hi != nullptr && p.out_f32 == nullptr && p.residual == nullptr)
-    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_PLANES>(a_hi, a_lo, w_hi, w_lo, p, st);
+    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_PLANES, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
   if (p.out_hi == nullptr && !p.relu)
-    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_F32>(a_hi, a_lo, w_hi, w_lo, p, st);
-  return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_ANY>(a_hi, a_lo, w_hi, w_lo, p, st);
+    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_F32, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
+  return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_ANY, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
 }
 
-std::atomic<int> g_gemm_block_k{32};  // tuning knob (lamp_set_tuning): 32 -> 64B swizzle / deep ring, 64 -> 128B swizzle
+std::atomic<int> g_gemm_block_k{0};   // tuning knob (lamp_set_tuning): 32 -> 64B swizzle / deep ring, 64 -> 128B swizzle,
+                                      // 0 -> automatic (64 for CTA pairs: 3 x 64 KB stages; 32 otherwise: 4 x 48 KB)
+std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group::2) for the 256-wide tiles, 0 -> single CTAs
 
 template <int BLOCK_KV, int KV_STAGES, int NTERMS>
 int launch_attn(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi, const CUtensorMap& kv_lo,
@@ -184,8 +201,12 @@ int lamp_device_check(void) { return arch_check(); }
 int lamp_sm_count(void) { return sm_count_cached(); }
 
 int lamp_set_tuning(int key, int value) {
-  if (key == LAMP_TUNE_GEMM_BLOCK_K && (value == 32 || value == 64)) {
+  if (key == LAMP_TUNE_GEMM_BLOCK_K && (value == 0 || value == 32 || value == 64)) {
     g_gemm_block_k.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
+    g_gemm_pair.store(value);
     return LAMP_OK;
   }
   return fail(LAMP_EINVAL, "set_tuning: unknown key/value %d/%d", key, value);
@@ -225,9 +246,11 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
   REQUIRE(!bias || aligned16(bias), "gemm: bias alignment");
   if (M == 0) return LAMP_OK;
   const bool wide = (N > 128);
-  const uint32_t box_n = wide ? 256 : 128;
+  const bool pair = wide && g_gemm_pair.load() != 0 && sm_count_cached() >= 2;
+  const uint32_t box_n = wide ? (pair ? 128 : 256) : 128;  // a pair's CTAs each stage half of the 256-row W tile
   CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
-  const int bk = g_gemm_block_k.load();
+  int bk = g_gemm_block_k.load();
+  if (bk == 0) bk = pair ? 64 : 32;
   if (int rc = make_tmap(&ta_hi, a_hi, K, M, 1, lda, GEMM_BLOCK_M, false, bk)) return rc;
   if (int rc = make_tmap(&tw_hi, w_hi, K, N, 1, ldw, box_n, false, bk)) return rc;
   if (three) {
@@ -247,10 +270,14 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
   cudaStream_t st = (cudaStream_t)stream;
 #define LAMP_GEMM_DISPATCH(BK)                                                                                      \
   do {                                                                                                             \
-    if (three) return wide ? launch_gemm<256, 3, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st)                            \
-                           : launch_gemm<128, 3, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                           \
-    return wide ? launch_gemm<256, 1, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st)                                       \
-                : launch_gemm<128, 1, BK>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                                      \
+    if (pair) {                                                                                                    \
+      if (three) return launch_gemm<256, 3, BK, 2>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                             \
+      return launch_gemm<256, 1, BK, 2>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                                        \
+    }                                                                                                              \
+    if (three) return wide ? launch_gemm<256, 3, BK, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st)                         \
+                           : launch_gemm<128, 3, BK, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                        \
+    return wide ? launch_gemm<256, 1, BK, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st)                                    \
+                : launch_gemm<128, 1, BK, 1>(ta_hi, ta_lo, tw_hi, tw_lo, p, st);                                   \
   } while (0)
   if (bk == 64) LAMP_GEMM_DISPATCH(64);
   LAMP_GEMM_DISPATCH(32);

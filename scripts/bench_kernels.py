@@ -39,16 +39,18 @@ def bench_gemm(prec=0):
         res = torch.randn(M, N, device=DEV) if mode == 'f32res' else None
         out = torch.empty(M, N, device=DEV) if mode == 'f32res' else None
         o_hi, o_lo = ops._empty_planes(M, N, prec, DEV) if mode == 'planes' else (None, None)
-        for bk in (32, 64):
+        for bk, pair in ((32, 1), (32, 0), (64, 1)):
             nat.check(nat.lib().lamp_set_tuning(1, bk), 'tune')
+            nat.check(nat.lib().lamp_set_tuning(2, pair), 'tune')
 
             def run():
                 ops.gemm(a_hi, a_lo, K, w_hi, w_lo, K, M, N, K, prec, residual=res, ldr=N, out_f32=out, ldo=N,
                          out_hi=o_hi, out_lo=o_lo, ldp=N)
             t = timeit(run)
-            print(f'gemm {name:9s} M={M} N={N} K={K} {mode:7s} prec={prec} BK={bk}: {t * 1e6:8.1f} us  '
+            print(f'gemm {name:9s} M={M} N={N} K={K} {mode:7s} prec={prec} BK={bk} pair={pair}: {t * 1e6:8.1f} us  '
                   f'{2.0 * M * N * K / t / 1e12:7.1f} TFLOP/s alg', flush=True)
-        nat.check(nat.lib().lamp_set_tuning(1, 32), 'tune')
+        nat.check(nat.lib().lamp_set_tuning(1, 0), 'tune')
+        nat.check(nat.lib().lamp_set_tuning(2, 1), 'tune')
 
 
 def bench_attn(prec=0):

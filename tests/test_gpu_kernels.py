@@ -54,13 +54,15 @@ def test_split_planes_roundtrip():
     (128, 128, 64, 0), (300, 128, 64, 0), (1000, 512, 512, 0), (257, 1536, 512, 0), (103, 64, 128, 0),
     (4096, 1024, 512, 0), (515, 192, 72, 0), (1000, 512, 512, 1), (300, 128, 64, 1), (5000, 256, 1024, 0),
 ])
-@pytest.mark.parametrize('bk', [32, 64])
-def test_gemm_planes(M, N, K, prec, bk):
+@pytest.mark.parametrize('bk,pair', [(0, 1), (32, 1), (64, 1), (32, 0), (64, 0)])
+def test_gemm_planes(M, N, K, prec, bk, pair):
     nat.check(nat.lib().lamp_set_tuning(1, bk), 'tune')
+    nat.check(nat.lib().lamp_set_tuning(2, pair), 'tune')
     try:
         _gemm_case(M, N, K, prec)
     finally:
-        nat.check(nat.lib().lamp_set_tuning(1, 32), 'tune')
+        nat.check(nat.lib().lamp_set_tuning(1, 0), 'tune')
+        nat.check(nat.lib().lamp_set_tuning(2, 1), 'tune')
 
 
 def _gemm_case(M, N, K, prec):
