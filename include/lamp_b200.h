@@ -63,6 +63,21 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
                      const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
                      void* out_lo, int64_t ldp, void* stream);
 
+/* lamp_gemm_planes with the residual given as split-bf16 planes (hi + lo reconstructs it to 2^-17 relative): lets a
+ * layer keep its activations in operand form only, without an fp32 copy in HBM.  res_lo may be NULL. */
+int lamp_gemm_planes_pres(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                          int64_t ldw, int M, int N, int K, int precision, const float* bias, const void* res_hi,
+                          const void* res_lo, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
+                          void* out_lo, int64_t ldp, void* stream);
+
+/* Same contraction with the residual add AND the LayerNorm of lamp/SubLayers.py:117 / :141 fused into the epilogue:
+ * out = LayerNorm(A W^T (+bias) (+residual)) * gamma + beta, written as fp32 and/or planes.  The whole output row
+ * must fit the on-chip accumulator: 256 < N <= 512 (otherwise LAMP_EINVAL: use lamp_gemm_planes + lamp_layernorm). */
+int lamp_gemm_ln_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                        int64_t ldw, int M, int N, int K, int precision, const float* bias, const float* residual,
+                        int64_t ldr, int resid_mod, const float* gamma, const float* beta, float eps, float* out_f32,
+                        int64_t ldo, void* out_hi, void* out_lo, int64_t ldp, void* stream);
+
 /* Masked softmax attention over label nodes for B samples x H heads (lamp/SubLayers.py:27-43 with the head
  * split/merge of :96-107 folded into the addressing).  Q planes: [B*Lq (or Lq if q_bcast), ldq], head h at
  * columns q_col0 + h*d; K/V planes: [B*Lk, ldkv] at k_col0 / v_col0 + h*d.  mask: NULL or bytes (non-zero =

@@ -115,7 +115,7 @@ class GraphDecoder(nn.Module):
         for i, layer in enumerate(self.layer_stack):
             x, x_int, slf_attn, enc_attn = layer.forward_act(
                 x, enc, B, L, T, slf_mask, pad_mask, return_attns, kv_proj=(kv_all, 2 * hd * i, 2 * hd * i + hd),
-                last=(i == n - 1))
+                last=(i == n - 1), want_int_f32=int_preds, want_out_f32=int_preds or i == n - 1)
             if int_preds:
                 if x_int is not None:
                     int_outs.append(x_int.f32.view(B, L, D))

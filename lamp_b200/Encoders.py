@@ -95,11 +95,13 @@ class GraphEncoder(nn.Module):
         prec = ops.default_precision() if self.layer_stack[0].pos_ffn.precision is None \
             else self.layer_stack[0].pos_ffn.precision
         pos_w = self.position_enc.weight if hasattr(self, 'position_enc') else None
-        x = ops.embed(src_seq, src_pos, self.src_word_emb.weight, pos_w, prec)
+        x = ops.embed(src_seq, src_pos, self.src_word_emb.weight, pos_w, prec, want_f32=False)
         mask = src_seq.eq(Constants.PAD).unsqueeze(1) if return_attns else None  # [B, 1, T]
         attns = []
-        for layer in self.layer_stack:
-            x, attn = layer.forward_act(x, B, T, mask, return_attns)
+        n = len(self.layer_stack)
+        for i, layer in enumerate(self.layer_stack):
+            # only the last layer's output is an API tensor (enc_output); in between activations stay in operand form
+            x, attn = layer.forward_act(x, B, T, mask, return_attns, want_f32=(i == n - 1))
             attns.append(attn)
         out = x.f32.view(B, T, self.d_model)
         if self.enc_transform == '':

@@ -18,11 +18,11 @@ class EncoderLayer(nn.Module):
         self.slf_attn = MultiHeadAttention(n_head, d_model, d_k, d_v, dropout=dropout)
         self.pos_ffn = PositionwiseFeedForward(d_model, d_inner_hid, dropout=dropout)
 
-    def forward_act(self, x: ops.Act, B: int, T: int, slf_attn_mask, want_attn: bool):
+    def forward_act(self, x: ops.Act, B: int, T: int, slf_attn_mask, want_attn: bool, want_f32: bool = True):
         attn = None
         if want_attn:
-            _, attn = self.slf_attn.forward_act(x, None, B, T, T, slf_attn_mask, True)
-        return self.pos_ffn.forward_act(x), attn
+            _, attn = self.slf_attn.forward_act(x, None, B, T, T, slf_attn_mask, True, want_f32=False)
+        return self.pos_ffn.forward_act(x, want_f32=want_f32), attn
 
     def forward(self, enc_input, slf_attn_mask=None, return_attn=True):
         nat.require_cuda(enc_input, slf_attn_mask)
@@ -56,14 +56,19 @@ class DecoderLayer(nn.Module):
         return ok and (not hasattr(self, 'slf_attn') or self.slf_attn.fused_ok())
 
     def forward_act(self, x: ops.Act, enc: ops.Act, B: int, L: int, T: int, slf_attn_mask, dec_enc_attn_mask,
-                    want_attn: bool, kv_proj=None, last: bool = False):
-        out, enc_attn = self.enc_attn.forward_act(x, enc, B, L, T, dec_enc_attn_mask, want_attn, kv_proj=kv_proj)
-        out = self.pos_ffn1.forward_act(out)
+                    want_attn: bool, kv_proj=None, last: bool = False, want_int_f32: bool = True,
+                    want_out_f32: bool = True):
+        """Inside the layer activations exist as tensor-core operand planes only; fp32 copies are written just for
+        the tensors the caller asked for (layer output, intermediate output)."""
+        out, enc_attn = self.enc_attn.forward_act(x, enc, B, L, T, dec_enc_attn_mask, want_attn, kv_proj=kv_proj,
+                                                  want_f32=False)
+        has_slf = hasattr(self, 'slf_attn')
+        out = self.pos_ffn1.forward_act(out, want_f32=want_int_f32 and has_slf)
         out_int, slf_attn = None, None
-        if hasattr(self, 'slf_attn'):
+        if has_slf:
             out_int = out
-            out, slf_attn = self.slf_attn.forward_act(out, None, B, L, L, slf_attn_mask, want_attn)
-        out = self.pos_ffn2.forward_act(out, want_planes=not last)
+            out, slf_attn = self.slf_attn.forward_act(out, None, B, L, L, slf_attn_mask, want_attn, want_f32=False)
+        out = self.pos_ffn2.forward_act(out, want_planes=not last, want_f32=want_out_f32 or last)
         return out, out_int, slf_attn, enc_attn
 
     def forward(self, dec_input, enc_output, slf_attn_mask=None, dec_enc_attn_mask=None, return_attns=True):

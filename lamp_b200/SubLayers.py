@@ -134,7 +134,7 @@ class MultiHeadAttention(nn.Module):
         return ops.default_precision() if self.precision is None else self.precision
 
     def forward_act(self, q: ops.Act, kv, B: int, Lq: int, Lk: int, attn_mask, want_attn: bool,
-                    kv_proj=None):
+                    kv_proj=None, want_f32: bool = True):
         """q: Act [B*Lq (or Lq, broadcast), D]; kv: None (self-attention) or Act [B*Lk, D].
         ``kv_proj``: optional precomputed ``(Act [B*Lk, ld], k_col0, v_col0)`` K|V projection (GraphDecoder batches
         the label<-input K|V projections of all its layers into one GEMM).  -> (Act out, probs or None)."""
@@ -158,10 +158,9 @@ class MultiHeadAttention(nn.Module):
         ln = self.layer_norm
         if H > 1:
             f_hi, f_lo = self._wp.get('fc', (self.fc.weight,), prec)
-            y = ops.linear_residual_f32(o, f_hi, f_lo, D, prec, residual=q)
-            out = ops.layernorm(y, ln.weight, ln.bias, ln.eps, prec)
+            out = ops.linear_residual_ln(o, f_hi, f_lo, D, prec, q, ln.weight, ln.bias, ln.eps, want_f32=want_f32)
         else:
-            out = ops.layernorm(o.f32, ln.weight, ln.bias, ln.eps, prec, add=q)
+            out = ops.layernorm(o.f32, ln.weight, ln.bias, ln.eps, prec, add=q, want_f32=want_f32)
         return out, probs
 
     def forward(self, q, k, v, attn_mask=None, dec_self=False, return_attn=True):
@@ -211,15 +210,15 @@ class PositionwiseFeedForward(nn.Module):
     def fused_ok(self) -> bool:
         return self.w_1.in_channels % 8 == 0 and self.w_1.out_channels % 8 == 0
 
-    def forward_act(self, x: ops.Act, want_planes: bool = True) -> ops.Act:
+    def forward_act(self, x: ops.Act, want_planes: bool = True, want_f32: bool = True) -> ops.Act:
         prec = ops.default_precision() if self.precision is None else self.precision
         D, dh = self.w_1.in_channels, self.w_1.out_channels
         w1_hi, w1_lo = self._wp.get('w1', (self.w_1.weight,), prec)
         w2_hi, w2_lo = self._wp.get('w2', (self.w_2.weight,), prec)
         h = ops.linear_planes(x, w1_hi, w1_lo, dh, prec, bias=self.w_1.bias, relu=True)
-        y = ops.linear_residual_f32(h, w2_hi, w2_lo, D, prec, residual=x, bias=self.w_2.bias)
         ln = self.layer_norm
-        return ops.layernorm(y, ln.weight, ln.bias, ln.eps, prec, want_planes=want_planes)
+        return ops.linear_residual_ln(h, w2_hi, w2_lo, D, prec, x, ln.weight, ln.bias, ln.eps, bias=self.w_2.bias,
+                                      want_planes=want_planes, want_f32=want_f32)
 
     def forward(self, x):
         nat.require_cuda(x)

@@ -31,6 +31,10 @@ _SIGNATURES = {
     'lamp_split_planes': ([_vp, _i64, _i, _i64, _vp, _vp, _i64, _vp], _i),
     'lamp_gemm_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp,
                           _i64, _vp], _i),
+    'lamp_gemm_planes_pres': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp,
+                               _vp, _i64, _vp], _i),
+    'lamp_gemm_ln_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _f, _vp, _i64,
+                             _vp, _vp, _i64, _vp], _i),
     'lamp_attn_core_planes': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,
                                _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp], _i),
     'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp], _i),

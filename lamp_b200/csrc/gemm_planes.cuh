@@ -25,6 +25,8 @@ struct GemmParams {
   int M, N, K;
   const float* bias;      // [N] or nullptr
   const float* residual;  // [*, ldr] or nullptr; row index = resid_mod ? row % resid_mod : row
+  const __nv_bfloat16* res_hi;  // alternative residual source: split-bf16 planes [*, ldr] (hi + lo, 2^-17 relative);
+  const __nv_bfloat16* res_lo;  // lets a layer keep its activations in operand form only (no fp32 copy in HBM)
   int ldr;
   int resid_mod;
   int relu;
@@ -33,7 +35,52 @@ struct GemmParams {
   __nv_bfloat16* out_hi;  // [M, ldp] or nullptr
   __nv_bfloat16* out_lo;  // [M, ldp] or nullptr (nullptr -> hi only)
   int ldp;
+  // EPI_LN only: out = LayerNorm(acc + bias + residual) * gamma + beta over the full row (N <= 2 * BLOCK_N)
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
 };
+
+// Residual values of the 8 rows (m_base + 4 i, i = 0..7) x 4 consecutive columns handled by one lane of the coalesced
+// epilogue phase: fp32 source, or reconstructed from the hi (+ lo) planes.  All loads of a lane are independent and
+// issued before any use (8 or 16 requests in flight per lane).
+__device__ __forceinline__ void gemm_load_residual8(const GemmParams& p, int m_base, int col, int rows_left, bool col_ok,
+                                                    float4 (&dst)[8]) {
+  if (p.residual != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * i < rows_left && col_ok) {
+        const int row = m_base + 4 * i;
+        const int rres = p.resid_mod ? (row % p.resid_mod) : row;
+        dst[i] = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rres) * p.ldr + col));
+      }
+    }
+    return;
+  }
+  uint2 h[8], l[8];
+  const __nv_bfloat16* lo_src = p.res_lo != nullptr ? p.res_lo : p.res_hi;  // branch-free: weight 0 without a lo plane
+  const float lo_w = p.res_lo != nullptr ? 1.0f : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = make_uint2(0u, 0u);
+    l[i] = make_uint2(0u, 0u);
+    if (4 * i < rows_left && col_ok) {
+      const int row = m_base + 4 * i;
+      const int rres = p.resid_mod ? (row % p.resid_mod) : row;
+      const size_t off = static_cast<size_t>(rres) * p.ldr + col;
+      h[i] = __ldg(reinterpret_cast<const uint2*>(p.res_hi + off));
+      l[i] = __ldg(reinterpret_cast<const uint2*>(lo_src + off));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    dst[i].x = fmaf(lo_w, __uint_as_float(l[i].x << 16), __uint_as_float(h[i].x << 16));
+    dst[i].y = fmaf(lo_w, __uint_as_float(l[i].x & 0xFFFF0000u), __uint_as_float(h[i].x & 0xFFFF0000u));
+    dst[i].z = fmaf(lo_w, __uint_as_float(l[i].y << 16), __uint_as_float(h[i].y << 16));
+    dst[i].w = fmaf(lo_w, __uint_as_float(l[i].y & 0xFFFF0000u), __uint_as_float(h[i].y & 0xFFFF0000u));
+  }
+}
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_EPI_WARPS = 8;
@@ -43,6 +90,9 @@ constexpr uint32_t GEMM_EPI_STAGING = GEMM_EPI_WARPS * 32 * 128;  // per epilogu
 constexpr int EPI_PLANES = 0;  // (+bias)(ReLU) -> hi/lo planes
 constexpr int EPI_F32 = 1;     // (+bias)(+residual) -> fp32
 constexpr int EPI_ANY = 2;     // everything, selected at run time (tests / rare combinations)
+constexpr int EPI_LN = 3;      // (+bias)(+residual) -> LayerNorm over the whole row -> fp32 and/or planes.  The two
+                               // 256-column accumulator stages hold the two halves of ONE 512-wide row block, so the
+                               // row statistics are complete on chip and the pre-norm tensor never touches HBM.
 
 template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP = 1>
 struct GemmCfg {
@@ -129,6 +179,19 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   const int num_tiles = num_m * num_n;
   const int tile0 = static_cast<int>(blockIdx.x) / CTA_GROUP;
   const int tile_step = static_cast<int>(gridDim.x) / CTA_GROUP;
+  // j-th tile of this CTA (pair) -> (m tile, n tile).  EPI_LN walks both n halves of an m tile back to back so that
+  // accumulator stage == n half; everything else strides over the flat tile index.
+  auto get_tile = [&](int j, int& mt, int& nt) -> bool {
+    if (EPI == EPI_LN) {
+      mt = tile0 + (j >> 1) * tile_step;
+      nt = j & 1;
+      return mt < num_m;
+    }
+    const int tile = tile0 + j * tile_step;
+    mt = tile / num_n;
+    nt = tile % num_n;
+    return tile < num_tiles;
+  };
 
   auto stage_ptr = [&](int s, int which) -> uint8_t* {
     // which: 0 = A_hi, 1 = W_hi, 2 = A_lo, 3 = W_lo
@@ -146,9 +209,10 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m0 = (tile / num_n) * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M;
-        const int n0 = (tile % num_n) * BLOCK_N + static_cast<int>(rank) * Cfg::W_ROWS;
+      int mt, nt;
+      for (int j = 0; get_tile(j, mt, nt); ++j) {
+        const int m0 = mt * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M;
+        const int n0 = nt * BLOCK_N + static_cast<int>(rank) * Cfg::W_ROWS;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const int k0 = kb * BLOCK_K;
@@ -183,7 +247,8 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      int mt, nt;
+      for (int j = 0; get_tile(j, mt, nt); ++j) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -232,15 +297,145 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const bool want_f32 = (EPI == EPI_F32) || (EPI == EPI_ANY && p.out_f32 != nullptr);
     const bool want_pl = (EPI == EPI_PLANES) || (EPI == EPI_ANY && p.out_hi != nullptr);
     const bool want_lo = want_pl && p.out_lo != nullptr;
-    const bool has_res = (EPI != EPI_PLANES) && p.residual != nullptr;
+    const bool has_res = (EPI != EPI_PLANES) && (p.residual != nullptr || p.res_hi != nullptr);
     const bool has_bias = p.bias != nullptr;
     const bool relu = (EPI != EPI_F32) && p.relu;
+    const uint32_t te_addr[2] = {mapa_shared(&tmem_empty[0], 0), mapa_shared(&tmem_empty[1], 0)};  // leader's copies
+    if constexpr (EPI == EPI_LN) {
+      // ---------------- LayerNorm-fused epilogue: stage 0 / 1 hold columns [0,256) / [256,512) of the same rows.
+      //   pass 1 (per stage, as soon as its MMAs retire): v = acc + bias + residual -> per-row sum / sum of squares
+      //   exchange between the two warps of a lane quarter, then
+      //   pass 2 (stage 0 first, released early so the next row block's MMAs can start): normalise, scale, store.
+      // row statistics are exchanged through the (idle between the passes) staging slices of the two sibling warps
+      float* red_mine = reinterpret_cast<float*>(stg);
+      const float* red_sib = reinterpret_cast<const float*>(staging + ((warp - 2) ^ 4) * (32 * 128));
+      const bool want_f32 = p.out_f32 != nullptr, want_pl = p.out_hi != nullptr, want_lo = p.out_lo != nullptr;
+      const bool has_res = (p.residual != nullptr || p.res_hi != nullptr), has_bias = p.bias != nullptr;
+      const float inv_n = 1.0f / static_cast<float>(p.N);
+      uint32_t ph = 0;
+      for (int mt2 = tile0; mt2 < num_m; mt2 += tile_step, ph ^= 1) {
+        const int m0 = mt2 * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
+        const int rows_left = p.M - m0 - sub_r;
+        float rsum[8], rsq[8], mean[8], rstd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rsum[i] = 0.f; rsq[i] = 0.f; mean[i] = 0.f; rstd[i] = 0.f; }
+        // one pass over a 256-column stage; final_pass = false: statistics, true: normalise + store
+        auto pass = [&](int a, bool final_pass) {
+          const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + a * BLOCK_N;
+          const int n0 = a * BLOCK_N;
+          // residual rows of one 32-column chunk (8 x 128-bit per lane); fetched one chunk AHEAD of their use so
+          // the global/L2 latency overlaps the TMEM load and the smem transpose of the current chunk
+          auto load_res = [&](int c0, float4 (&dst)[8]) {
+            const int col = n0 + c0 + sub_c * 4;
+            if (has_res && c0 < BLOCK_N) {
+              gemm_load_residual8(p, m0 + sub_r, col, rows_left, col < p.N, dst);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          };
+          float4 resv[8], resn[8];
+          load_res(half * 32, resv);
+#pragma unroll 1
+          for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+            uint32_t r[32];
+            tmem_ld32(t_row + c0, r);
+            load_res(c0 + 64, resn);
+            tmem_wait_ld();
+            const int col = n0 + c0 + sub_c * 4;
+            const bool col_ok = col < p.N;
+            if (n0 + c0 < p.N) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                    make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+              __syncwarp();
+              float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, b4 = bias4;
+              if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              if (final_pass && col_ok) {
+                g4 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col));
+                b4 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + sub_r;
+                float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((sub_c ^ (rr & 7)) << 4));
+                if (4 * i < rows_left && col_ok) {
+                  v.x += bias4.x + resv[i].x; v.y += bias4.y + resv[i].y;
+                  v.z += bias4.z + resv[i].z; v.w += bias4.w + resv[i].w;
+                  if (!final_pass) {
+                    rsum[i] += (v.x + v.y) + (v.z + v.w);
+                    rsq[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                  } else {
+                    v.x = (v.x - mean[i]) * rstd[i] * g4.x + b4.x;
+                    v.y = (v.y - mean[i]) * rstd[i] * g4.y + b4.y;
+                    v.z = (v.z - mean[i]) * rstd[i] * g4.z + b4.z;
+                    v.w = (v.w - mean[i]) * rstd[i] * g4.w + b4.w;
+                    const size_t row = static_cast<size_t>(m0 + 4 * i + sub_r);
+                    if (want_f32) *reinterpret_cast<float4*>(p.out_f32 + row * p.ldo + col) = v;
+                    if (want_pl) {
+                      uint2 hi, lo;
+                      split_bf16x2(v.x, v.y, hi.x, lo.x);
+                      split_bf16x2(v.z, v.w, hi.y, lo.y);
+                      *reinterpret_cast<uint2*>(p.out_hi + row * p.ldp + col) = hi;
+                      if (want_lo) *reinterpret_cast<uint2*>(p.out_lo + row * p.ldp + col) = lo;
+                    }
+                  }
+                }
+              }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) resv[i] = resn[i];
+          }
+        };
+        mbar_wait(&tmem_full[0], ph);
+        tcgen05_fence_after();
+        pass(0, false);
+        mbar_wait(&tmem_full[1], ph);
+        tcgen05_fence_after();
+        pass(1, false);
+        // row statistics: 8 lanes share a row -> butterfly over the low 3 lane bits, then the sibling warp via smem
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            rsum[i] += __shfl_xor_sync(0xFFFFFFFFu, rsum[i], o);
+            rsq[i] += __shfl_xor_sync(0xFFFFFFFFu, rsq[i], o);
+          }
+        }
+        if (sub_c == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            red_mine[(i * 4 + sub_r) * 2] = rsum[i];
+            red_mine[(i * 4 + sub_r) * 2 + 1] = rsq[i];
+          }
+        }
+        named_bar_sync(2, 32 * GEMM_EPI_WARPS);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + sub_r;
+          const float s1 = red_mine[rl * 2] + red_sib[rl * 2];
+          const float s2 = red_mine[rl * 2 + 1] + red_sib[rl * 2 + 1];
+          mean[i] = s1 * inv_n;
+          const float var = fmaxf(s2 * inv_n - mean[i] * mean[i], 0.0f);
+          rstd[i] = rsqrtf(var + p.ln_eps);
+        }
+        named_bar_sync(2, 32 * GEMM_EPI_WARPS);  // the staging slices are reused by pass 2 after this point
+        pass(0, true);
+        tcgen05_fence_before();
+        if (PAIR) mbar_arrive_cluster(te_addr[0]); else mbar_arrive(&tmem_empty[0]);
+        pass(1, true);
+        tcgen05_fence_before();
+        if (PAIR) mbar_arrive_cluster(te_addr[1]); else mbar_arrive(&tmem_empty[1]);
+      }
+    } else {
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t te_addr[2] = {mapa_shared(&tmem_empty[0], 0), mapa_shared(&tmem_empty[1], 0)};  // leader's copies
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m0 = (tile / num_n) * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
-      const int n0 = (tile % num_n) * BLOCK_N;
+    int mt, nt;
+    for (int j = 0; get_tile(j, mt, nt); ++j) {
+      const int m0 = mt * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
+      const int n0 = nt * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
@@ -263,17 +458,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         // residual rows first (8 independent 128-bit loads in flight), then the staged accumulators
         float4 resv[8];
-        if (has_res) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            resv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * i < rows_left && col_ok) {
-              const int row = m0 + i * 4 + sub_r;
-              const int rres = p.resid_mod ? (row % p.resid_mod) : row;
-              resv[i] = __ldg(reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(rres) * p.ldr + col));
-            }
-          }
-        }
+        if (has_res) gemm_load_residual8(p, m0 + sub_r, col, rows_left, col_ok, resv);
         float* of = want_f32 ? p.out_f32 + static_cast<size_t>(m0 + sub_r) * p.ldo + col : nullptr;
         const size_t poff = static_cast<size_t>(m0 + sub_r) * p.ldp + col;
 #pragma unroll
@@ -302,6 +487,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       tcgen05_fence_before();
       if (PAIR) mbar_arrive_cluster(te_addr[acc]); else mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
   }
 

@@ -127,7 +127,8 @@ int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUte
   static int once_rc = LAMP_OK;
   std::call_once(once, [kernel] { once_rc = set_smem(kernel, Cfg::SMEM_BYTES); });
   if (once_rc != LAMP_OK) return once_rc;
-  const int tiles = ((p.M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP)) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int m_tiles = (p.M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP);
+  const int tiles = (EPI == EPI_LN) ? m_tiles : m_tiles * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int max_groups = sm_count_cached() / CTA_GROUP;
   const int groups = tiles < max_groups ? tiles : max_groups;
   cudaLaunchConfig_t cfg{};
@@ -150,7 +151,13 @@ int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUte
 template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP>
 int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                 const GemmParams& p, cudaStream_t st) {
-  if (p.out_hi != nullptr && p.out_f32 == nullptr && p.residual == nullptr)
+  if (p.ln_gamma != nullptr) {
+    if constexpr (BLOCK_N == 256)
+      return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_LN, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
+    else
+      return fail(LAMP_EINVAL, "gemm: fused LayerNorm needs the 256-wide tile");
+  }
+  if (p.out_hi != nullptr && p.out_f32 == nullptr && p.residual == nullptr && p.res_hi == nullptr)
     return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_PLANES, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
   if (p.out_hi == nullptr && !p.relu)
     return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_F32, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
@@ -228,11 +235,19 @@ int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* 
   return launch_check();
 }
 
-int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
                      int64_t ldw, int M, int N, int K, int precision, const float* bias, int relu,
-                     const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
-                     void* out_lo, int64_t ldp, void* stream) {
+                     const float* residual, const void* res_hi, const void* res_lo, int64_t ldr, int resid_mod,
+                     float* out_f32, int64_t ldo, void* out_hi,
+                     void* out_lo, int64_t ldp, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                     void* stream) {
   if (int rc = arch_check()) return rc;
+  if (ln_gamma != nullptr) {
+    REQUIRE(ln_beta != nullptr, "gemm_ln: beta missing");
+    REQUIRE(N > 256 && N <= 512, "gemm_ln: the fused LayerNorm epilogue covers 256 < N <= 512 (got %d)", N);
+    REQUIRE(!relu, "gemm_ln: ReLU is not part of this epilogue");
+    REQUIRE(aligned16(ln_gamma) && aligned16(ln_beta), "gemm_ln: gamma/beta alignment");
+  }
   REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   REQUIRE(K % 8 == 0 && N % 8 == 0, "gemm: K (%d) and N (%d) must be multiples of 8", K, N);
   REQUIRE(a_hi && w_hi, "gemm: null operand");
@@ -243,6 +258,8 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
   REQUIRE(!out_f32 || (aligned16(out_f32) && ldo % 4 == 0), "gemm: out_f32 alignment");
   REQUIRE(!out_hi || (aligned16(out_hi) && ldp % 8 == 0 && (!out_lo || aligned16(out_lo))), "gemm: plane alignment");
   REQUIRE(!residual || (aligned16(residual) && ldr % 4 == 0), "gemm: residual alignment");
+  REQUIRE(!(residual && res_hi), "gemm: give the residual either as fp32 or as planes, not both");
+  REQUIRE(!res_hi || (aligned16(res_hi) && ldr % 8 == 0 && (!res_lo || aligned16(res_lo))), "gemm: residual plane alignment");
   REQUIRE(!bias || aligned16(bias), "gemm: bias alignment");
   if (M == 0) return LAMP_OK;
   const bool wide = (N > 128);
@@ -262,11 +279,14 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
   }
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.bias = bias; p.residual = residual; p.ldr = (int)ldr; p.resid_mod = resid_mod; p.relu = relu;
+  p.bias = bias; p.residual = residual; p.ldr = (int)ldr;
+  p.res_hi = static_cast<const __nv_bfloat16*>(res_hi);
+  p.res_lo = static_cast<const __nv_bfloat16*>(res_lo); p.resid_mod = resid_mod; p.relu = relu;
   p.out_f32 = out_f32; p.ldo = (int)ldo;
   p.out_hi = static_cast<__nv_bfloat16*>(out_hi);
   p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.ldp = (int)ldp;
+  p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;
   cudaStream_t st = (cudaStream_t)stream;
 #define LAMP_GEMM_DISPATCH(BK)                                                                                      \
   do {                                                                                                             \
@@ -282,6 +302,32 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
   if (bk == 64) LAMP_GEMM_DISPATCH(64);
   LAMP_GEMM_DISPATCH(32);
 #undef LAMP_GEMM_DISPATCH
+}
+
+int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                     int64_t ldw, int M, int N, int K, int precision, const float* bias, int relu,
+                     const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
+                     void* out_lo, int64_t ldp, void* stream) {
+  return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, relu, residual, nullptr, nullptr, ldr,
+                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, stream);
+}
+
+int lamp_gemm_planes_pres(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                          int64_t ldw, int M, int N, int K, int precision, const float* bias, const void* res_hi,
+                          const void* res_lo, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
+                          void* out_lo, int64_t ldp, void* stream) {
+  REQUIRE(res_hi != nullptr, "gemm_planes_pres: residual planes missing");
+  return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, 0, nullptr, res_hi, res_lo, ldr,
+                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, stream);
+}
+
+int lamp_gemm_ln_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                        int64_t ldw, int M, int N, int K, int precision, const float* bias, const float* residual,
+                        int64_t ldr, int resid_mod, const float* gamma, const float* beta, float eps, float* out_f32,
+                        int64_t ldo, void* out_hi, void* out_lo, int64_t ldp, void* stream) {
+  REQUIRE(gamma && beta, "gemm_ln: null gamma/beta");
+  return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, 0, residual, nullptr, nullptr, ldr,
+                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, gamma, beta, eps, stream);
 }
 
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,

@@ -179,27 +179,69 @@ def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=Fals
     return Act(None, hi, lo, x.rows, N, x.bcast_rows)
 
 
+def act_f32(a: Act) -> torch.Tensor:
+    """fp32 view of an activation; reconstructed from the planes when the fp32 copy was never materialised."""
+    if a.f32 is None:
+        a.f32 = a.hi.float() if a.lo is None else a.hi.float() + a.lo.float()
+    return a.f32
+
+
 def linear_residual_f32(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, *, bias=None) -> torch.Tensor:
-    """planes(x) @ W^T (+bias) + residual -> fp32 [rows, N] (pre-LayerNorm)."""
+    """planes(x) @ W^T (+bias) + residual -> fp32 [rows, N] (pre-LayerNorm).  The residual is read as fp32 when the
+    activation has an fp32 copy, otherwise reconstructed from its planes inside the epilogue."""
     y = torch.empty((x.rows, N), dtype=torch.float32, device=x.hi.device)
     mod = residual.rows if residual.bcast_rows else 0
-    gemm(x.hi, x.lo, x.cols, w_hi, w_lo, x.cols, x.rows, N, x.cols, prec, bias=bias, residual=residual.f32,
-         ldr=residual.cols, resid_mod=mod, out_f32=y, ldo=N)
+    if residual.f32 is not None:
+        gemm(x.hi, x.lo, x.cols, w_hi, w_lo, x.cols, x.rows, N, x.cols, prec, bias=bias, residual=residual.f32,
+             ldr=residual.cols, resid_mod=mod, out_f32=y, ldo=N)
+        return y
+    M, K = x.rows, x.cols
+    pl = 4 if prec == nat.PREC_FP32 else 2
+    STATS.call('gemm_planes', 1, nat.lib().lamp_gemm_planes_pres,
+               (nat.ptr(x.hi), nat.ptr(x.lo), K, nat.ptr(w_hi), nat.ptr(w_lo), K, M, N, K, prec, nat.ptr(bias),
+                nat.ptr(residual.hi), nat.ptr(residual.lo), residual.cols, mod, y.data_ptr(), N, None, None, 0,
+                nat.stream()), flops=2.0 * M * N * K, nbytes=M * K * pl + N * K * pl + M * N * 4 + M * N * pl)
     return y
 
 
+FUSE_LAYERNORM = False  # True: fc / w_2 GEMM epilogue normalises the row on chip when 256 < d_model <= 512 (measured
+# slower than GEMM + LayerNorm kernels on B200: the exposed two-pass epilogue costs more than the HBM round trip saves)
+
+
+def linear_residual_ln(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, gamma, beta, eps: float, *, bias=None,
+                       want_planes: bool = True, want_f32: bool = True) -> Act:
+    """LayerNorm(planes(x) @ W^T (+bias) + residual) -> Act (fp32 + planes).  One kernel when the output row fits
+    the 512-column TMEM accumulator (the pre-norm tensor never reaches HBM); GEMM + LayerNorm kernels otherwise."""
+    if not (FUSE_LAYERNORM and 256 < N <= 512 and residual.f32 is not None):
+        y = linear_residual_f32(x, w_hi, w_lo, N, prec, residual, bias=bias)
+        return layernorm(y, gamma, beta, eps, prec, want_planes=want_planes, want_f32=want_f32)
+    dev = x.hi.device
+    out = torch.empty((x.rows, N), dtype=torch.float32, device=dev)
+    hi, lo = _empty_planes(x.rows, N, prec, dev) if want_planes else (None, None)
+    mod = residual.rows if residual.bcast_rows else 0
+    M, K = x.rows, x.cols
+    pl = 4 if prec == nat.PREC_FP32 else 2
+    nbytes = M * K * pl + N * K * pl + M * N * 4 + (M * N * pl if want_planes else 0) + (0 if mod else M * N * 4)
+    STATS.call('gemm_ln_planes', 1, nat.lib().lamp_gemm_ln_planes,
+               (nat.ptr(x.hi), nat.ptr(x.lo), K, nat.ptr(w_hi), nat.ptr(w_lo), K, M, N, K, prec, nat.ptr(bias),
+                nat.ptr(residual.f32), residual.cols, mod, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                out.data_ptr(), N, nat.ptr(hi), nat.ptr(lo), N, nat.stream()), flops=2.0 * M * N * K, nbytes=nbytes)
+    return Act(out, hi, lo, x.rows, N)
+
+
 def layernorm(y: torch.Tensor, gamma, beta, eps: float, prec: int, *, add: Optional[Act] = None,
-              want_planes: bool = True) -> Act:
+              want_planes: bool = True, want_f32: bool = True) -> Act:
     rows, D = y.shape
-    out = torch.empty_like(y)
+    want_f32 = want_f32 or not want_planes
+    out = torch.empty_like(y) if want_f32 else None
     hi, lo = _empty_planes(rows, D, prec, y.device) if want_planes else (None, None)
     add_t, add_mod = (None, 0)
     if add is not None:
-        add_t, add_mod = add.f32, (add.rows if add.bcast_rows else 0)
+        add_t, add_mod = act_f32(add), (add.rows if add.bcast_rows else 0)
     STATS.call('layernorm', 1, nat.lib().lamp_layernorm,
                (y.data_ptr(), nat.ptr(add_t), add_mod, gamma.data_ptr(), beta.data_ptr(), float(eps), rows, D,
-                out.data_ptr(), nat.ptr(hi), nat.ptr(lo), nat.stream()),
-               nbytes=rows * D * (8 + (0 if hi is None else (4 if lo is not None else 2))))
+                nat.ptr(out), nat.ptr(hi), nat.ptr(lo), nat.stream()),
+               nbytes=rows * D * (4 + (4 if want_f32 else 0) + (0 if hi is None else (4 if lo is not None else 2))))
     return Act(out, hi, lo, rows, D)
 
 
@@ -270,19 +312,19 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask, temperature: f
 
 
 def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor, pos_emb: Optional[torch.Tensor],
-          prec: int) -> Act:
+          prec: int, want_f32: bool = True) -> Act:
     nat.require_cuda(seq, word_emb)
     seq = seq.contiguous().long()
     rows = seq.numel()
     D = word_emb.shape[1]
-    out = torch.empty((rows, D), dtype=torch.float32, device=seq.device)
+    out = torch.empty((rows, D), dtype=torch.float32, device=seq.device) if want_f32 else None
     hi, lo = _empty_planes(rows, D, prec, seq.device)
     if pos_emb is not None:
         pos = pos.contiguous().long()
     STATS.call('embed', 1, nat.lib().lamp_embed,
                (seq.data_ptr(), nat.ptr(pos) if pos_emb is not None else None, word_emb.data_ptr(), nat.ptr(pos_emb),
-                rows, D, out.data_ptr(), hi.data_ptr(), nat.ptr(lo), nat.stream()),
-               nbytes=rows * D * (4 + 4 + (4 if lo is not None else 2)))
+                rows, D, nat.ptr(out), hi.data_ptr(), nat.ptr(lo), nat.stream()),
+               nbytes=rows * D * (4 + (4 if want_f32 else 0) + (4 if lo is not None else 2)))
     return Act(out, hi, lo, rows, D)
 
 

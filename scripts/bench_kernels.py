@@ -53,6 +53,39 @@ def bench_gemm(prec=0):
         nat.check(nat.lib().lamp_set_tuning(2, 1), 'tune')
 
 
+def bench_gemm_ln(prec=0):
+    B = 1024
+    for name, M in (('enc', B * 300), ('dec', B * 103)):
+        N = K = 512
+        a = ops.Act(None, *ops.split(torch.randn(M, K, device=DEV), prec), M, K)
+        w_hi, w_lo = ops.split(torch.randn(N, K, device=DEV) / K ** 0.5, prec)
+        res = ops.Act(torch.randn(M, N, device=DEV), None, None, M, N)
+        g = torch.ones(N, device=DEV)
+        b = torch.zeros(N, device=DEV)
+        bias = torch.zeros(N, device=DEV)
+        for fuse in (True, False):
+            ops.FUSE_LAYERNORM = fuse
+            t = timeit(lambda: ops.linear_residual_ln(a, w_hi, w_lo, N, prec, res, g, b, 1e-5, bias=bias))
+            print(f'gemm+LN {name} M={M} fused={fuse}: {t * 1e6:8.1f} us  {2.0 * M * N * K / t / 1e12:7.1f} TFLOP/s alg',
+                  flush=True)
+        ops.FUSE_LAYERNORM = True
+
+
+def bench_gemm_pres(prec=0):
+    B = 1024
+    for name, M in (('enc', B * 300), ('dec', B * 103)):
+        N = K = 512
+        a = ops.Act(None, *ops.split(torch.randn(M, K, device=DEV), prec), M, K)
+        w_hi, w_lo = ops.split(torch.randn(N, K, device=DEV) / K ** 0.5, prec)
+        rf = torch.randn(M, N, device=DEV)
+        res_f = ops.Act(rf, None, None, M, N)
+        res_p = ops.Act(None, *ops.split(rf, prec), M, N)
+        for nm, r in (('fp32 residual', res_f), ('planes residual', res_p)):
+            t = timeit(lambda: ops.linear_residual_f32(a, w_hi, w_lo, N, prec, r))
+            print(f'gemm f32out {name} M={M} {nm}: {t * 1e6:8.1f} us  {2.0 * M * N * K / t / 1e12:7.1f} TFLOP/s alg',
+                  flush=True)
+
+
 def bench_attn(prec=0):
     B, H, d = 1024, 4, 128
     hd = H * d
@@ -89,6 +122,10 @@ if __name__ == '__main__':
         bench_gemm(0)
     if 'gemm1' in what:
         bench_gemm(1)
+    if 'gemm_pres' in what:
+        bench_gemm_pres(0)
+    if 'gemm_ln' in what:
+        bench_gemm_ln(0)
     if 'attn' in what:
         bench_attn(0)
     if 'ln' in what:

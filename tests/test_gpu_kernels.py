@@ -111,6 +111,47 @@ def _gemm_case(M, N, K, prec):
     assert rel_err(out, ref3) < tol
 
 
+@pytest.mark.parametrize('M,N,K,pair', [(1000, 512, 512, 1), (103, 512, 128, 1), (777, 384, 256, 1), (2048, 512, 64, 0),
+                                         (130, 264, 512, 1), (5000, 512, 1024, 1)])
+def test_gemm_fused_layernorm(M, N, K, pair):
+    """lamp_gemm_ln_planes: LayerNorm(A W^T + bias + residual) on chip, vs fp64."""
+    nat.check(nat.lib().lamp_set_tuning(2, pair), 'tune')
+    try:
+        g = torch.Generator(device='cpu').manual_seed(M + N + K)
+        a = torch.randn(M, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        bias = torch.randn(N, generator=g).to(DEV)
+        gam = (1 + 0.3 * torch.randn(N, generator=g)).to(DEV)
+        bet = torch.randn(N, generator=g).to(DEV)
+        L = nat.lib()
+        a_hi, a_lo = planes(a)
+        w_hi, w_lo = planes(w)
+        for mod in (0, 9):
+            res = torch.randn(mod if mod else M, N, generator=g).to(DEV) + 3.0   # non-zero mean rows
+            out = torch.full((M, N), float('nan'), device=DEV)
+            o_hi = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+            o_lo = torch.empty_like(o_hi)
+            nat.check(L.lamp_gemm_ln_planes(a_hi.data_ptr(), a_lo.data_ptr(), K, w_hi.data_ptr(), w_lo.data_ptr(), K, M, N,
+                                            K, 0, bias.data_ptr(), res.data_ptr(), N, mod, gam.data_ptr(), bet.data_ptr(),
+                                            1e-5, out.data_ptr(), N, o_hi.data_ptr(), o_lo.data_ptr(), N, nat.stream()),
+                      'gemm_ln')
+            torch.cuda.synchronize()
+            rr = res.double()[torch.arange(M, device=DEV) % mod] if mod else res.double()
+            ref = torch.nn.functional.layer_norm(a.double() @ w.double().T + bias.double() + rr, (N,), gam.double(),
+                                                 bet.double(), 1e-5)
+            e = rel_err(out, ref)
+            print(f'gemm_ln {M}x{N}x{K} pair={pair} mod={mod}: {e:.2e}')
+            assert e < 3e-5
+            assert torch.equal(o_hi, out.to(torch.bfloat16))
+            assert torch.equal(o_lo, (out - o_hi.float()).to(torch.bfloat16))
+        rc = L.lamp_gemm_ln_planes(a_hi.data_ptr(), a_lo.data_ptr(), K, w_hi.data_ptr(), w_lo.data_ptr(), K, M, 128, K, 0,
+                                   None, None, 0, 0, gam.data_ptr(), bet.data_ptr(), 1e-5, out.data_ptr(), 128, None, None,
+                                   0, nat.stream())
+        assert rc == -1   # row does not span two accumulator stages -> caller must use the unfused pair
+    finally:
+        nat.check(nat.lib().lamp_set_tuning(2, 1), 'tune')
+
+
 def run_sdpa(q, k, v, mask, temperature, prec=0, want_attn=True):
     N, Lq, d = q.shape
     Lk = k.shape[1]
