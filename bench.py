@@ -11,7 +11,8 @@ L=103 labels, T=300 tokens, d_model=512, n_head=4, 2+2 layers, d_inner=512, prio
   e2e   : same metric through the public API with HOST (pinned) token ids: H2D copy + forward + D2H of the logits
           inside the timed region
   roofline      : dominant kernel (projection GEMM, tensor-bound) -- algorithmic FLOPs / measured kernel time
-  roofline_attn : masked attention core kernel (HBM-bound)        -- algorithmic bytes / measured kernel time
+  roofline_attn : masked label<-label attention core kernel under the label-graph mask (HBM-bound) -- algorithmic
+                  bytes / measured kernel time; roofline_attn_enc: the same kernel on the label<-input shape (T=300)
   cpu_baseline  : the CPU oracle (oracle/lamp_oracle.py, a torch-CPU port of the reference incl. its discarded
                   encoder self-attention) timed on the host cores on a bounded sample
   --impl reference : only the CPU port, same config, "impl": "reference"
@@ -230,6 +231,16 @@ def main():
     e2e_value = total_samples / e2e_s
     pk = peaks()
 
+    # measured DRAM traffic per launch (dram__bytes_read + dram__bytes_write) from the committed ncu capture of
+    # this same command at the default batch (profiles/r01_traffic.json); null for any other configuration
+    traffic = {}
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath) and world == 1:
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get('batch') == args.batch and tj.get('precision') == args.precision:
+            traffic = tj.get('avg_bytes_per_launch', {})
+
     def roof(name, bound):
         k = per_kernel.get(name)
         if not k or k['ms'] <= 0:
@@ -239,7 +250,8 @@ def main():
             ach, peak, unit = k['flops'] / sec / 1e12, pk['tensor'], 'TFLOP/s'
         else:
             ach, peak, unit = k['bytes'] / sec / 1e9, pk['hbm'], 'GB/s'
-        return dict(kernel=name, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+        return dict(kernel=name, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak,
+                    traffic=traffic.get(name), alg_bytes_per_launch=k['bytes'] / k['calls'],
                     peak_source=pk['src'], launches=k['calls'], avg_launch_ms=k['ms'] / k['calls'],
                     share_of_step=k['ms'] / sum(v['ms'] for v in per_kernel.values()),
                     alg_gbs=k['bytes'] / sec / 1e9, alg_tflops=k['flops'] / sec / 1e12)
@@ -253,7 +265,8 @@ def main():
                  h2d_bytes_per_step=int(seq_h.numel() * 8 + pos_h.numel() * 8) * world,
                  d2h_bytes_per_step=int(logits_h.numel() * 4) * world),
         gpu_launches=launches, clocks=clocks,
-        roofline=roof('gemm_planes', 'tensor'), roofline_attn=roof('attn_core', 'hbm'),
+        roofline=roof('gemm_planes', 'tensor'), roofline_attn=roof('attn_core_self', 'hbm'),
+        roofline_attn_enc=roof('attn_core_enc', 'hbm'),
         kernels={k: dict(calls=v['calls'], ms=round(v['ms'], 3)) for k, v in per_kernel.items()})
 
     if rank == 0:

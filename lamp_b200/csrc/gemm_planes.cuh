@@ -436,16 +436,25 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     for (int j = 0; get_tile(j, mt, nt); ++j) {
       const int m0 = mt * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
       const int n0 = nt * BLOCK_N;
+      const int rows_left = p.M - m0 - sub_r;  // row (m0 + sub_r + 4 i) is valid iff 4 i < rows_left
+      // residual rows of a 32-column chunk: requested one chunk AHEAD (the first one while the MMAs of this tile are
+      // still running), so their L2/HBM latency never sits on the epilogue's critical path
+      auto load_res = [&](int c0, float4 (&dst)[8]) {
+        const int col = n0 + c0 + sub_c * 4;
+        if (has_res && c0 < BLOCK_N) gemm_load_residual8(p, m0 + sub_r, col, rows_left, col < p.N, dst);
+      };
+      float4 resv[8], resn[8];
+      load_res(half * 32, resv);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
-      const int rows_left = p.M - m0 - sub_r;  // row (m0 + sub_r + 4 i) is valid iff 4 i < rows_left
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(t_row + c0, r);
+        load_res(c0 + 64, resn);
         tmem_wait_ld();
-        if (n0 + c0 >= p.N) continue;  // warp-uniform: whole 32-column chunk out of range
+        if (n0 + c0 >= p.N) continue;  // warp-uniform: whole 32-column chunk out of range (so are all later ones)
         // registers (lane == row) -> swizzled staging: chunk c of row `lane` lives at chunk (c ^ (lane & 7))
 #pragma unroll
         for (int c = 0; c < 8; ++c)
@@ -456,9 +465,6 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const bool col_ok = col < p.N;  // N % 8 == 0 (host-checked) -> the 4 columns are all in or all out
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        // residual rows first (8 independent 128-bit loads in flight), then the staged accumulators
-        float4 resv[8];
-        if (has_res) gemm_load_residual8(p, m0 + sub_r, col, rows_left, col_ok, resv);
         float* of = want_f32 ? p.out_f32 + static_cast<size_t>(m0 + sub_r) * p.ldo + col : nullptr;
         const size_t poff = static_cast<size_t>(m0 + sub_r) * p.ldp + col;
 #pragma unroll
@@ -483,6 +489,10 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           }
         }
         __syncwarp();
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) resv[i] = resn[i];
+        }
       }
       tcgen05_fence_before();
       if (PAIR) mbar_arrive_cluster(te_addr[acc]); else mbar_arrive(&tmem_empty[acc]);

@@ -284,7 +284,7 @@ def attention(q: Act, q_col0: int, kv: Act, k_col0: int, v_col0: int, B: int, H:
     # algorithmic bytes of the attention core: Q + K + V read, O written, 4 B (fp32-equivalent
     # plane pair) or 2 B (bf16) per element; a broadcast Q is read once.
     nbytes = ((1 if q.bcast_rows else B) * Lq * hd + 2 * B * Lk * hd) * pl + B * Lq * hd * (4 if out_f32 else pl)
-    STATS.call('attn_core', 2 if want_probs else 1, nat.lib().lamp_attn_core_planes,
+    STATS.call('attn_core_self' if q is kv else 'attn_core_enc', 2 if want_probs else 1, nat.lib().lamp_attn_core_planes,
                (q.hi.data_ptr(), nat.ptr(q.lo), q.cols, q_col0, 1 if q.bcast_rows else 0,
                 kv.hi.data_ptr(), nat.ptr(kv.lo), kv.cols, k_col0, v_col0, B, H, Lq, Lk, d, float(math.sqrt(d)), prec,
                 mptr, sb, sq, sk, nat.ptr(o_hi), nat.ptr(o_lo), hd, nat.ptr(o32), hd, nat.ptr(rmax), nat.ptr(rsum),
