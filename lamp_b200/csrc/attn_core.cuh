@@ -16,7 +16,12 @@
 //              shared or global memory); O rescaled in TMEM when the running max moves.  The epilogue of the
 //              PREVIOUS item (1/sum, hi/lo split, stores into the head's column slice of the concatenated output)
 //              runs after the current unit's softmax, hiding the PV latency.
-// TMEM columns: S0 [0,128) | S1 [128,256) | P hi/lo [256,384) | O [384,512).
+// TMEM columns: S0/P0 [0,128) | S1/P1 [128,256) | S2/P2 [256,384) | O [384,512).  P overwrites S in place: the warp that owns a
+// 32-column chunk of the scores holds them in registers and writes the chunk's hi (16 columns) and lo (16 columns)
+// bf16 pairs back over the same 32 columns, so the three score buffers double as P buffers (three, so that S(u+1)
+// never has to wait for the PV product of unit u-1 that still reads its buffer).
+// Shared memory holds only Q, K (double-buffered when it fits) and V tiles whose row counts follow the label count
+// (box rows = L rounded up to 8 / 16), e.g. L = 103: Q 52 KB + 2 x K 52 KB + V 56 KB.
 // The label mask is read from its single [Lq, Lk] (or [B, Lk] key-padding) copy -- it is never tiled per head or
 // per sample (the reference materialises H*B*Lq*Lk bytes, lamp/SubLayers.py:102 / lamp/Decoders.py:141).
 #pragma once
@@ -38,11 +43,13 @@ struct AttnParams {
   int ldof;
   float* row_max;  // optional [H*B*Lq] (head-major) running max of the SCALED (log2 domain) scores
   float* row_sum;  // optional [H*B*Lq] softmax denominators
+  int qrows, krows, vrows;  // TMA box rows of the Q / K / V tiles (multiples of 8 / 8 / 16)
 };
 
 constexpr int ATTN_BLOCK_M = 128;
 constexpr uint32_t ATTN_TMEM_COLS = 512;
-constexpr uint32_t ATTN_TMEM_S = 0, ATTN_TMEM_P = 256, ATTN_TMEM_O = 384;
+constexpr uint32_t ATTN_TMEM_S = 0, ATTN_TMEM_O = 384;
+constexpr int ATTN_S_BUFS = 3;
 // row-statistics exchange between the column-warps of a row: max [2 units][NW][128] + sum [2 items][NW][128] floats
 constexpr uint32_t ATTN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
 __host__ __device__ constexpr int attn_threads(int block_kv) { return 64 + 128 * (block_kv / 32); }
@@ -54,75 +61,77 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // Shared-memory plan (bytes).  kb64 = ceil(d / 64) column blocks of 64 bf16 (= one 128 B swizzle row each).
-template <int BLOCK_KV, int KV_STAGES, int NTERMS>
-struct AttnSmem {
-  static constexpr int NPL = (NTERMS == 3) ? 2 : 1;
-  __host__ __device__ static constexpr uint32_t q_bytes(int kb64) { return NPL * kb64 * ATTN_BLOCK_M * 128; }
-  __host__ __device__ static constexpr uint32_t kv_bytes(int kb64) { return NPL * kb64 * BLOCK_KV * 128; }
-  __host__ __device__ static constexpr uint32_t total(int kb64) {
-    return q_bytes(kb64) + 2 * KV_STAGES * kv_bytes(kb64) + ATTN_RED_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  }
-};
+__host__ __device__ constexpr uint32_t attn_tile_bytes(int npl, int kb64, int rows) { return npl * kb64 * rows * 128; }
+__host__ __device__ constexpr uint32_t attn_smem_bytes(int npl, int kb64, int qrows, int krows, int vrows, int kst,
+                                                       int vst) {
+  return attn_tile_bytes(npl, kb64, qrows) + kst * attn_tile_bytes(npl, kb64, krows) +
+         vst * attn_tile_bytes(npl, kb64, vrows) + ATTN_RED_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+}
 
-template <int BLOCK_KV, int KV_STAGES, int NTERMS>
+template <int BLOCK_KV, int K_STAGES, int V_STAGES, int NTERMS>
 __global__ void __launch_bounds__(attn_threads(BLOCK_KV), 1)
 attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
-                 const __grid_constant__ CUtensorMap tmKV_hi, const __grid_constant__ CUtensorMap tmKV_lo,
+                 const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
+                 const __grid_constant__ CUtensorMap tmV_hi, const __grid_constant__ CUtensorMap tmV_lo,
                  const AttnParams p) {
-  using SM = AttnSmem<BLOCK_KV, KV_STAGES, NTERMS>;
-  constexpr int NPL = SM::NPL;
+  constexpr int NPL = (NTERMS == 3) ? 2 : 1;
   constexpr int NW = BLOCK_KV / 32;        // 32-column score chunks per row == softmax warps per lane quarter
   constexpr int NSW = 4 * NW * 32;         // softmax threads
-  constexpr uint32_t P_LO = BLOCK_KV / 2;  // TMEM column offset of the lo plane inside the P region
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kb64 = (p.d + 63) >> 6;
-  const uint32_t q_bytes = SM::q_bytes(kb64), kv_bytes = SM::kv_bytes(kb64);
+  const uint32_t q_bytes = attn_tile_bytes(NPL, kb64, p.qrows);
+  const uint32_t k_bytes = attn_tile_bytes(NPL, kb64, p.krows);
+  const uint32_t v_bytes = attn_tile_bytes(NPL, kb64, p.vrows);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + q_bytes;                   // KV_STAGES buffers
-  uint8_t* sV = sK + KV_STAGES * kv_bytes;      // KV_STAGES buffers
-  float* red_max = reinterpret_cast<float*>(sV + KV_STAGES * kv_bytes);  // [2][4][128]
-  float* red_l = red_max + 2 * 4 * 128;                                  // [2][4][128]
+  uint8_t* sK = sQ + q_bytes;              // K_STAGES buffers
+  uint8_t* sV = sK + K_STAGES * k_bytes;   // V_STAGES buffers
+  float* red_max = reinterpret_cast<float*>(sV + V_STAGES * v_bytes);  // [2][4][128]
+  float* red_l = red_max + 2 * 4 * 128;                                // [2][4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_max) + ATTN_RED_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* p_full = bars + 2;   // count NSW
   uint64_t* o_done = bars + 3;
-  uint64_t* s_full = bars + 4;   // [2]
-  uint64_t* s_free = bars + 6;   // [2], count NSW
-  uint64_t* k_full = bars + 8;   // [KV_STAGES]
-  uint64_t* k_empty = bars + 8 + KV_STAGES;
-  uint64_t* v_full = bars + 8 + 2 * KV_STAGES;
-  uint64_t* v_empty = bars + 8 + 3 * KV_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 4 * KV_STAGES);
+  uint64_t* s_full = bars + 4;   // [3]
+  uint64_t* s_free = bars + 7;   // [3]: score/P buffer released by the PV product that consumed it
+  uint64_t* k_full = bars + 10;  // [K_STAGES]
+  uint64_t* k_empty = bars + 10 + K_STAGES;
+  uint64_t* v_full = bars + 10 + 2 * K_STAGES;  // [V_STAGES]
+  uint64_t* v_empty = bars + 10 + 2 * K_STAGES + V_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * K_STAGES + 2 * V_STAGES);
 
   // plane pl (0 = hi, 1 = lo), 64-column block kb
-  auto q_tile = [&](int pl, int kb) { return sQ + (pl * kb64 + kb) * (ATTN_BLOCK_M * 128); };
-  auto k_tile = [&](int st, int pl, int kb) { return sK + st * kv_bytes + (pl * kb64 + kb) * (BLOCK_KV * 128); };
-  auto v_tile = [&](int st, int pl, int kb) { return sV + st * kv_bytes + (pl * kb64 + kb) * (BLOCK_KV * 128); };
+  auto q_tile = [&](int pl, int kb) { return sQ + (pl * kb64 + kb) * (p.qrows * 128); };
+  auto k_tile = [&](int st, int pl, int kb) { return sK + st * k_bytes + (pl * kb64 + kb) * (p.krows * 128); };
+  auto v_tile = [&](int st, int pl, int kb) { return sV + st * v_bytes + (pl * kb64 + kb) * (p.vrows * 128); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ_hi);
-    tma_prefetch_desc(&tmKV_hi);
+    tma_prefetch_desc(&tmK_hi);
+    tma_prefetch_desc(&tmV_hi);
     if (NPL == 2) {
       tma_prefetch_desc(&tmQ_lo);
-      tma_prefetch_desc(&tmKV_lo);
+      tma_prefetch_desc(&tmK_lo);
+      tma_prefetch_desc(&tmV_lo);
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(p_full, NSW);
     mbar_init(o_done, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ATTN_S_BUFS; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], NSW);
+      mbar_init(&s_free[i], 1);
     }
-    for (int i = 0; i < KV_STAGES; ++i) {
+    for (int i = 0; i < K_STAGES; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < V_STAGES; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
@@ -151,14 +160,14 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         const int h = (item / num_qt) % p.H;
         const int b = item / (num_qt * p.H);
         for (int j = 0; j < num_kv; ++j, ++u) {
-          const int st = u % KV_STAGES;
-          const uint32_t par = (u / KV_STAGES) & 1;
-          mbar_wait(&k_empty[st], par ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], kv_bytes);
+          const int kst = u % K_STAGES, vst = u % V_STAGES;
+          const uint32_t kpar = (u / K_STAGES) & 1, vpar = (u / V_STAGES) & 1;
+          mbar_wait(&k_empty[kst], kpar ^ 1);
+          mbar_arrive_expect_tx(&k_full[kst], k_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(k_tile(st, 0, kb), &tmKV_hi, &k_full[st], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            tma_load_3d(k_tile(kst, 0, kb), &tmK_hi, &k_full[kst], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
             if (NPL == 2)
-              tma_load_3d(k_tile(st, 1, kb), &tmKV_lo, &k_full[st], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+              tma_load_3d(k_tile(kst, 1, kb), &tmK_lo, &k_full[kst], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
           }
           if (j == 0) {
             mbar_wait(q_empty, (it & 1) ^ 1);
@@ -170,12 +179,12 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 tma_load_3d(q_tile(1, kb), &tmQ_lo, q_full, p.q_col0 + h * p.d + kb * 64, qt * ATTN_BLOCK_M, bq);
             }
           }
-          mbar_wait(&v_empty[st], par ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], kv_bytes);
+          mbar_wait(&v_empty[vst], vpar ^ 1);
+          mbar_arrive_expect_tx(&v_full[vst], v_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(v_tile(st, 0, kb), &tmKV_hi, &v_full[st], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            tma_load_3d(v_tile(vst, 0, kb), &tmV_hi, &v_full[vst], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
             if (NPL == 2)
-              tma_load_3d(v_tile(st, 1, kb), &tmKV_lo, &v_full[st], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+              tma_load_3d(v_tile(vst, 1, kb), &tmV_lo, &v_full[vst], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
           }
         }
       }
@@ -183,39 +192,40 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(ATTN_BLOCK_M, BLOCK_KV, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(ATTN_BLOCK_M, p.d, 0, 1);  // A = P from TMEM, B = V MN-major
       const int my_items = (num_items > static_cast<int>(blockIdx.x))
                                ? (num_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
       const uint32_t total_units = static_cast<uint32_t>(my_items) * num_kv;
 
-      // S(u) = Q K_u^T into score buffer u & 1
+      // S(u) = Q K_u^T into score buffer u & 1 (N = the tile's key count rounded up to 16)
       auto issue_s = [&](uint32_t u) {
         const uint32_t it = u / num_kv;
         const int j = static_cast<int>(u % num_kv);
-        const int st = u % KV_STAGES;
-        const uint32_t par = (u / KV_STAGES) & 1;
-        const uint32_t sb = u & 1;
+        const int kst = u % K_STAGES;
+        const uint32_t kpar = (u / K_STAGES) & 1;
+        const uint32_t sb = u % ATTN_S_BUFS;
+        const int kvn = (min(BLOCK_KV, p.Lk - j * BLOCK_KV) + 15) & ~15;
+        const uint32_t idesc_s = umma_idesc_bf16(ATTN_BLOCK_M, kvn, 0, 0);
         if (j == 0) mbar_wait(q_full, it & 1);
-        mbar_wait(&k_full[st], par);
-        mbar_wait(&s_free[sb], ((u >> 1) & 1) ^ 1);
+        mbar_wait(&k_full[kst], kpar);
+        mbar_wait(&s_free[sb], ((u / ATTN_S_BUFS) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128;
         for (int t = 0; t < ksteps_d; ++t) {
           const int kb = t >> 2;
           const uint32_t koff = (t & 3) * 32;
           const uint64_t dq_hi = umma_smem_desc(smem_u32(q_tile(0, kb)) + koff, 16, 1024);
-          const uint64_t dk_hi = umma_smem_desc(smem_u32(k_tile(st, 0, kb)) + koff, 16, 1024);
+          const uint64_t dk_hi = umma_smem_desc(smem_u32(k_tile(kst, 0, kb)) + koff, 16, 1024);
           umma_bf16_ss(tS, dq_hi, dk_hi, idesc_s, t != 0 ? 1u : 0u);
           if (NTERMS == 3) {
             const uint64_t dq_lo = umma_smem_desc(smem_u32(q_tile(1, kb)) + koff, 16, 1024);
-            const uint64_t dk_lo = umma_smem_desc(smem_u32(k_tile(st, 1, kb)) + koff, 16, 1024);
+            const uint64_t dk_lo = umma_smem_desc(smem_u32(k_tile(kst, 1, kb)) + koff, 16, 1024);
             umma_bf16_ss(tS, dq_hi, dk_lo, idesc_s, 1u);
             umma_bf16_ss(tS, dq_lo, dk_hi, idesc_s, 1u);
           }
         }
         umma_commit(&s_full[sb]);
-        umma_commit(&k_empty[st]);
+        umma_commit(&k_empty[kst]);
         if (j == num_kv - 1) umma_commit(q_empty);
       };
 
@@ -223,29 +233,33 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       for (uint32_t u = 0; u < total_units; ++u) {
         if (u + 1 < total_units) issue_s(u + 1);  // one unit ahead: overlaps the softmax of unit u
         const int j = static_cast<int>(u % num_kv);
-        const int st = u % KV_STAGES;
-        const uint32_t par = (u / KV_STAGES) & 1;
+        const int vst = u % V_STAGES;
+        const uint32_t vpar = (u / V_STAGES) & 1;
+        const uint32_t sb = u % ATTN_S_BUFS;
         mbar_wait(p_full, u & 1);
-        mbar_wait(&v_full[st], par);
+        mbar_wait(&v_full[vst], vpar);
         tcgen05_fence_after();
         const int kv_valid = min(BLOCK_KV, p.Lk - j * BLOCK_KV);
         const int ksteps_kv = (kv_valid + 15) >> 4;
         const uint32_t tO = tmem_base + ATTN_TMEM_O;
-        const uint32_t tP = tmem_base + ATTN_TMEM_P;
+        const uint32_t tP = tmem_base + ATTN_TMEM_S + sb * 128;  // P lives where S(u) was
         for (int t = 0; t < ksteps_kv; ++t) {
-          // A = P from TMEM: 16 bf16 (8 columns) per K-step.  B = V MN-major: K (= key index) advances by 16 rows of
-          // 128 B, LBO = distance between the 64-wide d blocks, SBO = 8 key rows.
-          const uint64_t dv_hi = umma_smem_desc(smem_u32(v_tile(st, 0, 0)) + t * 2048, BLOCK_KV * 128, 1024);
+          // A = P from TMEM: keys 16t..16t+15 sit in 32-column chunk t/2: hi pairs at +8*(t&1), lo pairs 16 further.
+          // B = V MN-major: K (= key index) advances by 16 rows of 128 B, LBO = distance between the 64-wide d
+          // blocks, SBO = 8 key rows.
+          const uint32_t pa = tP + 32 * (t >> 1) + 8 * (t & 1);
+          const uint64_t dv_hi = umma_smem_desc(smem_u32(v_tile(vst, 0, 0)) + t * 2048, p.vrows * 128, 1024);
           const uint32_t accum = (j != 0 || t != 0) ? 1u : 0u;
-          umma_bf16_ts(tO, tP + 8 * t, dv_hi, idesc_o, accum);
+          umma_bf16_ts(tO, pa, dv_hi, idesc_o, accum);
           if (NTERMS == 3) {
-            const uint64_t dv_lo = umma_smem_desc(smem_u32(v_tile(st, 1, 0)) + t * 2048, BLOCK_KV * 128, 1024);
-            umma_bf16_ts(tO, tP + 8 * t, dv_lo, idesc_o, 1u);
-            umma_bf16_ts(tO, tP + P_LO + 8 * t, dv_hi, idesc_o, 1u);
+            const uint64_t dv_lo = umma_smem_desc(smem_u32(v_tile(vst, 1, 0)) + t * 2048, p.vrows * 128, 1024);
+            umma_bf16_ts(tO, pa, dv_lo, idesc_o, 1u);
+            umma_bf16_ts(tO, pa + 16, dv_hi, idesc_o, 1u);
           }
         }
         umma_commit(o_done);
-        umma_commit(&v_empty[st]);
+        umma_commit(&v_empty[vst]);
+        umma_commit(&s_free[sb]);  // the score / P buffer may be overwritten by S(u + 3)
       }
     }
   } else {
@@ -255,7 +269,6 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
     const int row = wq * 32 + lane;    // row inside the q tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t tO = tmem_base + ATTN_TMEM_O + lane_sel;
-    const uint32_t tP = tmem_base + ATTN_TMEM_P + lane_sel;
     const int ngroups = p.d >> 4;      // 16-column groups of O; group g belongs to column-warp g % NW
     uint32_t mw = 0;                   // mask bits of (row, this warp's 32 columns); bit set = masked
     long long mkey = -1;               // (b, qt, j) combination the word was built for
@@ -321,9 +334,13 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       float m_run = -INFINITY, l_part = 0.0f;
       for (int j = 0; j < num_kv; ++j, ++u) {
         const int k0 = j * BLOCK_KV + 32 * cw;  // first key column of this warp's chunk
-        const uint32_t sb = u & 1;
+        const uint32_t sb = u % ATTN_S_BUFS;
         const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128 + lane_sel + 32 * cw;
-        // ---- mask word for (row, this chunk); cached while the addressed mask region is unchanged
+        // ---- mask word for (row, this chunk); cached while the addressed mask region is unchanged.  For a
+        //      key-padding mask (query stride 0: one byte per key, new every sample) the byte load is issued here and
+        //      consumed after the score tile has arrived, so its latency hides behind the barrier wait.
+        bool pad_pending = false;
+        uint32_t pad_byte = 0;
         {
           const long long key = (p.mask == nullptr)
                                     ? static_cast<long long>(j)
@@ -334,24 +351,29 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             mw = rem >= 32 ? 0u : (rem <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << rem));
             if (p.mask != nullptr) {
               const uint8_t* mb = p.mask + static_cast<long long>(b) * p.msb;
-              const int nrows = p.msq ? 32 : 1;
               const int kc = k0 + lane;
-              for (int rr = 0; rr < nrows; ++rr) {
-                const int qr = qt * ATTN_BLOCK_M + wq * 32 + rr;
-                uint32_t byte = 0;
-                if (kc < p.Lk && (qr < p.Lq || !p.msq))
-                  byte = mb[static_cast<long long>(qr) * p.msq + static_cast<long long>(kc) * p.msk];
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, byte != 0);
-                if (!p.msq || lane == rr) mw |= bal;
+              if (!p.msq) {
+                pad_pending = true;
+                if (kc < p.Lk) pad_byte = mb[static_cast<long long>(kc) * p.msk];
+              } else {
+                for (int rr = 0; rr < 32; ++rr) {
+                  const int qr = qt * ATTN_BLOCK_M + wq * 32 + rr;
+                  uint32_t byte = 0;
+                  if (kc < p.Lk && qr < p.Lq)
+                    byte = mb[static_cast<long long>(qr) * p.msq + static_cast<long long>(kc) * p.msk];
+                  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, byte != 0);
+                  if (lane == rr) mw |= bal;
+                }
               }
             }
           }
         }
-        mbar_wait(&s_full[sb], (u >> 1) & 1);
+        mbar_wait(&s_full[sb], (u / ATTN_S_BUFS) & 1);
         tcgen05_fence_after();
         // ---- pass 1: masked scores of this chunk stay in registers; chunk max -> smem -> row max
         uint32_t r[32];
         tmem_ld32(tS, r);
+        if (pad_pending) mw |= __ballot_sync(0xFFFFFFFFu, pad_byte != 0);
         tmem_wait_ld();
         float mx = -INFINITY;
 #pragma unroll
@@ -368,12 +390,10 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         const float m_new = fmaxf(m_run, mx);
         const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
         const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_run - m_new) * p.scale_log2);
-        // ---- the previous PV must have retired before P is overwritten / O is rescaled
-        if (u > 0) {
+        // ---- multi-tile rows: the previous PV must have retired before the partial output is rescaled
+        if (j > 0) {
           mbar_wait(o_done, (u - 1) & 1);
           tcgen05_fence_after();
-        }
-        if (j > 0) {  // running maximum moved: rescale the partial output in TMEM (this warp's column groups)
           for (int g = cw; g < ngroups; g += NW) {
             uint32_t o[16];
             tmem_ld16(tO + 16 * g, o);
@@ -394,17 +414,18 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
           sum += x0 + x1;
           split_bf16x2(x0, x1, ph_[e >> 1], pl_[e >> 1]);
         }
-        tmem_st16(tP + 16 * cw, ph_);
-        if (NPL == 2) tmem_st16(tP + P_LO + 16 * cw, pl_);
+        tmem_st16(tS, ph_);                      // P overwrites this warp's own 32 score columns: hi pairs ...
+        if (NPL == 2) tmem_st16(tS + 16, pl_);   // ... then lo pairs
         l_part = l_part * alpha + sum;
         m_run = m_new;
         if (j == num_kv - 1) red_l[((it & 1) * 4 + cw) * 128 + row] = l_part;  // read after the next unit's barrier
         tmem_wait_st();
         tcgen05_fence_before();
-        mbar_arrive(&s_free[sb]);  // score buffer consumed
-        // ---- deferred epilogue of the previous item: its O is complete (o_done above) and is only overwritten by
-        //      the PV of THIS unit, which cannot start before the p_full arrival below
+        // ---- deferred epilogue of the previous item: its O is complete once its last PV retired and is only
+        //      overwritten by the PV of THIS unit, which cannot start before the p_full arrival below
         if (j == 0 && have_prev) {
+          mbar_wait(o_done, (u - 1) & 1);
+          tcgen05_fence_after();
           epilogue(pb, ph, pqt, (it & 1) ^ 1, pm);
           tcgen05_fence_before();
         }

@@ -166,23 +166,33 @@ int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
 
 std::atomic<int> g_gemm_block_k{0};   // tuning knob (lamp_set_tuning): 32 -> 64B swizzle / deep ring, 64 -> 128B swizzle,
                                       // 0 -> automatic (64 for CTA pairs: 3 x 64 KB stages; 32 otherwise: 4 x 48 KB)
+std::atomic<int> g_attn_compact{1};   // tuning knob: 1 -> L-dependent tile rows + deepest K/V staging that fits, 0 -> full 128-row tiles, 1 stage
 std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group::2) for the 256-wide tiles, 0 -> single CTAs
 
-template <int BLOCK_KV, int KV_STAGES, int NTERMS>
-int launch_attn(const CUtensorMap& q_hi, const CUtensorMap& q_lo, const CUtensorMap& kv_hi, const CUtensorMap& kv_lo,
-                const AttnParams& p, cudaStream_t st) {
-  using SM = AttnSmem<BLOCK_KV, KV_STAGES, NTERMS>;
+constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB: the sm_100 per-CTA opt-in maximum
+
+template <int BLOCK_KV, int K_STAGES, int V_STAGES, int NTERMS>
+int launch_attn(const CUtensorMap (&tm)[6], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st) {
+  auto kernel = attn_core_kernel<BLOCK_KV, K_STAGES, V_STAGES, NTERMS>;
   static std::once_flag once;
   static int once_rc = LAMP_OK;
-  // <128,2> is only dispatched for d <= 64 (one 64-column block); the other two variants carry d <= 128.
-  constexpr int MAX_KB64 = (BLOCK_KV == 128 && KV_STAGES == 2) ? 1 : 2;
-  std::call_once(once, [] { once_rc = set_smem(attn_core_kernel<BLOCK_KV, KV_STAGES, NTERMS>, SM::total(MAX_KB64)); });
+  std::call_once(once, [kernel] { once_rc = set_smem(kernel, kMaxDynSmem); });
   if (once_rc != LAMP_OK) return once_rc;
-  const int kb64 = (p.d + 63) / 64;
   const int items = p.B * p.H * ((p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M);
   const int grid = items < sm_count_cached() ? items : sm_count_cached();
-  attn_core_kernel<BLOCK_KV, KV_STAGES, NTERMS><<<grid, attn_threads(BLOCK_KV), SM::total(kb64), st>>>(q_hi, q_lo, kv_hi, kv_lo, p);
+  kernel<<<grid, attn_threads(BLOCK_KV), smem_bytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
   return launch_check();
+}
+
+template <int BLOCK_KV, int NTERMS>
+int launch_attn_stages(const CUtensorMap (&tm)[6], const AttnParams& p, cudaStream_t st) {
+  const int npl = NTERMS == 3 ? 2 : 1, kb64 = (p.d + 63) / 64;
+  auto need = [&](int ks, int vs) { return attn_smem_bytes(npl, kb64, p.qrows, p.krows, p.vrows, ks, vs); };
+  const bool deep = g_attn_compact.load() != 0;
+  if (deep && need(2, 2) <= kMaxDynSmem) return launch_attn<BLOCK_KV, 2, 2, NTERMS>(tm, p, need(2, 2), st);
+  if (deep && need(2, 1) <= kMaxDynSmem) return launch_attn<BLOCK_KV, 2, 1, NTERMS>(tm, p, need(2, 1), st);
+  if (need(1, 1) <= kMaxDynSmem) return launch_attn<BLOCK_KV, 1, 1, NTERMS>(tm, p, need(1, 1), st);
+  return fail(LAMP_EINVAL, "attn: tile does not fit shared memory");
 }
 
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
@@ -210,6 +220,10 @@ int lamp_sm_count(void) { return sm_count_cached(); }
 int lamp_set_tuning(int key, int value) {
   if (key == LAMP_TUNE_GEMM_BLOCK_K && (value == 0 || value == 32 || value == 64)) {
     g_gemm_block_k.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_ATTN_COMPACT && (value == 0 || value == 1)) {
+    g_attn_compact.store(value);
     return LAMP_OK;
   }
   if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
@@ -350,15 +364,24 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   if (B == 0) return LAMP_OK;
   const bool multi = Lk > 128;
   const int block_kv = (d > 64 && multi) ? 64 : 128;
-  CUtensorMap tq_hi, tq_lo, tkv_hi, tkv_lo;
-  if (int rc = make_tmap(&tq_hi, q_hi, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, ATTN_BLOCK_M, true)) return rc;
-  if (int rc = make_tmap(&tkv_hi, kv_hi, (uint64_t)ldkv, Lk, B, ldkv, block_kv, true)) return rc;
+  auto round_up = [](int x, int m) { return (x + m - 1) / m * m; };
+  // TMA box rows follow the label count: a single-tile problem (Lk <= 128) only stages the rows that exist
+  const bool compact = g_attn_compact.load() != 0;
+  const int qrows = compact ? round_up(Lq < ATTN_BLOCK_M ? Lq : ATTN_BLOCK_M, 8) : ATTN_BLOCK_M;
+  const int krows = (multi || !compact) ? block_kv : round_up(Lk, 8);
+  const int vrows = (multi || !compact) ? block_kv : round_up(Lk, 16);  // PV consumes keys in steps of 16; TMA zero-fills rows >= Lk
+  CUtensorMap tm[6];
+  if (int rc = make_tmap(&tm[0], q_hi, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, qrows, true)) return rc;
+  if (int rc = make_tmap(&tm[2], kv_hi, (uint64_t)ldkv, Lk, B, ldkv, krows, true)) return rc;
+  if (int rc = make_tmap(&tm[4], kv_hi, (uint64_t)ldkv, Lk, B, ldkv, vrows, true)) return rc;
   if (three) {
-    if (int rc = make_tmap(&tq_lo, q_lo, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, ATTN_BLOCK_M, true)) return rc;
-    if (int rc = make_tmap(&tkv_lo, kv_lo, (uint64_t)ldkv, Lk, B, ldkv, block_kv, true)) return rc;
+    if (int rc = make_tmap(&tm[1], q_lo, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, qrows, true)) return rc;
+    if (int rc = make_tmap(&tm[3], kv_lo, (uint64_t)ldkv, Lk, B, ldkv, krows, true)) return rc;
+    if (int rc = make_tmap(&tm[5], kv_lo, (uint64_t)ldkv, Lk, B, ldkv, vrows, true)) return rc;
   } else {
-    tq_lo = tq_hi;
-    tkv_lo = tkv_hi;
+    tm[1] = tm[0];
+    tm[3] = tm[2];
+    tm[5] = tm[4];
   }
   AttnParams p;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.d = d;
@@ -369,18 +392,11 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   p.o_lo = static_cast<__nv_bfloat16*>(o_lo);
   p.ldo = (int)ldo; p.o_f32 = o_f32; p.ldof = (int)ldof;
   p.row_max = row_max; p.row_sum = row_sum;
+  p.qrows = qrows; p.krows = krows; p.vrows = vrows;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (d <= 64) {
-    rc = three ? launch_attn<128, 2, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
-               : launch_attn<128, 2, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
-  } else if (!multi) {
-    rc = three ? launch_attn<128, 1, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
-               : launch_attn<128, 1, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
-  } else {
-    rc = three ? launch_attn<64, 2, 3>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st)
-               : launch_attn<64, 2, 1>(tq_hi, tq_lo, tkv_hi, tkv_lo, p, st);
-  }
+  if (block_kv == 128) rc = three ? launch_attn_stages<128, 3>(tm, p, st) : launch_attn_stages<128, 1>(tm, p, st);
+  else rc = three ? launch_attn_stages<64, 3>(tm, p, st) : launch_attn_stages<64, 1>(tm, p, st);
   if (rc != LAMP_OK) return rc;
   if (probs) {
     ProbsParams pp;

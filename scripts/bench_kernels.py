@@ -100,10 +100,14 @@ def bench_attn(prec=0):
 
         def run():
             ops.attention(q, 0, kv, 0, hd, B, H, Lq, Lk, d, prec, mask if masked else None, False)
-        t = timeit(run)
         nbytes = (B * Lq * hd * 2 + 2 * B * Lk * hd) * 4
-        print(f'attn {name:11s} B={B} H={H} d={d}: {t * 1e6:8.1f} us  {nbytes / t / 1e9:7.1f} GB/s alg  '
-              f'{4.0 * B * H * Lq * Lk * d / t / 1e12:6.1f} TFLOP/s alg', flush=True)
+        for rep in range(2):
+            for compact in (1, 0):
+                nat.check(nat.lib().lamp_set_tuning(3, compact), 'tune')
+                t = timeit(run)
+                print(f'attn {name:11s} B={B} H={H} d={d} compact={compact}: {t * 1e6:8.1f} us  {nbytes / t / 1e9:7.1f} GB/s alg  '
+                      f'{4.0 * B * H * Lq * Lk * d / t / 1e12:6.1f} TFLOP/s alg', flush=True)
+        nat.check(nat.lib().lamp_set_tuning(3, 1), 'tune')
 
 
 def bench_ln(prec=0):
