@@ -204,7 +204,10 @@ class PositionwiseFeedForward(nn.Module):
         self._wp = ops.WeightPlanes()
 
     def _composed(self, x):
-        out = self.w_2(F.relu(self.w_1(x.transpose(1, 2)))).transpose(1, 2)
+        # Conv1d(k=1) == per-position linear map; F.linear keeps the training path in true fp32 (cuDNN convolutions
+        # default to TF32, which would put 1e-3-level noise into the gradients)
+        h = F.relu(F.linear(x, self.w_1.weight.squeeze(-1), self.w_1.bias))
+        out = F.linear(h, self.w_2.weight.squeeze(-1), self.w_2.bias)
         return self.layer_norm(self.dropout(out) + x)
 
     def fused_ok(self) -> bool:
