@@ -89,26 +89,77 @@ def cpu_reference_throughput(steps, warmup, batch):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled in-process through NVML (nvidia_ml_py) every 10 ms while the timed region
+    runs; falls back to an `nvidia-smi -lms` child when NVML cannot be loaded."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self._stop = [], None, None, threading.Event()
+        self.smax = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = index
+            if visible:
+                ids = [x.strip() for x in visible.split(',') if x.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = [('hw_slowdown', n.nvmlClocksEventReasonHwSlowdown if hasattr(n, 'nvmlClocksEventReasonHwSlowdown')
+                 else n.nvmlClocksThrottleReasonHwSlowdown),
+                ('hw_thermal_slowdown', getattr(n, 'nvmlClocksEventReasonHwThermalSlowdown',
+                                                getattr(n, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40))),
+                ('sw_thermal_slowdown', getattr(n, 'nvmlClocksEventReasonSwThermalSlowdown',
+                                                getattr(n, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20))),
+                ('sw_power_cap', getattr(n, 'nvmlClocksEventReasonSwPowerCap',
+                                         getattr(n, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)))]
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), sm, [name for name, bit in bits if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            inside = [(sm, rs) for ts, sm, rs in self.rows if t0 <= ts <= t1]
+            if not inside:
+                return dict(sm_mhz=None, sm_max_mhz=self.smax, reasons=[], samples=0, source='nvml')
+            reasons = sorted({r for _, rs in inside for r in rs})
+            return dict(sm_mhz=statistics.median(sm for sm, _ in inside), sm_max_mhz=self.smax, reasons=reasons,
+                        samples=len(inside), source='nvml')
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -128,8 +179,9 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(n)
         if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=smax or None, reasons=[], samples=0)
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+            return dict(sm_mhz=None, sm_max_mhz=smax or None, reasons=[], samples=0, source='nvidia-smi')
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm),
+                    source='nvidia-smi')
 
 
 def main():
@@ -193,12 +245,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # polls from here on; the timed window is cut out later
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             model((seq_d, pos_d), None, None, None)
         # ---------------- device-resident throughput, with per-kernel CUDA events inside the timed region
         barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
         ops.STATS.reset()
         t_wall0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -208,8 +260,8 @@ def main():
                 logits, _, _ = model((seq_d, pos_d), None, None, None)
             e1.record()
             barrier()
+            t_wall1 = time.perf_counter()
             per_kernel = ops.STATS.stop_timing()
-        t_wall1 = time.perf_counter()
         launches = ops.STATS.launches
         clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
         ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -218,13 +270,16 @@ def main():
             model((seq_h.to(dev, non_blocking=True), pos_h.to(dev, non_blocking=True)), None, None, None)
         barrier()
         t0 = time.perf_counter()
+        e0.record()
         for _ in range(args.steps):
             s_d = seq_h.to(dev, non_blocking=True)
             p_d = pos_h.to(dev, non_blocking=True)
             lg, _, _ = model((s_d, p_d), None, None, None)
             logits_h.copy_(lg, non_blocking=True)
+        e1.record()
         barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_s = max_over_ranks(time.perf_counter() - t0)  # host clock: launch overheads and the final D2H included
+        e2e_dev_ms = e0.elapsed_time(e1)
 
     total_samples = args.batch * world * args.steps
     value = total_samples / (ms_total * 1e-3)
@@ -263,7 +318,8 @@ def main():
         config=config,
         e2e=dict(value=e2e_value, unit='samples/s',
                  h2d_bytes_per_step=int(seq_h.numel() * 8 + pos_h.numel() * 8) * world,
-                 d2h_bytes_per_step=int(logits_h.numel() * 4) * world),
+                 d2h_bytes_per_step=int(logits_h.numel() * 4) * world, ms_per_step=e2e_s / args.steps * 1e3,
+                 device_ms_per_step=e2e_dev_ms / args.steps),
         gpu_launches=launches, clocks=clocks,
         roofline=roof('gemm_planes', 'tensor'), roofline_attn=roof('attn_core_self', 'hbm'),
         roofline_attn_enc=roof('attn_core_enc', 'hbm'),

@@ -58,18 +58,20 @@ int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* 
 
 /* C[M,N] = A[M,K] * W[N,K]^T, then (+bias[N]) (ReLU) (+residual[row % resid_mod or row, :]) and store as fp32
  * and/or planes.  Replaces the nn.Linear / Conv1d(k=1) contractions of lamp/SubLayers.py:91-93 (w_qs,w_ks,w_vs),
- * :110 (fc) and :133 (w_1, w_2).  K % 8 == 0, N % 8 == 0. */
+ * :110 (fc) and :133 (w_1, w_2).  K % 8 == 0, N % 8 == 0.  m_dev (nullable, device int32): process only
+ * min(M, *m_dev) rows -- the row count of a padding-aware (packed) batch lives on the device, so launching needs no
+ * host synchronisation. */
 int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
                      int64_t ldw, int M, int N, int K, int precision, const float* bias, int relu,
                      const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
-                     void* out_lo, int64_t ldp, void* stream);
+                     void* out_lo, int64_t ldp, const int32_t* m_dev, void* stream);
 
 /* lamp_gemm_planes with the residual given as split-bf16 planes (hi + lo reconstructs it to 2^-17 relative): lets a
  * layer keep its activations in operand form only, without an fp32 copy in HBM.  res_lo may be NULL. */
 int lamp_gemm_planes_pres(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
                           int64_t ldw, int M, int N, int K, int precision, const float* bias, const void* res_hi,
                           const void* res_lo, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
-                          void* out_lo, int64_t ldp, void* stream);
+                          void* out_lo, int64_t ldp, const int32_t* m_dev, void* stream);
 
 /* Same contraction with the residual add AND the LayerNorm of lamp/SubLayers.py:117 / :141 fused into the epilogue:
  * out = LayerNorm(A W^T (+bias) (+residual)) * gamma + beta, written as fp32 and/or planes.  The whole output row
@@ -86,21 +88,37 @@ int lamp_gemm_ln_planes(const void* a_hi, const void* a_lo, int64_t lda, const v
  * key padding -> msq = 0).  Outputs: planes and/or fp32 [B*Lq, ld], head h at columns h*d.  If `probs` is not
  * NULL it receives the attention probabilities [H*B, Lq, Lk] (head-major batch index h*B + b, as
  * lamp/SubLayers.py:96-98,121) and row_max/row_sum ([H*B*Lq] floats each) must be provided as scratch.
- * d % 16 == 0, d <= 128.  A fully masked row yields NaN exactly like the reference's softmax over all -inf. */
+ * d % 16 == 0, d <= 128.  A fully masked row yields NaN exactly like the reference's softmax over all -inf.
+ * Padding-aware keys: with kv_start / kv_len (device int32 [B], both or neither) the K/V plane matrix holds only the
+ * non-PAD tokens of the batch, packed (kv_rows rows in total); sample b attends to rows [kv_start[b], +kv_len[b]) and
+ * Lk is the upper bound of kv_len.  Equivalent to the key-padding mask of lamp/utils.py:26-34 without touching PAD
+ * keys at all.  In this mode `mask` (optional) is one byte per PACKED key row (msb = msq = 0; row kv_start[b] + j),
+ * and `probs` must be NULL. */
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
                           const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
                           int Lq, int Lk, int d, float temperature, int precision, const uint8_t* mask,
                           int64_t msb, int64_t msq, int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
-                          int64_t ldof, float* row_max, float* row_sum, float* probs, void* stream);
+                          int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
+                          const int32_t* kv_len, int64_t kv_rows, void* stream);
 
 /* out = LayerNorm(y (+ add[row % add_mod or row])) * gamma + beta  (torch.nn.LayerNorm semantics, eps inside the
  * sqrt; lamp/SubLayers.py:117,141).  Writes fp32 and/or planes (any may be NULL).  D % 4 == 0, D <= 4096. */
 int lamp_layernorm(const float* y, const float* add, int add_mod, const float* gamma, const float* beta, float eps,
-                   int64_t rows, int D, float* out, void* out_hi, void* out_lo, void* stream);
+                   int64_t rows, int D, float* out, void* out_hi, void* out_lo, const int32_t* m_dev, void* stream);
 
-/* out[r,:] = word_emb[seq[r],:] (+ pos_emb[pos[r],:])  (lamp/Encoders.py:66,75). seq/pos are int64. */
+/* out[r,:] = word_emb[seq[i],:] (+ pos_emb[pos[i],:]), i = row_index ? row_index[r] : r  (lamp/Encoders.py:66,75).
+ * seq/pos/row_index are int64; with row_index + m_dev only the first *m_dev listed tokens are embedded (packed batch). */
 int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, const float* pos_emb, int64_t rows,
-               int D, float* out, void* out_hi, void* out_lo, void* stream);
+               int D, float* out, void* out_hi, void* out_lo, const int64_t* row_index, const int32_t* m_dev,
+               void* stream);
+
+/* out[r,:] = src[index[r],:] (fp32): un-packs a packed activation into the dense [B*T, D] API tensor. */
+int lamp_gather_rows(const float* src, const int64_t* index, int64_t rows, int D, float* out, void* stream);
+
+/* Zero rows [*m_dev, *m_dev + nguard) of a packed plane matrix (rows >= max_rows are skipped): keeps the few rows a KV
+ * tile may read past the packed data finite. */
+int lamp_zero_guard_rows(void* hi, void* lo, int64_t ld, int cols, const int32_t* m_dev, int64_t max_rows, int nguard,
+                         void* stream);
 
 /* logits[b,l] = <x[b,l,:], W[l,:]> (+bias[l]) : the diagonal of the [B,L,L] projection, lamp/Models.py:124-126. */
 int lamp_diag_proj(const float* x, const float* W, const float* bias, int64_t B, int L, int D, float* logits,

@@ -95,13 +95,24 @@ class GraphDecoder(nn.Module):
         B, T, D = enc_output.shape
         L = self.n_tgt_vocab
         prec = self.layer_stack[0].enc_attn._prec()
-        enc = ops.act_from_tensor(enc_output, prec)
+        # Padding-aware keys: when the encoder output comes from lamp_b200's GraphEncoder it carries the PACKED
+        # non-PAD token rows (operand planes) and each sample's row range; the K|V projection and the label<-input
+        # attention then never touch PAD tokens.  Same result as the key-padding mask of lamp/Decoders.py:137-138.
+        packed = getattr(enc_output, '_lamp_packed', None)
+        kv_ranges = None
+        if (packed is not None and ops.PADDING_AWARE and not return_attns and not self.enc_vec
+                and packed['version'] == enc_output._version and packed['prec'] == prec and packed['shape'] == (B, T, D)):
+            enc = packed['act']
+            kv_ranges = (packed['kv_start'], packed['kv_len'])
+            pad_mask = packed['key_is_pad']  # one byte per packed row (all zero unless a PAD token carries a position)
+        else:
+            enc = ops.act_from_tensor(enc_output, prec)
+            pad_mask = None
+            if not self.enc_vec:
+                pad_mask = src_seq[:, 0:T].eq(Constants.PAD).unsqueeze(1)  # [B, 1, T] -> query stride 0
         emb = self.tgt_word_emb.weight
         e_hi, e_lo = self._wp.get('label_emb', (emb,), prec)
         x = ops.Act(emb.detach(), e_hi, e_lo, L, D, bcast_rows=B * L)  # shared by every sample
-        pad_mask = None
-        if not self.enc_vec:
-            pad_mask = src_seq[:, 0:T].eq(Constants.PAD).unsqueeze(1)  # [B, 1, T] -> query stride 0
         slf_mask = None if self._label_mask_dev is None else self._label_mask_dev.unsqueeze(0)  # [1, L, L]
         # one GEMM for the K|V projections of every layer
         kv_params = []
@@ -110,12 +121,14 @@ class GraphDecoder(nn.Module):
         hd = self.layer_stack[0].enc_attn.n_head * self.layer_stack[0].enc_attn.d_k
         w_hi, w_lo = self._wp.get('kv_all', tuple(kv_params), prec)
         kv_all = ops.linear_planes(enc, w_hi, w_lo, 2 * hd * len(self.layer_stack), prec)
+        if kv_ranges is not None:
+            ops.zero_guard_rows(kv_all)  # rows a KV tile may read past the packed keys must be finite
         int_outs, slf_attns, enc_attns = [], [], []
         n = len(self.layer_stack)
         for i, layer in enumerate(self.layer_stack):
             x, x_int, slf_attn, enc_attn = layer.forward_act(
                 x, enc, B, L, T, slf_mask, pad_mask, return_attns, kv_proj=(kv_all, 2 * hd * i, 2 * hd * i + hd),
-                last=(i == n - 1), want_int_f32=int_preds, want_out_f32=int_preds or i == n - 1)
+                last=(i == n - 1), want_int_f32=int_preds, want_out_f32=int_preds or i == n - 1, kv_ranges=kv_ranges)
             if int_preds:
                 if x_int is not None:
                     int_outs.append(x_int.f32.view(B, L, D))

@@ -95,10 +95,12 @@ class GraphEncoder(nn.Module):
         prec = ops.default_precision() if self.layer_stack[0].pos_ffn.precision is None \
             else self.layer_stack[0].pos_ffn.precision
         pos_w = self.position_enc.weight if hasattr(self, 'position_enc') else None
+        n = len(self.layer_stack)
+        if ops.PADDING_AWARE and not return_attns:
+            return self._forward_packed(src_seq, src_pos, pos_w, prec), [None] * n
         x = ops.embed(src_seq, src_pos, self.src_word_emb.weight, pos_w, prec, want_f32=False)
         mask = src_seq.eq(Constants.PAD).unsqueeze(1) if return_attns else None  # [B, 1, T]
         attns = []
-        n = len(self.layer_stack)
         for i, layer in enumerate(self.layer_stack):
             # only the last layer's output is an API tensor (enc_output); in between activations stay in operand form
             x, attn = layer.forward_act(x, B, T, mask, return_attns, want_f32=(i == n - 1))
@@ -107,6 +109,38 @@ class GraphEncoder(nn.Module):
         if self.enc_transform == '':
             ops.stash_planes(out, x, prec)
         return self._pool(out, src_seq, B), attns
+
+    def _forward_packed(self, src_seq, src_pos, pos_w, prec):
+        """Padding-aware encoder.  Every PAD position holds the same token (id 0) and -- as produced by the
+        reference loader, utils/data_loader.py:270 -- the same position id 0, so all those rows of every layer are
+        IDENTICAL; the encoder is a per-row map (embedding, FFN, LayerNorm: the token self-attention never reaches
+        the output, lamp/Layers.py:16-18).  We therefore run it on the packed list of distinct rows -- all rows that
+        are not (PAD, position 0), plus ONE representative of those -- and un-pack into the dense [B, T, D] API tensor
+        at the end.  The row count stays on the device (``m_dev``): no host synchronisation.  The packed planes and
+        each sample's row range travel with the returned tensor so that GraphDecoder can skip PAD keys altogether."""
+        B, T = src_seq.shape
+        R = B * T
+        seq_flat = src_seq.reshape(-1)
+        is_pad = seq_flat.eq(Constants.PAD)
+        rep = is_pad & src_pos.reshape(-1).eq(0) if pos_w is not None else is_pad  # rows equal to the representative
+        order = torch.argsort(rep.to(torch.uint8), stable=True)         # distinct rows first, in original order
+        n_keep = R - rep.sum()                                          # device scalar
+        m_dev = torch.clamp(n_keep + 1, max=R).to(torch.int32).reshape(1)  # + the representative (if any)
+        rank = torch.cumsum((~rep).to(torch.int64), 0) - 1
+        src_row = torch.where(rep, n_keep.to(torch.int64), rank)        # dense row -> packed row
+        x = ops.embed(src_seq, src_pos, self.src_word_emb.weight, pos_w, prec, want_f32=False, row_index=order,
+                      m_dev=m_dev)
+        n = len(self.layer_stack)
+        for i, layer in enumerate(self.layer_stack):
+            x, _ = layer.forward_act(x, B, T, None, False, want_f32=(i == n - 1))
+        out = ops.gather_rows(x.f32, src_row, self.d_model).view(B, T, self.d_model)
+        if self.enc_transform == '':
+            kv_len = (~rep).view(B, T).sum(dim=1)
+            kv_start = torch.cumsum(kv_len, 0) - kv_len
+            out._lamp_packed = dict(act=x, kv_start=kv_start.to(torch.int32), kv_len=kv_len.to(torch.int32),
+                                    key_is_pad=is_pad[order].to(torch.uint8), version=out._version, prec=prec,
+                                    shape=(B, T, self.d_model))
+        return self._pool(out, src_seq, B)
 
     def forward(self, src_seq, adj, src_pos, return_attns=False):
         nat.require_cuda(src_seq, src_pos)

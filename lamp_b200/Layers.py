@@ -57,11 +57,11 @@ class DecoderLayer(nn.Module):
 
     def forward_act(self, x: ops.Act, enc: ops.Act, B: int, L: int, T: int, slf_attn_mask, dec_enc_attn_mask,
                     want_attn: bool, kv_proj=None, last: bool = False, want_int_f32: bool = True,
-                    want_out_f32: bool = True):
+                    want_out_f32: bool = True, kv_ranges=None):
         """Inside the layer activations exist as tensor-core operand planes only; fp32 copies are written just for
         the tensors the caller asked for (layer output, intermediate output)."""
         out, enc_attn = self.enc_attn.forward_act(x, enc, B, L, T, dec_enc_attn_mask, want_attn, kv_proj=kv_proj,
-                                                  want_f32=False)
+                                                  want_f32=False, kv_ranges=kv_ranges)
         has_slf = hasattr(self, 'slf_attn')
         out = self.pos_ffn1.forward_act(out, want_f32=want_int_f32 and has_slf)
         out_int, slf_attn = None, None

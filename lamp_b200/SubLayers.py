@@ -134,7 +134,7 @@ class MultiHeadAttention(nn.Module):
         return ops.default_precision() if self.precision is None else self.precision
 
     def forward_act(self, q: ops.Act, kv, B: int, Lq: int, Lk: int, attn_mask, want_attn: bool,
-                    kv_proj=None, want_f32: bool = True):
+                    kv_proj=None, want_f32: bool = True, kv_ranges=None):
         """q: Act [B*Lq (or Lq, broadcast), D]; kv: None (self-attention) or Act [B*Lk, D].
         ``kv_proj``: optional precomputed ``(Act [B*Lk, ld], k_col0, v_col0)`` K|V projection (GraphDecoder batches
         the label<-input K|V projections of all its layers into one GEMM).  -> (Act out, probs or None)."""
@@ -153,8 +153,9 @@ class MultiHeadAttention(nn.Module):
             else:
                 w_hi, w_lo = self._wp.get('kv', (self.w_ks.weight, self.w_vs.weight), prec)
                 kvp, k_col0, v_col0 = ops.linear_planes(kv, w_hi, w_lo, 2 * hd, prec), 0, hd
+        kv_start, kv_len = kv_ranges if kv_ranges is not None else (None, None)  # packed (padding-aware) keys
         o, probs = ops.attention(qp, q_col0, kvp, k_col0, v_col0, B, H, Lq, Lk, d, prec, attn_mask, want_attn,
-                                 out_f32=(H == 1))
+                                 out_f32=(H == 1), kv_start=kv_start, kv_len=kv_len)
         ln = self.layer_norm
         if H > 1:
             f_hi, f_lo = self._wp.get('fc', (self.fc.weight,), prec)

@@ -30,15 +30,17 @@ _SIGNATURES = {
     'lamp_set_tuning': ([_i, _i], _i),
     'lamp_split_planes': ([_vp, _i64, _i, _i64, _vp, _vp, _i64, _vp], _i),
     'lamp_gemm_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp,
-                          _i64, _vp], _i),
+                          _i64, _vp, _vp], _i),
     'lamp_gemm_planes_pres': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp,
-                               _vp, _i64, _vp], _i),
+                               _vp, _i64, _vp, _vp], _i),
     'lamp_gemm_ln_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _f, _vp, _i64,
                              _vp, _vp, _i64, _vp], _i),
     'lamp_attn_core_planes': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,
-                               _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp], _i),
-    'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp], _i),
-    'lamp_embed': ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp], _i),
+                               _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _i),
+    'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp, _vp], _i),
+    'lamp_embed': ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    'lamp_gather_rows': ([_vp, _vp, _i64, _i, _vp, _vp], _i),
+    'lamp_zero_guard_rows': ([_vp, _vp, _i64, _i, _vp, _i64, _i, _vp], _i),
     'lamp_diag_proj': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp], _i),
     'lamp_sdpa_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'lamp_sdpa_fwd': ([_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp], _i),

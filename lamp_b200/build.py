@@ -32,17 +32,20 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """``defines`` + ``out``: debug variants (e.g. -DLAMP_ATTN_TRACE -> liblamp_b200_trace.so, scripts/attn_trace.py);
+    the product library is always the default ``OUT`` without defines."""
+    if not force and out == OUT and up_to_date():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f'-D{d}' for d in defines] + (['-Xptxas', '-v'] if verbose else []) + \
+        ['-o', out, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == '__main__':

@@ -44,7 +44,22 @@ struct AttnParams {
   float* row_max;  // optional [H*B*Lq] (head-major) running max of the SCALED (log2 domain) scores
   float* row_sum;  // optional [H*B*Lq] softmax denominators
   int qrows, krows, vrows;  // TMA box rows of the Q / K / V tiles (multiples of 8 / 8 / 16)
+  // Padding-aware keys (optional): the K/V matrix holds only the non-PAD tokens of the batch, packed; sample b owns
+  // rows [kv_start[b], kv_start[b] + kv_len[b]).  Lk then only bounds the per-sample key count.
+  const int* kv_start;
+  const int* kv_len;
 };
+
+#ifdef LAMP_ATTN_TRACE
+// Debug build only (scripts/attn_trace.py): clock64() stamps of CTA 0's pipeline events, [event][unit].
+__device__ unsigned long long g_attn_trace[16][64];
+#define ATTN_TRACE(ev, idx)                                                              \
+  do {                                                                                   \
+    if (blockIdx.x == 0 && (idx) < 64u) g_attn_trace[ev][idx] = clock64();                \
+  } while (0)
+#else
+#define ATTN_TRACE(ev, idx) do { } while (0)
+#endif
 
 constexpr int ATTN_BLOCK_M = 128;
 constexpr uint32_t ATTN_TMEM_COLS = 512;
@@ -147,9 +162,18 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_qt = (p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M;
-  const int num_kv = (p.Lk + BLOCK_KV - 1) / BLOCK_KV;
+  const int num_kv = (p.Lk + BLOCK_KV - 1) / BLOCK_KV;  // upper bound; per item: item_keys()
   const int num_items = p.B * p.H * num_qt;
   const int ksteps_d = p.d >> 4;  // UMMA K-steps over the head width
+  const bool varlen = p.kv_len != nullptr;
+  // keys of sample b: (count, first row in the K/V matrix, batch coordinate of the tensor map, KV tiles >= 1)
+  auto item_keys = [&](int b, int& lk, int& kbase, int& kbatch, int& nkv) {
+    lk = varlen ? min(__ldg(p.kv_len + b), p.Lk) : p.Lk;
+    kbase = varlen ? __ldg(p.kv_start + b) : 0;
+    kbatch = varlen ? 0 : b;
+    nkv = (lk + BLOCK_KV - 1) / BLOCK_KV;
+    if (nkv < 1) nkv = 1;  // a sample without keys still produces (NaN) rows, like a fully masked reference row
+  };
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -159,18 +183,23 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         const int qt = item % num_qt;
         const int h = (item / num_qt) % p.H;
         const int b = item / (num_qt * p.H);
-        for (int j = 0; j < num_kv; ++j, ++u) {
+        int lk, kbase, kbatch, nkv;
+        item_keys(b, lk, kbase, kbatch, nkv);
+        for (int j = 0; j < nkv; ++j, ++u) {
           const int kst = u % K_STAGES, vst = u % V_STAGES;
           const uint32_t kpar = (u / K_STAGES) & 1, vpar = (u / V_STAGES) & 1;
+          const int krow = kbase + j * BLOCK_KV;
           mbar_wait(&k_empty[kst], kpar ^ 1);
+          ATTN_TRACE(0, u);
           mbar_arrive_expect_tx(&k_full[kst], k_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(k_tile(kst, 0, kb), &tmK_hi, &k_full[kst], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            tma_load_3d(k_tile(kst, 0, kb), &tmK_hi, &k_full[kst], p.k_col0 + h * p.d + kb * 64, krow, kbatch);
             if (NPL == 2)
-              tma_load_3d(k_tile(kst, 1, kb), &tmK_lo, &k_full[kst], p.k_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+              tma_load_3d(k_tile(kst, 1, kb), &tmK_lo, &k_full[kst], p.k_col0 + h * p.d + kb * 64, krow, kbatch);
           }
           if (j == 0) {
             mbar_wait(q_empty, (it & 1) ^ 1);
+            ATTN_TRACE(1, u);
             mbar_arrive_expect_tx(q_full, q_bytes);
             const int bq = p.q_bcast ? 0 : b;
             for (int kb = 0; kb < kb64; ++kb) {
@@ -180,11 +209,12 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             }
           }
           mbar_wait(&v_empty[vst], vpar ^ 1);
+          ATTN_TRACE(2, u);
           mbar_arrive_expect_tx(&v_full[vst], v_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(v_tile(vst, 0, kb), &tmV_hi, &v_full[vst], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+            tma_load_3d(v_tile(vst, 0, kb), &tmV_hi, &v_full[vst], p.v_col0 + h * p.d + kb * 64, krow, kbatch);
             if (NPL == 2)
-              tma_load_3d(v_tile(vst, 1, kb), &tmV_lo, &v_full[vst], p.v_col0 + h * p.d + kb * 64, j * BLOCK_KV, b);
+              tma_load_3d(v_tile(vst, 1, kb), &tmV_lo, &v_full[vst], p.v_col0 + h * p.d + kb * 64, krow, kbatch);
           }
         }
       }
@@ -193,22 +223,39 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_o = umma_idesc_bf16(ATTN_BLOCK_M, p.d, 0, 1);  // A = P from TMEM, B = V MN-major
-      const int my_items = (num_items > static_cast<int>(blockIdx.x))
-                               ? (num_items - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-      const uint32_t total_units = static_cast<uint32_t>(my_items) * num_kv;
+      // (item, KV tile) iterator of this CTA; the S product runs one unit ahead of the PV product
+      struct UnitIt {
+        int item, j, nkv, lk;
+        uint32_t it;  // per-CTA item counter
+      };
+      auto load_it = [&](UnitIt& x) {
+        if (x.item < num_items) {
+          int kbase, kbatch;
+          item_keys(x.item / (num_qt * p.H), x.lk, kbase, kbatch, x.nkv);
+        }
+      };
+      auto advance = [&](UnitIt& x) {
+        if (++x.j == x.nkv) {
+          x.j = 0;
+          x.item += gridDim.x;
+          ++x.it;
+          load_it(x);
+        }
+      };
 
-      // S(u) = Q K_u^T into score buffer u & 1 (N = the tile's key count rounded up to 16)
-      auto issue_s = [&](uint32_t u) {
-        const uint32_t it = u / num_kv;
-        const int j = static_cast<int>(u % num_kv);
+      // S(u) = Q K_u^T into score buffer u % 3 (N = the tile's key count rounded up to 16)
+      auto issue_s = [&](const UnitIt& x, uint32_t u) {
         const int kst = u % K_STAGES;
         const uint32_t kpar = (u / K_STAGES) & 1;
         const uint32_t sb = u % ATTN_S_BUFS;
-        const int kvn = (min(BLOCK_KV, p.Lk - j * BLOCK_KV) + 15) & ~15;
+        int kvn = (min(BLOCK_KV, x.lk - x.j * BLOCK_KV) + 15) & ~15;
+        if (kvn < 16) kvn = 16;
         const uint32_t idesc_s = umma_idesc_bf16(ATTN_BLOCK_M, kvn, 0, 0);
-        if (j == 0) mbar_wait(q_full, it & 1);
+        if (x.j == 0) mbar_wait(q_full, x.it & 1);
         mbar_wait(&k_full[kst], kpar);
+        ATTN_TRACE(3, u);
         mbar_wait(&s_free[sb], ((u / ATTN_S_BUFS) & 1) ^ 1);
+        ATTN_TRACE(4, u);
         tcgen05_fence_after();
         const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128;
         for (int t = 0; t < ksteps_d; ++t) {
@@ -226,21 +273,27 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
         umma_commit(&s_full[sb]);
         umma_commit(&k_empty[kst]);
-        if (j == num_kv - 1) umma_commit(q_empty);
+        if (x.j == x.nkv - 1) umma_commit(q_empty);
       };
 
-      if (total_units > 0) issue_s(0);
-      for (uint32_t u = 0; u < total_units; ++u) {
-        if (u + 1 < total_units) issue_s(u + 1);  // one unit ahead: overlaps the softmax of unit u
-        const int j = static_cast<int>(u % num_kv);
+      UnitIt cur{static_cast<int>(blockIdx.x), 0, 1, 0, 0u};
+      load_it(cur);
+      UnitIt nxt = cur;
+      if (cur.item < num_items) issue_s(nxt, 0);
+      for (uint32_t u = 0; cur.item < num_items; ++u) {
+        advance(nxt);
+        if (nxt.item < num_items) issue_s(nxt, u + 1);  // one unit ahead: overlaps the softmax of unit u
+        const int j = cur.j;
         const int vst = u % V_STAGES;
         const uint32_t vpar = (u / V_STAGES) & 1;
         const uint32_t sb = u % ATTN_S_BUFS;
         mbar_wait(p_full, u & 1);
+        ATTN_TRACE(5, u);
         mbar_wait(&v_full[vst], vpar);
+        ATTN_TRACE(6, u);
         tcgen05_fence_after();
-        const int kv_valid = min(BLOCK_KV, p.Lk - j * BLOCK_KV);
-        const int ksteps_kv = (kv_valid + 15) >> 4;
+        const int kv_valid = max(0, min(BLOCK_KV, cur.lk - j * BLOCK_KV));
+        const int ksteps_kv = max(1, (kv_valid + 15) >> 4);
         const uint32_t tO = tmem_base + ATTN_TMEM_O;
         const uint32_t tP = tmem_base + ATTN_TMEM_S + sb * 128;  // P lives where S(u) was
         for (int t = 0; t < ksteps_kv; ++t) {
@@ -260,6 +313,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         umma_commit(o_done);
         umma_commit(&v_empty[vst]);
         umma_commit(&s_free[sb]);  // the score / P buffer may be overwritten by S(u + 3)
+        advance(cur);
       }
     }
   } else {
@@ -332,7 +386,9 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       const int h = (item / num_qt) % p.H;
       const int b = item / (num_qt * p.H);
       float m_run = -INFINITY, l_part = 0.0f;
-      for (int j = 0; j < num_kv; ++j, ++u) {
+      int lk, kbase, kbatch_unused, nkv;
+      item_keys(b, lk, kbase, kbatch_unused, nkv);
+      for (int j = 0; j < nkv; ++j, ++u) {
         const int k0 = j * BLOCK_KV + 32 * cw;  // first key column of this warp's chunk
         const uint32_t sb = u % ATTN_S_BUFS;
         const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128 + lane_sel + 32 * cw;
@@ -345,21 +401,21 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
           const long long key = (p.mask == nullptr)
                                     ? static_cast<long long>(j)
                                     : ((p.msb ? static_cast<long long>(b) : 0) * num_qt + (p.msq ? qt : 0)) * num_kv + j;
-          if (key != mkey) {
+          if (key != mkey || varlen) {  // per-sample key counts: the bounds word changes with every item
             mkey = key;
-            const int rem = p.Lk - k0;  // valid columns in this chunk
+            const int rem = lk - k0;  // valid columns in this chunk
             mw = rem >= 32 ? 0u : (rem <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << rem));
             if (p.mask != nullptr) {
               const uint8_t* mb = p.mask + static_cast<long long>(b) * p.msb;
               const int kc = k0 + lane;
               if (!p.msq) {
                 pad_pending = true;
-                if (kc < p.Lk) pad_byte = mb[static_cast<long long>(kc) * p.msk];
+                if (kc < lk) pad_byte = mb[static_cast<long long>(kbase + kc) * p.msk];  // packed keys: offset by the sample's first row
               } else {
                 for (int rr = 0; rr < 32; ++rr) {
                   const int qr = qt * ATTN_BLOCK_M + wq * 32 + rr;
                   uint32_t byte = 0;
-                  if (kc < p.Lk && qr < p.Lq)
+                  if (kc < lk && qr < p.Lq)
                     byte = mb[static_cast<long long>(qr) * p.msq + static_cast<long long>(kc) * p.msk];
                   const uint32_t bal = __ballot_sync(0xFFFFFFFFu, byte != 0);
                   if (lane == rr) mw |= bal;
@@ -369,6 +425,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
           }
         }
         mbar_wait(&s_full[sb], (u / ATTN_S_BUFS) & 1);
+        if (warp == 2 && lane == 0) ATTN_TRACE(7, u);
         tcgen05_fence_after();
         // ---- pass 1: masked scores of this chunk stay in registers; chunk max -> smem -> row max
         uint32_t r[32];
@@ -385,6 +442,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         float* rm = red_max + (u & 1) * (4 * 128);
         rm[cw * 128 + row] = mx;
         named_bar_sync(1, NSW);
+        if (warp == 2 && lane == 0) ATTN_TRACE(8, u);
 #pragma unroll
         for (int c = 0; c < NW; ++c) mx = fmaxf(mx, rm[c * 128 + row]);
         const float m_new = fmaxf(m_run, mx);
@@ -418,17 +476,20 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         if (NPL == 2) tmem_st16(tS + 16, pl_);   // ... then lo pairs
         l_part = l_part * alpha + sum;
         m_run = m_new;
-        if (j == num_kv - 1) red_l[((it & 1) * 4 + cw) * 128 + row] = l_part;  // read after the next unit's barrier
+        if (j == nkv - 1) red_l[((it & 1) * 4 + cw) * 128 + row] = l_part;  // read after the next unit's barrier
         tmem_wait_st();
+        if (warp == 2 && lane == 0) ATTN_TRACE(9, u);
         tcgen05_fence_before();
         // ---- deferred epilogue of the previous item: its O is complete once its last PV retired and is only
         //      overwritten by the PV of THIS unit, which cannot start before the p_full arrival below
         if (j == 0 && have_prev) {
           mbar_wait(o_done, (u - 1) & 1);
+          if (warp == 2 && lane == 0) ATTN_TRACE(10, u);
           tcgen05_fence_after();
           epilogue(pb, ph, pqt, (it & 1) ^ 1, pm);
           tcgen05_fence_before();
         }
+        if (warp == 2 && lane == 0) ATTN_TRACE(11, u);
         mbar_arrive(p_full);
       }
       have_prev = true;

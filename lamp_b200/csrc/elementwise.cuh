@@ -30,9 +30,10 @@ template <int MAXV>
 __global__ void layernorm_kernel(const float* __restrict__ y, const float* __restrict__ add, int add_mod,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  long long rows, int D, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-                                 __nv_bfloat16* __restrict__ out_lo) {
+                                 __nv_bfloat16* __restrict__ out_lo, const int* __restrict__ m_dev) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  if (m_dev != nullptr && rows > __ldg(m_dev)) rows = __ldg(m_dev);  // device-side row count (padding-aware runs)
   if (row >= rows) return;
   const int d4 = D >> 2;
   const float4* yr = reinterpret_cast<const float4*>(y + row * D);
@@ -91,17 +92,21 @@ __global__ void layernorm_kernel(const float* __restrict__ y, const float* __res
   }
 }
 
-// enc_input[r, :] = word_emb[src_seq[r], :] (+ pos_emb[src_pos[r], :])   -- lamp/Encoders.py:66,75.
-// Writes fp32 and/or planes.  One warp per token row.
+// enc_input[r, :] = word_emb[src_seq[i], :] (+ pos_emb[src_pos[i], :]),  i = row_index ? row_index[r] : r
+// -- lamp/Encoders.py:66,75.  Writes fp32 and/or planes.  One warp per output row.  With `row_index` / `m_dev` the
+// kernel gathers only the first *m_dev rows of an index list (the non-PAD tokens of the batch, packed).
 __global__ void embed_kernel(const long long* __restrict__ seq, const long long* __restrict__ pos,
                              const float* __restrict__ word_emb, const float* __restrict__ pos_emb, long long rows,
                              int D, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
-                             __nv_bfloat16* __restrict__ out_lo) {
+                             __nv_bfloat16* __restrict__ out_lo, const long long* __restrict__ row_index,
+                             const int* __restrict__ m_dev) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  if (m_dev != nullptr && rows > __ldg(m_dev)) rows = __ldg(m_dev);
   if (row >= rows) return;
-  const float4* w = reinterpret_cast<const float4*>(word_emb + seq[row] * D);
-  const float4* q = pos_emb ? reinterpret_cast<const float4*>(pos_emb + pos[row] * D) : nullptr;
+  const long long src = row_index ? row_index[row] : row;
+  const float4* w = reinterpret_cast<const float4*>(word_emb + seq[src] * D);
+  const float4* q = pos_emb ? reinterpret_cast<const float4*>(pos_emb + pos[src] * D) : nullptr;
   for (int idx = lane; idx < (D >> 2); idx += 32) {
     float4 v = __ldg(w + idx);
     if (q != nullptr) {
@@ -115,6 +120,35 @@ __global__ void embed_kernel(const long long* __restrict__ seq, const long long*
       split_bf16x2(v.z, v.w, h.y, l.y);
       reinterpret_cast<uint2*>(out_hi + row * D)[idx] = h;
       if (out_lo != nullptr) reinterpret_cast<uint2*>(out_lo + row * D)[idx] = l;
+    }
+  }
+}
+
+// out[r, :] = src[index[r], :]  (fp32 rows; un-packs the encoder output into the dense [B, T, D] API tensor, the
+// representative PAD row being replicated to every PAD position).  One warp per output row.
+__global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ index, long long rows,
+                                   int D, float* __restrict__ out) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* s4 = reinterpret_cast<const float4*>(src + index[row] * D);
+  float4* o4 = reinterpret_cast<float4*>(out + row * D);
+  for (int idx = lane; idx < (D >> 2); idx += 32) o4[idx] = __ldg(s4 + idx);
+}
+
+// Zero the `nguard` rows that follow the *m_dev rows in use of a packed plane matrix.  A KV tile of the last sample
+// may extend a few rows past the packed data; those keys carry probability 0, and 0 * (uninitialised NaN) must not
+// reach the PV product.
+__global__ void zero_guard_rows_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ld,
+                                       int cols, const int* __restrict__ m_dev, long long max_rows, int nguard) {
+  const long long first = __ldg(m_dev);
+  const long long total = static_cast<long long>(nguard) * cols;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = first + i / cols;
+    if (r < max_rows) {
+      hi[r * ld + i % cols] = __float2bfloat16(0.0f);
+      if (lo != nullptr) lo[r * ld + i % cols] = __float2bfloat16(0.0f);
     }
   }
 }

@@ -39,6 +39,9 @@ struct GemmParams {
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;
+  // optional device-side row count: the kernel processes min(M, *m_dev) rows (padding-aware execution: the number
+  // of non-PAD tokens of a batch is only known on the device; no host synchronisation is needed to launch)
+  const int* m_dev;
 };
 
 // Residual values of the 8 rows (m_base + 4 i, i = 0..7) x 4 consecutive columns handled by one lane of the coalesced
@@ -173,7 +176,8 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_m = (p.M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP);
+  const int M = (p.m_dev != nullptr) ? min(p.M, __ldg(p.m_dev)) : p.M;
+  const int num_m = (M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP);
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_tiles = num_m * num_n;
@@ -315,7 +319,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       uint32_t ph = 0;
       for (int mt2 = tile0; mt2 < num_m; mt2 += tile_step, ph ^= 1) {
         const int m0 = mt2 * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
-        const int rows_left = p.M - m0 - sub_r;
+        const int rows_left = M - m0 - sub_r;
         float rsum[8], rsq[8], mean[8], rstd[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { rsum[i] = 0.f; rsq[i] = 0.f; mean[i] = 0.f; rstd[i] = 0.f; }
@@ -436,7 +440,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     for (int j = 0; get_tile(j, mt, nt); ++j) {
       const int m0 = mt * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
       const int n0 = nt * BLOCK_N;
-      const int rows_left = p.M - m0 - sub_r;  // row (m0 + sub_r + 4 i) is valid iff 4 i < rows_left
+      const int rows_left = M - m0 - sub_r;  // row (m0 + sub_r + 4 i) is valid iff 4 i < rows_left
       // residual rows of a 32-column chunk: requested one chunk AHEAD (the first one while the MMAs of this tile are
       // still running), so their L2/HBM latency never sits on the epilogue's critical path
       auto load_res = [&](int c0, float4 (&dst)[8]) {

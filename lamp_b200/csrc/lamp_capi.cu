@@ -254,7 +254,7 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void
                      const float* residual, const void* res_hi, const void* res_lo, int64_t ldr, int resid_mod,
                      float* out_f32, int64_t ldo, void* out_hi,
                      void* out_lo, int64_t ldp, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                     void* stream) {
+                     const int32_t* m_dev, void* stream) {
   if (int rc = arch_check()) return rc;
   if (ln_gamma != nullptr) {
     REQUIRE(ln_beta != nullptr, "gemm_ln: beta missing");
@@ -301,6 +301,7 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void
   p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
   p.ldp = (int)ldp;
   p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;
+  p.m_dev = m_dev;
   cudaStream_t st = (cudaStream_t)stream;
 #define LAMP_GEMM_DISPATCH(BK)                                                                                      \
   do {                                                                                                             \
@@ -321,18 +322,18 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void
 int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
                      int64_t ldw, int M, int N, int K, int precision, const float* bias, int relu,
                      const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
-                     void* out_lo, int64_t ldp, void* stream) {
+                     void* out_lo, int64_t ldp, const int32_t* m_dev, void* stream) {
   return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, relu, residual, nullptr, nullptr, ldr,
-                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, stream);
+                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, m_dev, stream);
 }
 
 int lamp_gemm_planes_pres(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
                           int64_t ldw, int M, int N, int K, int precision, const float* bias, const void* res_hi,
                           const void* res_lo, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
-                          void* out_lo, int64_t ldp, void* stream) {
+                          void* out_lo, int64_t ldp, const int32_t* m_dev, void* stream) {
   REQUIRE(res_hi != nullptr, "gemm_planes_pres: residual planes missing");
   return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, 0, nullptr, res_hi, res_lo, ldr,
-                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, stream);
+                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, m_dev, stream);
 }
 
 int lamp_gemm_ln_planes(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
@@ -341,15 +342,19 @@ int lamp_gemm_ln_planes(const void* a_hi, const void* a_lo, int64_t lda, const v
                         int64_t ldo, void* out_hi, void* out_lo, int64_t ldp, void* stream) {
   REQUIRE(gamma && beta, "gemm_ln: null gamma/beta");
   return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, 0, residual, nullptr, nullptr, ldr,
-                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, gamma, beta, eps, stream);
+                   resid_mod, out_f32, ldo, out_hi, out_lo, ldp, gamma, beta, eps, nullptr, stream);
 }
 
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
                           const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
                           int Lq, int Lk, int d, float temperature, int precision, const uint8_t* mask,
                           int64_t msb, int64_t msq, int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
-                          int64_t ldof, float* row_max, float* row_sum, float* probs, void* stream) {
+                          int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
+                          const int32_t* kv_len, int64_t kv_rows, void* stream) {
   if (int rc = arch_check()) return rc;
+  REQUIRE((kv_start == nullptr) == (kv_len == nullptr), "attn: kv_start and kv_len go together");
+  REQUIRE(!kv_len || (!probs && kv_rows > 0), "attn: packed keys exclude the probability output");
+  REQUIRE(!kv_len || !mask || (msb == 0 && msq == 0), "attn: with packed keys the mask is one byte per packed key row");
   REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "attn: bad shape B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
   REQUIRE(d % 16 == 0 && d >= 16 && d <= 128, "attn: head width %d must be a multiple of 16 in [16,128]", d);
   REQUIRE(precision == LAMP_PREC_FP32 || precision == LAMP_PREC_BF16, "attn: unknown precision %d", precision);
@@ -372,12 +377,14 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   const int vrows = (multi || !compact) ? block_kv : round_up(Lk, 16);  // PV consumes keys in steps of 16; TMA zero-fills rows >= Lk
   CUtensorMap tm[6];
   if (int rc = make_tmap(&tm[0], q_hi, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, qrows, true)) return rc;
-  if (int rc = make_tmap(&tm[2], kv_hi, (uint64_t)ldkv, Lk, B, ldkv, krows, true)) return rc;
-  if (int rc = make_tmap(&tm[4], kv_hi, (uint64_t)ldkv, Lk, B, ldkv, vrows, true)) return rc;
+  const uint64_t kv_tm_rows = kv_len ? (uint64_t)kv_rows : (uint64_t)Lk;  // packed keys: one long row dimension
+  const uint64_t kv_tm_batch = kv_len ? 1 : (uint64_t)B;
+  if (int rc = make_tmap(&tm[2], kv_hi, (uint64_t)ldkv, kv_tm_rows, kv_tm_batch, ldkv, krows, true)) return rc;
+  if (int rc = make_tmap(&tm[4], kv_hi, (uint64_t)ldkv, kv_tm_rows, kv_tm_batch, ldkv, vrows, true)) return rc;
   if (three) {
     if (int rc = make_tmap(&tm[1], q_lo, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, qrows, true)) return rc;
-    if (int rc = make_tmap(&tm[3], kv_lo, (uint64_t)ldkv, Lk, B, ldkv, krows, true)) return rc;
-    if (int rc = make_tmap(&tm[5], kv_lo, (uint64_t)ldkv, Lk, B, ldkv, vrows, true)) return rc;
+    if (int rc = make_tmap(&tm[3], kv_lo, (uint64_t)ldkv, kv_tm_rows, kv_tm_batch, ldkv, krows, true)) return rc;
+    if (int rc = make_tmap(&tm[5], kv_lo, (uint64_t)ldkv, kv_tm_rows, kv_tm_batch, ldkv, vrows, true)) return rc;
   } else {
     tm[1] = tm[0];
     tm[3] = tm[2];
@@ -393,6 +400,7 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   p.ldo = (int)ldo; p.o_f32 = o_f32; p.ldof = (int)ldof;
   p.row_max = row_max; p.row_sum = row_sum;
   p.qrows = qrows; p.krows = krows; p.vrows = vrows;
+  p.kv_start = kv_start; p.kv_len = kv_len;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (block_kv == 128) rc = three ? launch_attn_stages<128, 3>(tm, p, st) : launch_attn_stages<128, 1>(tm, p, st);
@@ -416,8 +424,16 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   return rc;
 }
 
+#ifdef LAMP_ATTN_TRACE
+/* debug build only: copies the [16][64] clock64() stamps of CTA 0 of the last attention launch to the host */
+int lamp_debug_attn_trace(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, lamp::g_attn_trace, sizeof(unsigned long long) * 16 * 64) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 int lamp_layernorm(const float* y, const float* add, int add_mod, const float* gamma, const float* beta, float eps,
-                   int64_t rows, int D, float* out, void* out_hi, void* out_lo, void* stream) {
+                   int64_t rows, int D, float* out, void* out_hi, void* out_lo, const int32_t* m_dev, void* stream) {
   if (int rc = arch_check()) return rc;
   REQUIRE(y && gamma && beta && (out || out_hi), "layernorm: null pointer");
   REQUIRE(D % 4 == 0 && D > 0 && D <= 4096, "layernorm: D=%d must be a multiple of 4, <= 4096", D);
@@ -428,16 +444,17 @@ int lamp_layernorm(const float* y, const float* add, int add_mod, const float* g
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(out_hi);
   __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(out_lo);
   if (D <= 512)
-    layernorm_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo);
+    layernorm_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo, m_dev);
   else if (D <= 1024)
-    layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo);
+    layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo, m_dev);
   else
-    layernorm_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo);
+    layernorm_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo, m_dev);
   return launch_check();
 }
 
 int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, const float* pos_emb, int64_t rows,
-               int D, float* out, void* out_hi, void* out_lo, void* stream) {
+               int D, float* out, void* out_hi, void* out_lo, const int64_t* row_index, const int32_t* m_dev,
+               void* stream) {
   if (int rc = arch_check()) return rc;
   REQUIRE(seq && word_emb && (out || out_hi), "embed: null pointer");
   REQUIRE(!pos_emb || pos, "embed: pos_emb without pos ids");
@@ -446,7 +463,29 @@ int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, co
   const long long blocks = (rows * 32 + 255) / 256;
   embed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const long long*>(seq), reinterpret_cast<const long long*>(pos), word_emb, pos_emb, rows, D,
-      out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo));
+      out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
+      reinterpret_cast<const long long*>(row_index), m_dev);
+  return launch_check();
+}
+
+int lamp_gather_rows(const float* src, const int64_t* index, int64_t rows, int D, float* out, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(src && index && out, "gather_rows: null pointer");
+  REQUIRE(D % 4 == 0 && aligned16(src) && aligned16(out), "gather_rows: D multiple of 4 and 16-byte alignment required");
+  if (rows == 0) return LAMP_OK;
+  const long long blocks = (rows * 32 + 255) / 256;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<const long long*>(index),
+                                                                          rows, D, out);
+  return launch_check();
+}
+
+int lamp_zero_guard_rows(void* hi, void* lo, int64_t ld, int cols, const int32_t* m_dev, int64_t max_rows, int nguard,
+                         void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(hi && m_dev && nguard > 0 && cols > 0, "zero_guard_rows: bad arguments");
+  zero_guard_rows_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(static_cast<__nv_bfloat16*>(hi),
+                                                               static_cast<__nv_bfloat16*>(lo), ld, cols, m_dev,
+                                                               max_rows, nguard);
   return launch_check();
 }
 
@@ -492,7 +531,7 @@ int lamp_sdpa_fwd(const float* q, const float* k, const float* v, const uint8_t*
   if (int rc = lamp_split_planes(k, (int64_t)N * Lk, d, d, kvp, kvlo, 2 * d, stream)) return rc;
   if (int rc = lamp_split_planes(v, (int64_t)N * Lk, d, d, kvp + d, three ? kvlo + d : nullptr, 2 * d, stream)) return rc;
   return lamp_attn_core_planes(qp, qlo, d, 0, 0, kvp, kvlo, 2 * d, 0, d, N, 1, Lq, Lk, d, temperature, precision, mask,
-                               msb, msq, msk, nullptr, nullptr, 0, out, d, stats, stats + (size_t)N * Lq, attn, stream);
+                               msb, msq, msk, nullptr, nullptr, 0, out, d, stats, stats + (size_t)N * Lq, attn, nullptr, nullptr, 0, stream);
 }
 
 namespace {
@@ -553,14 +592,14 @@ int lamp_mha_fwd(const float* q, const float* kv, const float* Wq, const float* 
   int k_col0, v_col0;
   if (self_attn) {
     if (int rc = lamp_gemm_planes(hi(pl.xq), lo(pl.xq, mq * D), D, hi(pl.wqkv), lo(pl.wqkv, 3 * hd * D), D, (int)mq, (int)(3 * hd), D, precision,
-                                  nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.qkv), lo(pl.qkv, mq * 3 * hd), 3 * hd, stream)) return rc;
+                                  nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.qkv), lo(pl.qkv, mq * 3 * hd), 3 * hd, nullptr, stream)) return rc;
     qh = kvh = hi(pl.qkv); ql = kvl = lo(pl.qkv, mq * 3 * hd);
     ldq = ldkv = 3 * hd; k_col0 = (int)hd; v_col0 = (int)(2 * hd);
   } else {
     if (int rc = lamp_gemm_planes(hi(pl.xq), lo(pl.xq, mq * D), D, hi(pl.wqkv), lo(pl.wqkv, 3 * hd * D), D, (int)mq, (int)hd, D, precision,
-                                  nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.qkv), lo(pl.qkv, mq * hd), hd, stream)) return rc;
+                                  nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.qkv), lo(pl.qkv, mq * hd), hd, nullptr, stream)) return rc;
     if (int rc = lamp_gemm_planes(hi(pl.xkv), lo(pl.xkv, mk * D), D, hi(pl.wqkv) + hd * D, three ? lo(pl.wqkv, 3 * hd * D) + hd * D : nullptr, D,
-                                  (int)mk, (int)(2 * hd), D, precision, nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.kv), lo(pl.kv, mk * 2 * hd), 2 * hd, stream)) return rc;
+                                  (int)mk, (int)(2 * hd), D, precision, nullptr, 0, nullptr, 0, 0, nullptr, 0, hi(pl.kv), lo(pl.kv, mk * 2 * hd), 2 * hd, nullptr, stream)) return rc;
     qh = hi(pl.qkv); ql = lo(pl.qkv, mq * hd); kvh = hi(pl.kv); kvl = lo(pl.kv, mk * 2 * hd);
     ldq = hd; ldkv = 2 * hd; k_col0 = 0; v_col0 = (int)hd;
   }
@@ -570,14 +609,14 @@ int lamp_mha_fwd(const float* q, const float* kv, const float* Wq, const float* 
   const float temperature = sqrtf((float)d);
   if (int rc = lamp_attn_core_planes(qh, ql, ldq, 0, 0, kvh, kvl, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature, precision, mask, msb,
                                      msq, msk, H > 1 ? hi(pl.o) : nullptr, H > 1 ? lo(pl.o, mq * hd) : nullptr, hd, H > 1 ? nullptr : y, hd,
-                                     stats, stats ? stats + (size_t)H * mq : nullptr, attn, stream)) return rc;
+                                     stats, stats ? stats + (size_t)H * mq : nullptr, attn, nullptr, nullptr, 0, stream)) return rc;
   // 4. fc + residual (:110,:117) then LayerNorm
   if (H > 1) {
     if (int rc = lamp_gemm_planes(hi(pl.o), lo(pl.o, mq * hd), hd, hi(pl.wfc), lo(pl.wfc, hd * D), hd, (int)mq, D, (int)hd, precision, nullptr, 0,
-                                  q, D, 0, y, D, nullptr, nullptr, 0, stream)) return rc;
-    return lamp_layernorm(y, nullptr, 0, ln_w, ln_b, ln_eps, mq, D, out, nullptr, nullptr, stream);
+                                  q, D, 0, y, D, nullptr, nullptr, 0, nullptr, stream)) return rc;
+    return lamp_layernorm(y, nullptr, 0, ln_w, ln_b, ln_eps, mq, D, out, nullptr, nullptr, nullptr, stream);
   }
-  return lamp_layernorm(y, q, 0, ln_w, ln_b, ln_eps, mq, D, out, nullptr, nullptr, stream);
+  return lamp_layernorm(y, q, 0, ln_w, ln_b, ln_eps, mq, D, out, nullptr, nullptr, nullptr, stream);
 }
 
 size_t lamp_ffn_workspace_bytes(int64_t rows, int D, int d_inner) {
@@ -611,11 +650,11 @@ int lamp_ffn_fwd(const float* x, const float* W1, const float* b1, const float* 
   if (int rc = lamp_split_planes(W2, D, d_inner, d_inner, w2p, lo(w2p, nw), d_inner, stream)) return rc;
   // w_1 + ReLU (lamp/SubLayers.py:138), hidden kept as planes only
   if (int rc = lamp_gemm_planes(xp, lo(xp, nx), D, w1p, lo(w1p, nw), D, (int)rows, d_inner, D, precision, b1, 1, nullptr, 0, 0, nullptr, 0, hp,
-                                lo(hp, nh), d_inner, stream)) return rc;
+                                lo(hp, nh), d_inner, nullptr, stream)) return rc;
   // w_2 + residual (:138-141)
   if (int rc = lamp_gemm_planes(hp, lo(hp, nh), d_inner, w2p, lo(w2p, nw), d_inner, (int)rows, D, d_inner, precision, b2, 0, x, D, 0, y, D, nullptr,
-                                nullptr, 0, stream)) return rc;
-  return lamp_layernorm(y, nullptr, 0, ln_w, ln_b, ln_eps, rows, D, out, nullptr, nullptr, stream);
+                                nullptr, 0, nullptr, stream)) return rc;
+  return lamp_layernorm(y, nullptr, 0, ln_w, ln_b, ln_eps, rows, D, out, nullptr, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

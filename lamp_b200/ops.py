@@ -58,15 +58,29 @@ class LaunchStats:
         ev, self._events = self._events or [], None
         torch.cuda.synchronize()
         out: Dict[str, dict] = {}
-        for name, e0, e1, flops, nbytes in ev:
+        counts: Dict[int, int] = {}  # device row counts, read back once per tensor
+        for name, e0, e1, flops, nbytes, rows_dev in ev:
             d = out.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
             d['calls'] += 1
             d['ms'] += e0.elapsed_time(e1)
+            if callable(flops) or callable(nbytes):
+                # padding-aware launches: the rows actually processed are only known on the device
+                m = None
+                if rows_dev is not None:
+                    key = id(rows_dev)
+                    if key not in counts:
+                        counts[key] = int(rows_dev.sum().item())
+                    m = counts[key]
+                flops = flops(m) if callable(flops) else flops
+                nbytes = nbytes(m) if callable(nbytes) else nbytes
             d['flops'] += flops
             d['bytes'] += nbytes
         return out
 
-    def call(self, name: str, n_kernels: int, fn, args, flops: float = 0.0, nbytes: float = 0.0):
+    def call(self, name: str, n_kernels: int, fn, args, flops=0.0, nbytes=0.0, rows_dev=None):
+        """``flops`` / ``nbytes``: algorithmic work of the launch -- numbers, or functions of the row count that the
+        kernel reads from the device (``rows_dev``: int32 tensor whose sum is that count; ``None`` is passed to the
+        function when the launch is dense), evaluated after the timed region."""
         self.launches += n_kernels
         self.by_kernel[name] = self.by_kernel.get(name, 0) + n_kernels
         if self._events is None:
@@ -76,7 +90,7 @@ class LaunchStats:
         e0.record()
         nat.check(fn(*args), name)
         e1.record()
-        self._events.append((name, e0, e1, flops, nbytes))
+        self._events.append((name, e0, e1, flops, nbytes, rows_dev))
 
 
 STATS = LaunchStats()
@@ -92,6 +106,7 @@ class Act:
     rows: int
     cols: int
     bcast_rows: int = 0
+    m_dev: Optional[torch.Tensor] = None  # device int32 scalar: rows actually in use (padding-aware packed batch)
 
     @property
     def has_planes(self) -> bool:
@@ -161,22 +176,26 @@ class WeightPlanes:
 
 def gemm(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, prec: int, *, bias=None, relu=False,
          residual=None, ldr: int = 0, resid_mod: int = 0, out_f32=None, ldo: int = 0, out_hi=None, out_lo=None,
-         ldp: int = 0) -> None:
+         ldp: int = 0, m_dev=None) -> None:
     pl = 4 if prec == nat.PREC_FP32 else 2  # bytes per element of a plane pair
-    nbytes = M * K * pl + N * K * pl + (M * N * 4 if out_f32 is not None else 0) + \
-        (M * N * pl if out_hi is not None else 0) + (M * N * 4 if residual is not None and not resid_mod else 0)
+    row_bytes = K * pl + (N * 4 if out_f32 is not None else 0) + (N * pl if out_hi is not None else 0) + \
+        (N * 4 if residual is not None and not resid_mod else 0)
+
+    def rows(m):
+        return M if m is None else min(M, m)
     STATS.call('gemm_planes', 1, nat.lib().lamp_gemm_planes,
                (nat.ptr(a_hi), nat.ptr(a_lo), lda, nat.ptr(w_hi), nat.ptr(w_lo), ldw, M, N, K, prec, nat.ptr(bias),
                 int(relu), nat.ptr(residual), ldr, resid_mod, nat.ptr(out_f32), ldo, nat.ptr(out_hi), nat.ptr(out_lo),
-                ldp, nat.stream()), flops=2.0 * M * N * K, nbytes=nbytes)
+                ldp, nat.ptr(m_dev), nat.stream()), flops=lambda m: 2.0 * rows(m) * N * K,
+               nbytes=lambda m: rows(m) * row_bytes + N * K * pl, rows_dev=m_dev)
 
 
 def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=False) -> Act:
     """planes(x) @ W^T (+bias)(ReLU) -> planes only (operand for the next tensor-core stage)."""
     hi, lo = _empty_planes(x.rows, N, prec, x.hi.device)
     gemm(x.hi, x.lo, x.cols, w_hi, w_lo, x.cols, x.rows, N, x.cols, prec, bias=bias, relu=relu, out_hi=hi, out_lo=lo,
-         ldp=N)
-    return Act(None, hi, lo, x.rows, N, x.bcast_rows)
+         ldp=N, m_dev=x.m_dev)
+    return Act(None, hi, lo, x.rows, N, x.bcast_rows, x.m_dev)
 
 
 def act_f32(a: Act) -> torch.Tensor:
@@ -193,17 +212,20 @@ def linear_residual_f32(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, *,
     mod = residual.rows if residual.bcast_rows else 0
     if residual.f32 is not None:
         gemm(x.hi, x.lo, x.cols, w_hi, w_lo, x.cols, x.rows, N, x.cols, prec, bias=bias, residual=residual.f32,
-             ldr=residual.cols, resid_mod=mod, out_f32=y, ldo=N)
+             ldr=residual.cols, resid_mod=mod, out_f32=y, ldo=N, m_dev=x.m_dev)
         return y
     M, K = x.rows, x.cols
     pl = 4 if prec == nat.PREC_FP32 else 2
     STATS.call('gemm_planes', 1, nat.lib().lamp_gemm_planes_pres,
                (nat.ptr(x.hi), nat.ptr(x.lo), K, nat.ptr(w_hi), nat.ptr(w_lo), K, M, N, K, prec, nat.ptr(bias),
                 nat.ptr(residual.hi), nat.ptr(residual.lo), residual.cols, mod, y.data_ptr(), N, None, None, 0,
-                nat.stream()), flops=2.0 * M * N * K, nbytes=M * K * pl + N * K * pl + M * N * 4 + M * N * pl)
+                nat.ptr(x.m_dev), nat.stream()), flops=lambda m: 2.0 * (M if m is None else min(M, m)) * N * K,
+               nbytes=lambda m: (M if m is None else min(M, m)) * (K * pl + N * 4 + N * pl) + N * K * pl,
+               rows_dev=x.m_dev)
     return y
 
 
+PADDING_AWARE = True  # GraphEncoder/GraphDecoder compute only non-PAD token rows (results identical, see Encoders.py)
 FUSE_LAYERNORM = False  # True: fc / w_2 GEMM epilogue normalises the row on chip when 256 < d_model <= 512 (measured
 # slower than GEMM + LayerNorm kernels on B200: the exposed two-pass epilogue costs more than the HBM round trip saves)
 
@@ -214,7 +236,7 @@ def linear_residual_ln(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, gam
     the 512-column TMEM accumulator (the pre-norm tensor never reaches HBM); GEMM + LayerNorm kernels otherwise."""
     if not (FUSE_LAYERNORM and 256 < N <= 512 and residual.f32 is not None):
         y = linear_residual_f32(x, w_hi, w_lo, N, prec, residual, bias=bias)
-        return layernorm(y, gamma, beta, eps, prec, want_planes=want_planes, want_f32=want_f32)
+        return layernorm(y, gamma, beta, eps, prec, want_planes=want_planes, want_f32=want_f32, m_dev=x.m_dev)
     dev = x.hi.device
     out = torch.empty((x.rows, N), dtype=torch.float32, device=dev)
     hi, lo = _empty_planes(x.rows, N, prec, dev) if want_planes else (None, None)
@@ -230,7 +252,7 @@ def linear_residual_ln(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, gam
 
 
 def layernorm(y: torch.Tensor, gamma, beta, eps: float, prec: int, *, add: Optional[Act] = None,
-              want_planes: bool = True, want_f32: bool = True) -> Act:
+              want_planes: bool = True, want_f32: bool = True, m_dev=None) -> Act:
     rows, D = y.shape
     want_f32 = want_f32 or not want_planes
     out = torch.empty_like(y) if want_f32 else None
@@ -240,9 +262,10 @@ def layernorm(y: torch.Tensor, gamma, beta, eps: float, prec: int, *, add: Optio
         add_t, add_mod = act_f32(add), (add.rows if add.bcast_rows else 0)
     STATS.call('layernorm', 1, nat.lib().lamp_layernorm,
                (y.data_ptr(), nat.ptr(add_t), add_mod, gamma.data_ptr(), beta.data_ptr(), float(eps), rows, D,
-                nat.ptr(out), nat.ptr(hi), nat.ptr(lo), nat.stream()),
-               nbytes=rows * D * (4 + (4 if want_f32 else 0) + (0 if hi is None else (4 if lo is not None else 2))))
-    return Act(out, hi, lo, rows, D)
+                nat.ptr(out), nat.ptr(hi), nat.ptr(lo), nat.ptr(m_dev), nat.stream()),
+               nbytes=lambda m: (rows if m is None else min(rows, m)) * D *
+               (4 + (4 if want_f32 else 0) + (0 if hi is None else (4 if lo is not None else 2))), rows_dev=m_dev)
+    return Act(out, hi, lo, rows, D, 0, m_dev)
 
 
 def mask_args(mask: Optional[torch.Tensor], B: int, Lq: int, Lk: int):
@@ -265,7 +288,8 @@ def mask_args(mask: Optional[torch.Tensor], B: int, Lq: int, Lk: int):
 
 
 def attention(q: Act, q_col0: int, kv: Act, k_col0: int, v_col0: int, B: int, H: int, Lq: int, Lk: int, d: int,
-              prec: int, mask: Optional[torch.Tensor], want_probs: bool, out_f32: bool = False):
+              prec: int, mask: Optional[torch.Tensor], want_probs: bool, out_f32: bool = False, kv_start=None,
+              kv_len=None):
     """-> (O as Act [B*Lq, H*d] (planes, or fp32 when out_f32), probs [H*B, Lq, Lk] or None)."""
     dev = q.hi.device
     hd = H * d
@@ -279,16 +303,27 @@ def attention(q: Act, q_col0: int, kv: Act, k_col0: int, v_col0: int, B: int, H:
         probs = torch.empty((H * B, Lq, Lk), dtype=torch.float32, device=dev)
         rmax = torch.empty((H * B * Lq,), dtype=torch.float32, device=dev)
         rsum = torch.empty_like(rmax)
-    keep, mptr, sb, sq, sk = mask_args(mask, B, Lq, Lk)
+    if kv_len is not None:
+        # packed keys: `mask` (optional) is one uint8 per packed key row
+        keep = None if mask is None else mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+        mptr, sb, sq, sk = (None if keep is None else keep.data_ptr()), 0, 0, 1
+    else:
+        keep, mptr, sb, sq, sk = mask_args(mask, B, Lq, Lk)
     pl = 4 if prec == nat.PREC_FP32 else 2
     # algorithmic bytes of the attention core: Q + K + V read, O written, 4 B (fp32-equivalent
     # plane pair) or 2 B (bf16) per element; a broadcast Q is read once.
-    nbytes = ((1 if q.bcast_rows else B) * Lq * hd + 2 * B * Lk * hd) * pl + B * Lq * hd * (4 if out_f32 else pl)
+    # With packed keys only sum(kv_len) key rows exist: both figures follow the keys actually attended to.
+    qo_bytes = (1 if q.bcast_rows else B) * Lq * hd * pl + B * Lq * hd * (4 if out_f32 else pl)
+
+    def keys(m):
+        return B * Lk if m is None else m
     STATS.call('attn_core_self' if q is kv else 'attn_core_enc', 2 if want_probs else 1, nat.lib().lamp_attn_core_planes,
                (q.hi.data_ptr(), nat.ptr(q.lo), q.cols, q_col0, 1 if q.bcast_rows else 0,
                 kv.hi.data_ptr(), nat.ptr(kv.lo), kv.cols, k_col0, v_col0, B, H, Lq, Lk, d, float(math.sqrt(d)), prec,
                 mptr, sb, sq, sk, nat.ptr(o_hi), nat.ptr(o_lo), hd, nat.ptr(o32), hd, nat.ptr(rmax), nat.ptr(rsum),
-                nat.ptr(probs), nat.stream()), flops=4.0 * B * H * Lq * Lk * d, nbytes=nbytes)
+                nat.ptr(probs), nat.ptr(kv_start), nat.ptr(kv_len), kv.rows if kv_len is not None else 0,
+                nat.stream()), flops=lambda m: 4.0 * H * Lq * d * keys(m),
+               nbytes=lambda m: qo_bytes + 2 * keys(m) * hd * pl, rows_dev=kv_len)
     del keep
     return Act(o32, o_hi, o_lo, B * Lq, hd), probs
 
@@ -312,7 +347,7 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask, temperature: f
 
 
 def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor, pos_emb: Optional[torch.Tensor],
-          prec: int, want_f32: bool = True) -> Act:
+          prec: int, want_f32: bool = True, row_index=None, m_dev=None) -> Act:
     nat.require_cuda(seq, word_emb)
     seq = seq.contiguous().long()
     rows = seq.numel()
@@ -323,9 +358,27 @@ def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor
         pos = pos.contiguous().long()
     STATS.call('embed', 1, nat.lib().lamp_embed,
                (seq.data_ptr(), nat.ptr(pos) if pos_emb is not None else None, word_emb.data_ptr(), nat.ptr(pos_emb),
-                rows, D, nat.ptr(out), hi.data_ptr(), nat.ptr(lo), nat.stream()),
-               nbytes=rows * D * (4 + (4 if want_f32 else 0) + (4 if lo is not None else 2)))
-    return Act(out, hi, lo, rows, D)
+                rows, D, nat.ptr(out), hi.data_ptr(), nat.ptr(lo), nat.ptr(row_index), nat.ptr(m_dev), nat.stream()),
+               nbytes=lambda m: (rows if m is None else min(rows, m)) * D *
+               (4 + (4 if want_f32 else 0) + (4 if lo is not None else 2)), rows_dev=m_dev)
+    return Act(out, hi, lo, rows, D, 0, m_dev)
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, D: int) -> torch.Tensor:
+    """out[r, :] = src[index[r], :] (fp32) -- dense API tensor from a packed activation."""
+    rows = index.numel()
+    out = torch.empty((rows, D), dtype=torch.float32, device=src.device)
+    STATS.call('gather_rows', 1, nat.lib().lamp_gather_rows,
+               (src.data_ptr(), index.data_ptr(), rows, D, out.data_ptr(), nat.stream()), nbytes=rows * D * 8)
+    return out
+
+
+def zero_guard_rows(a: Act, nguard: int = 128) -> None:
+    """Zero the rows that follow the rows in use of a packed Act (see zero_guard_rows_kernel)."""
+    if a.m_dev is None:
+        return
+    STATS.call('zero_guard_rows', 1, nat.lib().lamp_zero_guard_rows,
+               (a.hi.data_ptr(), nat.ptr(a.lo), a.cols, a.cols, a.m_dev.data_ptr(), a.rows, nguard, nat.stream()))
 
 
 def diag_proj(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Pipeline timeline of the attention core (debug build with -DLAMP_ATTN_TRACE): clock64() stamps of CTA 0 for the
+first 64 units of one launch, printed relative to the first stamp.  usage: python scripts/attn_trace.py [self|enc]
+
+Events: 0 K load issued | 1 Q load issued | 2 V load issued | 3 Q,K landed (MMA warp) | 4 S issued | 5 P ready seen by
+MMA warp | 6 V landed -> PV issued | 7 S complete seen by softmax | 8 row-max barrier passed | 9 P stored |
+10 previous O complete (epilogue starts) | 11 epilogue done (p_full arrive)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lamp_b200 import build as b  # noqa: E402
+from lamp_b200 import _native as nat  # noqa: E402
+
+TRACE_LIB = os.path.join(ROOT, 'lamp_b200', 'liblamp_b200_trace.so')
+if not os.path.exists(TRACE_LIB) or '--rebuild' in sys.argv:
+    b.build(force=True, out=TRACE_LIB, defines=('LAMP_ATTN_TRACE',))
+nat.LIB_PATH = TRACE_LIB
+from lamp_b200 import ops  # noqa: E402
+
+DEV = 'cuda'
+NAMES = ['Kld', 'Qld', 'Vld', 'QKin', 'Siss', 'Pseen', 'PViss', 'Sdone', 'maxbar', 'Pst', 'Odone', 'epiend']
+
+
+def main():
+    which = 'enc' if 'enc' in sys.argv else 'self'
+    B, H, d, prec = 1100, 4, 128, 0
+    hd = H * d
+    Lq, Lk = (103, 300) if which == 'enc' else (103, 103)
+    torch.manual_seed(0)
+    if which == 'self':
+        qkv = ops.Act(None, *ops.split(torch.randn(B * Lq, 3 * hd, device=DEV), prec), B * Lq, 3 * hd)
+        q = kv = qkv
+        qc, kc, vc = 0, hd, 2 * hd
+        mask = (torch.rand(1, Lq, Lk, device=DEV) < 0.5)
+        mask[:, torch.arange(Lq), torch.arange(Lq)] = False
+    else:
+        q = ops.Act(None, *ops.split(torch.randn(B * Lq, hd, device=DEV), prec), B * Lq, hd)
+        kv = ops.Act(None, *ops.split(torch.randn(B * Lk, 2 * hd, device=DEV), prec), B * Lk, 2 * hd)
+        qc, kc, vc = 0, 0, hd
+        mask = (torch.rand(B, 1, Lk, device=DEV) < 0.3)
+        mask[:, :, 0] = False
+    for _ in range(3):
+        ops.attention(q, qc, kv, kc, vc, B, H, Lq, Lk, d, prec, mask, False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.attention(q, qc, kv, kc, vc, B, H, Lq, Lk, d, prec, mask, False)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f'{which}: launch {e0.elapsed_time(e1) * 1e3:.1f} us')
+    buf = (C.c_ulonglong * (16 * 64))()
+    fn = nat.lib().lamp_debug_attn_trace
+    fn.argtypes = [C.c_void_p]
+    fn.restype = C.c_int
+    assert fn(C.addressof(buf)) == 0
+    t = [[buf[e * 64 + u] for u in range(64)] for e in range(16)]
+    base = min(x for row in t[:12] for x in row if x)
+    print('unit ' + ' '.join(f'{n:>7s}' for n in NAMES))
+    for u in range(4, 28):
+        print(f'{u:4d} ' + ' '.join(f'{(t[e][u] - base) if t[e][u] else -1:7d}' for e in range(12)))
+    # steady-state per-unit period and stage gaps (cycles)
+    us = range(8, 28)
+    per = (t[6][27] - t[6][8]) / 19.0
+    print(f'period (PV issue to PV issue): {per:.0f} cycles')
+    def gap(a, b, shift=0):
+        v = [t[b][u + shift] - t[a][u] for u in us if t[a][u] and t[b][u + shift]]
+        return sum(v) / max(len(v), 1)
+    print(f'K load issue -> Q,K landed (same unit): {gap(0, 3):.0f}')
+    print(f'V load issue -> PV issue (same unit):   {gap(2, 6):.0f}')
+    print(f'S issued -> S complete seen:            {gap(4, 7):.0f}')
+    print(f'S complete -> max barrier:              {gap(7, 8):.0f}')
+    print(f'max barrier -> P stored:                {gap(8, 9):.0f}')
+    print(f'P stored -> prev O done seen:           {gap(9, 10):.0f}')
+    print(f'epilogue:                               {gap(10, 11):.0f}')
+    print(f'epilogue end -> P seen by MMA:          {gap(11, 5):.0f}')
+    print(f'P seen -> PV issue (wait V):            {gap(5, 6):.0f}')
+    print(f'PV issue(u) -> O done seen (u+1):       {gap(6, 10, 1):.0f}')
+    print(f'PV issue(u) -> V load issue (u+1):      {gap(6, 2, 1):.0f}')
+
+
+if __name__ == '__main__':
+    main()

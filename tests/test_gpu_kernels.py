@@ -80,7 +80,7 @@ def _gemm_case(M, N, K, prec):
     L = nat.lib()
     # plain product
     nat.check(L.lamp_gemm_planes(a_hi.data_ptr(), nat.ptr(a_lo), K, w_hi.data_ptr(), nat.ptr(w_lo), K, M, N, K, prec,
-                                 None, 0, None, 0, 0, out.data_ptr(), N, None, None, 0, nat.stream()), 'gemm')
+                                 None, 0, None, 0, 0, out.data_ptr(), N, None, None, 0, None, nat.stream()), 'gemm')
     torch.cuda.synchronize()
     if three:
         ref = a.double() @ w.double().T
@@ -94,7 +94,7 @@ def _gemm_case(M, N, K, prec):
     # bias + relu + residual, fp32 and plane outputs
     nat.check(L.lamp_gemm_planes(a_hi.data_ptr(), nat.ptr(a_lo), K, w_hi.data_ptr(), nat.ptr(w_lo), K, M, N, K, prec,
                                  bias.data_ptr(), 1, res.data_ptr(), N, 0, out.data_ptr(), N, o_hi.data_ptr(),
-                                 nat.ptr(o_lo), N, nat.stream()), 'gemm-epi')
+                                 nat.ptr(o_lo), N, None, nat.stream()), 'gemm-epi')
     torch.cuda.synchronize()
     ref2 = torch.relu(ref + bias.double()) + res.double()
     assert rel_err(out, ref2) < tol
@@ -104,7 +104,7 @@ def _gemm_case(M, N, K, prec):
     # residual broadcast (row % resid_mod)
     mod = 7
     nat.check(L.lamp_gemm_planes(a_hi.data_ptr(), nat.ptr(a_lo), K, w_hi.data_ptr(), nat.ptr(w_lo), K, M, N, K, prec,
-                                 None, 0, res.data_ptr(), N, mod, out.data_ptr(), N, None, None, 0, nat.stream()),
+                                 None, 0, res.data_ptr(), N, mod, out.data_ptr(), N, None, None, 0, None, nat.stream()),
               'gemm-mod')
     torch.cuda.synchronize()
     ref3 = ref + res.double()[torch.arange(M, device=DEV) % mod]
@@ -328,7 +328,7 @@ def test_layernorm_embed_diag():
         hi = torch.empty(rows, D, dtype=torch.bfloat16, device=DEV)
         lo = torch.empty_like(hi)
         nat.check(L.lamp_layernorm(y.data_ptr(), add.data_ptr(), 4, gam.data_ptr(), bet.data_ptr(), 1e-5, rows, D,
-                                   out.data_ptr(), hi.data_ptr(), lo.data_ptr(), nat.stream()), 'ln')
+                                   out.data_ptr(), hi.data_ptr(), lo.data_ptr(), None, nat.stream()), 'ln')
         z = y.double() + add.double()[torch.arange(rows, device=DEV) % 4]
         ref = torch.nn.functional.layer_norm(z, (D,), gam.double(), bet.double(), 1e-5)
         assert rel_err(out, ref) < 1e-5
@@ -341,7 +341,7 @@ def test_layernorm_embed_diag():
     pos = torch.randint(0, P, (rows,), generator=g).to(DEV)
     out = torch.empty(rows, D, device=DEV)
     nat.check(L.lamp_embed(seq.data_ptr(), pos.data_ptr(), we.data_ptr(), pe.data_ptr(), rows, D, out.data_ptr(), None,
-                           None, nat.stream()), 'embed')
+                           None, None, None, nat.stream()), 'embed')
     assert torch.equal(out, we[seq] + pe[pos])
     B, Ln = 7, 37
     x = torch.randn(B, Ln, D, generator=g).to(DEV)

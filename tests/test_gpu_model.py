@@ -214,3 +214,40 @@ def test_full_size_properties_cfg2():
     assert rel_err(attn_s.sum(-1), torch.ones_like(attn_s.sum(-1))) < 1e-5
     ref, _ = orc.mha(p, '', x[:2].cpu(), x[:2].cpu(), x[:2].cpu(), mask[:2], c['H'])
     assert rel_err(out[:2], ref) < TOL
+
+
+def test_padding_aware_path_equals_dense_path_and_oracle():
+    """The packed (PAD-skipping) encoder / K|V projection / label<-input attention gives the same enc_output (PAD rows
+    included) and logits as the dense path and the oracle -- also for inputs the reference loader never produces
+    (PAD in the middle of a row, a PAD token carrying a non-zero position id, a row that is entirely PAD-free)."""
+    from lamp_b200 import ops
+    c = dict(cases.MODEL_CASES['lamp_L37_none'], B=6)
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    src_seq, src_pos = src_seq.clone(), src_pos.clone()
+    src_seq[1, 5] = 0
+    src_pos[1, 5] = 0           # PAD in the middle of a row
+    src_seq[2, 7] = 0           # PAD token that keeps its position id (not equal to the representative row)
+    src_seq[3] = src_seq[0]
+    src_pos[3] = src_pos[0]     # no padding at all (row 0 is full length by construction)
+    model = build_model(c, p, adj)
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+    outs = {}
+    for aware in (True, False):
+        ops.PADDING_AWARE = aware
+        try:
+            with torch.no_grad():
+                outs[aware] = model(src, None, None, None)
+        finally:
+            ops.PADDING_AWARE = True
+    lm = orc.label_mask_from(c['L'], adj, c['mask'])
+    ref_logits, ref_enc = orc.lamp_forward(p, cfg, src_seq, src_pos, lm)
+    for aware in (True, False):
+        logits, enc_out, _ = outs[aware]
+        assert rel_err(logits, ref_logits) < TOL, aware
+        assert rel_err(enc_out, ref_enc) < TOL, aware
+    assert rel_err(outs[True][0], outs[False][0]) < 1e-4
+    assert rel_err(outs[True][1], outs[False][1]) < 1e-5
+    # int_preds / return_attns still work (they fall back to dense keys where the layout demands it)
+    with torch.no_grad():
+        l2, _, enc_attns, dec_rest = model(src, None, None, None, return_attns=True)
+    assert rel_err(l2, ref_logits) < TOL
