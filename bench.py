@@ -7,10 +7,14 @@ projection; lamp/Models.py:110-137) in eval mode over one batch of synthetic doc
 L=103 labels, T=300 tokens, d_model=512, n_head=4, 2+2 layers, d_inner=512, prior label mask, fp32 in/out
 (LAMP_PREC_FP32: 3-term split-bf16 tensor-core products, parity-checked at 1e-3 against the reference).
 
-  value : samples/s, whole job, token ids already resident in HBM, CUDA-event timed, max over ranks
-  e2e   : same metric through the public API with HOST (pinned) token ids: H2D copy + forward + D2H of the logits
-          inside the timed region
-  roofline      : dominant kernel (projection GEMM, tensor-bound) -- algorithmic FLOPs / measured kernel time
+  value : samples/s, whole job, token ids already resident in HBM, CUDA-event timed, max over ranks.  Each step is one
+          replay of the CUDA graph of LAMP.forward (lamp_b200.GraphedForward, the package's serving API; --no-graph
+          launches kernel by kernel from Python instead)
+  e2e   : same metric through that public API with HOST (pinned) token ids: H2D copy + forward + D2H of the logits
+          inside the timed region, host clock
+  roofline      : dominant kernel (projection GEMM, tensor-bound) -- algorithmic FLOPs / measured kernel time.  The
+                  per-kernel durations come from a second timed region of the same K steps, launched eagerly with a
+                  CUDA-event pair around every native call (`eager_ms_per_step` is that region's step time)
   roofline_attn : masked label<-label attention core kernel under the label-graph mask (HBM-bound) -- algorithmic
                   bytes / measured kernel time; roofline_attn_enc: the same kernel on the label<-input shape (T=300)
   cpu_baseline  : the CPU oracle (oracle/lamp_oracle.py, a torch-CPU port of the reference incl. its discarded
@@ -21,6 +25,7 @@ Launch: ``python bench.py --gpus N --steps K --warmup W`` (N > 1 under torchrun,
 sharded, the label graph and weights replicated, no forward collective -> "scaling": "weak").
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -49,6 +54,9 @@ def parse():
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
     ap.add_argument('--cpu-batch', type=int, default=32)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every step kernel by kernel from Python')
+    ap.add_argument('--tune', action='append', default=[], metavar='KEY=VALUE',
+                    help='lamp_set_tuning knob (include/lamp_b200.h), for experiments only')
     return ap.parse_args()
 
 
@@ -218,6 +226,11 @@ def main():
     from lamp_b200 import ops
     from lamp_b200.Models import LAMP
     lamp_b200.set_default_precision(args.precision)
+    for kv in args.tune:
+        k, v = kv.split('=')
+        from lamp_b200 import _native as nat
+        nat.check(nat.lib().lamp_set_tuning(int(k), int(v)), 'tune')
+        config['tune'] = args.tune
     dev = torch.device('cuda', local_rank)
 
     params, adj, src_seq, src_pos = synth(args.batch, 100 + rank)
@@ -246,40 +259,69 @@ def main():
         return float(t.item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # polls from here on; the timed window is cut out later
+    runner, launch_mode = None, 'eager'
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             model((seq_d, pos_d), None, None, None)
-        # ---------------- device-resident throughput, with per-kernel CUDA events inside the timed region
+        if not args.no_graph:
+            # the public serving API: one CUDA-graph launch per step (lamp_b200/graphs.py); same kernels as eager
+            runner = lamp_b200.GraphedForward(model, args.batch, c['T'], example=(seq_d, pos_d))
+            launch_mode = f'cuda-graph replay ({runner.kernels_per_replay} native kernels per step)'
+            for _ in range(max(args.warmup, 3)):
+                runner.replay()
+        config['launch'] = launch_mode
+        gc.collect()
+        gc.disable()  # a generation-2 collection inside a timed region costs a few hundred ms of launch stall
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # ---------------- (A) device-resident throughput: token ids already in HBM, K steps
         barrier()
         ops.STATS.reset()
         t_wall0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            if runner is not None:
+                logits, _ = runner.replay()
+            else:
+                logits, _, _ = model((seq_d, pos_d), None, None, None)
+        e1.record()
+        barrier()
+        launches = ops.STATS.launches
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        # ---------------- (B) the same K steps launched kernel by kernel with a CUDA-event pair around every native
+        #                  call: per-kernel durations for the roofline figures (and the eager-launch step time)
+        barrier()
         with ops.STATS.timed():
             e0.record()
+            host_t = [time.perf_counter()]
             for _ in range(args.steps):
-                logits, _, _ = model((seq_d, pos_d), None, None, None)
+                model((seq_d, pos_d), None, None, None)
+                host_t.append(time.perf_counter())
             e1.record()
             barrier()
             t_wall1 = time.perf_counter()
             per_kernel = ops.STATS.stop_timing()
-        launches = ops.STATS.launches
+        eager_ms = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-        ms_total = max_over_ranks(e0.elapsed_time(e1))
-        # ---------------- end to end: pinned host ids -> H2D -> forward -> D2H logits, every step
+        # ---------------- (C) end to end: pinned host ids -> H2D -> forward -> D2H logits, every step
+        def e2e_step():
+            if runner is not None:
+                lg, _ = runner(seq_h, pos_h)
+            else:
+                lg, _, _ = model((seq_h.to(dev, non_blocking=True), pos_h.to(dev, non_blocking=True)), None, None,
+                                 None)
+            logits_h.copy_(lg, non_blocking=True)
         for _ in range(2):
-            model((seq_h.to(dev, non_blocking=True), pos_h.to(dev, non_blocking=True)), None, None, None)
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
-            s_d = seq_h.to(dev, non_blocking=True)
-            p_d = pos_h.to(dev, non_blocking=True)
-            lg, _, _ = model((s_d, p_d), None, None, None)
-            logits_h.copy_(lg, non_blocking=True)
+            e2e_step()
         e1.record()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)  # host clock: launch overheads and the final D2H included
         e2e_dev_ms = e0.elapsed_time(e1)
+        gc.enable()
 
     total_samples = args.batch * world * args.steps
     value = total_samples / (ms_total * 1e-3)
@@ -321,6 +363,9 @@ def main():
                  d2h_bytes_per_step=int(logits_h.numel() * 4) * world, ms_per_step=e2e_s / args.steps * 1e3,
                  device_ms_per_step=e2e_dev_ms / args.steps),
         gpu_launches=launches, clocks=clocks,
+        eager_ms_per_step=eager_ms / args.steps,
+        host_launch_ms=dict(median=statistics.median(b - a for a, b in zip(host_t, host_t[1:])) * 1e3,
+                            max=max(b - a for a, b in zip(host_t, host_t[1:])) * 1e3),
         roofline=roof('gemm_planes', 'tensor'), roofline_attn=roof('attn_core_self', 'hbm'),
         roofline_attn_enc=roof('attn_core_enc', 'hbm'),
         kernels={k: dict(calls=v['calls'], ms=round(v['ms'], 3)) for k, v in per_kernel.items()})

@@ -47,6 +47,7 @@ int lamp_sm_count(void);
 /* Process-wide tuning knobs (benchmarking aid; results are identical for every setting). */
 #define LAMP_TUNE_GEMM_BLOCK_K 1  /* 0 (default: automatic), 32 (64B swizzle, deeper TMA ring) or 64 (128B swizzle) */
 #define LAMP_TUNE_ATTN_COMPACT 3  /* 1 (default: tile rows follow L, deepest K/V staging that fits) or 0 (128-row tiles) */
+#define LAMP_TUNE_ATTN_STAGE 4    /* 1 (default: attention output planes leave through smem staging + TMA stores) or 0 */
 #define LAMP_TUNE_GEMM_CTA_PAIR 2 /* 1 (default: tcgen05 cta_group::2 pairs for 256-wide tiles) or 0 (single CTAs) */
 int lamp_set_tuning(int key, int value);
 

@@ -4,24 +4,28 @@
 // One persistent CTA per SM walks a sequence of "units" = (work item (b, h, 128-row q tile), KV tile j):
 //   warp 0   : TMA producer -- 3D tensor maps {cols, L, B}: rows >= L are zero-filled by the hardware, so ragged
 //              label counts (L = 103, 159, 983 ...) need no padding in HBM.  Q/K/V arrive as 128B-swizzled
-//              [rows x 64] bf16 boxes of the split-bf16 planes written by the projection GEMM.  Q, K and V have
-//              independent buffers/barriers, so the next unit's operands stream in while the current one computes.
-//   warp 1   : MMA issuer   -- S = Q K^T (A, B from smem, K-major) into one of TWO TMEM score buffers, issued one
-//              unit ahead of the softmax; O (+)= P V with P read from TENSOR MEMORY (TS form) and V consumed
-//              MN-major straight from its natural [keys x d] layout (no transpose pass); 3-term split-bf16 products.
-//   warps 2.. : softmax     -- 4 * (BLOCK_KV/32) warps: TMEM lane == query row and every warp owns one 32-column
-//              chunk of the rows of its lane quarter (4 warps per scheduler hide the ALU/MUFU latency of the
-//              exp2 / split chain).  Strided byte mask -> bit words via warp ballots, row max exchanged through
-//              2 KB of smem, online max/sum across KV tiles, ex2, hi/lo split, P written back to TMEM (never to
-//              shared or global memory); O rescaled in TMEM when the running max moves.  The epilogue of the
-//              PREVIOUS item (1/sum, hi/lo split, stores into the head's column slice of the concatenated output)
-//              runs after the current unit's softmax, hiding the PV latency.
-// TMEM columns: S0/P0 [0,128) | S1/P1 [128,256) | S2/P2 [256,384) | O [384,512).  P overwrites S in place: the warp that owns a
-// 32-column chunk of the scores holds them in registers and writes the chunk's hi (16 columns) and lo (16 columns)
-// bf16 pairs back over the same 32 columns, so the three score buffers double as P buffers (three, so that S(u+1)
-// never has to wait for the PV product of unit u-1 that still reads its buffer).
-// Shared memory holds only Q, K (double-buffered when it fits) and V tiles whose row counts follow the label count
-// (box rows = L rounded up to 8 / 16), e.g. L = 103: Q 52 KB + 2 x K 52 KB + V 56 KB.
+//              [rows x 64] bf16 boxes of the split-bf16 planes written by the projection GEMM.  K and V tiles go
+//              through ONE ring of `kv_slots` equal slots (K(u), V(u), K(u+1), ...), each slot with its own
+//              full/empty barrier, so a slot is refilled the moment the MMA that read it retires.
+//   warp 1   : MMA issuer   -- event driven: one thread polls (mbarrier.test_wait) the operands of the next S = Q K^T
+//              and of the next O (+)= P V and issues whichever is ready; S goes to one of two TMEM score buffers,
+//              O to one of two TMEM output buffers (item parity), so neither the next item's PV nor the next S ever
+//              waits for the epilogue.  P is read from TENSOR MEMORY (TS form), V is consumed MN-major straight from
+//              its natural [keys x d] layout (no transpose pass); 3-term split-bf16 products.
+//   warp 2   : output store -- one thread issues the TMA stores of the O tile staged in shared memory.
+//   warps 4.. : softmax     -- 4 * (BLOCK_KV/32) warps: TMEM lane == query row and every warp owns one 32-column
+//              chunk of the rows of its lane quarter.  Strided byte mask -> bit words via warp ballots, row max
+//              exchanged through smem, online max/sum across KV tiles with a LAZY rescale (the reference maximum only
+//              moves when it grew by more than 2^8, so the O accumulator is rarely touched and PV(u) does not
+//              serialise behind PV(u-1)), ex2, hi/lo split, P written back over S in TMEM.  The epilogue of the
+//              PREVIOUS item (1/sum, hi/lo split) runs after the current unit's P is published; it writes the tile
+//              in the 128B-swizzled box layout into a staging buffer from which warp 2 stores it with TMA
+//              (coalesced, asynchronous, rows >= L clipped by the tensor map).
+// TMEM columns: S0/P0 [0,128) | S1/P1 [128,256) | O0 [256,384) | O1 [384,512).  P overwrites S in place: the warp
+// that owns a 32-column chunk of the scores holds them in registers and writes the chunk's hi (16 columns) and lo
+// (16 columns) bf16 pairs back over the same 32 columns.
+// Shared memory: Q tile | O staging tile (same shape) | ring of K/V slots; tile rows follow the label count
+// (box rows = L rounded up to 8 / 16), e.g. L = 103: Q 52 KB + O 52 KB + 2 x 56 KB.
 // The label mask is read from its single [Lq, Lk] (or [B, Lk] key-padding) copy -- it is never tiled per head or
 // per sample (the reference materialises H*B*Lq*Lk bytes, lamp/SubLayers.py:102 / lamp/Decoders.py:141).
 #pragma once
@@ -41,13 +45,16 @@ struct AttnParams {
   int ldo;
   float* o_f32;  // optional fp32 copy, [B*Lq, ldof]
   int ldof;
-  float* row_max;  // optional [H*B*Lq] (head-major) running max of the SCALED (log2 domain) scores
-  float* row_sum;  // optional [H*B*Lq] softmax denominators
+  float* row_max;  // optional [H*B*Lq] (head-major) reference maximum of the SCALED (log2 domain) scores
+  float* row_sum;  // optional [H*B*Lq] softmax denominators (relative to row_max)
   int qrows, krows, vrows;  // TMA box rows of the Q / K / V tiles (multiples of 8 / 8 / 16)
   // Padding-aware keys (optional): the K/V matrix holds only the non-PAD tokens of the batch, packed; sample b owns
   // rows [kv_start[b], kv_start[b] + kv_len[b]).  Lk then only bounds the per-sample key count.
   const int* kv_start;
   const int* kv_len;
+  int kv_slots;         // K/V ring depth (2 .. ATTN_MAX_SLOTS)
+  uint32_t slot_bytes;  // bytes of one ring slot (fits a K tile and a V tile)
+  int staged;           // 1: O planes leave through the smem staging tile + TMA store (needs d % 64 == 0)
 };
 
 #ifdef LAMP_ATTN_TRACE
@@ -63,11 +70,14 @@ __device__ unsigned long long g_attn_trace[16][64];
 
 constexpr int ATTN_BLOCK_M = 128;
 constexpr uint32_t ATTN_TMEM_COLS = 512;
-constexpr uint32_t ATTN_TMEM_S = 0, ATTN_TMEM_O = 384;
-constexpr int ATTN_S_BUFS = 3;
+constexpr uint32_t ATTN_TMEM_S = 0, ATTN_TMEM_O = 256;
+constexpr int ATTN_MAX_SLOTS = 6;
+constexpr float ATTN_RESCALE_LOG2 = 8.0f;  // lazy rescale: P stays below 2^8, harmless for fp32 accumulation
 // row-statistics exchange between the column-warps of a row: max [2 units][NW][128] + sum [2 items][NW][128] floats
 constexpr uint32_t ATTN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
-__host__ __device__ constexpr int attn_threads(int block_kv) { return 64 + 128 * (block_kv / 32); }
+constexpr uint32_t ATTN_BAR_BYTES = 256;
+// warps 0..3: TMA producer, MMA issuer, output store, (idle); warps 4..: softmax (warp % 4 = TMEM lane quarter)
+__host__ __device__ constexpr int attn_threads(int block_kv) { return 128 + 128 * (block_kv / 32); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -77,17 +87,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // Shared-memory plan (bytes).  kb64 = ceil(d / 64) column blocks of 64 bf16 (= one 128 B swizzle row each).
 __host__ __device__ constexpr uint32_t attn_tile_bytes(int npl, int kb64, int rows) { return npl * kb64 * rows * 128; }
-__host__ __device__ constexpr uint32_t attn_smem_bytes(int npl, int kb64, int qrows, int krows, int vrows, int kst,
-                                                       int vst) {
-  return attn_tile_bytes(npl, kb64, qrows) + kst * attn_tile_bytes(npl, kb64, krows) +
-         vst * attn_tile_bytes(npl, kb64, vrows) + ATTN_RED_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr uint32_t attn_smem_bytes(uint32_t q_bytes, uint32_t slot_bytes, int slots, int staged) {
+  return q_bytes * (staged ? 2 : 1) + slots * slot_bytes + ATTN_RED_BYTES + 1024 /*align*/ + ATTN_BAR_BYTES;
 }
 
-template <int BLOCK_KV, int K_STAGES, int V_STAGES, int NTERMS>
+template <int BLOCK_KV, int NTERMS>
 __global__ void __launch_bounds__(attn_threads(BLOCK_KV), 1)
 attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
                  const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
                  const __grid_constant__ CUtensorMap tmV_hi, const __grid_constant__ CUtensorMap tmV_lo,
+                 const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                  const AttnParams p) {
   constexpr int NPL = (NTERMS == 3) ? 2 : 1;
   constexpr int NW = BLOCK_KV / 32;        // 32-column score chunks per row == softmax warps per lane quarter
@@ -96,31 +105,34 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kb64 = (p.d + 63) >> 6;
+  const int R = p.kv_slots;
   const uint32_t q_bytes = attn_tile_bytes(NPL, kb64, p.qrows);
   const uint32_t k_bytes = attn_tile_bytes(NPL, kb64, p.krows);
   const uint32_t v_bytes = attn_tile_bytes(NPL, kb64, p.vrows);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + q_bytes;              // K_STAGES buffers
-  uint8_t* sV = sK + K_STAGES * k_bytes;   // V_STAGES buffers
-  float* red_max = reinterpret_cast<float*>(sV + V_STAGES * v_bytes);  // [2][4][128]
-  float* red_l = red_max + 2 * 4 * 128;                                // [2][4][128]
+  uint8_t* sO = sQ + q_bytes;                          // staging tile, same geometry as Q (absent if !staged)
+  uint8_t* sKV = sO + (p.staged ? q_bytes : 0);        // ring of R slots
+  float* red_max = reinterpret_cast<float*>(sKV + R * p.slot_bytes);  // [2][4][128]
+  float* red_l = red_max + 2 * 4 * 128;                               // [2][4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_max) + ATTN_RED_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* p_full = bars + 2;   // count NSW
-  uint64_t* o_done = bars + 3;
-  uint64_t* s_full = bars + 4;   // [3]
-  uint64_t* s_free = bars + 7;   // [3]: score/P buffer released by the PV product that consumed it
-  uint64_t* k_full = bars + 10;  // [K_STAGES]
-  uint64_t* k_empty = bars + 10 + K_STAGES;
-  uint64_t* v_full = bars + 10 + 2 * K_STAGES;  // [V_STAGES]
-  uint64_t* v_empty = bars + 10 + 2 * K_STAGES + V_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * K_STAGES + 2 * V_STAGES);
+  uint64_t* s_full = bars + 2;     // [2] S(u) complete (tcgen05.commit)
+  uint64_t* s_free = bars + 4;     // [2] score/P buffer released by the PV product that consumed it
+  uint64_t* p_full = bars + 6;     // [2] P(u) published by the NSW softmax threads
+  uint64_t* pv_done = bars + 8;    // [2] PV(u) complete, indexed by unit parity
+  uint64_t* o_free = bars + 10;    // [2] O buffer (item parity) drained by the epilogue, count NSW
+  uint64_t* ostage_full = bars + 12;   // staging tile written, count NSW
+  uint64_t* ostage_free = bars + 13;   // TMA store has read the staging tile
+  uint64_t* kv_full = bars + 14;   // [ATTN_MAX_SLOTS]
+  uint64_t* kv_empty = bars + 14 + ATTN_MAX_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * ATTN_MAX_SLOTS);
 
   // plane pl (0 = hi, 1 = lo), 64-column block kb
   auto q_tile = [&](int pl, int kb) { return sQ + (pl * kb64 + kb) * (p.qrows * 128); };
-  auto k_tile = [&](int st, int pl, int kb) { return sK + st * k_bytes + (pl * kb64 + kb) * (p.krows * 128); };
-  auto v_tile = [&](int st, int pl, int kb) { return sV + st * v_bytes + (pl * kb64 + kb) * (p.vrows * 128); };
+  auto o_tile = [&](int pl, int kb) { return sO + (pl * kb64 + kb) * (p.qrows * 128); };
+  auto k_tile = [&](int slot, int pl, int kb) { return sKV + slot * p.slot_bytes + (pl * kb64 + kb) * (p.krows * 128); };
+  auto v_tile = [&](int slot, int pl, int kb) { return sKV + slot * p.slot_bytes + (pl * kb64 + kb) * (p.vrows * 128); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -134,21 +146,24 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       tma_prefetch_desc(&tmK_lo);
       tma_prefetch_desc(&tmV_lo);
     }
+    if (p.staged) {
+      tma_prefetch_desc(&tmO_hi);
+      if (NPL == 2) tma_prefetch_desc(&tmO_lo);
+    }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    mbar_init(p_full, NSW);
-    mbar_init(o_done, 1);
-    for (int i = 0; i < ATTN_S_BUFS; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 1);
+      mbar_init(&p_full[i], NSW);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_free[i], NSW);
     }
-    for (int i = 0; i < K_STAGES; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-    }
-    for (int i = 0; i < V_STAGES; ++i) {
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+    mbar_init(ostage_full, NSW);
+    mbar_init(ostage_free, 1);
+    for (int i = 0; i < ATTN_MAX_SLOTS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -178,7 +193,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      uint32_t it = 0, u = 0;  // per-CTA item / unit counters -> barrier stages and parities
+      uint32_t it = 0, u = 0;  // per-CTA item / unit counters -> ring positions and barrier parities
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int qt = item % num_qt;
         const int h = (item / num_qt) % p.H;
@@ -186,16 +201,16 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         int lk, kbase, kbatch, nkv;
         item_keys(b, lk, kbase, kbatch, nkv);
         for (int j = 0; j < nkv; ++j, ++u) {
-          const int kst = u % K_STAGES, vst = u % V_STAGES;
-          const uint32_t kpar = (u / K_STAGES) & 1, vpar = (u / V_STAGES) & 1;
+          const uint32_t kpos = 2 * u, vpos = 2 * u + 1;
+          const int ks = kpos % R, vs = vpos % R;
           const int krow = kbase + j * BLOCK_KV;
-          mbar_wait(&k_empty[kst], kpar ^ 1);
+          mbar_wait(&kv_empty[ks], ((kpos / R) & 1) ^ 1);
           ATTN_TRACE(0, u);
-          mbar_arrive_expect_tx(&k_full[kst], k_bytes);
+          mbar_arrive_expect_tx(&kv_full[ks], k_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(k_tile(kst, 0, kb), &tmK_hi, &k_full[kst], p.k_col0 + h * p.d + kb * 64, krow, kbatch);
+            tma_load_3d(k_tile(ks, 0, kb), &tmK_hi, &kv_full[ks], p.k_col0 + h * p.d + kb * 64, krow, kbatch);
             if (NPL == 2)
-              tma_load_3d(k_tile(kst, 1, kb), &tmK_lo, &k_full[kst], p.k_col0 + h * p.d + kb * 64, krow, kbatch);
+              tma_load_3d(k_tile(ks, 1, kb), &tmK_lo, &kv_full[ks], p.k_col0 + h * p.d + kb * 64, krow, kbatch);
           }
           if (j == 0) {
             mbar_wait(q_empty, (it & 1) ^ 1);
@@ -208,25 +223,24 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 tma_load_3d(q_tile(1, kb), &tmQ_lo, q_full, p.q_col0 + h * p.d + kb * 64, qt * ATTN_BLOCK_M, bq);
             }
           }
-          mbar_wait(&v_empty[vst], vpar ^ 1);
+          mbar_wait(&kv_empty[vs], ((vpos / R) & 1) ^ 1);
           ATTN_TRACE(2, u);
-          mbar_arrive_expect_tx(&v_full[vst], v_bytes);
+          mbar_arrive_expect_tx(&kv_full[vs], v_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
-            tma_load_3d(v_tile(vst, 0, kb), &tmV_hi, &v_full[vst], p.v_col0 + h * p.d + kb * 64, krow, kbatch);
+            tma_load_3d(v_tile(vs, 0, kb), &tmV_hi, &kv_full[vs], p.v_col0 + h * p.d + kb * 64, krow, kbatch);
             if (NPL == 2)
-              tma_load_3d(v_tile(vst, 1, kb), &tmV_lo, &v_full[vst], p.v_col0 + h * p.d + kb * 64, krow, kbatch);
+              tma_load_3d(v_tile(vs, 1, kb), &tmV_lo, &kv_full[vs], p.v_col0 + h * p.d + kb * 64, krow, kbatch);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+    // ---------------------------------------------------------------- MMA issuer (event driven)
     if (lane == 0) {
       const uint32_t idesc_o = umma_idesc_bf16(ATTN_BLOCK_M, p.d, 0, 1);  // A = P from TMEM, B = V MN-major
-      // (item, KV tile) iterator of this CTA; the S product runs one unit ahead of the PV product
       struct UnitIt {
         int item, j, nkv, lk;
-        uint32_t it;  // per-CTA item counter
+        uint32_t it, u;  // per-CTA item / unit counters
       };
       auto load_it = [&](UnitIt& x) {
         if (x.item < num_items) {
@@ -235,6 +249,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
       };
       auto advance = [&](UnitIt& x) {
+        ++x.u;
         if (++x.j == x.nkv) {
           x.j = 0;
           x.item += gridDim.x;
@@ -243,18 +258,14 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
       };
 
-      // S(u) = Q K_u^T into score buffer u % 3 (N = the tile's key count rounded up to 16)
-      auto issue_s = [&](const UnitIt& x, uint32_t u) {
-        const int kst = u % K_STAGES;
-        const uint32_t kpar = (u / K_STAGES) & 1;
-        const uint32_t sb = u % ATTN_S_BUFS;
+      // S(u) = Q K_u^T into score buffer u & 1 (N = the tile's key count rounded up to 16)
+      auto issue_s = [&](const UnitIt& x) {
+        const uint32_t u = x.u;
+        const int ks = (2 * u) % R;
+        const uint32_t sb = u & 1;
         int kvn = (min(BLOCK_KV, x.lk - x.j * BLOCK_KV) + 15) & ~15;
         if (kvn < 16) kvn = 16;
         const uint32_t idesc_s = umma_idesc_bf16(ATTN_BLOCK_M, kvn, 0, 0);
-        if (x.j == 0) mbar_wait(q_full, x.it & 1);
-        mbar_wait(&k_full[kst], kpar);
-        ATTN_TRACE(3, u);
-        mbar_wait(&s_free[sb], ((u / ATTN_S_BUFS) & 1) ^ 1);
         ATTN_TRACE(4, u);
         tcgen05_fence_after();
         const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128;
@@ -262,73 +273,120 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
           const int kb = t >> 2;
           const uint32_t koff = (t & 3) * 32;
           const uint64_t dq_hi = umma_smem_desc(smem_u32(q_tile(0, kb)) + koff, 16, 1024);
-          const uint64_t dk_hi = umma_smem_desc(smem_u32(k_tile(kst, 0, kb)) + koff, 16, 1024);
+          const uint64_t dk_hi = umma_smem_desc(smem_u32(k_tile(ks, 0, kb)) + koff, 16, 1024);
           umma_bf16_ss(tS, dq_hi, dk_hi, idesc_s, t != 0 ? 1u : 0u);
           if (NTERMS == 3) {
             const uint64_t dq_lo = umma_smem_desc(smem_u32(q_tile(1, kb)) + koff, 16, 1024);
-            const uint64_t dk_lo = umma_smem_desc(smem_u32(k_tile(kst, 1, kb)) + koff, 16, 1024);
+            const uint64_t dk_lo = umma_smem_desc(smem_u32(k_tile(ks, 1, kb)) + koff, 16, 1024);
             umma_bf16_ss(tS, dq_hi, dk_lo, idesc_s, 1u);
             umma_bf16_ss(tS, dq_lo, dk_hi, idesc_s, 1u);
           }
         }
         umma_commit(&s_full[sb]);
-        umma_commit(&k_empty[kst]);
+        umma_commit(&kv_empty[ks]);
         if (x.j == x.nkv - 1) umma_commit(q_empty);
       };
 
-      UnitIt cur{static_cast<int>(blockIdx.x), 0, 1, 0, 0u};
-      load_it(cur);
-      UnitIt nxt = cur;
-      if (cur.item < num_items) issue_s(nxt, 0);
-      for (uint32_t u = 0; cur.item < num_items; ++u) {
-        advance(nxt);
-        if (nxt.item < num_items) issue_s(nxt, u + 1);  // one unit ahead: overlaps the softmax of unit u
-        const int j = cur.j;
-        const int vst = u % V_STAGES;
-        const uint32_t vpar = (u / V_STAGES) & 1;
-        const uint32_t sb = u % ATTN_S_BUFS;
-        mbar_wait(p_full, u & 1);
-        ATTN_TRACE(5, u);
-        mbar_wait(&v_full[vst], vpar);
+      // O(item parity) (+)= P(u) V_u
+      auto issue_pv = [&](const UnitIt& x) {
+        const uint32_t u = x.u;
+        const int vs = (2 * u + 1) % R;
+        const uint32_t sb = u & 1;
         ATTN_TRACE(6, u);
         tcgen05_fence_after();
-        const int kv_valid = max(0, min(BLOCK_KV, cur.lk - j * BLOCK_KV));
+        const int kv_valid = max(0, min(BLOCK_KV, x.lk - x.j * BLOCK_KV));
         const int ksteps_kv = max(1, (kv_valid + 15) >> 4);
-        const uint32_t tO = tmem_base + ATTN_TMEM_O;
+        const uint32_t tO = tmem_base + ATTN_TMEM_O + (x.it & 1) * 128;
         const uint32_t tP = tmem_base + ATTN_TMEM_S + sb * 128;  // P lives where S(u) was
         for (int t = 0; t < ksteps_kv; ++t) {
           // A = P from TMEM: keys 16t..16t+15 sit in 32-column chunk t/2: hi pairs at +8*(t&1), lo pairs 16 further.
           // B = V MN-major: K (= key index) advances by 16 rows of 128 B, LBO = distance between the 64-wide d
           // blocks, SBO = 8 key rows.
           const uint32_t pa = tP + 32 * (t >> 1) + 8 * (t & 1);
-          const uint64_t dv_hi = umma_smem_desc(smem_u32(v_tile(vst, 0, 0)) + t * 2048, p.vrows * 128, 1024);
-          const uint32_t accum = (j != 0 || t != 0) ? 1u : 0u;
+          const uint64_t dv_hi = umma_smem_desc(smem_u32(v_tile(vs, 0, 0)) + t * 2048, p.vrows * 128, 1024);
+          const uint32_t accum = (x.j != 0 || t != 0) ? 1u : 0u;
           umma_bf16_ts(tO, pa, dv_hi, idesc_o, accum);
           if (NTERMS == 3) {
-            const uint64_t dv_lo = umma_smem_desc(smem_u32(v_tile(vst, 1, 0)) + t * 2048, p.vrows * 128, 1024);
+            const uint64_t dv_lo = umma_smem_desc(smem_u32(v_tile(vs, 1, 0)) + t * 2048, p.vrows * 128, 1024);
             umma_bf16_ts(tO, pa, dv_lo, idesc_o, 1u);
             umma_bf16_ts(tO, pa + 16, dv_hi, idesc_o, 1u);
           }
         }
-        umma_commit(o_done);
-        umma_commit(&v_empty[vst]);
-        umma_commit(&s_free[sb]);  // the score / P buffer may be overwritten by S(u + 3)
-        advance(cur);
+        umma_commit(&pv_done[sb]);
+        umma_commit(&kv_empty[vs]);
+        umma_commit(&s_free[sb]);  // the score / P buffer may be overwritten by S(u + 2)
+      };
+
+      UnitIt si{static_cast<int>(blockIdx.x), 0, 1, 0, 0u, 0u};
+      load_it(si);
+      UnitIt pi = si;
+      bool s_q = false, s_k = false, s_b = false;  // latched readiness of the next S: Q tile, K tile, score buffer
+      bool v_p = false, v_v = false, v_o = false;  // ... of the next PV: P published, V tile, O buffer
+      uint32_t idle = 0;
+      while (pi.item < num_items) {
+        bool progressed = false;
+        if (si.item < num_items) {
+          const uint32_t u = si.u, kpos = 2 * u;
+          if (!s_q) s_q = (si.j != 0) || mbar_test_wait(q_full, si.it & 1);
+          if (!s_k) s_k = mbar_test_wait(&kv_full[kpos % R], (kpos / R) & 1);
+          if (!s_b) s_b = mbar_test_wait(&s_free[u & 1], ((u >> 1) & 1) ^ 1);
+          if (s_q && s_k && s_b) {
+            issue_s(si);
+            advance(si);
+            s_q = s_k = s_b = false;
+            progressed = true;
+          }
+        }
+        {
+          const uint32_t u = pi.u, vpos = 2 * u + 1;
+          if (!v_p) v_p = mbar_test_wait(&p_full[u & 1], (u >> 1) & 1);
+          if (!v_v) v_v = mbar_test_wait(&kv_full[vpos % R], (vpos / R) & 1);
+          if (!v_o) v_o = (pi.j != 0) || mbar_test_wait(&o_free[pi.it & 1], ((pi.it >> 1) & 1) ^ 1);
+          if (v_p && v_v && v_o) {
+            issue_pv(pi);
+            advance(pi);
+            v_p = v_v = v_o = false;
+            progressed = true;
+          }
+        }
+        if (progressed) idle = 0;
+        else if (++idle > LAMP_WAIT_LIMIT) __trap();
       }
     }
-  } else {
-    // ---------------------------------------------------------------- softmax + epilogue (warps 2 .. 2+4*NW)
+  } else if (warp == 2) {
+    // ---------------------------------------------------------------- output store (TMA, from the staging tile)
+    if (lane == 0 && p.staged) {
+      uint32_t n = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
+        const int qt = item % num_qt;
+        const int h = (item / num_qt) % p.H;
+        const int b = item / (num_qt * p.H);
+        mbar_wait(ostage_full, n & 1);
+        for (int kb = 0; kb < kb64; ++kb) {
+          tma_store_3d(&tmO_hi, o_tile(0, kb), h * p.d + kb * 64, qt * ATTN_BLOCK_M, b);
+          if (NPL == 2 && p.o_lo != nullptr) tma_store_3d(&tmO_lo, o_tile(1, kb), h * p.d + kb * 64, qt * ATTN_BLOCK_M, b);
+        }
+        tma_store_commit();
+        tma_store_wait_read0();  // the staging tile may be overwritten
+        mbar_arrive(ostage_free);
+      }
+      tma_store_wait_all0();  // global writes complete before the CTA exits
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax + epilogue (warps 4 .. 4+4*NW)
     const int wq = warp & 3;           // TMEM lane quarter (hardware rule: warp_id % 4)
-    const int cw = (warp - 2) >> 2;    // 32-column chunk of the score tile owned by this warp
+    const int cw = (warp - 4) >> 2;    // 32-column chunk of the score tile owned by this warp
     const int row = wq * 32 + lane;    // row inside the q tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tO = tmem_base + ATTN_TMEM_O + lane_sel;
     const int ngroups = p.d >> 4;      // 16-column groups of O; group g belongs to column-warp g % NW
+    const bool tracer = (warp == 4 && lane == 0);
     uint32_t mw = 0;                   // mask bits of (row, this warp's 32 columns); bit set = masked
     long long mkey = -1;               // (b, qt, j) combination the word was built for
 
-    // O / l -> this head's column slice of the concatenated output.  Each thread writes full 32 B sectors.
-    auto epilogue = [&](int b, int h, int qt, int par, float m_run) {
+    // O / l of item `pit` -> this head's column slice of the concatenated output.
+    auto epilogue = [&](int b, int h, int qt, uint32_t pit, float m_run) {
+      const int par = pit & 1;
+      const uint32_t tO = tmem_base + ATTN_TMEM_O + par * 128 + lane_sel;
       float l_tot = 0.0f;
 #pragma unroll
       for (int c = 0; c < NW; ++c) l_tot += red_l[(par * 4 + c) * 128 + row];
@@ -336,14 +394,38 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       const int qrow = qt * ATTN_BLOCK_M + row;
       const bool row_ok = qrow < p.Lq;
       const size_t grow = static_cast<size_t>(b) * p.Lq + qrow;
+      if (p.staged) mbar_wait(ostage_free, (pit & 1) ^ 1);  // the previous item's TMA store has read the tile
       for (int g = cw; g < ngroups; g += NW) {
         uint32_t r[16];
         tmem_ld16(tO + 16 * g, r);
         tmem_wait_ld();
-        if (row_ok) {
-          float v[16];
+        float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) * inv;
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]) * inv;
+        uint4 hi[2], lo[2];
+        if (p.o_hi != nullptr) {
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            split_bf16x2(v[8 * q2 + 0], v[8 * q2 + 1], hi[q2].x, lo[q2].x);
+            split_bf16x2(v[8 * q2 + 2], v[8 * q2 + 3], hi[q2].y, lo[q2].y);
+            split_bf16x2(v[8 * q2 + 4], v[8 * q2 + 5], hi[q2].z, lo[q2].z);
+            split_bf16x2(v[8 * q2 + 6], v[8 * q2 + 7], hi[q2].w, lo[q2].w);
+          }
+        }
+        if (p.staged) {
+          // 128B-swizzled box layout: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+          if (row < p.qrows) {
+            const int kb = g >> 2, c0 = (g & 3) * 2, sw = row & 7;
+            uint8_t* th = o_tile(0, kb) + row * 128;
+            *reinterpret_cast<uint4*>(th + ((c0 ^ sw) << 4)) = hi[0];
+            *reinterpret_cast<uint4*>(th + (((c0 + 1) ^ sw) << 4)) = hi[1];
+            if (NPL == 2) {
+              uint8_t* tl = o_tile(1, kb) + row * 128;
+              *reinterpret_cast<uint4*>(tl + ((c0 ^ sw) << 4)) = lo[0];
+              *reinterpret_cast<uint4*>(tl + (((c0 + 1) ^ sw) << 4)) = lo[1];
+            }
+          }
+        } else if (row_ok) {
           const int col = h * p.d + 16 * g;
           if (p.o_f32 != nullptr) {
             float4* o = reinterpret_cast<float4*>(p.o_f32 + grow * p.ldof + col);
@@ -351,14 +433,6 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             for (int e = 0; e < 4; ++e) o[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
           }
           if (p.o_hi != nullptr) {
-            uint4 hi[2], lo[2];
-#pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2) {
-              split_bf16x2(v[8 * q2 + 0], v[8 * q2 + 1], hi[q2].x, lo[q2].x);
-              split_bf16x2(v[8 * q2 + 2], v[8 * q2 + 3], hi[q2].y, lo[q2].y);
-              split_bf16x2(v[8 * q2 + 4], v[8 * q2 + 5], hi[q2].z, lo[q2].z);
-              split_bf16x2(v[8 * q2 + 6], v[8 * q2 + 7], hi[q2].w, lo[q2].w);
-            }
             uint4* oh = reinterpret_cast<uint4*>(p.o_hi + grow * p.ldo + col);
             oh[0] = hi[0];
             oh[1] = hi[1];
@@ -369,6 +443,12 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             }
           }
         }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&o_free[par]);  // this thread's part of the O buffer has been read
+      if (p.staged) {
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+        mbar_arrive(ostage_full);
       }
       if (cw == 0 && row_ok && p.row_sum != nullptr) {
         const size_t si = (static_cast<size_t>(h) * p.B + b) * p.Lq + qrow;
@@ -385,12 +465,13 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       const int qt = item % num_qt;
       const int h = (item / num_qt) % p.H;
       const int b = item / (num_qt * p.H);
-      float m_run = -INFINITY, l_part = 0.0f;
+      const uint32_t tO = tmem_base + ATTN_TMEM_O + (it & 1) * 128 + lane_sel;
+      float m_run = -INFINITY, l_part = 0.0f;  // m_run: the reference maximum the exponentials are taken against
       int lk, kbase, kbatch_unused, nkv;
       item_keys(b, lk, kbase, kbatch_unused, nkv);
       for (int j = 0; j < nkv; ++j, ++u) {
         const int k0 = j * BLOCK_KV + 32 * cw;  // first key column of this warp's chunk
-        const uint32_t sb = u % ATTN_S_BUFS;
+        const uint32_t sb = u & 1;
         const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128 + lane_sel + 32 * cw;
         // ---- mask word for (row, this chunk); cached while the addressed mask region is unchanged.  For a
         //      key-padding mask (query stride 0: one byte per key, new every sample) the byte load is issued here and
@@ -424,8 +505,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             }
           }
         }
-        mbar_wait(&s_full[sb], (u / ATTN_S_BUFS) & 1);
-        if (warp == 2 && lane == 0) ATTN_TRACE(7, u);
+        mbar_wait(&s_full[sb], (u >> 1) & 1);
+        if (tracer) ATTN_TRACE(7, u);
         tcgen05_fence_after();
         // ---- pass 1: masked scores of this chunk stay in registers; chunk max -> smem -> row max
         uint32_t r[32];
@@ -442,15 +523,19 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         float* rm = red_max + (u & 1) * (4 * 128);
         rm[cw * 128 + row] = mx;
         named_bar_sync(1, NSW);
-        if (warp == 2 && lane == 0) ATTN_TRACE(8, u);
+        if (tracer) ATTN_TRACE(8, u);
 #pragma unroll
         for (int c = 0; c < NW; ++c) mx = fmaxf(mx, rm[c * 128 + row]);
-        const float m_new = fmaxf(m_run, mx);
+        // ---- lazy reference maximum: move it only when the tile maximum exceeds it by more than 2^8 (or on the
+        //      first finite score).  The decision depends on the row only, so the NW column-warps of a row agree.
+        const bool move = (j == 0) || ((mx - m_run) * p.scale_log2 > ATTN_RESCALE_LOG2);
+        const float m_new = move ? fmaxf(m_run, mx) : m_run;
         const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2_approx((m_run - m_new) * p.scale_log2);
-        // ---- multi-tile rows: the previous PV must have retired before the partial output is rescaled
-        if (j > 0) {
-          mbar_wait(o_done, (u - 1) & 1);
+        const float alpha = (!move || m_new == -INFINITY) ? 1.0f : ex2_approx((m_run - m_new) * p.scale_log2);
+        // ---- multi-tile rows whose reference moved: the previous PV must have retired before the partial output
+        //      is rescaled (warp-collective TMEM access -> the whole warp takes part when any row needs it)
+        if (j > 0 && __any_sync(0xFFFFFFFFu, alpha != 1.0f)) {
+          mbar_wait(&pv_done[(u - 1) & 1], ((u - 1) >> 1) & 1);
           tcgen05_fence_after();
           for (int g = cw; g < ngroups; g += NW) {
             uint32_t o[16];
@@ -478,28 +563,26 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         m_run = m_new;
         if (j == nkv - 1) red_l[((it & 1) * 4 + cw) * 128 + row] = l_part;  // read after the next unit's barrier
         tmem_wait_st();
-        if (warp == 2 && lane == 0) ATTN_TRACE(9, u);
+        if (tracer) ATTN_TRACE(9, u);
         tcgen05_fence_before();
-        // ---- deferred epilogue of the previous item: its O is complete once its last PV retired and is only
-        //      overwritten by the PV of THIS unit, which cannot start before the p_full arrival below
+        mbar_arrive(&p_full[sb]);
+        // ---- deferred epilogue of the previous item (its O buffer is the other one): overlaps PV(u)
         if (j == 0 && have_prev) {
-          mbar_wait(o_done, (u - 1) & 1);
-          if (warp == 2 && lane == 0) ATTN_TRACE(10, u);
+          mbar_wait(&pv_done[(u - 1) & 1], ((u - 1) >> 1) & 1);
+          if (tracer) ATTN_TRACE(10, u);
           tcgen05_fence_after();
-          epilogue(pb, ph, pqt, (it & 1) ^ 1, pm);
-          tcgen05_fence_before();
+          epilogue(pb, ph, pqt, it - 1, pm);
+          if (tracer) ATTN_TRACE(11, u);
         }
-        if (warp == 2 && lane == 0) ATTN_TRACE(11, u);
-        mbar_arrive(p_full);
       }
       have_prev = true;
       pb = b; ph = h; pqt = qt; pm = m_run;
     }
     if (have_prev) {
       named_bar_sync(1, NSW);  // make the last item's row sums visible
-      mbar_wait(o_done, (u - 1) & 1);
+      mbar_wait(&pv_done[(u - 1) & 1], ((u - 1) >> 1) & 1);
       tcgen05_fence_after();
-      epilogue(pb, ph, pqt, (it & 1) ^ 1, pm);
+      epilogue(pb, ph, pqt, it - 1, pm);
     }
   }
 

@@ -167,32 +167,44 @@ int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensor
 std::atomic<int> g_gemm_block_k{0};   // tuning knob (lamp_set_tuning): 32 -> 64B swizzle / deep ring, 64 -> 128B swizzle,
                                       // 0 -> automatic (64 for CTA pairs: 3 x 64 KB stages; 32 otherwise: 4 x 48 KB)
 std::atomic<int> g_attn_compact{1};   // tuning knob: 1 -> L-dependent tile rows + deepest K/V staging that fits, 0 -> full 128-row tiles, 1 stage
+std::atomic<int> g_attn_stage{1};     // tuning knob: 1 -> O planes leave through the smem staging tile + TMA stores when it fits
 std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group::2) for the 256-wide tiles, 0 -> single CTAs
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB: the sm_100 per-CTA opt-in maximum
 
-template <int BLOCK_KV, int K_STAGES, int V_STAGES, int NTERMS>
-int launch_attn(const CUtensorMap (&tm)[6], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st) {
-  auto kernel = attn_core_kernel<BLOCK_KV, K_STAGES, V_STAGES, NTERMS>;
+template <int BLOCK_KV, int NTERMS>
+int launch_attn(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st) {
+  auto kernel = attn_core_kernel<BLOCK_KV, NTERMS>;
   static std::once_flag once;
   static int once_rc = LAMP_OK;
   std::call_once(once, [kernel] { once_rc = set_smem(kernel, kMaxDynSmem); });
   if (once_rc != LAMP_OK) return once_rc;
   const int items = p.B * p.H * ((p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M);
   const int grid = items < sm_count_cached() ? items : sm_count_cached();
-  kernel<<<grid, attn_threads(BLOCK_KV), smem_bytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+  kernel<<<grid, attn_threads(BLOCK_KV), smem_bytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], p);
   return launch_check();
 }
 
+// Shared-memory plan: Q tile (+ an equally shaped O staging tile when the planes leave through TMA stores) + as many
+// K/V ring slots as fit.  Staging is used when it still leaves >= 3 slots, or 2 for single-tile problems (one K and
+// one V slot in flight is all such an item has).
 template <int BLOCK_KV, int NTERMS>
-int launch_attn_stages(const CUtensorMap (&tm)[6], const AttnParams& p, cudaStream_t st) {
+int launch_attn_plan(const CUtensorMap (&tm)[8], AttnParams& p, bool can_stage, cudaStream_t st) {
   const int npl = NTERMS == 3 ? 2 : 1, kb64 = (p.d + 63) / 64;
-  auto need = [&](int ks, int vs) { return attn_smem_bytes(npl, kb64, p.qrows, p.krows, p.vrows, ks, vs); };
-  const bool deep = g_attn_compact.load() != 0;
-  if (deep && need(2, 2) <= kMaxDynSmem) return launch_attn<BLOCK_KV, 2, 2, NTERMS>(tm, p, need(2, 2), st);
-  if (deep && need(2, 1) <= kMaxDynSmem) return launch_attn<BLOCK_KV, 2, 1, NTERMS>(tm, p, need(2, 1), st);
-  if (need(1, 1) <= kMaxDynSmem) return launch_attn<BLOCK_KV, 1, 1, NTERMS>(tm, p, need(1, 1), st);
-  return fail(LAMP_EINVAL, "attn: tile does not fit shared memory");
+  const uint32_t q_bytes = attn_tile_bytes(npl, kb64, p.qrows);
+  p.slot_bytes = attn_tile_bytes(npl, kb64, p.krows > p.vrows ? p.krows : p.vrows);
+  auto slots_for = [&](int staged) {
+    const uint32_t fixed = attn_smem_bytes(q_bytes, p.slot_bytes, 0, staged);
+    if (fixed >= kMaxDynSmem) return 0;
+    const int n = (int)((kMaxDynSmem - fixed) / p.slot_bytes);
+    return n > ATTN_MAX_SLOTS ? ATTN_MAX_SLOTS : n;
+  };
+  const bool single = p.Lk <= BLOCK_KV;
+  const int ns = can_stage && g_attn_stage.load() ? slots_for(1) : 0;
+  p.staged = (ns >= 3 || (single && ns >= 2)) ? 1 : 0;
+  p.kv_slots = p.staged ? ns : slots_for(0);
+  if (p.kv_slots < 2) return fail(LAMP_EINVAL, "attn: tile does not fit shared memory");
+  return launch_attn<BLOCK_KV, NTERMS>(tm, p, attn_smem_bytes(q_bytes, p.slot_bytes, p.kv_slots, p.staged), st);
 }
 
 inline size_t align_up(size_t x, size_t a = 1024) { return (x + a - 1) / a * a; }
@@ -224,6 +236,10 @@ int lamp_set_tuning(int key, int value) {
   }
   if (key == LAMP_TUNE_ATTN_COMPACT && (value == 0 || value == 1)) {
     g_attn_compact.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_ATTN_STAGE && (value == 0 || value == 1)) {
+    g_attn_stage.store(value);
     return LAMP_OK;
   }
   if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
@@ -375,7 +391,7 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   const int qrows = compact ? round_up(Lq < ATTN_BLOCK_M ? Lq : ATTN_BLOCK_M, 8) : ATTN_BLOCK_M;
   const int krows = (multi || !compact) ? block_kv : round_up(Lk, 8);
   const int vrows = (multi || !compact) ? block_kv : round_up(Lk, 16);  // PV consumes keys in steps of 16; TMA zero-fills rows >= Lk
-  CUtensorMap tm[6];
+  CUtensorMap tm[8];
   if (int rc = make_tmap(&tm[0], q_hi, (uint64_t)ldq, Lq, q_bcast ? 1 : B, ldq, qrows, true)) return rc;
   const uint64_t kv_tm_rows = kv_len ? (uint64_t)kv_rows : (uint64_t)Lk;  // packed keys: one long row dimension
   const uint64_t kv_tm_batch = kv_len ? 1 : (uint64_t)B;
@@ -390,6 +406,19 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
     tm[3] = tm[2];
     tm[5] = tm[4];
   }
+  // output planes as TMA-store targets: {ldo cols, Lq, B}; rows >= Lq and nothing else are clipped
+  const bool can_stage = o_hi != nullptr && o_f32 == nullptr && d % 64 == 0 && (!three || o_lo != nullptr);
+  if (can_stage) {
+    if (int rc = make_tmap(&tm[6], o_hi, (uint64_t)ldo, Lq, B, ldo, qrows, true)) return rc;
+    if (three) {
+      if (int rc = make_tmap(&tm[7], o_lo, (uint64_t)ldo, Lq, B, ldo, qrows, true)) return rc;
+    } else {
+      tm[7] = tm[6];
+    }
+  } else {
+    tm[6] = tm[0];
+    tm[7] = tm[0];
+  }
   AttnParams p;
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.d = d;
   p.scale_log2 = 1.4426950408889634f / temperature;
@@ -403,8 +432,10 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   p.kv_start = kv_start; p.kv_len = kv_len;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (block_kv == 128) rc = three ? launch_attn_stages<128, 3>(tm, p, st) : launch_attn_stages<128, 1>(tm, p, st);
-  else rc = three ? launch_attn_stages<64, 3>(tm, p, st) : launch_attn_stages<64, 1>(tm, p, st);
+  if (block_kv == 128)
+    rc = three ? launch_attn_plan<128, 3>(tm, p, can_stage, st) : launch_attn_plan<128, 1>(tm, p, can_stage, st);
+  else
+    rc = three ? launch_attn_plan<64, 3>(tm, p, can_stage, st) : launch_attn_plan<64, 1>(tm, p, can_stage, st);
   if (rc != LAMP_OK) return rc;
   if (probs) {
     ProbsParams pp;

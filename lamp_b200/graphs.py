@@ -1,0 +1,72 @@
+"""CUDA-graph replay of the label-graph forward for serving-style inference.
+
+``LAMP.forward`` (lamp/Models.py:110-137) enqueues ~40 native kernels plus a handful of index computations per
+call; at a few milliseconds of GPU work per batch the Python launch path is of the same order and is exposed to host
+jitter.  The whole eval forward is shape-static for a fixed ``(batch, seq_len)`` -- the only data-dependent
+quantity, the number of non-PAD token rows of the packed batch, lives in a device scalar read by the kernels
+(``m_dev``) -- so it can be captured once and replayed with one launch per step.
+
+    runner = lamp_b200.GraphedForward(model, batch=1100, seq_len=300)
+    logits, enc_output = runner(src_seq, src_pos)      # host (pinned) or device int64 tensors, [batch, seq_len]
+
+The returned tensors are the graph's static output buffers: they are overwritten by the next call (``.clone()``
+to keep them).  The captured forward is the module's own fused path, so results are identical to the eager call.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nat
+
+
+class GraphedForward:
+    def __init__(self, model, batch: int, seq_len: int, device=None, warmup: int = 2, example=None):
+        """``example``: optional ``(src_seq, src_pos)`` used for the warm-up / capture runs (any valid ids; defaults
+        to a full-length batch of token id 4)."""
+        if model.training:
+            raise RuntimeError('GraphedForward captures the eval forward: call model.eval() first')
+        p = next(model.parameters())
+        nat.require_cuda(p)
+        self.model = model
+        self.device = torch.device(device) if device is not None else p.device
+        self.batch, self.seq_len = batch, seq_len
+        self.src_seq = torch.empty((batch, seq_len), dtype=torch.int64, device=self.device)
+        self.src_pos = torch.empty((batch, seq_len), dtype=torch.int64, device=self.device)
+        if example is not None:
+            self.src_seq.copy_(example[0])
+            self.src_pos.copy_(example[1])
+        else:
+            self.src_seq.fill_(4)
+            self.src_pos.copy_(torch.arange(1, seq_len + 1, device=self.device).expand(batch, seq_len))
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):  # weight planes, smem attributes, allocator pools: all outside the graph
+                model((self.src_seq, self.src_pos), None, None, None)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        from . import ops
+        n0 = ops.STATS.launches
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            logits, enc_output, *_ = model((self.src_seq, self.src_pos), None, None, None)
+        self.kernels_per_replay = ops.STATS.launches - n0   # native kernel launches captured in the graph
+        self.logits, self.enc_output = logits, enc_output
+
+    def load(self, src_seq: torch.Tensor, src_pos: torch.Tensor) -> None:
+        """Copy a batch of token / position ids into the graph's input buffers (H2D when they live on the host)."""
+        if tuple(src_seq.shape) != (self.batch, self.seq_len) or tuple(src_pos.shape) != (self.batch, self.seq_len):
+            raise RuntimeError(f'GraphedForward was captured for [{self.batch}, {self.seq_len}] inputs, got '
+                               f'{tuple(src_seq.shape)} / {tuple(src_pos.shape)}')
+        self.src_seq.copy_(src_seq, non_blocking=True)
+        self.src_pos.copy_(src_pos, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        from . import ops
+        ops.STATS.launches += self.kernels_per_replay
+        return self.logits, self.enc_output
+
+    def __call__(self, src_seq: torch.Tensor, src_pos: torch.Tensor):
+        self.load(src_seq, src_pos)
+        return self.replay()

@@ -2,9 +2,9 @@
 """Pipeline timeline of the attention core (debug build with -DLAMP_ATTN_TRACE): clock64() stamps of CTA 0 for the
 first 64 units of one launch, printed relative to the first stamp.  usage: python scripts/attn_trace.py [self|enc]
 
-Events: 0 K load issued | 1 Q load issued | 2 V load issued | 3 Q,K landed (MMA warp) | 4 S issued | 5 P ready seen by
-MMA warp | 6 V landed -> PV issued | 7 S complete seen by softmax | 8 row-max barrier passed | 9 P stored |
-10 previous O complete (epilogue starts) | 11 epilogue done (p_full arrive)."""
+Events: 0 K load issued | 1 Q load issued | 2 V load issued | 4 S issued (operands landed, score buffer free) |
+6 PV issued (P published, V landed, O buffer free) | 7 S complete seen by softmax | 8 row-max barrier passed |
+9 P stored | 10 previous item's O complete (epilogue starts) | 11 epilogue done (tracer warp)."""
 import ctypes as C
 import os
 import sys
@@ -23,7 +23,7 @@ nat.LIB_PATH = TRACE_LIB
 from lamp_b200 import ops  # noqa: E402
 
 DEV = 'cuda'
-NAMES = ['Kld', 'Qld', 'Vld', 'QKin', 'Siss', 'Pseen', 'PViss', 'Sdone', 'maxbar', 'Pst', 'Odone', 'epiend']
+NAMES = ['Kld', 'Qld', 'Vld', '-', 'Siss', '-', 'PViss', 'Sdone', 'maxbar', 'Pst', 'Odone', 'epiend']
 
 
 def main():
@@ -44,7 +44,7 @@ def main():
         qc, kc, vc = 0, 0, hd
         mask = (torch.rand(B, 1, Lk, device=DEV) < 0.3)
         mask[:, :, 0] = False
-    for _ in range(3):
+    for _ in range(300):  # long enough for the clocks to settle
         ops.attention(q, qc, kv, kc, vc, B, H, Lq, Lk, d, prec, mask, False)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -70,18 +70,18 @@ def main():
     def gap(a, b, shift=0):
         v = [t[b][u + shift] - t[a][u] for u in us if t[a][u] and t[b][u + shift]]
         return sum(v) / max(len(v), 1)
-    print(f'K load issue -> Q,K landed (same unit): {gap(0, 3):.0f}')
+    print(f'K load issue -> S issue (same unit):    {gap(0, 4):.0f}')
+    print(f'K load issue -> Q load issue:           {gap(0, 1):.0f}')
     print(f'V load issue -> PV issue (same unit):   {gap(2, 6):.0f}')
+    print(f'V load issue(u) -> K load issue(u+1):   {gap(2, 0, 1):.0f}')
     print(f'S issued -> S complete seen:            {gap(4, 7):.0f}')
     print(f'S complete -> max barrier:              {gap(7, 8):.0f}')
     print(f'max barrier -> P stored:                {gap(8, 9):.0f}')
+    print(f'P stored -> PV issue:                   {gap(9, 6):.0f}')
     print(f'P stored -> prev O done seen:           {gap(9, 10):.0f}')
-    print(f'epilogue:                               {gap(10, 11):.0f}')
-    print(f'epilogue end -> P seen by MMA:          {gap(11, 5):.0f}')
-    print(f'P seen -> PV issue (wait V):            {gap(5, 6):.0f}')
+    print(f'epilogue (tracer warp):                 {gap(10, 11):.0f}')
     print(f'PV issue(u) -> O done seen (u+1):       {gap(6, 10, 1):.0f}')
     print(f'PV issue(u) -> V load issue (u+1):      {gap(6, 2, 1):.0f}')
-
 
 if __name__ == '__main__':
     main()

@@ -360,3 +360,58 @@ def test_error_codes_not_exceptions():
     rc = L.lamp_mha_fwd(x.data_ptr(), None, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, x.data_ptr(), x.data_ptr(),
                         None, 0, 0, 0, x.data_ptr(), None, 1, 4, 4, 8, 2, 4, 0, 1e-5, None, 0, nat.stream())
     assert rc == -1  # fc weight missing with n_head > 1
+
+
+@pytest.mark.parametrize('B,H,Lq,Lk,d,maskkind', [
+    (5, 4, 103, 103, 128, 'label'),   # bench shape: single KV tile, staged TMA-store epilogue
+    (3, 2, 103, 300, 128, 'pad'),     # label<-input: 64-key tiles through a 3-slot ring
+    (2, 8, 159, 159, 64, 'none'),     # cfg-3 dims: two q tiles, two KV tiles of 128
+    (2, 2, 300, 520, 64, 'label'),    # long rows: the lazy reference maximum is exercised over 5 tiles
+    (40, 4, 103, 103, 128, 'label'),  # more items than SMs (persistent loop, O / staging buffers reused)
+])
+@pytest.mark.parametrize('growth', [0.0, 3.0])
+def test_attn_core_planes_epilogues_and_lazy_rescale(B, H, Lq, Lk, d, maskkind, growth):
+    """lamp_attn_core_planes (A1, lamp/SubLayers.py:27-43) on plane operands: the staged (TMA store) and the direct
+    epilogue agree with an fp64 softmax(QK^T/temperature)V of the same operands, also when the scores grow along the
+    key axis so that the running maximum moves by far more (and by far less) than the lazy-rescale threshold."""
+    from lamp_b200 import ops
+    g = torch.Generator().manual_seed(B * 7 + Lq + Lk + d + int(growth))
+    hd = H * d
+    q = torch.randn(B * Lq, hd, generator=g)
+    kv = torch.randn(B * Lk, 2 * hd, generator=g)
+    if growth:
+        ramp = 1.0 + growth * torch.arange(Lk, dtype=torch.float32) / Lk   # later keys score higher
+        kv[:, :hd] *= ramp.repeat(B)[:, None]
+    mask = None
+    if maskkind == 'label':
+        m = torch.rand(Lq, Lk, generator=g) < 0.6
+        m[torch.arange(Lq), torch.arange(Lq) % Lk] = False
+        mask = m.unsqueeze(0)
+    elif maskkind == 'pad':
+        lens = torch.randint(1, Lk + 1, (B,), generator=g)
+        mask = (torch.arange(Lk)[None, :] >= lens[:, None]).unsqueeze(1)
+    qa = ops.Act(None, *ops.split(q.to(DEV), 0), B * Lq, hd)
+    kva = ops.Act(None, *ops.split(kv.to(DEV), 0), B * Lk, 2 * hd)
+    # fp64 reference on the operands as the kernel sees them (hi + lo)
+    qd = (qa.hi.double() + qa.lo.double()).view(B, Lq, H, d).permute(0, 2, 1, 3)
+    kd = (kva.hi.double() + kva.lo.double())[:, :hd].reshape(B, Lk, H, d).permute(0, 2, 1, 3)
+    vd = (kva.hi.double() + kva.lo.double())[:, hd:].reshape(B, Lk, H, d).permute(0, 2, 1, 3)
+    s = qd @ kd.transpose(-1, -2) / float(np.power(d, 0.5))
+    if mask is not None:
+        s = s.masked_fill(mask.to(DEV)[:, None].expand(B, H, Lq, Lk) if mask.shape[0] == B
+                          else mask.to(DEV)[None].expand(B, H, Lq, Lk), float('-inf'))
+    ref = (torch.softmax(s, -1) @ vd).permute(0, 2, 1, 3).reshape(B * Lq, hd)
+    outs = []
+    try:
+        for stage in (1, 0):
+            nat.check(nat.lib().lamp_set_tuning(4, stage), 'tune')
+            o, _ = ops.attention(qa, 0, kva, 0, hd, B, H, Lq, Lk, d, 0, None if mask is None else mask.to(DEV), False)
+            torch.cuda.synchronize()
+            out = o.hi.float() + o.lo.float()
+            e = rel_err(out, ref)
+            print(f'attn planes B={B} H={H} Lq={Lq} Lk={Lk} d={d} {maskkind} growth={growth} stage={stage}: {e:.2e}')
+            assert e < 2e-5
+            outs.append(out)
+    finally:
+        nat.check(nat.lib().lamp_set_tuning(4, 1), 'tune')
+    assert torch.equal(outs[0], outs[1])   # same arithmetic, only the way out of the SM differs

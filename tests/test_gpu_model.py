@@ -251,3 +251,33 @@ def test_padding_aware_path_equals_dense_path_and_oracle():
     with torch.no_grad():
         l2, _, enc_attns, dec_rest = model(src, None, None, None, return_attns=True)
     assert rel_err(l2, ref_logits) < TOL
+
+
+def test_graphed_forward_replays_equal_eager_for_new_batches():
+    """GraphedForward (CUDA-graph replay of LAMP.forward): replaying with NEW token ids -- different padding, hence a
+    different device-side packed row count -- gives bit-identical logits / enc_output to the eager call."""
+    import lamp_b200
+    c = dict(cases.MODEL_CASES['lamp_L37_none'], B=6)
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    model = build_model(c, p, adj)
+    runner = lamp_b200.GraphedForward(model, batch=src_seq.shape[0], seq_len=src_seq.shape[1])
+    assert runner.kernels_per_replay > 10
+    g = torch.Generator().manual_seed(3)
+    for trial in range(3):
+        seq, pos = src_seq.clone(), src_pos.clone()
+        if trial:
+            for b in range(seq.shape[0]):  # new lengths and ids
+                n = int(torch.randint(1, seq.shape[1] + 1, (1,), generator=g))
+                seq[b, :n] = torch.randint(4, c['V'] + 4, (n,), generator=g)
+                pos[b, :n] = torch.arange(1, n + 1)
+                seq[b, n:] = 0
+                pos[b, n:] = 0
+        with torch.no_grad():
+            ref_logits, ref_enc, _ = model((seq.to(DEV), pos.to(DEV)), None, None, None)
+        src = (seq.pin_memory(), pos.pin_memory()) if trial == 1 else (seq.to(DEV), pos.to(DEV))
+        logits, enc = runner(*src)
+        torch.cuda.synchronize()
+        assert torch.equal(logits, ref_logits), trial
+        assert torch.equal(enc, ref_enc), trial
+    with pytest.raises(RuntimeError):
+        runner(src_seq[:2].to(DEV), src_pos[:2].to(DEV))
