@@ -82,6 +82,42 @@ int lamp_gemm_ln_planes(const void* a_hi, const void* a_lo, int64_t lda, const v
                         int64_t ldr, int resid_mod, const float* gamma, const float* beta, float eps, float* out_f32,
                         int64_t ldo, void* out_hi, void* out_lo, int64_t ldp, void* stream);
 
+/* ---- deferred LayerNorm.  Between two GEMMs the LayerNorm of lamp/SubLayers.py:117 / :141 need not run as a pass of
+ * its own: the producing GEMM writes the PRE-norm tensor y as planes together with per-row partial sums
+ * {sum y, sum y^2} ("row stats", float2 [rows][nparts], nparts = lamp_gemm_stats_parts(N)), and every consumer applies
+ * the normalisation itself.  Results equal LayerNorm(y)*gamma+beta up to fp32 rounding (variance as E[y^2]-mean^2). */
+int lamp_gemm_stats_parts(int N);
+
+/* Consumer, A operand:  C = LayerNorm_gamma,beta(y) W^T (+bias) (ReLU) -> planes, computed as
+ * rstd*(y Wg^T - mean*colsum) + biasf with Wg = W*diag(gamma) given as the weight planes, colsum[n] = sum_k Wg[n,k]
+ * and biasf[n] = bias[n] + sum_k beta[k] W[n,k] (both folded by the caller once per weight version).  The LayerNorm
+ * width is K. */
+int lamp_gemm_planes_dln(const void* y_hi, const void* y_lo, int64_t lda, const float* a_stats, int a_nparts,
+                         float a_eps, const void* wg_hi, const void* wg_lo, int64_t ldw, const float* colsum,
+                         const float* biasf, int M, int N, int K, int precision, int relu, void* out_hi, void* out_lo,
+                         int64_t ldp, const int32_t* m_dev, void* stream);
+
+/* Producer:  y = A W^T (+bias) + residual -> planes + row stats of y (stats_out: float2 [M][lamp_gemm_stats_parts(N)]).
+ * The residual is fp32 (`residual`, rows modulo resid_mod when > 0), plain planes (res_hi/res_lo), or -- with r_stats
+ * -- itself a deferred LayerNorm of width N: planes of the pre-norm tensor, normalised element-wise with r_gamma /
+ * r_beta / r_eps while it is added. */
+int lamp_gemm_planes_rstats(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                            int64_t ldw, int M, int N, int K, int precision, const float* bias, const float* residual,
+                            const void* res_hi, const void* res_lo, int64_t ldr, int resid_mod, const float* r_stats,
+                            int r_nparts, float r_eps, const float* r_gamma, const float* r_beta, void* out_hi,
+                            void* out_lo, int64_t ldp, float* stats_out, const int32_t* m_dev, void* stream);
+
+/* Materialise a deferred LayerNorm: out[r,:] = LayerNorm(y[index ? index[r] : r, :])*gamma+beta as fp32 and/or planes
+ * (with `index` also the un-packing gather of the encoder output). */
+int lamp_ln_apply(const void* y_hi, const void* y_lo, const float* stats, int nparts, const float* gamma,
+                  const float* beta, float eps, int64_t rows, int D, const int64_t* index, float* out, void* out_hi,
+                  void* out_lo, const int32_t* m_dev, void* stream);
+
+/* lamp_diag_proj on a deferred LayerNorm: logits[b,l] = <LayerNorm(y[b,l,:])*gamma+beta, W[l,:]> (+bias[l]). */
+int lamp_diag_proj_ln(const void* y_hi, const void* y_lo, const float* stats, int nparts, const float* gamma,
+                      const float* beta, float eps, const float* W, const float* bias, int64_t B, int L, int D,
+                      float* logits, void* stream);
+
 /* Masked softmax attention over label nodes for B samples x H heads (lamp/SubLayers.py:27-43 with the head
  * split/merge of :96-107 folded into the addressing).  Q planes: [B*Lq (or Lq if q_bcast), ldq], head h at
  * columns q_col0 + h*d; K/V planes: [B*Lk, ldkv] at k_col0 / v_col0 + h*d.  mask: NULL or bytes (non-zero =

@@ -91,7 +91,7 @@ class GraphDecoder(nn.Module):
         return out, int_outs, slf_attns, enc_attns
 
     # ------------------------------------------------------------------ fused path
-    def _forward_fused(self, src_seq, enc_output, return_attns, int_preds):
+    def _forward_fused(self, src_seq, enc_output, return_attns, int_preds, defer_out=False):
         B, T, D = enc_output.shape
         L = self.n_tgt_vocab
         prec = self.layer_stack[0].enc_attn._prec()
@@ -119,8 +119,7 @@ class GraphDecoder(nn.Module):
         for layer in self.layer_stack:
             kv_params += [layer.enc_attn.w_ks.weight, layer.enc_attn.w_vs.weight]
         hd = self.layer_stack[0].enc_attn.n_head * self.layer_stack[0].enc_attn.d_k
-        w_hi, w_lo = self._wp.get('kv_all', tuple(kv_params), prec)
-        kv_all = ops.linear_planes(enc, w_hi, w_lo, 2 * hd * len(self.layer_stack), prec)
+        kv_all = ops.project(enc, self._wp, 'kv_all', tuple(kv_params), 2 * hd * len(self.layer_stack), prec)
         if kv_ranges is not None:
             ops.zero_guard_rows(kv_all)  # rows a KV tile may read past the packed keys must be finite
         int_outs, slf_attns, enc_attns = [], [], []
@@ -128,7 +127,8 @@ class GraphDecoder(nn.Module):
         for i, layer in enumerate(self.layer_stack):
             x, x_int, slf_attn, enc_attn = layer.forward_act(
                 x, enc, B, L, T, slf_mask, pad_mask, return_attns, kv_proj=(kv_all, 2 * hd * i, 2 * hd * i + hd),
-                last=(i == n - 1), want_int_f32=int_preds, want_out_f32=int_preds or i == n - 1, kv_ranges=kv_ranges)
+                last=(i == n - 1), want_int_f32=int_preds, want_out_f32=int_preds or i == n - 1, kv_ranges=kv_ranges,
+                defer_out=defer_out and i == n - 1 and not int_preds)
             if int_preds:
                 if x_int is not None:
                     int_outs.append(x_int.f32.view(B, L, D))
@@ -136,16 +136,21 @@ class GraphDecoder(nn.Module):
             if return_attns:
                 slf_attns.append(slf_attn)
                 enc_attns.append(enc_attn)
-        return x.f32.view(B, L, D), int_outs, slf_attns, enc_attns
+        if x.ln is not None and defer_out:
+            return x, int_outs, slf_attns, enc_attns  # deferred-LayerNorm Act [B*L, D] (see LAMP.forward)
+        return ops.act_f32(x).view(B, L, D), int_outs, slf_attns, enc_attns
 
-    def forward(self, tgt, src_seq, enc_output, return_attns=False, int_preds=False):
+    def forward(self, tgt, src_seq, enc_output, return_attns=False, int_preds=False, _defer_out=False):
         """``tgt`` is unused (as in the reference).  Returns ``(dec_output, None)`` | ``(dec_output, int_outs)``
-        | ``(dec_output, dec_slf_attns, dec_enc_attns)`` exactly like lamp/Decoders.py:158-163."""
+        | ``(dec_output, dec_slf_attns, dec_enc_attns)`` exactly like lamp/Decoders.py:158-163.
+        ``_defer_out`` (internal, used by ``LAMP.forward``): ``dec_output`` may come back as an ``ops.Act`` whose final
+        LayerNorm is still pending, to be applied inside the label-projection kernel."""
         nat.require_cuda(src_seq, enc_output)
         if _needs_autograd(self, enc_output) or not self.fused_ok():
             out, int_outs, slf_attns, enc_attns = self._forward_composed(src_seq, enc_output, return_attns, int_preds)
         else:
-            out, int_outs, slf_attns, enc_attns = self._forward_fused(src_seq, enc_output, return_attns, int_preds)
+            out, int_outs, slf_attns, enc_attns = self._forward_fused(src_seq, enc_output, return_attns, int_preds,
+                                                                      defer_out=_defer_out)
         if int_preds:
             return out, int_outs
         if return_attns:

@@ -132,8 +132,14 @@ class GraphEncoder(nn.Module):
                       m_dev=m_dev)
         n = len(self.layer_stack)
         for i, layer in enumerate(self.layer_stack):
-            x, _ = layer.forward_act(x, B, T, None, False, want_f32=(i == n - 1))
-        out = ops.gather_rows(x.f32, src_row, self.d_model).view(B, T, self.d_model)
+            x, _ = layer.forward_act(x, B, T, None, False, want_f32=(i == n - 1) and not ops.DEFER_LAYERNORM)
+        if x.ln is not None:
+            # the last LayerNorm is still pending: apply it while un-packing into the dense API tensor; the decoder's
+            # K|V projection consumes the deferred packed activation directly
+            out = ops.materialize(x, prec, want_f32=True, want_planes=False, index=src_row).f32
+        else:
+            out = ops.gather_rows(ops.act_f32(x), src_row, self.d_model)
+        out = out.view(B, T, self.d_model)
         if self.enc_transform == '':
             kv_len = (~rep).view(B, T).sum(dim=1)
             kv_start = torch.cumsum(kv_len, 0) - kv_len

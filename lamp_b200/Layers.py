@@ -57,9 +57,11 @@ class DecoderLayer(nn.Module):
 
     def forward_act(self, x: ops.Act, enc: ops.Act, B: int, L: int, T: int, slf_attn_mask, dec_enc_attn_mask,
                     want_attn: bool, kv_proj=None, last: bool = False, want_int_f32: bool = True,
-                    want_out_f32: bool = True, kv_ranges=None):
-        """Inside the layer activations exist as tensor-core operand planes only; fp32 copies are written just for
-        the tensors the caller asked for (layer output, intermediate output)."""
+                    want_out_f32: bool = True, kv_ranges=None, defer_out: bool = False):
+        """Inside the layer activations exist as tensor-core operand planes only (with ``ops.DEFER_LAYERNORM`` as
+        PRE-LayerNorm planes + row statistics, normalised by their consumers); fp32 copies are written just for the
+        tensors the caller asked for (layer output, intermediate output).  ``defer_out``: the caller accepts the layer
+        output as a deferred-LayerNorm Act (GraphDecoder -> LAMP's fused label projection)."""
         out, enc_attn = self.enc_attn.forward_act(x, enc, B, L, T, dec_enc_attn_mask, want_attn, kv_proj=kv_proj,
                                                   want_f32=False, kv_ranges=kv_ranges)
         has_slf = hasattr(self, 'slf_attn')
@@ -68,7 +70,7 @@ class DecoderLayer(nn.Module):
         if has_slf:
             out_int = out
             out, slf_attn = self.slf_attn.forward_act(out, None, B, L, L, slf_attn_mask, want_attn, want_f32=False)
-        out = self.pos_ffn2.forward_act(out, want_planes=not last, want_f32=want_out_f32 or last)
+        out = self.pos_ffn2.forward_act(out, want_planes=not last, want_f32=(want_out_f32 or last) and not defer_out)
         return out, out_int, slf_attn, enc_attn
 
     def forward(self, dec_input, enc_output, slf_attn_mask=None, dec_enc_attn_mask=None, return_attns=True):

@@ -75,9 +75,16 @@ class LAMP(nn.Module):
         batch_size = src_seq.size(0)
         fused = not _needs_autograd(self)
         enc_output, *enc_self_attns = self.encoder(src_seq, adj, src_pos, return_attns=return_attns)
+        # fused inference: the decoder may hand over its output with the last LayerNorm still pending; it is then
+        # applied inside the diagonal label-projection kernel (dec_output itself is not part of LAMP's return value)
+        defer = fused and self.proj_share_weight and not int_preds and not return_attns
         dec_output, *dec_output2 = self.decoder(tgt_seq, src_seq, enc_output, return_attns=return_attns,
-                                                int_preds=int_preds)
-        seq_logit = self._project(dec_output, fused)
+                                                int_preds=int_preds, **({'_defer_out': True} if defer else {}))
+        if isinstance(dec_output, ops.Act):
+            lin = self.tgt_word_proj.linear
+            seq_logit = ops.diag_proj_act(dec_output, batch_size, self.decoder.n_tgt_vocab, lin.weight, lin.bias)
+        else:
+            seq_logit = self._project(dec_output, fused)
         seq_logit = seq_logit.reshape(-1, seq_logit.size(-1))
         if int_preds:
             w = self.tgt_word_proj.linear.weight.detach()

@@ -142,17 +142,15 @@ class MultiHeadAttention(nn.Module):
         H, d, D = self.n_head, self.d_k, self.d_model
         hd = H * d
         if kv is None and kv_proj is None:
-            w_hi, w_lo = self._wp.get('qkv', (self.w_qs.weight, self.w_ks.weight, self.w_vs.weight), prec)
-            qkv = ops.linear_planes(q, w_hi, w_lo, 3 * hd, prec)
+            qkv = ops.project(q, self._wp, 'qkv', (self.w_qs.weight, self.w_ks.weight, self.w_vs.weight), 3 * hd, prec)
             qp, q_col0, kvp, k_col0, v_col0 = qkv, 0, qkv, hd, 2 * hd
         else:
-            w_hi, w_lo = self._wp.get('q', (self.w_qs.weight,), prec)
-            qp, q_col0 = ops.linear_planes(q, w_hi, w_lo, hd, prec), 0
+            qp, q_col0 = ops.project(q, self._wp, 'q', (self.w_qs.weight,), hd, prec), 0
             if kv_proj is not None:
                 kvp, k_col0, v_col0 = kv_proj
             else:
-                w_hi, w_lo = self._wp.get('kv', (self.w_ks.weight, self.w_vs.weight), prec)
-                kvp, k_col0, v_col0 = ops.linear_planes(kv, w_hi, w_lo, 2 * hd, prec), 0, hd
+                kvp = ops.project(kv, self._wp, 'kv', (self.w_ks.weight, self.w_vs.weight), 2 * hd, prec)
+                k_col0, v_col0 = 0, hd
         kv_start, kv_len = kv_ranges if kv_ranges is not None else (None, None)  # packed (padding-aware) keys
         o, probs = ops.attention(qp, q_col0, kvp, k_col0, v_col0, B, H, Lq, Lk, d, prec, attn_mask, want_attn,
                                  out_f32=(H == 1), kv_start=kv_start, kv_len=kv_len)
@@ -217,9 +215,8 @@ class PositionwiseFeedForward(nn.Module):
     def forward_act(self, x: ops.Act, want_planes: bool = True, want_f32: bool = True) -> ops.Act:
         prec = ops.default_precision() if self.precision is None else self.precision
         D, dh = self.w_1.in_channels, self.w_1.out_channels
-        w1_hi, w1_lo = self._wp.get('w1', (self.w_1.weight,), prec)
         w2_hi, w2_lo = self._wp.get('w2', (self.w_2.weight,), prec)
-        h = ops.linear_planes(x, w1_hi, w1_lo, dh, prec, bias=self.w_1.bias, relu=True)
+        h = ops.project(x, self._wp, 'w1', (self.w_1.weight,), dh, prec, bias=self.w_1.bias, relu=True)
         ln = self.layer_norm
         return ops.linear_residual_ln(h, w2_hi, w2_lo, D, prec, x, ln.weight, ln.bias, ln.eps, bias=self.w_2.bias,
                                       want_planes=want_planes, want_f32=want_f32)

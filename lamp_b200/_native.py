@@ -35,6 +35,13 @@ _SIGNATURES = {
                                _vp, _i64, _vp, _vp], _i),
     'lamp_gemm_ln_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _f, _vp, _i64,
                              _vp, _vp, _i64, _vp], _i),
+    'lamp_gemm_stats_parts': ([_i], _i),
+    'lamp_gemm_planes_dln': ([_vp, _vp, _i64, _vp, _i, _f, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i64,
+                              _vp, _vp], _i),
+    'lamp_gemm_planes_rstats': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i,
+                                 _f, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], _i),
+    'lamp_ln_apply': ([_vp, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    'lamp_diag_proj_ln': ([_vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _vp, _vp], _i),
     'lamp_attn_core_planes': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,
                                _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _i),
     'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp, _vp], _i),

@@ -174,4 +174,95 @@ __global__ void diag_proj_kernel(const float* __restrict__ x, const float* __res
   if (lane == 0) logits[row] = s + (bias ? bias[l] : 0.0f);
 }
 
+// ---- deferred LayerNorm (see GemmParams in gemm_planes.cuh): the activation travels as PRE-norm planes y plus per-row
+// partial sums {sum y, sum y^2}; these kernels apply the normalisation where a real tensor has to leave the GEMM chain.
+__device__ __forceinline__ void dln_row_stats(const float2* __restrict__ stats, int nparts, long long row, int D,
+                                              float eps, float& mean, float& rstd) {
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int q = 0; q < nparts; ++q) {
+    const float2 e = __ldg(stats + row * nparts + q);
+    s1 += e.x;
+    s2 += e.y;
+  }
+  mean = s1 / D;
+  rstd = rsqrtf(fmaxf(s2 / D - mean * mean, 0.0f) + eps);
+}
+
+__device__ __forceinline__ float4 planes_load4(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                               long long off) {
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(hi + off));
+  float4 v = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xFFFF0000u), __uint_as_float(h.y << 16),
+                         __uint_as_float(h.y & 0xFFFF0000u));
+  if (lo != nullptr) {
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo + off));
+    v.x += __uint_as_float(l.x << 16); v.y += __uint_as_float(l.x & 0xFFFF0000u);
+    v.z += __uint_as_float(l.y << 16); v.w += __uint_as_float(l.y & 0xFFFF0000u);
+  }
+  return v;
+}
+
+// out[r, :] = LayerNorm(y[index ? index[r] : r, :]) * gamma + beta -> fp32 and/or planes.  One warp per output row.
+// With `index` this is also the un-packing gather of the encoder output (dense [B, T, D] API tensor).
+__global__ void ln_apply_kernel(const __nv_bfloat16* __restrict__ y_hi, const __nv_bfloat16* __restrict__ y_lo,
+                                const float2* __restrict__ stats, int nparts, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, long long rows, int D,
+                                const long long* __restrict__ index, float* __restrict__ out,
+                                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                const int* __restrict__ m_dev) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m_dev != nullptr && rows > __ldg(m_dev)) rows = __ldg(m_dev);
+  if (row >= rows) return;
+  const long long src = index ? index[row] : row;
+  float mean, rstd;
+  dln_row_stats(stats, nparts, src, D, eps, mean, rstd);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  for (int idx = lane; idx < (D >> 2); idx += 32) {
+    const float4 v = planes_load4(y_hi, y_lo, src * D + 4 * idx);
+    const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+    float4 o;
+    o.x = (v.x - mean) * rstd * g.x + b.x;
+    o.y = (v.y - mean) * rstd * g.y + b.y;
+    o.z = (v.z - mean) * rstd * g.z + b.z;
+    o.w = (v.w - mean) * rstd * g.w + b.w;
+    if (out != nullptr) reinterpret_cast<float4*>(out + row * D)[idx] = o;
+    if (out_hi != nullptr) {
+      uint2 h, l;
+      split_bf16x2(o.x, o.y, h.x, l.x);
+      split_bf16x2(o.z, o.w, h.y, l.y);
+      reinterpret_cast<uint2*>(out_hi + row * D)[idx] = h;
+      if (out_lo != nullptr) reinterpret_cast<uint2*>(out_lo + row * D)[idx] = l;
+    }
+  }
+}
+
+// logits[b, l] = <LayerNorm(y[b, l, :]) * gamma + beta, W[l, :]> (+ bias[l]): the diagonal label projection
+// (lamp/Models.py:124-126) applied directly to the deferred output of the last decoder layer.
+__global__ void diag_proj_ln_kernel(const __nv_bfloat16* __restrict__ y_hi, const __nv_bfloat16* __restrict__ y_lo,
+                                    const float2* __restrict__ stats, int nparts, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float eps, const float* __restrict__ W,
+                                    const float* __restrict__ bias, long long rows, int L, int D,
+                                    float* __restrict__ logits) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int l = static_cast<int>(row % L);
+  float mean, rstd;
+  dln_row_stats(stats, nparts, row, D, eps, mean, rstd);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  const float4* wr = reinterpret_cast<const float4*>(W + static_cast<long long>(l) * D);
+  float s = 0.0f;
+  for (int idx = lane; idx < (D >> 2); idx += 32) {
+    const float4 v = planes_load4(y_hi, y_lo, row * D + 4 * idx);
+    const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx), w = __ldg(wr + idx);
+    s += (((v.x - mean) * rstd * g.x + b.x) * w.x + ((v.y - mean) * rstd * g.y + b.y) * w.y) +
+         (((v.z - mean) * rstd * g.z + b.z) * w.z + ((v.w - mean) * rstd * g.w + b.w) * w.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) logits[row] = s + (bias ? bias[l] : 0.0f);
+}
+
 }  // namespace lamp

@@ -42,6 +42,23 @@ struct GemmParams {
   // optional device-side row count: the kernel processes min(M, *m_dev) rows (padding-aware execution: the number
   // of non-PAD tokens of a batch is only known on the device; no host synchronisation is needed to launch)
   const int* m_dev;
+  // ---- deferred LayerNorm (EPI_DLN_A / EPI_RSTATS).  A "deferred" activation is the PRE-norm tensor y (planes) plus
+  // per-row partial sums {sum y, sum y^2} ("row stats": [rows][nparts] float2); the LayerNorm itself is applied by
+  // whoever consumes it, so no LayerNorm kernel (one HBM read + one write of the activation) runs between two GEMMs:
+  //   * as the A operand (EPI_DLN_A):  LN(y) W^T = rstd (y (gamma o W)^T - mean colsum) + W beta.  The host folds gamma
+  //     into the weight planes; a_colsum[n] = sum_k gamma_k W[n,k], and `bias` carries bias[n] + sum_k beta_k W[n,k].
+  //   * as the residual (EPI_RSTATS): normalised element-wise while it is added.
+  // EPI_RSTATS also emits the row stats of ITS output (slot nt*2 + half of [M][2*num_n]).
+  const float2* a_stats;  // [M][a_nparts]
+  int a_nparts;
+  float a_eps;
+  const float* a_colsum;  // [N]
+  const float2* r_stats;  // [M][r_nparts] or nullptr (plain residual)
+  int r_nparts;
+  float r_eps;
+  const float* r_gamma;   // [N]
+  const float* r_beta;    // [N]
+  float2* stats_out;      // [M][2 * num_n]
 };
 
 // Residual values of the 8 rows (m_base + 4 i, i = 0..7) x 4 consecutive columns handled by one lane of the coalesced
@@ -96,6 +113,8 @@ constexpr int EPI_ANY = 2;     // everything, selected at run time (tests / rare
 constexpr int EPI_LN = 3;      // (+bias)(+residual) -> LayerNorm over the whole row -> fp32 and/or planes.  The two
                                // 256-column accumulator stages hold the two halves of ONE 512-wide row block, so the
                                // row statistics are complete on chip and the pre-norm tensor never touches HBM.
+constexpr int EPI_DLN_A = 4;   // A operand is a deferred LayerNorm: rstd*(acc - mean*colsum) + bias' (ReLU) -> planes
+constexpr int EPI_RSTATS = 5;  // (+bias) + residual (fp32 | planes | deferred-LayerNorm planes) -> planes + row stats
 
 template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP = 1>
 struct GemmCfg {
@@ -296,14 +315,18 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int wq = warp & 3;          // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2; // which of the two warps of this quarter: handles chunks half, half+2, ...
     uint8_t* stg = staging + (warp - 2) * (32 * 128);
+    const uint32_t stg_s = smem_u32(stg);  // shared-space address of this warp's staging slice (forces LDS / STS)
     const int sub_r = lane >> 3;  // coalesced phase: 8 lanes per row, 4 rows per pass
     const int sub_c = lane & 7;   // 16-byte chunk (4 fp32) inside the 128 B row segment
+    constexpr bool DLN_A = (EPI == EPI_DLN_A);
+    constexpr bool RSTATS = (EPI == EPI_RSTATS);
     const bool want_f32 = (EPI == EPI_F32) || (EPI == EPI_ANY && p.out_f32 != nullptr);
-    const bool want_pl = (EPI == EPI_PLANES) || (EPI == EPI_ANY && p.out_hi != nullptr);
+    const bool want_pl = (EPI == EPI_PLANES) || DLN_A || RSTATS || (EPI == EPI_ANY && p.out_hi != nullptr);
     const bool want_lo = want_pl && p.out_lo != nullptr;
-    const bool has_res = (EPI != EPI_PLANES) && (p.residual != nullptr || p.res_hi != nullptr);
+    const bool has_res = (EPI != EPI_PLANES) && !DLN_A && (p.residual != nullptr || p.res_hi != nullptr);
     const bool has_bias = p.bias != nullptr;
-    const bool relu = (EPI != EPI_F32) && p.relu;
+    const bool relu = (EPI != EPI_F32) && !RSTATS && p.relu;
+    const bool res_dln = RSTATS && p.r_stats != nullptr;  // the residual is a deferred LayerNorm
     const uint32_t te_addr[2] = {mapa_shared(&tmem_empty[0], 0), mapa_shared(&tmem_empty[1], 0)};  // leader's copies
     if constexpr (EPI == EPI_LN) {
       // ---------------- LayerNorm-fused epilogue: stage 0 / 1 hold columns [0,256) / [256,512) of the same rows.
@@ -351,8 +374,7 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (n0 + c0 < p.N) {
 #pragma unroll
               for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-                    make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+                sts128(stg_s + lane * 128 + ((c ^ (lane & 7)) << 4), make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
               __syncwarp();
               float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = bias4, b4 = bias4;
               if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
@@ -363,7 +385,8 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int rr = i * 4 + sub_r;
-                float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((sub_c ^ (rr & 7)) << 4));
+                const uint4 vb = lds128(stg_s + rr * 128 + ((sub_c ^ (rr & 7)) << 4));
+                float4 v = make_float4(__uint_as_float(vb.x), __uint_as_float(vb.y), __uint_as_float(vb.z), __uint_as_float(vb.w));
                 if (4 * i < rows_left && col_ok) {
                   v.x += bias4.x + resv[i].x; v.y += bias4.y + resv[i].y;
                   v.z += bias4.z + resv[i].z; v.w += bias4.w + resv[i].w;
@@ -434,6 +457,19 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         if (PAIR) mbar_arrive_cluster(te_addr[1]); else mbar_arrive(&tmem_empty[1]);
       }
     } else {
+    // The epilogue of a 128x256 tile has ~13K SM clocks (the tile's MMAs) to retire 32 chunk passes of 32x32 outputs:
+    // at 2 warps per scheduler it is ISSUE bound, so the per-element instruction stream is kept minimal --
+    // everything that depends on the row only (residual row offsets incl. the `% resid_mod`, validity, LayerNorm
+    // mean / rstd) is computed once per tile, loads are unconditional on clamped addresses (no per-row branches),
+    // and the residual of the NEXT chunk is fetched as raw bits into a ping-pong buffer and only decoded at use.
+    const bool res_f32 = p.residual != nullptr;
+    const uint16_t* rsrc_hi = reinterpret_cast<const uint16_t*>(p.res_hi);
+    const uint16_t* rsrc_lo = reinterpret_cast<const uint16_t*>(p.res_lo != nullptr ? p.res_lo : p.res_hi);
+    const uint32_t lo_keep = (p.res_lo != nullptr) ? 0xFFFFFFFFu : 0u;  // no lo plane: its bits are masked to +0
+    struct ResBuf {
+      uint4 raw[8];   // fp32 residual: the 4 floats; planes: {hi pair 0, hi pair 1, lo pair 0, lo pair 1}
+      float4 g, b;    // deferred residual: gamma / beta of the chunk's columns
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     int mt, nt;
@@ -441,46 +477,128 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       const int m0 = mt * (GEMM_BLOCK_M * CTA_GROUP) + static_cast<int>(rank) * GEMM_BLOCK_M + wq * 32;
       const int n0 = nt * BLOCK_N;
       const int rows_left = M - m0 - sub_r;  // row (m0 + sub_r + 4 i) is valid iff 4 i < rows_left
-      // residual rows of a 32-column chunk: requested one chunk AHEAD (the first one while the MMAs of this tile are
-      // still running), so their L2/HBM latency never sits on the epilogue's critical path
-      auto load_res = [&](int c0, float4 (&dst)[8]) {
+      // element offset of the residual row of each of this lane's 8 rows (clamped to a valid row; host-checked to
+      // fit 32 bits)
+      int roff[8];
+      if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = min(m0 + sub_r + 4 * i, M - 1);
+          roff[i] = (p.resid_mod ? (row % p.resid_mod) : row) * p.ldr;
+        }
+      }
+      auto load_res = [&](int c0, ResBuf& d) {
+        if (!has_res || c0 >= BLOCK_N) return;
         const int col = n0 + c0 + sub_c * 4;
-        if (has_res && c0 < BLOCK_N) gemm_load_residual8(p, m0 + sub_r, col, rows_left, col < p.N, dst);
+        const int colc = col < p.N ? col : 0;
+        if (res_f32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d.raw[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + roff[i] + colc));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint2 h = __ldg(reinterpret_cast<const uint2*>(rsrc_hi + roff[i] + colc));
+            const uint2 l = __ldg(reinterpret_cast<const uint2*>(rsrc_lo + roff[i] + colc));
+            d.raw[i] = make_uint4(h.x, h.y, l.x & lo_keep, l.y & lo_keep);
+          }
+        }
+        if (res_dln) {
+          d.g = __ldg(reinterpret_cast<const float4*>(p.r_gamma + colc));
+          d.b = __ldg(reinterpret_cast<const float4*>(p.r_beta + colc));
+        }
       };
-      float4 resv[8], resn[8];
-      load_res(half * 32, resv);
+      ResBuf rb0, rb1;
+      load_res(half * 32, rb0);
+      // deferred LayerNorm: scale / shift of this lane's 8 rows (of the A operand, or of the residual), from the
+      // partial sums written by the producing GEMM: LN(y) = (y * ra + rc) * gamma + beta, ra = rstd, rc = -mean*rstd
+      float ra[8], rc[8];
+      if (DLN_A || res_dln) {
+        const float2* st = DLN_A ? p.a_stats : p.r_stats;
+        const int np = DLN_A ? p.a_nparts : p.r_nparts;
+        const float inv_w = 1.0f / static_cast<float>(DLN_A ? p.K : p.N);
+        const float eps = DLN_A ? p.a_eps : p.r_eps;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2* sr = st + static_cast<size_t>(min(m0 + sub_r + 4 * i, M - 1)) * np;
+          float s1 = 0.f, s2 = 0.f;
+          if (np == 4) {  // the common case (256 < N <= 512): two 128-bit loads
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(sr));
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(sr) + 1);
+            s1 = (e0.x + e0.z) + (e1.x + e1.z);
+            s2 = (e0.y + e0.w) + (e1.y + e1.w);
+          } else {
+            for (int q = 0; q < np; ++q) {
+              const float2 e = __ldg(sr + q);
+              s1 += e.x;
+              s2 += e.y;
+            }
+          }
+          const float mean = s1 * inv_w;
+          ra[i] = rsqrtf(fmaxf(s2 * inv_w - mean * mean, 0.0f) + eps);
+          rc[i] = -mean * ra[i];
+        }
+      }
+      float st1[8], st2[8];  // EPI_RSTATS: running row sums of this lane's columns
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+      // one 32-column chunk: `cur` holds its residual, `nxt` receives the residual of the chunk 64 columns further
+      auto chunk = [&](int c0, const ResBuf& cur, ResBuf& nxt) {
         uint32_t r[32];
         tmem_ld32(t_row + c0, r);
-        load_res(c0 + 64, resn);
         tmem_wait_ld();
-        if (n0 + c0 >= p.N) continue;  // warp-uniform: whole 32-column chunk out of range (so are all later ones)
+        if (n0 + c0 >= p.N) return;  // warp-uniform: whole 32-column chunk out of range (so are all later ones)
         // registers (lane == row) -> swizzled staging: chunk c of row `lane` lives at chunk (c ^ (lane & 7))
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-              make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+          sts128(stg_s + lane * 128 + ((c ^ (lane & 7)) << 4), make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
         __syncwarp();
+        load_res(c0 + 64, nxt);  // issued once the accumulator registers are dead; consumed a whole chunk later
         const int col = n0 + c0 + sub_c * 4;
         const bool col_ok = col < p.N;  // N % 8 == 0 (host-checked) -> the 4 columns are all in or all out
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        const int colc = col_ok ? col : 0;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = bias4;
+        if (has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + colc));
+        if (DLN_A) cs4 = __ldg(reinterpret_cast<const float4*>(p.a_colsum + colc));
         float* of = want_f32 ? p.out_f32 + static_cast<size_t>(m0 + sub_r) * p.ldo + col : nullptr;
         const size_t poff = static_cast<size_t>(m0 + sub_r) * p.ldp + col;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub_r;
-          float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + ((sub_c ^ (rr & 7)) << 4));
-          if (4 * i < rows_left && col_ok) {
-            if (has_bias) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
-            if (relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          const uint4 vb = lds128(stg_s + rr * 128 + ((sub_c ^ (rr & 7)) << 4));
+          float4 v = make_float4(__uint_as_float(vb.x), __uint_as_float(vb.y), __uint_as_float(vb.z), __uint_as_float(vb.w));
+          if (DLN_A) {
+            v.x = fmaf(ra[i], v.x, rc[i] * cs4.x); v.y = fmaf(ra[i], v.y, rc[i] * cs4.y);
+            v.z = fmaf(ra[i], v.z, rc[i] * cs4.z); v.w = fmaf(ra[i], v.w, rc[i] * cs4.w);
+          }
+          if (has_bias) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+          if (relu) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+          if (has_res) {
+            const uint4 q = cur.raw[i];
+            float4 rv;
+            if (res_f32) {
+              rv = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+            } else {
+              rv.x = __uint_as_float(q.x << 16) + __uint_as_float(q.z << 16);
+              rv.y = __uint_as_float(q.x & 0xFFFF0000u) + __uint_as_float(q.z & 0xFFFF0000u);
+              rv.z = __uint_as_float(q.y << 16) + __uint_as_float(q.w << 16);
+              rv.w = __uint_as_float(q.y & 0xFFFF0000u) + __uint_as_float(q.w & 0xFFFF0000u);
             }
-            if (has_res) { v.x += resv[i].x; v.y += resv[i].y; v.z += resv[i].z; v.w += resv[i].w; }
+            if (res_dln) {
+              rv.x = fmaf(fmaf(rv.x, ra[i], rc[i]), cur.g.x, cur.b.x); rv.y = fmaf(fmaf(rv.y, ra[i], rc[i]), cur.g.y, cur.b.y);
+              rv.z = fmaf(fmaf(rv.z, ra[i], rc[i]), cur.g.z, cur.b.z); rv.w = fmaf(fmaf(rv.w, ra[i], rc[i]), cur.g.w, cur.b.w);
+            }
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+          }
+          if (4 * i < rows_left && col_ok) {
+            if (RSTATS) {
+              st1[i] += (v.x + v.y) + (v.z + v.w);
+              st2[i] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, st2[i]))));
+            }
             if (want_f32) *reinterpret_cast<float4*>(of + static_cast<size_t>(4 * i) * p.ldo) = v;
             if (want_pl) {
               uint2 hi, lo;
@@ -493,9 +611,28 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           }
         }
         __syncwarp();
-        if (has_res) {
+      };
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 128) {
+        chunk(c0, rb0, rb1);
+        chunk(c0 + 64, rb1, rb0);
+      }
+      if (RSTATS) {
+        // 8 lanes (sub_c) share a row: butterfly over the low 3 lane bits, then one float2 per row and warp
 #pragma unroll
-          for (int i = 0; i < 8; ++i) resv[i] = resn[i];
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            st1[i] += __shfl_xor_sync(0xFFFFFFFFu, st1[i], o);
+            st2[i] += __shfl_xor_sync(0xFFFFFFFFu, st2[i], o);
+          }
+        }
+        if (sub_c == 0) {
+          const int np = 2 * num_n;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (4 * i < rows_left)
+              p.stats_out[static_cast<size_t>(m0 + sub_r + 4 * i) * np + nt * 2 + half] = make_float2(st1[i], st2[i]);
         }
       }
       tcgen05_fence_before();

@@ -151,6 +151,10 @@ int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUte
 template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP>
 int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                 const GemmParams& p, cudaStream_t st) {
+  if (p.a_stats != nullptr)
+    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_DLN_A, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
+  if (p.stats_out != nullptr)
+    return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_RSTATS, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
   if (p.ln_gamma != nullptr) {
     if constexpr (BLOCK_N == 256)
       return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_LN, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
@@ -265,12 +269,20 @@ int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* 
   return launch_check();
 }
 
+namespace {
+struct DlnArgs {  // deferred-LayerNorm extras of a GEMM launch (all null / 0: none)
+  const float* a_stats = nullptr; int a_nparts = 0; float a_eps = 0.f; const float* a_colsum = nullptr;
+  const float* r_stats = nullptr; int r_nparts = 0; float r_eps = 0.f; const float* r_gamma = nullptr;
+  const float* r_beta = nullptr; float* stats_out = nullptr;
+};
+}  // namespace
+
 static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
                      int64_t ldw, int M, int N, int K, int precision, const float* bias, int relu,
                      const float* residual, const void* res_hi, const void* res_lo, int64_t ldr, int resid_mod,
                      float* out_f32, int64_t ldo, void* out_hi,
                      void* out_lo, int64_t ldp, const float* ln_gamma, const float* ln_beta, float ln_eps,
-                     const int32_t* m_dev, void* stream) {
+                     const int32_t* m_dev, void* stream, const DlnArgs& dln = DlnArgs()) {
   if (int rc = arch_check()) return rc;
   if (ln_gamma != nullptr) {
     REQUIRE(ln_beta != nullptr, "gemm_ln: beta missing");
@@ -291,6 +303,8 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void
   REQUIRE(!(residual && res_hi), "gemm: give the residual either as fp32 or as planes, not both");
   REQUIRE(!res_hi || (aligned16(res_hi) && ldr % 8 == 0 && (!res_lo || aligned16(res_lo))), "gemm: residual plane alignment");
   REQUIRE(!bias || aligned16(bias), "gemm: bias alignment");
+  REQUIRE(!(residual || res_hi) || ((int64_t)(resid_mod ? resid_mod : M) + 1) * ldr < (int64_t)1 << 31,
+          "gemm: residual matrix too large for 32-bit row offsets");
   if (M == 0) return LAMP_OK;
   const bool wide = (N > 128);
   const bool pair = wide && g_gemm_pair.load() != 0 && sm_count_cached() >= 2;
@@ -318,6 +332,11 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void
   p.ldp = (int)ldp;
   p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.ln_eps = ln_eps;
   p.m_dev = m_dev;
+  p.a_stats = reinterpret_cast<const float2*>(dln.a_stats); p.a_nparts = dln.a_nparts; p.a_eps = dln.a_eps;
+  p.a_colsum = dln.a_colsum;
+  p.r_stats = reinterpret_cast<const float2*>(dln.r_stats); p.r_nparts = dln.r_nparts; p.r_eps = dln.r_eps;
+  p.r_gamma = dln.r_gamma; p.r_beta = dln.r_beta;
+  p.stats_out = reinterpret_cast<float2*>(dln.stats_out);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAMP_GEMM_DISPATCH(BK)                                                                                      \
   do {                                                                                                             \
@@ -359,6 +378,74 @@ int lamp_gemm_ln_planes(const void* a_hi, const void* a_lo, int64_t lda, const v
   REQUIRE(gamma && beta, "gemm_ln: null gamma/beta");
   return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, 0, residual, nullptr, nullptr, ldr,
                    resid_mod, out_f32, ldo, out_hi, out_lo, ldp, gamma, beta, eps, nullptr, stream);
+}
+
+int lamp_gemm_stats_parts(int N) {
+  const int block_n = N > 128 ? 256 : 128;  // tile width chosen by gemm_impl
+  return 2 * ((N + block_n - 1) / block_n);
+}
+
+int lamp_gemm_planes_dln(const void* y_hi, const void* y_lo, int64_t lda, const float* a_stats, int a_nparts,
+                         float a_eps, const void* wg_hi, const void* wg_lo, int64_t ldw, const float* colsum,
+                         const float* biasf, int M, int N, int K, int precision, int relu, void* out_hi, void* out_lo,
+                         int64_t ldp, const int32_t* m_dev, void* stream) {
+  REQUIRE(a_stats && colsum && biasf && out_hi, "gemm_dln: null pointer");
+  REQUIRE(a_nparts > 0 && a_eps >= 0.0f, "gemm_dln: bad row-stat layout");
+  REQUIRE(aligned16(colsum) && (reinterpret_cast<uintptr_t>(a_stats) % 8 == 0), "gemm_dln: alignment");
+  DlnArgs d;
+  d.a_stats = a_stats; d.a_nparts = a_nparts; d.a_eps = a_eps; d.a_colsum = colsum;
+  return gemm_impl(y_hi, y_lo, lda, wg_hi, wg_lo, ldw, M, N, K, precision, biasf, relu, nullptr, nullptr, nullptr, 0, 0,
+                   nullptr, 0, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, m_dev, stream, d);
+}
+
+int lamp_gemm_planes_rstats(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                            int64_t ldw, int M, int N, int K, int precision, const float* bias, const float* residual,
+                            const void* res_hi, const void* res_lo, int64_t ldr, int resid_mod, const float* r_stats,
+                            int r_nparts, float r_eps, const float* r_gamma, const float* r_beta, void* out_hi,
+                            void* out_lo, int64_t ldp, float* stats_out, const int32_t* m_dev, void* stream) {
+  REQUIRE(out_hi && stats_out, "gemm_rstats: null output");
+  REQUIRE(reinterpret_cast<uintptr_t>(stats_out) % 8 == 0, "gemm_rstats: stats alignment");
+  DlnArgs d;
+  if (r_stats != nullptr) {
+    REQUIRE(res_hi && r_gamma && r_beta && r_nparts > 0 && resid_mod == 0, "gemm_rstats: deferred residual needs planes, gamma, beta");
+    REQUIRE(aligned16(r_gamma) && aligned16(r_beta) && (reinterpret_cast<uintptr_t>(r_stats) % 8 == 0), "gemm_rstats: alignment");
+    d.r_stats = r_stats; d.r_nparts = r_nparts; d.r_eps = r_eps; d.r_gamma = r_gamma; d.r_beta = r_beta;
+  }
+  d.stats_out = stats_out;
+  return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, 0, residual, res_hi, res_lo, ldr,
+                   resid_mod, nullptr, 0, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, m_dev, stream, d);
+}
+
+int lamp_ln_apply(const void* y_hi, const void* y_lo, const float* stats, int nparts, const float* gamma,
+                  const float* beta, float eps, int64_t rows, int D, const int64_t* index, float* out, void* out_hi,
+                  void* out_lo, const int32_t* m_dev, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(y_hi && stats && gamma && beta && (out || out_hi), "ln_apply: null pointer");
+  REQUIRE(D % 4 == 0 && D > 0 && nparts > 0, "ln_apply: D=%d must be a positive multiple of 4", D);
+  REQUIRE(aligned16(gamma) && aligned16(beta) && (!out || aligned16(out)), "ln_apply: alignment");
+  if (rows == 0) return LAMP_OK;
+  const long long blocks = (rows * 32 + 255) / 256;
+  ln_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(y_hi), static_cast<const __nv_bfloat16*>(y_lo),
+      reinterpret_cast<const float2*>(stats), nparts, gamma, beta, eps, rows, D,
+      reinterpret_cast<const long long*>(index), out, static_cast<__nv_bfloat16*>(out_hi),
+      static_cast<__nv_bfloat16*>(out_lo), m_dev);
+  return launch_check();
+}
+
+int lamp_diag_proj_ln(const void* y_hi, const void* y_lo, const float* stats, int nparts, const float* gamma,
+                      const float* beta, float eps, const float* W, const float* bias, int64_t B, int L, int D,
+                      float* logits, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(y_hi && stats && gamma && beta && W && logits, "diag_proj_ln: null pointer");
+  REQUIRE(D % 4 == 0 && nparts > 0 && aligned16(W) && aligned16(gamma) && aligned16(beta), "diag_proj_ln: D multiple of 4 and 16-byte alignment required");
+  const long long rows = B * L;
+  if (rows == 0) return LAMP_OK;
+  const long long blocks = (rows * 32 + 255) / 256;
+  diag_proj_ln_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<const __nv_bfloat16*>(y_hi), static_cast<const __nv_bfloat16*>(y_lo),
+      reinterpret_cast<const float2*>(stats), nparts, gamma, beta, eps, W, bias, rows, L, D, logits);
+  return launch_check();
 }
 
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,

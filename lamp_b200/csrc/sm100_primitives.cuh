@@ -287,6 +287,26 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Explicit shared-state-space accesses.  The dynamic-smem base is re-aligned through an integer cast, after which the
+// compiler no longer knows the address space and emits GENERIC loads/stores (LD.E / ST.E: long-scoreboard latency, the
+// dominant stall of the GEMM epilogue in the first ncu capture); these helpers force LDS / STS.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // Named barrier among a subset of warps (id 1..15; 0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -8,6 +8,7 @@ version.  Everything is enqueued on torch's current CUDA stream; torch only prov
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -97,6 +98,19 @@ STATS = LaunchStats()
 
 
 @dataclass
+class DeferredLN:
+    """A LayerNorm that has not been applied yet: the planes of the owning :class:`Act` hold the PRE-norm tensor
+    ``y`` and ``stats`` the per-row partial sums ``{sum y, sum y^2}`` (float32 ``[rows, nparts, 2]``) written by the
+    producing GEMM.  Consumers (the next GEMM's epilogue, the residual add, the label projection) normalise on the
+    fly, so the LayerNorm of lamp/SubLayers.py:117,141 costs no pass over HBM of its own."""
+    stats: torch.Tensor
+    nparts: int
+    gamma: torch.Tensor
+    beta: torch.Tensor
+    eps: float
+
+
+@dataclass
 class Act:
     """fp32 activation ``[rows, cols]`` and/or its planes.  ``bcast``: logical row count when the ``rows``
     physical rows are shared by every sample (label embeddings: rows = L, logical rows = B*L)."""
@@ -107,6 +121,7 @@ class Act:
     cols: int
     bcast_rows: int = 0
     m_dev: Optional[torch.Tensor] = None  # device int32 scalar: rows actually in use (padding-aware packed batch)
+    ln: Optional[DeferredLN] = None       # set: hi/lo are the pre-norm tensor of a deferred LayerNorm (f32 is None)
 
     @property
     def has_planes(self) -> bool:
@@ -173,6 +188,30 @@ class WeightPlanes:
         self._cache[key] = (sig, hi, lo)
         return hi, lo
 
+    def get_folded(self, key: str, params, ln: 'DeferredLN', bias, prec: int):
+        """Weights of a GEMM whose A operand is a deferred LayerNorm (gamma, beta):
+        ``LN(y) W^T + bias = rstd * (y (W*gamma)^T - mean * colsum) + (bias + W beta)``.
+        -> (planes of W*diag(gamma), colsum [N] fp32, folded bias [N] fp32), cached per parameter versions."""
+        deps = tuple(params) + (ln.gamma, ln.beta) + ((bias,) if bias is not None else ())
+        sig = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in deps) + (prec, bias is None)
+        ck = key + '@ln'
+        hit = self._cache.get(ck)
+        if hit is not None and hit[0] == sig:
+            return hit[1:]
+        with torch.no_grad():
+            mats = [p.detach().reshape(p.shape[0], -1).float() for p in params]
+            w = mats[0] if len(mats) == 1 else torch.cat(mats, dim=0)
+            wg = (w * ln.gamma.detach().float().unsqueeze(0)).contiguous()
+            hi, lo = split(wg, prec)
+            # colsum from the operand planes themselves, so that `y Wg^T - mean * colsum` cancels exactly
+            colsum = (hi.float() if lo is None else hi.float() + lo.float()).sum(dim=1).contiguous()
+            biasf = w.double() @ ln.beta.detach().double()
+            if bias is not None:
+                biasf = biasf + bias.detach().double()
+            biasf = biasf.float().contiguous()
+        self._cache[ck] = (sig, hi, lo, colsum, biasf)
+        return hi, lo, colsum, biasf
+
 
 def gemm(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, prec: int, *, bias=None, relu=False,
          residual=None, ldr: int = 0, resid_mod: int = 0, out_f32=None, ldo: int = 0, out_hi=None, out_lo=None,
@@ -198,8 +237,53 @@ def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=Fals
     return Act(None, hi, lo, x.rows, N, x.bcast_rows, x.m_dev)
 
 
+def project(x: Act, wp: WeightPlanes, key: str, params, N: int, prec: int, *, bias=None, relu=False) -> Act:
+    """``x @ cat(params)^T (+bias)(ReLU)`` -> planes.  ``x`` may be a deferred LayerNorm: the normalisation is then
+    folded into the weights and the epilogue of this GEMM (see :class:`DeferredLN`)."""
+    if x.ln is None:
+        w_hi, w_lo = wp.get(key, params, prec)
+        return linear_planes(x, w_hi, w_lo, N, prec, bias=bias, relu=relu)
+    ln = x.ln
+    wg_hi, wg_lo, colsum, biasf = wp.get_folded(key, params, ln, bias, prec)
+    hi, lo = _empty_planes(x.rows, N, prec, x.hi.device)
+    M, K = x.rows, x.cols
+    pl = 4 if prec == nat.PREC_FP32 else 2
+    STATS.call('gemm_planes', 1, nat.lib().lamp_gemm_planes_dln,
+               (x.hi.data_ptr(), nat.ptr(x.lo), K, ln.stats.data_ptr(), ln.nparts, float(ln.eps), wg_hi.data_ptr(),
+                nat.ptr(wg_lo), K, colsum.data_ptr(), biasf.data_ptr(), M, N, K, prec, int(relu), hi.data_ptr(),
+                nat.ptr(lo), N, nat.ptr(x.m_dev), nat.stream()),
+               flops=lambda m: 2.0 * (M if m is None else min(M, m)) * N * K,
+               nbytes=lambda m: (M if m is None else min(M, m)) * (K * pl + N * pl + 8 * ln.nparts) + N * K * pl,
+               rows_dev=x.m_dev)
+    return Act(None, hi, lo, x.rows, N, x.bcast_rows, x.m_dev)
+
+
+def materialize(a: Act, prec: int, *, want_f32: bool = True, want_planes: bool = True, index=None) -> Act:
+    """Apply a deferred LayerNorm -> ordinary Act (fp32 and/or planes).  ``index`` (int64 [rows_out]): output row r
+    is the LayerNorm of source row index[r] (un-packing gather of the encoder output)."""
+    if a.ln is None:
+        return a
+    ln = a.ln
+    rows = a.rows if index is None else index.numel()
+    D = a.cols
+    dev = a.hi.device
+    out = torch.empty((rows, D), dtype=torch.float32, device=dev) if want_f32 else None
+    hi, lo = _empty_planes(rows, D, prec, dev) if want_planes else (None, None)
+    m_dev = a.m_dev if index is None else None
+    pl_in = 2 if a.lo is None else 4
+    pl_out = (4 if want_f32 else 0) + (0 if hi is None else (4 if lo is not None else 2))
+    STATS.call('ln_apply', 1, nat.lib().lamp_ln_apply,
+               (a.hi.data_ptr(), nat.ptr(a.lo), ln.stats.data_ptr(), ln.nparts, ln.gamma.data_ptr(), ln.beta.data_ptr(),
+                float(ln.eps), rows, D, nat.ptr(index), nat.ptr(out), nat.ptr(hi), nat.ptr(lo), nat.ptr(m_dev),
+                nat.stream()),
+               nbytes=lambda m: (rows if m is None else min(rows, m)) * D * (pl_in + pl_out), rows_dev=m_dev)
+    return Act(out, hi, lo, rows, D, 0, m_dev)
+
+
 def act_f32(a: Act) -> torch.Tensor:
     """fp32 view of an activation; reconstructed from the planes when the fp32 copy was never materialised."""
+    if a.ln is not None:
+        return materialize(a, nat.PREC_FP32, want_f32=True, want_planes=False).f32
     if a.f32 is None:
         a.f32 = a.hi.float() if a.lo is None else a.hi.float() + a.lo.float()
     return a.f32
@@ -225,8 +309,38 @@ def linear_residual_f32(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, *,
     return y
 
 
+def linear_residual_deferred(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, gamma, beta, eps: float, *,
+                             bias=None) -> Act:
+    """``y = planes(x) @ W^T (+bias) + residual`` -> planes of y + its row statistics: an Act whose LayerNorm
+    (gamma, beta, eps) is deferred to the consumers.  The residual may itself be a deferred LayerNorm."""
+    M, K = x.rows, x.cols
+    dev = x.hi.device
+    hi, lo = _empty_planes(M, N, prec, dev)
+    nparts = nat.lib().lamp_gemm_stats_parts(N)
+    stats = torch.empty((M, nparts, 2), dtype=torch.float32, device=dev)
+    mod = residual.rows if residual.bcast_rows else 0
+    rl = residual.ln
+    res_f32 = residual.f32 if rl is None else None
+    res_hi, res_lo = (None, None) if res_f32 is not None else (residual.hi, residual.lo)
+    pl = 4 if prec == nat.PREC_FP32 else 2
+    row_bytes = K * pl + N * pl + 8 * nparts + (0 if mod else N * (4 if res_f32 is not None else pl))
+    STATS.call('gemm_planes', 1, nat.lib().lamp_gemm_planes_rstats,
+               (x.hi.data_ptr(), nat.ptr(x.lo), K, w_hi.data_ptr(), nat.ptr(w_lo), K, M, N, K, prec, nat.ptr(bias),
+                nat.ptr(res_f32), nat.ptr(res_hi), nat.ptr(res_lo), residual.cols, mod,
+                None if rl is None else rl.stats.data_ptr(), 0 if rl is None else rl.nparts,
+                0.0 if rl is None else float(rl.eps), None if rl is None else rl.gamma.data_ptr(),
+                None if rl is None else rl.beta.data_ptr(), hi.data_ptr(), nat.ptr(lo), N, stats.data_ptr(),
+                nat.ptr(x.m_dev), nat.stream()),
+               flops=lambda m: 2.0 * (M if m is None else min(M, m)) * N * K,
+               nbytes=lambda m: (M if m is None else min(M, m)) * row_bytes + N * K * pl, rows_dev=x.m_dev)
+    return Act(None, hi, lo, M, N, 0, x.m_dev, DeferredLN(stats, nparts, gamma, beta, eps))
+
+
 PADDING_AWARE = True  # GraphEncoder/GraphDecoder compute only non-PAD token rows (results identical, see Encoders.py)
-FUSE_LAYERNORM = False  # True: fc / w_2 GEMM epilogue normalises the row on chip when 256 < d_model <= 512 (measured
+# fc / w_2 GEMMs emit pre-norm planes + row statistics and the LayerNorm is applied by the consumers (no LayerNorm
+# kernels inside the stack).  LAMP_DEFER_LN=0/1 overrides the default (benchmarking aid; results agree to fp32 rounding).
+DEFER_LAYERNORM = os.environ.get('LAMP_DEFER_LN', '0') != '0'
+FUSE_LAYERNORM = os.environ.get('LAMP_FUSE_LN', '0') != '0'  # True: fc / w_2 GEMM epilogue normalises the row on chip when 256 < d_model <= 512 (measured
 # slower than GEMM + LayerNorm kernels on B200: the exposed two-pass epilogue costs more than the HBM round trip saves)
 
 
@@ -234,6 +348,13 @@ def linear_residual_ln(x: Act, w_hi, w_lo, N: int, prec: int, residual: Act, gam
                        want_planes: bool = True, want_f32: bool = True) -> Act:
     """LayerNorm(planes(x) @ W^T (+bias) + residual) -> Act (fp32 + planes).  One kernel when the output row fits
     the 512-column TMEM accumulator (the pre-norm tensor never reaches HBM); GEMM + LayerNorm kernels otherwise."""
+    if DEFER_LAYERNORM and x.ln is None and N % 8 == 0:
+        out = linear_residual_deferred(x, w_hi, w_lo, N, prec, residual, gamma, beta, eps, bias=bias)
+        if want_f32:  # the caller needs the real tensor (API boundary, intermediate predictions)
+            out = materialize(out, prec, want_f32=True, want_planes=want_planes)
+        return out
+    if residual.ln is not None:
+        residual = materialize(residual, prec, want_f32=True, want_planes=False)
     if not (FUSE_LAYERNORM and 256 < N <= 512 and residual.f32 is not None):
         y = linear_residual_f32(x, w_hi, w_lo, N, prec, residual, bias=bias)
         return layernorm(y, gamma, beta, eps, prec, want_planes=want_planes, want_f32=want_f32, m_dev=x.m_dev)
@@ -379,6 +500,20 @@ def zero_guard_rows(a: Act, nguard: int = 128) -> None:
         return
     STATS.call('zero_guard_rows', 1, nat.lib().lamp_zero_guard_rows,
                (a.hi.data_ptr(), nat.ptr(a.lo), a.cols, a.cols, a.m_dev.data_ptr(), a.rows, nguard, nat.stream()))
+
+
+def diag_proj_act(a: Act, B: int, L: int, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Label projection of the decoder output given as an Act ([B*L, D], possibly a deferred LayerNorm)."""
+    if a.ln is None:
+        return diag_proj(act_f32(a).view(B, L, a.cols), W, bias)
+    ln = a.ln
+    D = a.cols
+    out = torch.empty((B, L), dtype=torch.float32, device=a.hi.device)
+    STATS.call('diag_proj', 1, nat.lib().lamp_diag_proj_ln,
+               (a.hi.data_ptr(), nat.ptr(a.lo), ln.stats.data_ptr(), ln.nparts, ln.gamma.data_ptr(), ln.beta.data_ptr(),
+                float(ln.eps), W.data_ptr(), nat.ptr(bias), B, L, D, out.data_ptr(), nat.stream()),
+               flops=2.0 * B * L * D, nbytes=B * L * D * (2 if a.lo is None else 4))
+    return out
 
 
 def diag_proj(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

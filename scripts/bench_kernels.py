@@ -65,10 +65,11 @@ def bench_gemm_ln(prec=0):
         bias = torch.zeros(N, device=DEV)
         for fuse in (True, False):
             ops.FUSE_LAYERNORM = fuse
+            ops.DEFER_LAYERNORM = False
             t = timeit(lambda: ops.linear_residual_ln(a, w_hi, w_lo, N, prec, res, g, b, 1e-5, bias=bias))
             print(f'gemm+LN {name} M={M} fused={fuse}: {t * 1e6:8.1f} us  {2.0 * M * N * K / t / 1e12:7.1f} TFLOP/s alg',
                   flush=True)
-        ops.FUSE_LAYERNORM = True
+        ops.FUSE_LAYERNORM = False
 
 
 def bench_gemm_pres(prec=0):
@@ -84,6 +85,40 @@ def bench_gemm_pres(prec=0):
             t = timeit(lambda: ops.linear_residual_f32(a, w_hi, w_lo, N, prec, r))
             print(f'gemm f32out {name} M={M} {nm}: {t * 1e6:8.1f} us  {2.0 * M * N * K / t / 1e12:7.1f} TFLOP/s alg',
                   flush=True)
+
+
+def bench_dln(prec=0):
+    """Deferred-LayerNorm GEMM flavours next to their plain counterparts (same shapes as the bench step)."""
+    B = 1024
+    for name, M in (('enc', B * 160), ('dec', B * 103)):
+        N = K = 512
+        a = ops.Act(None, *ops.split(torch.randn(M, K, device=DEV), prec), M, K)
+        w_hi, w_lo = ops.split(torch.randn(N, K, device=DEV) / K ** 0.5, prec)
+        rf = torch.randn(M, N, device=DEV)
+        g = torch.ones(N, device=DEV)
+        b = torch.zeros(N, device=DEV)
+        bias = torch.zeros(N, device=DEV)
+        res_f = ops.Act(rf, None, None, M, N)
+        res_p = ops.Act(None, *ops.split(rf, prec), M, N)
+        res_d = ops.linear_residual_deferred(a, w_hi, w_lo, N, prec, res_p, g, b, 1e-5, bias=bias)
+        for nm, r in (('fp32 residual', res_f), ('planes residual', res_p)):
+            t = timeit(lambda: ops.linear_residual_f32(a, w_hi, w_lo, N, prec, r, bias=bias))
+            print(f'gemm f32out  {name} M={M} {nm:18s}: {t * 1e6:8.1f} us  {2.0 * M * N * K / t / 1e12:7.1f} TFLOP/s alg',
+                  flush=True)
+        for nm, r in (('fp32 residual', res_f), ('planes residual', res_p), ('deferred residual', res_d)):
+            t = timeit(lambda: ops.linear_residual_deferred(a, w_hi, w_lo, N, prec, r, g, b, 1e-5, bias=bias))
+            print(f'gemm rstats  {name} M={M} {nm:18s}: {t * 1e6:8.1f} us  {2.0 * M * N * K / t / 1e12:7.1f} TFLOP/s alg',
+                  flush=True)
+        wp = ops.WeightPlanes()
+        for N2 in (512, 1536, 2048):
+            w2 = torch.nn.Parameter(torch.randn(N2, K, device=DEV) / K ** 0.5)
+            b2 = torch.nn.Parameter(torch.zeros(N2, device=DEV))
+            for nm, x in (('plain A', res_p), ('deferred A', res_d)):
+                t = timeit(lambda: ops.project(x, wp, f'w{N2}', (w2,), N2, prec, bias=b2, relu=True))
+                print(f'gemm planes  {name} M={M} N={N2} {nm:11s}: {t * 1e6:8.1f} us  '
+                      f'{2.0 * M * N2 * K / t / 1e12:7.1f} TFLOP/s alg', flush=True)
+        t = timeit(lambda: ops.materialize(res_d, prec, want_f32=True, want_planes=False))
+        print(f'ln_apply     {name} M={M}: {t * 1e6:8.1f} us  {M * N * 8 / t / 1e9:7.1f} GB/s', flush=True)
 
 
 def bench_attn(prec=0):
@@ -130,6 +165,8 @@ if __name__ == '__main__':
         bench_gemm_pres(0)
     if 'gemm_ln' in what:
         bench_gemm_ln(0)
+    if 'dln' in what:
+        bench_dln(0)
     if 'attn' in what:
         bench_attn(0)
     if 'ln' in what:

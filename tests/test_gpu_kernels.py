@@ -152,6 +152,111 @@ def test_gemm_fused_layernorm(M, N, K, pair):
         nat.check(nat.lib().lamp_set_tuning(2, 1), 'tune')
 
 
+@pytest.mark.parametrize('M,N,K,N2,pair', [(1000, 512, 512, 1536, 1), (103, 512, 128, 512, 1), (777, 384, 256, 64, 1),
+                                            (2048, 512, 64, 2048, 0), (130, 264, 512, 128, 1), (5000, 128, 1024, 512, 1),
+                                            (300, 1024, 256, 256, 1)])
+def test_gemm_deferred_layernorm_chain(M, N, K, N2, pair):
+    """Deferred LayerNorm: producer GEMM (pre-norm planes + row stats, plain / broadcast / deferred residual) ->
+    consumers (A-operand GEMM with folded gamma, lamp_ln_apply incl. gather, lamp_diag_proj_ln), each vs fp64."""
+    nat.check(nat.lib().lamp_set_tuning(2, pair), 'tune')
+    try:
+        g = torch.Generator(device='cpu').manual_seed(M + N + K + N2)
+        L = nat.lib()
+        a = torch.randn(M, K, generator=g).to(DEV)
+        w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+        bias = torch.randn(N, generator=g).to(DEV)
+        gam = (1 + 0.3 * torch.randn(N, generator=g)).to(DEV)
+        bet = torch.randn(N, generator=g).to(DEV)
+        a_hi, a_lo = planes(a)
+        w_hi, w_lo = planes(w)
+        np_ = L.lamp_gemm_stats_parts(N)
+        assert np_ == 2 * ((N + 255) // 256 if N > 128 else 1)
+
+        def producer(res32=None, mod=0, res_planes=None, rstats=None, rgam=None, rbet=None):
+            y_hi = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+            y_lo = torch.empty_like(y_hi)
+            st = torch.full((M, np_, 2), float('nan'), device=DEV)
+            rh, rl = res_planes if res_planes is not None else (None, None)
+            nat.check(L.lamp_gemm_planes_rstats(
+                a_hi.data_ptr(), a_lo.data_ptr(), K, w_hi.data_ptr(), w_lo.data_ptr(), K, M, N, K, 0, bias.data_ptr(),
+                nat.ptr(res32), nat.ptr(rh), nat.ptr(rl), N, mod, nat.ptr(rstats), np_ if rstats is not None else 0, 1e-5,
+                nat.ptr(rgam), nat.ptr(rbet), y_hi.data_ptr(), y_lo.data_ptr(), N, st.data_ptr(), None, nat.stream()),
+                'rstats')
+            torch.cuda.synchronize()
+            return y_hi, y_lo, st
+
+        base = a.double() @ w.double().T + bias.double()
+        # 1. plain fp32 residual, full and broadcast (row % mod)
+        res = torch.randn(M, N, generator=g).to(DEV) + 2.0
+        y_hi, y_lo, st = producer(res32=res)
+        y_ref = base + res.double()
+        assert rel_err(y_hi.float() + y_lo.float(), y_ref) < 3e-5
+        s = st.double().sum(1)
+        assert rel_err(s[:, 0], y_ref.sum(1)) < 1e-5 and rel_err(s[:, 1], (y_ref ** 2).sum(1)) < 1e-5
+        res9 = torch.randn(9, N, generator=g).to(DEV)
+        yb_hi, yb_lo, _ = producer(res32=res9, mod=9)
+        assert rel_err(yb_hi.float() + yb_lo.float(), base + res9.double()[torch.arange(M, device=DEV) % 9]) < 3e-5
+        # 2. plain planes residual
+        yp_hi, yp_lo, _ = producer(res_planes=planes(res))
+        assert rel_err(yp_hi.float() + yp_lo.float(), y_ref) < 3e-5
+        # 3. deferred residual: residual = LayerNorm(y) of a previous producer
+        ln_ref = torch.nn.functional.layer_norm(y_ref, (N,), gam.double(), bet.double(), 1e-5)
+        y2_hi, y2_lo, st2 = producer(res_planes=(y_hi, y_lo), rstats=st, rgam=gam, rbet=bet)
+        e = rel_err(y2_hi.float() + y2_lo.float(), base + ln_ref)
+        print(f'deferred residual {M}x{N}x{K}: {e:.2e}')
+        assert e < 3e-5
+        # 4. materialise (plain and through a gather index)
+        out = torch.full((M, N), float('nan'), device=DEV)
+        o_hi = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        o_lo = torch.empty_like(o_hi)
+        nat.check(L.lamp_ln_apply(y_hi.data_ptr(), y_lo.data_ptr(), st.data_ptr(), np_, gam.data_ptr(), bet.data_ptr(),
+                                  1e-5, M, N, None, out.data_ptr(), o_hi.data_ptr(), o_lo.data_ptr(), None, nat.stream()),
+                  'ln_apply')
+        torch.cuda.synchronize()
+        assert rel_err(out, ln_ref) < 3e-5
+        assert torch.equal(o_hi, out.to(torch.bfloat16)) and torch.equal(o_lo, (out - o_hi.float()).to(torch.bfloat16))
+        idx = torch.randint(0, M, (2 * M + 3,), generator=g).to(DEV)
+        outg = torch.empty(idx.numel(), N, device=DEV)
+        nat.check(L.lamp_ln_apply(y_hi.data_ptr(), y_lo.data_ptr(), st.data_ptr(), np_, gam.data_ptr(), bet.data_ptr(),
+                                  1e-5, idx.numel(), N, idx.data_ptr(), outg.data_ptr(), None, None, None, nat.stream()),
+                  'ln_apply-gather')
+        torch.cuda.synchronize()
+        assert torch.equal(outg, out[idx])
+        # 5. consumer GEMM: LN(y) W2^T + b2 (ReLU) with gamma folded into the weight planes
+        w2 = (torch.randn(N2, N, generator=g) / N ** 0.5).to(DEV)
+        b2 = torch.randn(N2, generator=g).to(DEV)
+        wg_hi, wg_lo = planes((w2 * gam.unsqueeze(0)).contiguous())
+        colsum = (wg_hi.float() + wg_lo.float()).sum(1).contiguous()
+        biasf = (w2.double() @ bet.double() + b2.double()).float().contiguous()
+        for relu in (0, 1):
+            c_hi = torch.empty(M, N2, dtype=torch.bfloat16, device=DEV)
+            c_lo = torch.empty_like(c_hi)
+            nat.check(L.lamp_gemm_planes_dln(y_hi.data_ptr(), y_lo.data_ptr(), N, st.data_ptr(), np_, 1e-5,
+                                             wg_hi.data_ptr(), wg_lo.data_ptr(), N, colsum.data_ptr(), biasf.data_ptr(), M,
+                                             N2, N, 0, relu, c_hi.data_ptr(), c_lo.data_ptr(), N2, None, nat.stream()),
+                      'dln')
+            torch.cuda.synchronize()
+            ref = ln_ref @ w2.double().T + b2.double()
+            if relu:
+                ref = ref.clamp_min(0)
+            e = rel_err(c_hi.float() + c_lo.float(), ref)
+            print(f'deferred A {M}x{N2}x{N} relu={relu}: {e:.2e}')
+            assert e < 3e-5
+        # 6. label projection on the deferred tensor (rows = B*Lb)
+        Lb = 7 if M % 7 == 0 else (5 if M % 5 == 0 else 1)
+        Wl = torch.randn(Lb, N, generator=g).to(DEV)
+        bl = torch.randn(Lb, generator=g).to(DEV)
+        logits = torch.empty(M // Lb, Lb, device=DEV)
+        nat.check(L.lamp_diag_proj_ln(y_hi.data_ptr(), y_lo.data_ptr(), st.data_ptr(), np_, gam.data_ptr(), bet.data_ptr(),
+                                      1e-5, Wl.data_ptr(), bl.data_ptr(), M // Lb, Lb, N, logits.data_ptr(), nat.stream()),
+                  'diag_ln')
+        torch.cuda.synchronize()
+        ref = (ln_ref.view(M // Lb, Lb, N) * Wl.double()).sum(-1) + bl.double()
+        assert rel_err(logits, ref) < 3e-5
+    finally:
+        nat.check(nat.lib().lamp_set_tuning(2, 1), 'tune')
+
+
 def run_sdpa(q, k, v, mask, temperature, prec=0, want_attn=True):
     N, Lq, d = q.shape
     Lk = k.shape[1]

@@ -253,6 +253,43 @@ def test_padding_aware_path_equals_dense_path_and_oracle():
     assert rel_err(l2, ref_logits) < TOL
 
 
+@pytest.mark.parametrize('name', ['lamp_L103_prior', 'lamp_L37_none', 'lamp_L20_meanvec'])
+def test_deferred_layernorm_equals_explicit_layernorm_and_oracle(name):
+    """ops.DEFER_LAYERNORM (LayerNorm folded into the consumers' epilogues, no LayerNorm kernels inside the stack) vs
+    the explicit GEMM + LayerNorm kernels vs the oracle, incl. int_preds / return_attns (materialised tensors)."""
+    from lamp_b200 import ops
+    c = cases.MODEL_CASES[name]
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    # non-trivial gamma / beta everywhere so that the folding is exercised
+    g = torch.Generator().manual_seed(7)
+    p = {k: (v + 0.2 * torch.randn(v.shape, generator=g) if 'layer_norm' in k else v) for k, v in p.items()}
+    model = build_model(c, p, adj)
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+    lm = orc.label_mask_from(c['L'], adj, c['mask'])
+    ref_logits, ref_enc = orc.lamp_forward(p, cfg, src_seq, src_pos, lm)
+    outs = {}
+    default = ops.DEFER_LAYERNORM
+    for defer in (True, False):
+        ops.DEFER_LAYERNORM = defer
+        try:
+            ops.STATS.reset()
+            with torch.no_grad():
+                outs[defer] = model(src, None, None, None)
+                ints = model(src, None, None, None, int_preds=True)
+                attn = model(src, None, None, None, return_attns=True)
+            torch.cuda.synchronize()
+            kern = dict(ops.STATS.by_kernel)
+        finally:
+            ops.DEFER_LAYERNORM = default
+        logits, enc_out, _ = outs[defer]
+        e1, e2 = rel_err(logits, ref_logits), rel_err(enc_out, ref_enc)
+        print(f'{name} defer={defer}: logits {e1:.2e} enc {e2:.2e} kernels {kern}')
+        assert e1 < TOL and e2 < TOL
+        assert rel_err(ints[0], ref_logits) < TOL and rel_err(attn[0], ref_logits) < TOL
+    assert rel_err(outs[True][0], outs[False][0]) < 1e-4
+    assert rel_err(outs[True][1], outs[False][1]) < 1e-4
+
+
 def test_graphed_forward_replays_equal_eager_for_new_batches():
     """GraphedForward (CUDA-graph replay of LAMP.forward): replaying with NEW token ids -- different padding, hence a
     different device-side packed row count -- gives bit-identical logits / enc_output to the eager call."""
