@@ -48,6 +48,7 @@ int lamp_sm_count(void);
 #define LAMP_TUNE_GEMM_BLOCK_K 1  /* 0 (default: automatic), 32 (64B swizzle, deeper TMA ring) or 64 (128B swizzle) */
 #define LAMP_TUNE_ATTN_COMPACT 3  /* 1 (default: tile rows follow L, deepest K/V staging that fits) or 0 (128-row tiles) */
 #define LAMP_TUNE_ATTN_STAGE 4    /* 1 (default: attention output planes leave through smem staging + TMA stores) or 0 */
+#define LAMP_TUNE_ATTN_PV_SPLIT 5  /* 0 (default) or 1: O += P V as two interleaved N = 64 accumulation chains (d == 128) */
 #define LAMP_TUNE_GEMM_CTA_PAIR 2 /* 1 (default: tcgen05 cta_group::2 pairs for 256-wide tiles) or 0 (single CTAs) */
 int lamp_set_tuning(int key, int value);
 
@@ -137,6 +138,20 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
                           int64_t msb, int64_t msq, int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
                           int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
                           const int32_t* kv_len, int64_t kv_rows, void* stream);
+
+/* Bit-packed form of a [Bm, Lq, Lk] byte mask (strides msb/msq/msk as above; Bm = 1 for a mask shared by the batch):
+ * words[(b*Lq + q)*W + (k >> 5)] bit (k & 31) = mask[b,q,k] != 0, W = ceil(Lk/32).  The label-graph mask of
+ * lamp/Decoders.py:113 is packed once per model and read as one 32-bit word per thread and KV tile. */
+int lamp_pack_mask_bits(const uint8_t* mask, int64_t msb, int64_t msq, int64_t msk, int64_t Bm, int Lq, int Lk,
+                        uint32_t* words, void* stream);
+
+/* lamp_attn_core_planes with the mask given in that packed form (word strides: mbb per sample -- 0 when shared --
+ * and mbq per query row, mbq >= ceil(Lk/32)); no probability output, no packed keys. */
+int lamp_attn_core_planes_mbits(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                                const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
+                                int Lq, int Lk, int d, float temperature, int precision, const uint32_t* mask_bits,
+                                int64_t mbb, int64_t mbq, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
+                                int64_t ldof, void* stream);
 
 /* out = LayerNorm(y (+ add[row % add_mod or row])) * gamma + beta  (torch.nn.LayerNorm semantics, eps inside the
  * sqrt; lamp/SubLayers.py:117,141).  Writes fp32 and/or planes (any may be NULL).  D % 4 == 0, D <= 4096. */

@@ -44,6 +44,9 @@ _SIGNATURES = {
     'lamp_diag_proj_ln': ([_vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _i64, _i, _i, _vp, _vp], _i),
     'lamp_attn_core_planes': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,
                                _i64, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _i),
+    'lamp_pack_mask_bits': ([_vp, _i64, _i64, _i64, _i64, _i, _i, _vp, _vp], _i),
+    'lamp_attn_core_planes_mbits': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,
+                                     _i64, _vp, _vp, _i64, _vp, _i64, _vp], _i),
     'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp, _vp], _i),
     'lamp_embed': ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     'lamp_gather_rows': ([_vp, _vp, _i64, _i, _vp, _vp], _i),
@@ -75,6 +78,10 @@ def lib() -> C.CDLL:
             fn.argtypes = argtypes
             fn.restype = restype
         _lib = handle
+        # LAMP_TUNE="key=value,key=value": process-wide tuning knobs (include/lamp_b200.h) for experiments
+        for kv in filter(None, os.environ.get('LAMP_TUNE', '').split(',')):
+            k, v = kv.split('=')
+            check(handle.lamp_set_tuning(int(k), int(v)), f'LAMP_TUNE {kv}')
     return _lib
 
 

@@ -4,15 +4,19 @@
 // One persistent CTA per SM walks a sequence of "units" = (work item (b, h, 128-row q tile), KV tile j):
 //   warp 0   : TMA producer -- 3D tensor maps {cols, L, B}: rows >= L are zero-filled by the hardware, so ragged
 //              label counts (L = 103, 159, 983 ...) need no padding in HBM.  Q/K/V arrive as 128B-swizzled
-//              [rows x 64] bf16 boxes of the split-bf16 planes written by the projection GEMM.  K and V tiles go
-//              through ONE ring of `kv_slots` equal slots (K(u), V(u), K(u+1), ...), each slot with its own
-//              full/empty barrier, so a slot is refilled the moment the MMA that read it retires.
+//              [rows x 64] bf16 boxes of the split-bf16 planes written by the projection GEMM.  The `kv_slots` equal
+//              slots are split into a K ring (first kv_slots/2 slots) and a V ring (the rest), each slot with its own
+//              full/empty barrier; warp 0 feeds Q and the K ring, warp 3 the V ring.  A K slot is free as soon as its
+//              S = Q K^T retires (early in a unit), a V slot only after its PV product (late), so with separate rings
+//              and producers the K tiles run ahead by the ring depth instead of queueing behind the V loads -- with
+//              multi-tile rows (L = 983) the measured load-to-use latency is ~4400 clocks, i.e. 1.5 unit periods.
 //   warp 1   : MMA issuer   -- event driven: one thread polls (mbarrier.test_wait) the operands of the next S = Q K^T
 //              and of the next O (+)= P V and issues whichever is ready; S goes to one of two TMEM score buffers,
 //              O to one of two TMEM output buffers (item parity), so neither the next item's PV nor the next S ever
 //              waits for the epilogue.  P is read from TENSOR MEMORY (TS form), V is consumed MN-major straight from
 //              its natural [keys x d] layout (no transpose pass); 3-term split-bf16 products.
 //   warp 2   : output store -- one thread issues the TMA stores of the O tile staged in shared memory.
+//   warp 3   : TMA producer of the V ring.
 //   warps 4.. : softmax     -- 4 * (BLOCK_KV/32) warps: TMEM lane == query row and every warp owns one 32-column
 //              chunk of the rows of its lane quarter.  Strided byte mask -> bit words via warp ballots, row max
 //              exchanged through smem, online max/sum across KV tiles with a LAZY rescale (the reference maximum only
@@ -40,6 +44,11 @@ struct AttnParams {
   int q_bcast;                 // 1: Q is shared by every sample (batch coordinate forced to 0)
   const uint8_t* mask;         // nullptr or bytes (non-zero = masked), element strides below
   long long msb, msq, msk;
+  // alternative mask form: bit-packed words (bit k & 31 of word [b*mbb + q*mbq + (k >> 5)] set = masked), produced by
+  // lamp_pack_mask_bits.  One 4-byte load per thread and KV tile instead of 32 byte loads + ballots: the form used
+  // whenever a [.., Lq, Lk] mask meets more than one KV tile (L = 983: the byte path cost 4x the tile's MMAs).
+  const uint32_t* mask_bits;
+  long long mbb, mbq;
   __nv_bfloat16* o_hi;  // [B*Lq, ldo] planes, head h at column h*d (nullable)
   __nv_bfloat16* o_lo;  // nullable
   int ldo;
@@ -55,17 +64,23 @@ struct AttnParams {
   int kv_slots;         // K/V ring depth (2 .. ATTN_MAX_SLOTS)
   uint32_t slot_bytes;  // bytes of one ring slot (fits a K tile and a V tile)
   int staged;           // 1: O planes leave through the smem staging tile + TMA store (needs d % 64 == 0)
+  int pv_split;         // 1 (d == 128 only): O (+)= P V issued as two interleaved N = 64 accumulation chains
 };
 
 #ifdef LAMP_ATTN_TRACE
 // Debug build only (scripts/attn_trace.py): clock64() stamps of CTA 0's pipeline events, [event][unit].
-__device__ unsigned long long g_attn_trace[16][64];
+__device__ unsigned long long g_attn_trace[16 + 48][64];  // rows 16..: per softmax warp (16 warps x {S seen, max bar, P stored})
 #define ATTN_TRACE(ev, idx)                                                              \
   do {                                                                                   \
     if (blockIdx.x == 0 && (idx) < 64u) g_attn_trace[ev][idx] = clock64();                \
   } while (0)
+#define ATTN_TRACE_W(k, idx)                                                                              \
+  do {                                                                                                    \
+    if (blockIdx.x == 0 && lane == 0 && (idx) < 64u) g_attn_trace[16 + (warp - 4) * 3 + (k)][idx] = clock64(); \
+  } while (0)
 #else
 #define ATTN_TRACE(ev, idx) do { } while (0)
+#define ATTN_TRACE_W(k, idx) do { } while (0)
 #endif
 
 constexpr int ATTN_BLOCK_M = 128;
@@ -76,7 +91,7 @@ constexpr float ATTN_RESCALE_LOG2 = 8.0f;  // lazy rescale: P stays below 2^8, h
 // row-statistics exchange between the column-warps of a row: max [2 units][NW][128] + sum [2 items][NW][128] floats
 constexpr uint32_t ATTN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
 constexpr uint32_t ATTN_BAR_BYTES = 256;
-// warps 0..3: TMA producer, MMA issuer, output store, (idle); warps 4..: softmax (warp % 4 = TMEM lane quarter)
+// warps 0..3: Q/K TMA producer, MMA issuer, output store, V TMA producer; warps 4..: softmax (warp % 4 = TMEM lane quarter)
 __host__ __device__ constexpr int attn_threads(int block_kv) { return 128 + 128 * (block_kv / 32); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -106,6 +121,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kb64 = (p.d + 63) >> 6;
   const int R = p.kv_slots;
+  const int RK = R >> 1, RV = R - RK;  // K ring: slots [0, RK), V ring: slots [RK, R)
   const uint32_t q_bytes = attn_tile_bytes(NPL, kb64, p.qrows);
   const uint32_t k_bytes = attn_tile_bytes(NPL, kb64, p.krows);
   const uint32_t v_bytes = attn_tile_bytes(NPL, kb64, p.vrows);
@@ -201,10 +217,9 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         int lk, kbase, kbatch, nkv;
         item_keys(b, lk, kbase, kbatch, nkv);
         for (int j = 0; j < nkv; ++j, ++u) {
-          const uint32_t kpos = 2 * u, vpos = 2 * u + 1;
-          const int ks = kpos % R, vs = vpos % R;
+          const int ks = u % RK;
           const int krow = kbase + j * BLOCK_KV;
-          mbar_wait(&kv_empty[ks], ((kpos / R) & 1) ^ 1);
+          mbar_wait(&kv_empty[ks], ((u / RK) & 1) ^ 1);
           ATTN_TRACE(0, u);
           mbar_arrive_expect_tx(&kv_full[ks], k_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
@@ -223,7 +238,22 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
                 tma_load_3d(q_tile(1, kb), &tmQ_lo, q_full, p.q_col0 + h * p.d + kb * 64, qt * ATTN_BLOCK_M, bq);
             }
           }
-          mbar_wait(&kv_empty[vs], ((vpos / R) & 1) ^ 1);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------------------------------------------------------- TMA producer of the V ring
+    if (lane == 0) {
+      uint32_t u = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int h = (item / num_qt) % p.H;
+        const int b = item / (num_qt * p.H);
+        int lk, kbase, kbatch, nkv;
+        item_keys(b, lk, kbase, kbatch, nkv);
+        for (int j = 0; j < nkv; ++j, ++u) {
+          const int vs = RK + u % RV;
+          const int krow = kbase + j * BLOCK_KV;
+          mbar_wait(&kv_empty[vs], ((u / RV) & 1) ^ 1);
           ATTN_TRACE(2, u);
           mbar_arrive_expect_tx(&kv_full[vs], v_bytes);
           for (int kb = 0; kb < kb64; ++kb) {
@@ -261,7 +291,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       // S(u) = Q K_u^T into score buffer u & 1 (N = the tile's key count rounded up to 16)
       auto issue_s = [&](const UnitIt& x) {
         const uint32_t u = x.u;
-        const int ks = (2 * u) % R;
+        const int ks = u % RK;
         const uint32_t sb = u & 1;
         int kvn = (min(BLOCK_KV, x.lk - x.j * BLOCK_KV) + 15) & ~15;
         if (kvn < 16) kvn = 16;
@@ -290,7 +320,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       // O(item parity) (+)= P(u) V_u
       auto issue_pv = [&](const UnitIt& x) {
         const uint32_t u = x.u;
-        const int vs = (2 * u + 1) % R;
+        const int vs = RK + u % RV;
         const uint32_t sb = u & 1;
         ATTN_TRACE(6, u);
         tcgen05_fence_after();
@@ -298,6 +328,27 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         const int ksteps_kv = max(1, (kv_valid + 15) >> 4);
         const uint32_t tO = tmem_base + ATTN_TMEM_O + (x.it & 1) * 128;
         const uint32_t tP = tmem_base + ATTN_TMEM_S + sb * 128;  // P lives where S(u) was
+        if (p.pv_split) {
+          // two independent N = 64 chains (the two 64-wide d blocks of V, O columns [0,64) / [64,128)), interleaved
+          const uint32_t idesc_h = umma_idesc_bf16(ATTN_BLOCK_M, 64, 0, 1);
+          for (int t = 0; t < ksteps_kv; ++t) {
+            const uint32_t pa = tP + 32 * (t >> 1) + 8 * (t & 1);
+            const uint32_t accum = (x.j != 0 || t != 0) ? 1u : 0u;
+            uint64_t dvh[2], dvl[2];
+            for (int kb = 0; kb < 2; ++kb) {
+              dvh[kb] = umma_smem_desc(smem_u32(v_tile(vs, 0, kb)) + t * 2048, p.vrows * 128, 1024);
+              dvl[kb] = umma_smem_desc(smem_u32(v_tile(vs, 1, kb)) + t * 2048, p.vrows * 128, 1024);
+            }
+            umma_bf16_ts(tO, pa, dvh[0], idesc_h, accum);
+            umma_bf16_ts(tO + 64, pa, dvh[1], idesc_h, accum);
+            if (NTERMS == 3) {
+              umma_bf16_ts(tO, pa, dvl[0], idesc_h, 1u);
+              umma_bf16_ts(tO + 64, pa, dvl[1], idesc_h, 1u);
+              umma_bf16_ts(tO, pa + 16, dvh[0], idesc_h, 1u);
+              umma_bf16_ts(tO + 64, pa + 16, dvh[1], idesc_h, 1u);
+            }
+          }
+        } else
         for (int t = 0; t < ksteps_kv; ++t) {
           // A = P from TMEM: keys 16t..16t+15 sit in 32-column chunk t/2: hi pairs at +8*(t&1), lo pairs 16 further.
           // B = V MN-major: K (= key index) advances by 16 rows of 128 B, LBO = distance between the 64-wide d
@@ -326,10 +377,10 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       while (pi.item < num_items) {
         bool progressed = false;
         if (si.item < num_items) {
-          const uint32_t u = si.u, kpos = 2 * u;
+          const uint32_t u = si.u;
           if (!s_q) s_q = (si.j != 0) || mbar_test_wait(q_full, si.it & 1);
-          if (!s_k) s_k = mbar_test_wait(&kv_full[kpos % R], (kpos / R) & 1);
-          if (!s_b) s_b = mbar_test_wait(&s_free[u & 1], ((u >> 1) & 1) ^ 1);
+          if (!s_k && (s_k = mbar_test_wait(&kv_full[u % RK], (u / RK) & 1))) ATTN_TRACE(14, u);
+          if (!s_b && (s_b = mbar_test_wait(&s_free[u & 1], ((u >> 1) & 1) ^ 1))) ATTN_TRACE(15, u);
           if (s_q && s_k && s_b) {
             issue_s(si);
             advance(si);
@@ -338,9 +389,9 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
           }
         }
         {
-          const uint32_t u = pi.u, vpos = 2 * u + 1;
-          if (!v_p) v_p = mbar_test_wait(&p_full[u & 1], (u >> 1) & 1);
-          if (!v_v) v_v = mbar_test_wait(&kv_full[vpos % R], (vpos / R) & 1);
+          const uint32_t u = pi.u;
+          if (!v_p && (v_p = mbar_test_wait(&p_full[u & 1], (u >> 1) & 1))) ATTN_TRACE(12, u);
+          if (!v_v && (v_v = mbar_test_wait(&kv_full[RK + u % RV], (u / RV) & 1))) ATTN_TRACE(13, u);
           if (!v_o) v_o = (pi.j != 0) || mbar_test_wait(&o_free[pi.it & 1], ((pi.it >> 1) & 1) ^ 1);
           if (v_p && v_v && v_o) {
             issue_pv(pi);
@@ -478,7 +529,16 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         //      consumed after the score tile has arrived, so its latency hides behind the barrier wait.
         bool pad_pending = false;
         uint32_t pad_byte = 0;
-        {
+        if (p.mask_bits != nullptr) {
+          // packed mask: issue this thread's word now, OR it in after the score tile has arrived
+          const int rem = lk - k0;
+          mw = rem >= 32 ? 0u : (rem <= 0 ? 0xFFFFFFFFu : (0xFFFFFFFFu << rem));
+          const int qr = qt * ATTN_BLOCK_M + row;
+          pad_pending = true;  // (reuses the deferred-OR slot of the key-padding path; see below)
+          if (rem > 0 && qr < p.Lq)
+            pad_byte = __ldg(p.mask_bits + static_cast<long long>(b) * p.mbb + static_cast<long long>(qr) * p.mbq + (k0 >> 5));
+          mkey = -1;
+        } else {
           const long long key = (p.mask == nullptr)
                                     ? static_cast<long long>(j)
                                     : ((p.msb ? static_cast<long long>(b) : 0) * num_qt + (p.msq ? qt : 0)) * num_kv + j;
@@ -507,11 +567,12 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
         mbar_wait(&s_full[sb], (u >> 1) & 1);
         if (tracer) ATTN_TRACE(7, u);
+        ATTN_TRACE_W(0, u);
         tcgen05_fence_after();
         // ---- pass 1: masked scores of this chunk stay in registers; chunk max -> smem -> row max
         uint32_t r[32];
         tmem_ld32(tS, r);
-        if (pad_pending) mw |= __ballot_sync(0xFFFFFFFFu, pad_byte != 0);
+        if (pad_pending) mw |= (p.mask_bits != nullptr) ? pad_byte : __ballot_sync(0xFFFFFFFFu, pad_byte != 0);
         tmem_wait_ld();
         float mx = -INFINITY;
 #pragma unroll
@@ -524,6 +585,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         rm[cw * 128 + row] = mx;
         named_bar_sync(1, NSW);
         if (tracer) ATTN_TRACE(8, u);
+        ATTN_TRACE_W(1, u);
 #pragma unroll
         for (int c = 0; c < NW; ++c) mx = fmaxf(mx, rm[c * 128 + row]);
         // ---- lazy reference maximum: move it only when the tile maximum exceeds it by more than 2^8 (or on the
@@ -564,6 +626,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         if (j == nkv - 1) red_l[((it & 1) * 4 + cw) * 128 + row] = l_part;  // read after the next unit's barrier
         tmem_wait_st();
         if (tracer) ATTN_TRACE(9, u);
+        ATTN_TRACE_W(2, u);
         tcgen05_fence_before();
         mbar_arrive(&p_full[sb]);
         // ---- deferred epilogue of the previous item (its O buffer is the other one): overlaps PV(u)

@@ -265,4 +265,21 @@ __global__ void diag_proj_ln_kernel(const __nv_bfloat16* __restrict__ y_hi, cons
   if (lane == 0) logits[row] = s + (bias ? bias[l] : 0.0f);
 }
 
+// Byte mask (non-zero = masked, element strides msb/msq/msk) -> bit words [Bm][Lq][W], W = ceil(Lk / 32); bit (k & 31) of
+// word k >> 5 belongs to key k, keys >= Lk read as 0.  One warp per output word.
+__global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, long long msb, long long msq, long long msk,
+                                 long long Bm, int Lq, int Lk, uint32_t* __restrict__ words) {
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int W = (Lk + 31) >> 5;
+  if (wid >= Bm * Lq * W) return;
+  const int w = static_cast<int>(wid % W);
+  const int q = static_cast<int>((wid / W) % Lq);
+  const long long b = wid / (static_cast<long long>(W) * Lq);
+  const int k = w * 32 + lane;
+  const bool m = k < Lk && mask[b * msb + q * msq + k * msk] != 0;
+  const uint32_t bits = __ballot_sync(0xFFFFFFFFu, m);
+  if (lane == 0) words[wid] = bits;
+}
+
 }  // namespace lamp

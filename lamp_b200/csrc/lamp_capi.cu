@@ -172,6 +172,7 @@ std::atomic<int> g_gemm_block_k{0};   // tuning knob (lamp_set_tuning): 32 -> 64
                                       // 0 -> automatic (64 for CTA pairs: 3 x 64 KB stages; 32 otherwise: 4 x 48 KB)
 std::atomic<int> g_attn_compact{1};   // tuning knob: 1 -> L-dependent tile rows + deepest K/V staging that fits, 0 -> full 128-row tiles, 1 stage
 std::atomic<int> g_attn_stage{1};     // tuning knob: 1 -> O planes leave through the smem staging tile + TMA stores when it fits
+std::atomic<int> g_attn_pv_split{0};  // tuning knob: 1 -> PV product as two interleaved N = 64 chains when d == 128
 std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group::2) for the 256-wide tiles, 0 -> single CTAs
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB: the sm_100 per-CTA opt-in maximum
@@ -190,7 +191,7 @@ int launch_attn(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_b
 }
 
 // Shared-memory plan: Q tile (+ an equally shaped O staging tile when the planes leave through TMA stores) + as many
-// K/V ring slots as fit.  Staging is used when it still leaves >= 3 slots, or 2 for single-tile problems (one K and
+// K/V ring slots as fit.  Staging is used when it still leaves >= 4 slots, or 2 for single-tile problems (one K and
 // one V slot in flight is all such an item has).
 template <int BLOCK_KV, int NTERMS>
 int launch_attn_plan(const CUtensorMap (&tm)[8], AttnParams& p, bool can_stage, cudaStream_t st) {
@@ -205,7 +206,9 @@ int launch_attn_plan(const CUtensorMap (&tm)[8], AttnParams& p, bool can_stage, 
   };
   const bool single = p.Lk <= BLOCK_KV;
   const int ns = can_stage && g_attn_stage.load() ? slots_for(1) : 0;
-  p.staged = (ns >= 3 || (single && ns >= 2)) ? 1 : 0;
+  // multi-tile rows need ring depth more than they need the staged store (K and V rings of >= 2 slots each: the
+  // load-to-use latency is ~1.5 unit periods), single-tile problems have one K and one V tile in flight anyway
+  p.staged = ((!single && ns >= 4) || (single && ns >= 2)) ? 1 : 0;
   p.kv_slots = p.staged ? ns : slots_for(0);
   if (p.kv_slots < 2) return fail(LAMP_EINVAL, "attn: tile does not fit shared memory");
   return launch_attn<BLOCK_KV, NTERMS>(tm, p, attn_smem_bytes(q_bytes, p.slot_bytes, p.kv_slots, p.staged), st);
@@ -244,6 +247,10 @@ int lamp_set_tuning(int key, int value) {
   }
   if (key == LAMP_TUNE_ATTN_STAGE && (value == 0 || value == 1)) {
     g_attn_stage.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_ATTN_PV_SPLIT && (value == 0 || value == 1)) {
+    g_attn_pv_split.store(value);
     return LAMP_OK;
   }
   if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
@@ -448,12 +455,54 @@ int lamp_diag_proj_ln(const void* y_hi, const void* y_lo, const float* stats, in
   return launch_check();
 }
 
+int lamp_pack_mask_bits(const uint8_t* mask, int64_t msb, int64_t msq, int64_t msk, int64_t Bm, int Lq, int Lk,
+                        uint32_t* words, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(mask && words && Bm >= 0 && Lq > 0 && Lk > 0, "pack_mask_bits: bad arguments");
+  const long long nwords = Bm * Lq * ((Lk + 31) / 32);
+  if (nwords == 0) return LAMP_OK;
+  const long long blocks = (nwords * 32 + 255) / 256;
+  pack_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mask, msb, msq, msk, Bm, Lq, Lk, words);
+  return launch_check();
+}
+
+static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                     const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
+                     int Lq, int Lk, int d, float temperature, int precision, const uint8_t* mask,
+                     int64_t msb, int64_t msq, int64_t msk, const uint32_t* mask_bits, int64_t mbb, int64_t mbq,
+                     void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
+                     int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
+                     const int32_t* kv_len, int64_t kv_rows, void* stream);
+
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
                           const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
                           int Lq, int Lk, int d, float temperature, int precision, const uint8_t* mask,
                           int64_t msb, int64_t msq, int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
                           int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
                           const int32_t* kv_len, int64_t kv_rows, void* stream) {
+  return attn_impl(q_hi, q_lo, ldq, q_col0, q_bcast, kv_hi, kv_lo, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature,
+                   precision, mask, msb, msq, msk, nullptr, 0, 0, o_hi, o_lo, ldo, o_f32, ldof, row_max, row_sum, probs,
+                   kv_start, kv_len, kv_rows, stream);
+}
+
+int lamp_attn_core_planes_mbits(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                                const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
+                                int Lq, int Lk, int d, float temperature, int precision, const uint32_t* mask_bits,
+                                int64_t mbb, int64_t mbq, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
+                                int64_t ldof, void* stream) {
+  REQUIRE(mask_bits != nullptr && mbq >= (Lk + 31) / 32, "attn_mbits: packed mask missing or row stride too small");
+  return attn_impl(q_hi, q_lo, ldq, q_col0, q_bcast, kv_hi, kv_lo, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature,
+                   precision, nullptr, 0, 0, 0, mask_bits, mbb, mbq, o_hi, o_lo, ldo, o_f32, ldof, nullptr, nullptr,
+                   nullptr, nullptr, nullptr, 0, stream);
+}
+
+static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                     const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
+                     int Lq, int Lk, int d, float temperature, int precision, const uint8_t* mask,
+                     int64_t msb, int64_t msq, int64_t msk, const uint32_t* mask_bits, int64_t mbb, int64_t mbq,
+                     void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
+                     int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
+                     const int32_t* kv_len, int64_t kv_rows, void* stream) {
   if (int rc = arch_check()) return rc;
   REQUIRE((kv_start == nullptr) == (kv_len == nullptr), "attn: kv_start and kv_len go together");
   REQUIRE(!kv_len || (!probs && kv_rows > 0), "attn: packed keys exclude the probability output");
@@ -511,12 +560,14 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
   p.scale_log2 = 1.4426950408889634f / temperature;
   p.q_col0 = q_col0; p.k_col0 = k_col0; p.v_col0 = v_col0; p.q_bcast = q_bcast;
   p.mask = mask; p.msb = msb; p.msq = msq; p.msk = msk;
+  p.mask_bits = mask_bits; p.mbb = mbb; p.mbq = mbq;
   p.o_hi = static_cast<__nv_bfloat16*>(o_hi);
   p.o_lo = static_cast<__nv_bfloat16*>(o_lo);
   p.ldo = (int)ldo; p.o_f32 = o_f32; p.ldof = (int)ldof;
   p.row_max = row_max; p.row_sum = row_sum;
   p.qrows = qrows; p.krows = krows; p.vrows = vrows;
   p.kv_start = kv_start; p.kv_len = kv_len;
+  p.pv_split = (d == 128 && g_attn_pv_split.load() != 0) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (block_kv == 128)
@@ -543,10 +594,10 @@ int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q
 }
 
 #ifdef LAMP_ATTN_TRACE
-/* debug build only: copies the [16][64] clock64() stamps of CTA 0 of the last attention launch to the host */
+/* debug build only: copies the [64][64] clock64() stamps of CTA 0 of the last attention launch to the host */
 int lamp_debug_attn_trace(unsigned long long* out) {
   cudaDeviceSynchronize();
-  return cudaMemcpyFromSymbol(out, lamp::g_attn_trace, sizeof(unsigned long long) * 16 * 64) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out, lamp::g_attn_trace, sizeof(unsigned long long) * 64 * 64) == cudaSuccess ? 0 : -1;
 }
 #endif
 

@@ -408,6 +408,29 @@ def mask_args(mask: Optional[torch.Tensor], B: int, Lq: int, Lk: int):
     return m8, m8.data_ptr(), sb, sq, sk
 
 
+_MASK_BITS: Dict[tuple, tuple] = {}  # packed label masks, keyed by the byte mask's storage; a handful of entries at most
+
+
+def mask_bits(m8: torch.Tensor, B: int, Lq: int, Lk: int):
+    """Bit-packed form of an expanded uint8 mask view [B, Lq, Lk] (``lamp_pack_mask_bits``) -> (words, mbb, mbq).
+    A mask shared by the batch (stride 0: the label-graph mask) is packed once and cached against its storage."""
+    sb, sq, sk = m8.stride()
+    Bm = 1 if sb == 0 else B
+    W = (Lk + 31) // 32
+    key = (m8.data_ptr(), m8._version, Lq, Lk, sq, sk) if sb == 0 else None
+    hit = _MASK_BITS.get(key) if key is not None else None
+    if hit is not None:
+        return hit[0], 0, W
+    words = torch.empty((Bm, Lq, W), dtype=torch.int32, device=m8.device)
+    STATS.call('pack_mask_bits', 1, nat.lib().lamp_pack_mask_bits,
+               (m8.data_ptr(), sb, sq, sk, Bm, Lq, Lk, words.data_ptr(), nat.stream()), nbytes=Bm * Lq * Lk)
+    if key is not None:
+        if len(_MASK_BITS) >= 16:
+            _MASK_BITS.clear()
+        _MASK_BITS[key] = (words, m8)  # the byte mask is kept alive so that its address cannot be recycled
+    return words, (0 if sb == 0 else Lq * W), W
+
+
 def attention(q: Act, q_col0: int, kv: Act, k_col0: int, v_col0: int, B: int, H: int, Lq: int, Lk: int, d: int,
               prec: int, mask: Optional[torch.Tensor], want_probs: bool, out_f32: bool = False, kv_start=None,
               kv_len=None):
@@ -438,7 +461,18 @@ def attention(q: Act, q_col0: int, kv: Act, k_col0: int, v_col0: int, B: int, H:
 
     def keys(m):
         return B * Lk if m is None else m
-    STATS.call('attn_core_self' if q is kv else 'attn_core_enc', 2 if want_probs else 1, nat.lib().lamp_attn_core_planes,
+    name = 'attn_core_self' if q is kv else 'attn_core_enc'
+    if keep is not None and kv_len is None and not want_probs and sq != 0 and (Lk > 128 or sb != 0):
+        # a real [.., Lq, Lk] mask that the kernel would have to rebuild for every KV tile / sample: hand it over
+        # bit-packed (one word per thread and tile; the shared label-graph mask is packed once and cached)
+        words, mbb, mbq = mask_bits(keep, B, Lq, Lk)
+        STATS.call(name, 1, nat.lib().lamp_attn_core_planes_mbits,
+                   (q.hi.data_ptr(), nat.ptr(q.lo), q.cols, q_col0, 1 if q.bcast_rows else 0,
+                    kv.hi.data_ptr(), nat.ptr(kv.lo), kv.cols, k_col0, v_col0, B, H, Lq, Lk, d, float(math.sqrt(d)),
+                    prec, words.data_ptr(), mbb, mbq, nat.ptr(o_hi), nat.ptr(o_lo), hd, nat.ptr(o32), hd, nat.stream()),
+                   flops=4.0 * H * Lq * d * B * Lk, nbytes=qo_bytes + 2 * B * Lk * hd * pl)
+        return Act(o32, o_hi, o_lo, B * Lq, hd), None
+    STATS.call(name, 2 if want_probs else 1, nat.lib().lamp_attn_core_planes,
                (q.hi.data_ptr(), nat.ptr(q.lo), q.cols, q_col0, 1 if q.bcast_rows else 0,
                 kv.hi.data_ptr(), nat.ptr(kv.lo), kv.cols, k_col0, v_col0, B, H, Lq, Lk, d, float(math.sqrt(d)), prec,
                 mptr, sb, sq, sk, nat.ptr(o_hi), nat.ptr(o_lo), hd, nat.ptr(o32), hd, nat.ptr(rmax), nat.ptr(rsum),

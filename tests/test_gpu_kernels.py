@@ -520,3 +520,49 @@ def test_attn_core_planes_epilogues_and_lazy_rescale(B, H, Lq, Lk, d, maskkind, 
     finally:
         nat.check(nat.lib().lamp_set_tuning(4, 1), 'tune')
     assert torch.equal(outs[0], outs[1])   # same arithmetic, only the way out of the SM differs
+
+
+@pytest.mark.parametrize('B,H,Lq,Lk,d,per_sample', [(2, 4, 983, 983, 128, False), (3, 2, 300, 520, 64, False),
+                                                      (3, 2, 103, 103, 128, True), (2, 8, 159, 159, 64, True),
+                                                      (2, 2, 70, 333, 32, True)])
+def test_attn_core_packed_mask_equals_byte_mask(B, H, Lq, Lk, d, per_sample):
+    """lamp_pack_mask_bits + lamp_attn_core_planes_mbits (one mask word per thread and KV tile) give bit-identical
+    output to the byte-mask path of lamp_attn_core_planes, for the shared [Lq, Lk] label mask (cfg-4 dims incl.) and
+    for per-sample [B, Lq, Lk] masks; the packed words equal a host-side packing."""
+    from lamp_b200 import ops
+    g = torch.Generator().manual_seed(B + H + Lq + Lk + d)
+    hd = H * d
+    qa = ops.Act(None, *ops.split(torch.randn(B * Lq, hd, generator=g).to(DEV), 0), B * Lq, hd)
+    kva = ops.Act(None, *ops.split(torch.randn(B * Lk, 2 * hd, generator=g).to(DEV), 0), B * Lk, 2 * hd)
+    m = torch.rand(B if per_sample else 1, Lq, Lk, generator=g) < 0.7
+    m[:, torch.arange(Lq), torch.arange(Lq) % Lk] = False
+    m8 = m.to(DEV).view(torch.uint8).expand(B, Lq, Lk)
+    # packing kernel vs host packing
+    words, mbb, mbq = ops.mask_bits(m8, B, Lq, Lk)
+    W = (Lk + 31) // 32
+    pad = torch.zeros(m.shape[0], Lq, W * 32, dtype=torch.int64)
+    pad[:, :, :Lk] = m.long()
+    ref_words = (pad.view(m.shape[0], Lq, W, 32) << torch.arange(32)).sum(-1)
+    ref_words = torch.where(ref_words >= 2 ** 31, ref_words - 2 ** 32, ref_words).to(torch.int32)
+    assert torch.equal(words.cpu(), ref_words)
+    assert mbq == W and mbb == (Lq * W if per_sample else 0)
+    L = nat.lib()
+    outs = []
+    for packed in (True, False):
+        o_hi = torch.full((B * Lq, hd), float('nan'), dtype=torch.bfloat16, device=DEV)
+        o_lo = torch.full_like(o_hi, float('nan'))
+        sb, sq, sk = m8.stride()
+        if packed:
+            nat.check(L.lamp_attn_core_planes_mbits(qa.hi.data_ptr(), qa.lo.data_ptr(), hd, 0, 0, kva.hi.data_ptr(),
+                                                    kva.lo.data_ptr(), 2 * hd, 0, hd, B, H, Lq, Lk, d, float(d ** 0.5), 0,
+                                                    words.data_ptr(), mbb, mbq, o_hi.data_ptr(), o_lo.data_ptr(), hd,
+                                                    None, 0, nat.stream()), 'mbits')
+        else:
+            nat.check(L.lamp_attn_core_planes(qa.hi.data_ptr(), qa.lo.data_ptr(), hd, 0, 0, kva.hi.data_ptr(),
+                                              kva.lo.data_ptr(), 2 * hd, 0, hd, B, H, Lq, Lk, d, float(d ** 0.5), 0,
+                                              m8.data_ptr(), sb, sq, sk, o_hi.data_ptr(), o_lo.data_ptr(), hd, None, 0,
+                                              None, None, None, None, None, 0, nat.stream()), 'bytes')
+        torch.cuda.synchronize()
+        outs.append((o_hi.clone(), o_lo.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert not torch.isnan(outs[0][0].float()).any()
