@@ -38,6 +38,10 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':  # the version banner is a bare printf to stdout
+    os.environ['NCCL_DEBUG'] = 'WARN'
 
 CFG = dict(L=103, T=300, V=20000, D=512, d_inner=512, H=4, n_enc=2, n_dec=2, mask='prior', seed=0)
 
