@@ -153,6 +153,15 @@ int lamp_attn_core_planes_mbits(const void* q_hi, const void* q_lo, int64_t ldq,
                                 int64_t mbb, int64_t mbq, void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
                                 int64_t ldof, void* stream);
 
+/* Backward of the attention core (training path; lamp/SubLayers.py:27-43 differentiated):
+ * given q [N,Lq,d], k,v [N,Lk,d], the forward's output O and probabilities P [N,Lq,Lk] (before dropout) and A (after
+ * dropout; NULL = no dropout, A == P), and dO, computes dq, dk, dv (fp32, same shapes as q, k, v).  dS [N,Lq,Lk] is
+ * caller-provided scratch.  p_drop is the dropout rate the forward used (scale 1/(1-p)); the kept set is read off A.
+ * Masked entries need no mask here: their P is 0.  d % 16 == 0, d <= 128.  Deterministic (no atomics). */
+int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const float* dO, const float* O, const float* P,
+                       const float* A, float* dS, float* dq, float* dk, float* dv, int N, int Lq, int Lk, int d,
+                       float temperature, float p_drop, void* stream);
+
 /* out = LayerNorm(y (+ add[row % add_mod or row])) * gamma + beta  (torch.nn.LayerNorm semantics, eps inside the
  * sqrt; lamp/SubLayers.py:117,141).  Writes fp32 and/or planes (any may be NULL).  D % 4 == 0, D <= 4096. */
 int lamp_layernorm(const float* y, const float* add, int add_mod, const float* gamma, const float* beta, float eps,

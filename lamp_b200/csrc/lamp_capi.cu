@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "attn_bwd.cuh"
 #include "attn_core.cuh"
 #include "elementwise.cuh"
 #include "gemm_planes.cuh"
@@ -591,6 +592,40 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
     rc = launch_check();
   }
   return rc;
+}
+
+int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const float* dO, const float* O, const float* P,
+                       const float* A, float* dS, float* dq, float* dk, float* dv, int N, int Lq, int Lk, int d,
+                       float temperature, float p_drop, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(q && k && v && dO && O && P && dS && dq && dk && dv, "attn_bwd: null pointer");
+  REQUIRE(N >= 0 && Lq > 0 && Lk > 0, "attn_bwd: bad shape N=%d Lq=%d Lk=%d", N, Lq, Lk);
+  REQUIRE(d % 16 == 0 && d >= 16 && d <= BWD_DMAX, "attn_bwd: head width %d must be a multiple of 16 in [16,128]", d);
+  REQUIRE(temperature > 0.0f && p_drop >= 0.0f && p_drop < 1.0f, "attn_bwd: bad temperature / dropout rate");
+  REQUIRE((long long)N * Lq * Lk < (1LL << 40), "attn_bwd: probability tensor too large");
+  if (N == 0) return LAMP_OK;
+  AttnBwdParams p;
+  p.N = N; p.Lq = Lq; p.Lk = Lk; p.d = d;
+  p.inv_temp = 1.0f / temperature;
+  p.drop_scale = 1.0f / (1.0f - p_drop);
+  p.q = q; p.k = k; p.v = v; p.dO = dO; p.O = O; p.P = P; p.A = A ? A : P;
+  p.dS = dS; p.dq = dq; p.dk = dk; p.dv = dv;
+  const uint32_t smem = (uint32_t)attn_bwd_smem_bytes(d);
+  static std::once_flag once;
+  static int once_rc = LAMP_OK;
+  std::call_once(once, [] {
+    once_rc = set_smem(attn_bwd_dq_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
+    if (once_rc == LAMP_OK) once_rc = set_smem(attn_bwd_dkv_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
+  });
+  if (once_rc != LAMP_OK) return once_rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long gq = (long long)N * ((Lq + BWD_TILE - 1) / BWD_TILE);
+  const long long gk = (long long)N * ((Lk + BWD_TILE - 1) / BWD_TILE);
+  REQUIRE(gq < (1LL << 31) && gk < (1LL << 31), "attn_bwd: grid too large");
+  attn_bwd_dq_kernel<<<(unsigned)gq, BWD_THREADS, smem, st>>>(p);
+  if (int rc = launch_check()) return rc;
+  attn_bwd_dkv_kernel<<<(unsigned)gk, BWD_THREADS, smem, st>>>(p);
+  return launch_check();
 }
 
 #ifdef LAMP_ATTN_TRACE

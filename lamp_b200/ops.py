@@ -501,6 +501,44 @@ def sdpa(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask, temperature: f
     return out, attn
 
 
+def sdpa_backward(q, k, v, out, probs, attn, grad_out, temperature: float, p_drop: float):
+    """Backward of the attention core through ``lamp_attn_core_bwd`` -> (dq, dk, dv).  ``probs``: softmax output
+    before dropout [N, Lq, Lk]; ``attn``: after dropout (``None`` / same tensor when dropout is off)."""
+    nat.require_cuda(q, k, v, out, probs, grad_out)
+    q, k, v, out, probs = (t.contiguous().float() for t in (q, k, v, out, probs))
+    grad_out = grad_out.contiguous().float()
+    N, Lq, d = q.shape
+    Lk = k.shape[1]
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dS = torch.empty_like(probs)
+    a = None if attn is None or attn is probs else attn.contiguous().float()
+    STATS.call('attn_core_bwd', 2, nat.lib().lamp_attn_core_bwd,
+               (q.data_ptr(), k.data_ptr(), v.data_ptr(), grad_out.data_ptr(), out.data_ptr(), probs.data_ptr(),
+                nat.ptr(a), dS.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), N, Lq, Lk, d,
+                float(temperature), float(p_drop), nat.stream()), flops=10.0 * N * Lq * Lk * d)
+    return dq, dk, dv
+
+
+class SDPAFunction(torch.autograd.Function):
+    """Differentiable attention core on the native kernels: forward = ``lamp_sdpa_fwd`` (the probabilities are kept,
+    as the reference keeps ``attn``), backward = ``lamp_attn_core_bwd``.  No gradient flows through the returned
+    attention map (the reference's layers never use it for the loss)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, temperature, prec):
+        out, attn = sdpa(q, k, v, mask, temperature, prec, want_attn=True)
+        ctx.save_for_backward(q, k, v, out, attn)
+        ctx.temperature = temperature
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_attn):
+        q, k, v, out, attn = ctx.saved_tensors
+        dq, dk, dv = sdpa_backward(q, k, v, out, attn, None, grad_out, ctx.temperature, 0.0)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None
+
+
 def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor, pos_emb: Optional[torch.Tensor],
           prec: int, want_f32: bool = True, row_index=None, m_dev=None) -> Act:
     nat.require_cuda(seq, word_emb)

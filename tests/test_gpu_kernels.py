@@ -566,3 +566,40 @@ def test_attn_core_packed_mask_equals_byte_mask(B, H, Lq, Lk, d, per_sample):
         outs.append((o_hi.clone(), o_lo.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert not torch.isnan(outs[0][0].float()).any()
+
+
+@pytest.mark.parametrize('N,Lq,Lk,d,maskkind', [(6, 103, 103, 128, 'label'), (4, 103, 300, 128, 'pad'),
+                                                 (5, 159, 159, 64, 'none'), (3, 70, 45, 32, 'label'),
+                                                 (2, 200, 130, 48, 'pad'), (2, 33, 17, 16, 'none'),
+                                                 (2, 260, 257, 112, 'label')])
+def test_attn_core_backward_vs_autograd(N, Lq, Lk, d, maskkind):
+    """lamp_attn_core_bwd (dq, dk, dv of softmax(mask(q k^T / T)) v) against fp64 torch autograd of the same function,
+    through ops.SDPAFunction (native forward + native backward)."""
+    from lamp_b200 import ops
+    g = torch.Generator().manual_seed(N + Lq + Lk + d)
+    q = torch.randn(N, Lq, d, generator=g).to(DEV).requires_grad_(True)
+    k = torch.randn(N, Lk, d, generator=g).to(DEV).requires_grad_(True)
+    v = torch.randn(N, Lk, d, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(N, Lq, d, generator=g).to(DEV)
+    mask = None
+    if maskkind == 'label':
+        m = torch.rand(Lq, Lk, generator=g) < 0.6
+        m[torch.arange(Lq), torch.arange(Lq) % Lk] = False
+        mask = m.unsqueeze(0).expand(N, Lq, Lk).to(DEV)
+    elif maskkind == 'pad':
+        lens = torch.randint(1, Lk + 1, (N,), generator=g)
+        mask = (torch.arange(Lk)[None, :] >= lens[:, None]).unsqueeze(1).expand(N, Lq, Lk).to(DEV)
+    T = float(np.power(d, 0.5))
+    out, attn = ops.SDPAFunction.apply(q, k, v, mask, T, 0)
+    out.backward(go)
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    s = qd @ kd.transpose(1, 2) / T
+    if mask is not None:
+        s = s.masked_fill(mask, float('-inf'))
+    ref = torch.softmax(s, -1) @ vd
+    ref.backward(go.double())
+    assert rel_err(out, ref) < 2e-5
+    for name, a, b in (('dq', q.grad, qd.grad), ('dk', k.grad, kd.grad), ('dv', v.grad, vd.grad)):
+        e = rel_err(a, b)
+        print(f'attn bwd N={N} Lq={Lq} Lk={Lk} d={d} {maskkind} {name}: {e:.2e}')
+        assert e < 5e-5, name
