@@ -3,8 +3,9 @@ signatures / return tuples and ``state_dict`` keys -- with the arithmetic execut
 
 * inference (``torch.no_grad()`` or ``module.eval()``): the fused kernel path
   (``lamp_b200.ops`` -> ``liblamp_b200.so``);
-* training (``module.train()`` with grad enabled): a differentiable composition of torch CUDA ops with identical semantics
-  (dropout included); fusing the backward is listed as "next" in DESIGN.md.
+* training (``module.train()`` with grad enabled): the attention core runs on the native kernels in both directions
+  (``ops.SDPAFunction``: forward with in-kernel dropout, ``lamp_attn_core_bwd``); projections, FFN and LayerNorm are
+  a differentiable composition of torch CUDA ops with identical semantics (their native backward is "next" in DESIGN.md).
 
 There is no CPU path: CPU tensors raise.  Reference rough edges fixed at the boundary: masks may be
 ``bool`` or ``uint8``; nothing calls ``.cuda()`` unconditionally.
@@ -61,12 +62,26 @@ class ScaledDotProductAttention(nn.Module):
         attn = self.dropout(attn)
         return torch.bmm(attn, v), attn
 
+    def _kernel_ok(self, q, k, v) -> bool:
+        d = q.shape[-1]
+        return (self.attn_kind == 'softmax' and d % 16 == 0 and d <= 128 and k.shape[-1] == d and v.shape[-1] == d)
+
+    def train_core(self, q, k, v, attn_mask):
+        """Differentiable attention core for the training path: native forward (dropout on the probabilities inside
+        the kernel, seeded from torch's CPU generator) and native backward (``ops.SDPAFunction``); the composed torch
+        ops remain for shapes the kernels do not cover and when ``ops.NATIVE_ATTENTION_BACKWARD`` is off."""
+        if not (ops.NATIVE_ATTENTION_BACKWARD and self._kernel_ok(q, k, v) and q.dtype == torch.float32):
+            return self._composed(q, k, v, attn_mask)
+        p = float(self.dropout.p) if self.training else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+        prec = ops.default_precision() if self.precision is None else self.precision
+        return ops.SDPAFunction.apply(q, k, v, attn_mask, self.temperature, prec, p, seed)
+
     def forward(self, q, k, v, attn_mask=None, stop_sig=False):
         nat.require_cuda(q, k, v, attn_mask)
-        d = q.shape[-1]
-        fused_ok = (self.attn_kind == 'softmax' and d % 16 == 0 and d <= 128 and k.shape[-1] == d
-                    and v.shape[-1] == d)
-        if _needs_autograd(self, q, k, v) or not fused_ok:
+        if _needs_autograd(self, q, k, v):
+            return self.train_core(q, k, v, attn_mask)
+        if not self._kernel_ok(q, k, v):
             return self._composed(q, k, v, attn_mask)
         prec = ops.default_precision() if self.precision is None else self.precision
         return ops.sdpa(q, k, v, attn_mask, self.temperature, prec, want_attn=True)
@@ -117,7 +132,7 @@ class MultiHeadAttention(nn.Module):
         vh = self.w_vs(v).view(sz_b, len_v, n_head, d_v).permute(2, 0, 1, 3).reshape(-1, len_v, d_v)
         if attn_mask is not None:
             attn_mask = attn_mask.bool().repeat(n_head, 1, 1)
-        out, attn = self.attention._composed(qh, kh, vh, attn_mask)
+        out, attn = self.attention.train_core(qh, kh, vh, attn_mask)  # native forward + backward of the core
         out = out.view(n_head, sz_b, len_q, d_v).permute(1, 2, 0, 3).reshape(sz_b, len_q, -1)
         if hasattr(self, 'fc'):
             out = self.fc(out)

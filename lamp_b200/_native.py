@@ -55,6 +55,8 @@ _SIGNATURES = {
     'lamp_diag_proj': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp], _i),
     'lamp_sdpa_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'lamp_sdpa_fwd': ([_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp], _i),
+    'lamp_sdpa_fwd_train': ([_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _f, C.c_uint64,
+                             _vp, _sz, _vp], _i),
     'lamp_mha_workspace_bytes': ([_i, _i, _i, _i, _i, _i, _i, _i], _sz),
     'lamp_mha_fwd': ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i,
                       _i, _f, _vp, _sz, _vp], _i),

@@ -65,7 +65,25 @@ struct AttnParams {
   uint32_t slot_bytes;  // bytes of one ring slot (fits a K tile and a V tile)
   int staged;           // 1: O planes leave through the smem staging tile + TMA store (needs d % 64 == 0)
   int pv_split;         // 1 (d == 128 only): O (+)= P V issued as two interleaved N = 64 accumulation chains
+  // training forward: dropout on the probabilities (lamp/SubLayers.py:40).  keep(n, i, j) is a pure function of
+  // (drop_seed, head-major row (h*B + b)*Lq + i, key j), so the probability kernel reproduces the same kept set.
+  uint32_t drop_thresh;  // 0: off; else an element is dropped iff hash < drop_thresh (= p * 2^32)
+  float drop_scale;      // 1 / (1 - p)
+  unsigned long long drop_seed;
 };
+
+__device__ __forceinline__ uint32_t drop_rowhash(unsigned long long seed, unsigned long long rowkey) {
+  unsigned long long z = seed + rowkey * 0x9E3779B97F4A7C15ull;  // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<uint32_t>(z >> 32);
+}
+__device__ __forceinline__ bool drop_keep(uint32_t rowhash, uint32_t col, uint32_t thresh) {
+  uint32_t h = rowhash ^ (col * 0x9E3779B9u);  // murmur3 finaliser
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h >= thresh;
+}
 
 #ifdef LAMP_ATTN_TRACE
 // Debug build only (scripts/attn_trace.py): clock64() stamps of CTA 0's pipeline events, [event][unit].
@@ -612,11 +630,19 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         float sum = 0.0f;
         const float mb2 = m_use * p.scale_log2;
         uint32_t ph_[16], pl_[16];
+        const uint32_t rh = p.drop_thresh
+                                ? drop_rowhash(p.drop_seed, (static_cast<unsigned long long>(h) * p.B + b) * p.Lq +
+                                                                qt * ATTN_BLOCK_M + row)
+                                : 0u;
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float x0 = ex2_approx(fmaf(__uint_as_float(r[e]), p.scale_log2, -mb2));      // 2^(-inf) = 0 for masked
-          const float x1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), p.scale_log2, -mb2));
-          sum += x0 + x1;
+          float x0 = ex2_approx(fmaf(__uint_as_float(r[e]), p.scale_log2, -mb2));      // 2^(-inf) = 0 for masked
+          float x1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), p.scale_log2, -mb2));
+          sum += x0 + x1;  // the softmax denominator is taken before dropout
+          if (p.drop_thresh) {
+            x0 = drop_keep(rh, static_cast<uint32_t>(k0 + e), p.drop_thresh) ? x0 * p.drop_scale : 0.0f;
+            x1 = drop_keep(rh, static_cast<uint32_t>(k0 + e + 1), p.drop_thresh) ? x1 * p.drop_scale : 0.0f;
+          }
           split_bf16x2(x0, x1, ph_[e >> 1], pl_[e >> 1]);
         }
         tmem_st16(tS, ph_);                      // P overwrites this warp's own 32 score columns: hi pairs ...
@@ -668,7 +694,11 @@ struct ProbsParams {
   const uint8_t* mask;
   long long msb, msq, msk;
   const float *row_max, *row_sum;
-  float* probs;  // [H*B, Lq, Lk]
+  float* probs;      // [H*B, Lq, Lk] (after dropout when drop_thresh != 0: what the reference returns as `attn`)
+  float* probs_pre;  // optional: the probabilities before dropout (saved for the backward)
+  uint32_t drop_thresh;
+  float drop_scale;
+  unsigned long long drop_seed;
 };
 
 __global__ void attn_probs_kernel(const ProbsParams p) {
@@ -685,6 +715,7 @@ __global__ void attn_probs_kernel(const ProbsParams p) {
   const __nv_bfloat16* ql = p.q_lo ? p.q_lo + qrow * p.ldq + p.q_col0 + h * p.d : nullptr;
   const float mx = p.row_max[warp_g], inv = 1.0f / p.row_sum[warp_g];
   float* out = p.probs + warp_g * p.Lk;
+  const uint32_t rh = p.drop_thresh ? drop_rowhash(p.drop_seed, static_cast<unsigned long long>(warp_g)) : 0u;
   for (int j = lane; j < p.Lk; j += 32) {
     const size_t krow = static_cast<size_t>(b) * p.Lk + j;
     const __nv_bfloat16* kh = p.kv_hi + krow * p.ldkv + p.k_col0 + h * p.d;
@@ -700,7 +731,11 @@ __global__ void attn_probs_kernel(const ProbsParams p) {
     if (p.mask != nullptr)
       masked = p.mask[static_cast<long long>(b) * p.msb + static_cast<long long>(i) * p.msq +
                       static_cast<long long>(j) * p.msk] != 0;
-    out[j] = masked ? (0.0f * inv) : exp2f(s * p.scale_log2 - mx) * inv;
+    float pr = masked ? (0.0f * inv) : exp2f(s * p.scale_log2 - mx) * inv;
+    if (p.probs_pre != nullptr) p.probs_pre[warp_g * p.Lk + j] = pr;
+    if (p.drop_thresh && !drop_keep(rh, static_cast<uint32_t>(j), p.drop_thresh)) pr = 0.0f;
+    else if (p.drop_thresh) pr *= p.drop_scale;
+    out[j] = pr;
   }
 }
 

@@ -473,7 +473,8 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
                      int64_t msb, int64_t msq, int64_t msk, const uint32_t* mask_bits, int64_t mbb, int64_t mbq,
                      void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
                      int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
-                     const int32_t* kv_len, int64_t kv_rows, void* stream);
+                     const int32_t* kv_len, int64_t kv_rows, void* stream, float p_drop = 0.0f, uint64_t seed = 0,
+                     float* probs_pre = nullptr);
 
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
                           const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
@@ -503,8 +504,12 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
                      int64_t msb, int64_t msq, int64_t msk, const uint32_t* mask_bits, int64_t mbb, int64_t mbq,
                      void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
                      int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
-                     const int32_t* kv_len, int64_t kv_rows, void* stream) {
+                     const int32_t* kv_len, int64_t kv_rows, void* stream, float p_drop, uint64_t seed,
+                     float* probs_pre) {
   if (int rc = arch_check()) return rc;
+  REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "attn: dropout rate %f outside [0, 1)", (double)p_drop);
+  REQUIRE(p_drop == 0.0f || (!kv_len && !mask_bits), "attn: dropout is a training-path feature (dense keys, byte mask)");
+  REQUIRE(!probs_pre || probs, "attn: probs_pre goes with probs");
   REQUIRE((kv_start == nullptr) == (kv_len == nullptr), "attn: kv_start and kv_len go together");
   REQUIRE(!kv_len || (!probs && kv_rows > 0), "attn: packed keys exclude the probability output");
   REQUIRE(!kv_len || !mask || (msb == 0 && msq == 0), "attn: with packed keys the mask is one byte per packed key row");
@@ -569,6 +574,10 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
   p.qrows = qrows; p.krows = krows; p.vrows = vrows;
   p.kv_start = kv_start; p.kv_len = kv_len;
   p.pv_split = (d == 128 && g_attn_pv_split.load() != 0) ? 1 : 0;
+  p.drop_thresh = p_drop > 0.0f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
+  if (p_drop > 0.0f && p.drop_thresh == 0u) p.drop_thresh = 1u;
+  p.drop_scale = 1.0f / (1.0f - p_drop);
+  p.drop_seed = seed;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (block_kv == 128)
@@ -586,6 +595,7 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
     pp.ldq = (int)ldq; pp.ldkv = (int)ldkv; pp.q_col0 = q_col0; pp.k_col0 = k_col0; pp.q_bcast = q_bcast;
     pp.mask = mask; pp.msb = msb; pp.msq = msq; pp.msk = msk;
     pp.row_max = row_max; pp.row_sum = row_sum; pp.probs = probs;
+    pp.probs_pre = probs_pre; pp.drop_thresh = p.drop_thresh; pp.drop_scale = p.drop_scale; pp.drop_seed = seed;
     const long long nrows = (long long)H * B * Lq;
     const long long blocks = (nrows * 32 + 255) / 256;
     attn_probs_kernel<<<(unsigned)blocks, 256, 0, st>>>(pp);
@@ -715,9 +725,32 @@ size_t lamp_sdpa_workspace_bytes(int N, int Lq, int Lk, int d) {
   return c.off;
 }
 
+static int sdpa_impl(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
+                     int64_t msk, float* out, float* attn, float* probs_pre, int N, int Lq, int Lk, int d,
+                     float temperature, int precision, float p_drop, uint64_t seed, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 int lamp_sdpa_fwd(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
                   int64_t msk, float* out, float* attn, int N, int Lq, int Lk, int d, float temperature,
                   int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  return sdpa_impl(q, k, v, mask, msb, msq, msk, out, attn, nullptr, N, Lq, Lk, d, temperature, precision, 0.0f, 0,
+                   workspace, workspace_bytes, stream);
+}
+
+int lamp_sdpa_fwd_train(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
+                        int64_t msk, float* out, float* attn, float* probs_pre, int N, int Lq, int Lk, int d,
+                        float temperature, int precision, float p_drop, uint64_t seed, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  REQUIRE(attn != nullptr, "sdpa_train: the attention map is part of the training forward");
+  REQUIRE(p_drop == 0.0f || probs_pre != nullptr, "sdpa_train: probs_pre is required when dropout is active");
+  return sdpa_impl(q, k, v, mask, msb, msq, msk, out, attn, probs_pre, N, Lq, Lk, d, temperature, precision, p_drop,
+                   seed, workspace, workspace_bytes, stream);
+}
+
+static int sdpa_impl(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
+                     int64_t msk, float* out, float* attn, float* probs_pre, int N, int Lq, int Lk, int d,
+                     float temperature, int precision, float p_drop, uint64_t seed, void* workspace,
+                     size_t workspace_bytes, void* stream) {
   REQUIRE(q && k && v && out, "sdpa: null pointer");
   REQUIRE(N >= 0 && Lq > 0 && Lk > 0 && d > 0, "sdpa: bad shape");
   if (!workspace || workspace_bytes < lamp_sdpa_workspace_bytes(N, Lq, Lk, d))
@@ -734,8 +767,9 @@ int lamp_sdpa_fwd(const float* q, const float* k, const float* v, const uint8_t*
   // K and V side by side in one [N*Lk, 2d] matrix so that a single tensor map serves both operands
   if (int rc = lamp_split_planes(k, (int64_t)N * Lk, d, d, kvp, kvlo, 2 * d, stream)) return rc;
   if (int rc = lamp_split_planes(v, (int64_t)N * Lk, d, d, kvp + d, three ? kvlo + d : nullptr, 2 * d, stream)) return rc;
-  return lamp_attn_core_planes(qp, qlo, d, 0, 0, kvp, kvlo, 2 * d, 0, d, N, 1, Lq, Lk, d, temperature, precision, mask,
-                               msb, msq, msk, nullptr, nullptr, 0, out, d, stats, stats + (size_t)N * Lq, attn, nullptr, nullptr, 0, stream);
+  return attn_impl(qp, qlo, d, 0, 0, kvp, kvlo, 2 * d, 0, d, N, 1, Lq, Lk, d, temperature, precision, mask, msb, msq, msk,
+                   nullptr, 0, 0, nullptr, nullptr, 0, out, d, stats, stats + (size_t)N * Lq, attn, nullptr, nullptr, 0,
+                   stream, p_drop, seed, probs_pre);
 }
 
 namespace {

@@ -336,6 +336,7 @@ def linear_residual_deferred(x: Act, w_hi, w_lo, N: int, prec: int, residual: Ac
     return Act(None, hi, lo, M, N, 0, x.m_dev, DeferredLN(stats, nparts, gamma, beta, eps))
 
 
+NATIVE_ATTENTION_BACKWARD = os.environ.get('LAMP_NATIVE_ATTN_BWD', '1') != '0'  # training: attention core fwd+bwd native
 PADDING_AWARE = True  # GraphEncoder/GraphDecoder compute only non-PAD token rows (results identical, see Encoders.py)
 # fc / w_2 GEMMs emit pre-norm planes + row statistics and the LayerNorm is applied by the consumers (no LayerNorm
 # kernels inside the stack).  LAMP_DEFER_LN=0/1 overrides the default (benchmarking aid; results agree to fp32 rounding).
@@ -519,24 +520,46 @@ def sdpa_backward(q, k, v, out, probs, attn, grad_out, temperature: float, p_dro
     return dq, dk, dv
 
 
+def sdpa_train(q, k, v, mask, temperature: float, prec: int, p_drop: float, seed: int):
+    """Training forward of the attention core (dropout inside the kernel) -> (out, attn after dropout, probabilities
+    before dropout -- the same tensor as attn when p_drop == 0)."""
+    nat.require_cuda(q, k, v)
+    q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+    N, Lq, d = q.shape
+    Lk = k.shape[1]
+    L = nat.lib()
+    out = torch.empty((N, Lq, d), dtype=torch.float32, device=q.device)
+    attn = torch.empty((N, Lq, Lk), dtype=torch.float32, device=q.device)
+    pre = torch.empty_like(attn) if p_drop > 0 else None
+    ws = torch.empty((max(L.lamp_sdpa_workspace_bytes(N, Lq, Lk, d), 16),), dtype=torch.uint8, device=q.device)
+    keep, mptr, sb, sq, sk = mask_args(mask, N, Lq, Lk)
+    STATS.call('sdpa_fwd_train', 5, L.lamp_sdpa_fwd_train,
+               (q.data_ptr(), k.data_ptr(), v.data_ptr(), mptr, sb, sq, sk, out.data_ptr(), attn.data_ptr(), nat.ptr(pre),
+                N, Lq, Lk, d, float(temperature), prec, float(p_drop), int(seed), ws.data_ptr(), ws.numel(),
+                nat.stream()), flops=4.0 * N * Lq * Lk * d)
+    del keep
+    return out, attn, (attn if pre is None else pre)
+
+
 class SDPAFunction(torch.autograd.Function):
-    """Differentiable attention core on the native kernels: forward = ``lamp_sdpa_fwd`` (the probabilities are kept,
-    as the reference keeps ``attn``), backward = ``lamp_attn_core_bwd``.  No gradient flows through the returned
-    attention map (the reference's layers never use it for the loss)."""
+    """Differentiable attention core on the native kernels: forward = ``lamp_sdpa_fwd_train`` (dropout inside the
+    kernel; the probabilities are kept, as the reference keeps ``attn``), backward = ``lamp_attn_core_bwd``.  No
+    gradient flows through the returned attention map (the reference's layers never use it for the loss)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, mask, temperature, prec):
-        out, attn = sdpa(q, k, v, mask, temperature, prec, want_attn=True)
-        ctx.save_for_backward(q, k, v, out, attn)
-        ctx.temperature = temperature
+    def forward(ctx, q, k, v, mask, temperature, prec, p_drop=0.0, seed=0):
+        out, attn, pre = sdpa_train(q, k, v, mask, temperature, prec, p_drop, seed)
+        ctx.save_for_backward(q, k, v, out, pre, attn)
+        ctx.temperature, ctx.p_drop = temperature, p_drop
         ctx.mark_non_differentiable(attn)
         return out, attn
 
     @staticmethod
     def backward(ctx, grad_out, _grad_attn):
-        q, k, v, out, attn = ctx.saved_tensors
-        dq, dk, dv = sdpa_backward(q, k, v, out, attn, None, grad_out, ctx.temperature, 0.0)
-        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None
+        q, k, v, out, pre, attn = ctx.saved_tensors
+        dq, dk, dv = sdpa_backward(q, k, v, out, pre, attn if ctx.p_drop > 0 else None, grad_out, ctx.temperature,
+                                   ctx.p_drop)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None, None, None
 
 
 def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor, pos_emb: Optional[torch.Tensor],

@@ -603,3 +603,49 @@ def test_attn_core_backward_vs_autograd(N, Lq, Lk, d, maskkind):
         e = rel_err(a, b)
         print(f'attn bwd N={N} Lq={Lq} Lk={Lk} d={d} {maskkind} {name}: {e:.2e}')
         assert e < 5e-5, name
+
+
+@pytest.mark.parametrize('N,Lq,Lk,d,pdrop', [(8, 103, 103, 128, 0.2), (4, 103, 300, 128, 0.1), (4, 159, 159, 64, 0.5),
+                                              (3, 260, 257, 32, 0.3)])
+def test_attn_core_training_forward_dropout_and_backward(N, Lq, Lk, d, pdrop):
+    """lamp_sdpa_fwd_train: dropout on the probabilities inside the attention kernel (lamp/SubLayers.py:40).
+    (i) probs_pre is the softmax, attn == probs_pre * keep / (1 - p) for a kept set of the right size that changes
+    with the seed and not with anything else, (ii) out == attn @ v, i.e. the PV product consumed exactly the kept set
+    the probability kernel reports, (iii) the backward equals fp64 autograd of the same function with that kept set."""
+    from lamp_b200 import ops
+    g = torch.Generator().manual_seed(N + Lq + Lk + d)
+    q = torch.randn(N, Lq, d, generator=g).to(DEV).requires_grad_(True)
+    k = torch.randn(N, Lk, d, generator=g).to(DEV).requires_grad_(True)
+    v = torch.randn(N, Lk, d, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(N, Lq, d, generator=g).to(DEV)
+    m = torch.rand(Lq, Lk, generator=g) < 0.3
+    m[torch.arange(Lq), torch.arange(Lq) % Lk] = False
+    mask = m.unsqueeze(0).expand(N, Lq, Lk).to(DEV)
+    T = float(np.power(d, 0.5))
+    out, attn, pre = ops.sdpa_train(q.detach(), k.detach(), v.detach(), mask, T, 0, pdrop, 1234)
+    out2, attn2, _ = ops.sdpa_train(q.detach(), k.detach(), v.detach(), mask, T, 0, pdrop, 1234)
+    out3, attn3, _ = ops.sdpa_train(q.detach(), k.detach(), v.detach(), mask, T, 0, pdrop, 99)
+    torch.cuda.synchronize()
+    assert torch.equal(attn, attn2) and torch.equal(out, out2)          # same seed -> same kept set
+    assert not torch.equal(attn != 0, attn3 != 0)                        # another seed -> another kept set
+    s = (q.detach().double() @ k.detach().double().transpose(1, 2) / T).masked_fill(mask, float('-inf'))
+    P = torch.softmax(s, -1)
+    assert rel_err(pre, P) < 2e-5
+    keep = attn != 0
+    live = P > 1e-30
+    frac = float(keep[live].double().mean())
+    assert abs(frac - (1 - pdrop)) < 0.01, frac
+    assert rel_err(attn, P * keep / (1 - pdrop)) < 2e-5
+    assert rel_err(out, (P * keep / (1 - pdrop)) @ v.detach().double()) < 2e-5
+    # backward through the Function with the same seed
+    o, a = ops.SDPAFunction.apply(q, k, v, mask, T, 0, pdrop, 1234)
+    assert torch.equal(a, attn)
+    o.backward(go)
+    qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    sd = (qd @ kd.transpose(1, 2) / T).masked_fill(mask, float('-inf'))
+    ref = (torch.softmax(sd, -1) * keep / (1 - pdrop)) @ vd
+    ref.backward(go.double())
+    for name, x, y in (('dq', q.grad, qd.grad), ('dk', k.grad, kd.grad), ('dv', v.grad, vd.grad)):
+        e = rel_err(x.detach(), y)
+        print(f'attn train p={pdrop} N={N} Lq={Lq} Lk={Lk} d={d} {name}: {e:.2e}')
+        assert e < 5e-5, name

@@ -104,6 +104,66 @@ def test_training_path_is_differentiable_and_matches_oracle_without_dropout():
     assert all(('encoder.layer_stack' in n and 'slf_attn' in n) or n == 'encoder.position_enc.weight' for n in dead), dead
 
 
+def test_training_gradients_native_attention_core_equals_composed_path():
+    """Training step with the attention core native in both directions (ops.SDPAFunction) vs the all-torch composed
+    path: same logits and the same gradient for every parameter (dropout off so that both are deterministic)."""
+    from lamp_b200 import ops
+    c = dict(cases.MODEL_CASES['lamp_L37_none'])
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+    res = {}
+    for native in (True, False):
+        ops.NATIVE_ATTENTION_BACKWARD = native
+        try:
+            model = build_model(c, p, adj)
+            model.train()
+            for mod in model.modules():
+                if isinstance(mod, torch.nn.Dropout):
+                    mod.p = 0.0
+            ops.STATS.reset()
+            logits, _, _ = model(src, None, None, None)
+            tgt = (torch.arange(logits.numel(), device=DEV).view_as(logits) % 3 == 0).float()
+            torch.nn.functional.binary_cross_entropy_with_logits(logits, tgt).backward()
+            torch.cuda.synchronize()
+            res[native] = (logits.detach(), {n: q.grad.clone() for n, q in model.named_parameters() if q.grad is not None},
+                           dict(ops.STATS.by_kernel))
+        finally:
+            ops.NATIVE_ATTENTION_BACKWARD = True
+    assert res[True][2].get('attn_core_bwd', 0) > 0 and res[False][2].get('attn_core_bwd', 0) == 0
+    assert rel_err(res[True][0], res[False][0]) < 1e-4
+    assert res[True][1].keys() == res[False][1].keys()
+    worst = max((rel_err(res[True][1][n], res[False][1][n]), n) for n in res[True][1])
+    print('worst gradient difference native vs composed:', worst)
+    assert worst[0] < 1e-3, worst
+
+
+def test_training_with_dropout_runs_native_core_and_is_seeded():
+    """model.train() with the reference's dropout rates: the native core applies dropout to the probabilities, two
+    steps with the same torch seed give identical losses and gradients, another seed gives different ones."""
+    from lamp_b200 import ops
+    c = dict(cases.MODEL_CASES['lamp_L37_none'])
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+
+    def step(seed):
+        torch.manual_seed(seed)
+        model = build_model(c, p, adj)
+        model.train()
+        logits, _, _ = model(src, None, None, None)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, torch.zeros_like(logits))
+        loss.backward()
+        return float(loss), model.decoder.layer_stack[0].slf_attn.w_qs.weight.grad.clone()
+
+    ops.STATS.reset()
+    l1, g1 = step(5)
+    assert ops.STATS.by_kernel.get('attn_core_bwd', 0) > 0
+    l2, g2 = step(5)
+    l3, g3 = step(6)
+    assert l1 == l2 and torch.equal(g1, g2)
+    assert l1 != l3 and not torch.equal(g1, g3)
+    assert torch.isfinite(g1).all()
+
+
 @pytest.mark.parametrize('name', ['self_L103_H4_prior', 'enc_L103_T300_H4_pad', 'self_L40_H1_nofc',
                                   'self_L983_H4_prior'])
 def test_mha_module(name):
