@@ -162,6 +162,17 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
                        const float* A, float* dS, float* dq, float* dk, float* dv, int N, int Lq, int Lk, int d,
                        float temperature, float p_drop, void* stream);
 
+/* Backward of out = LayerNorm(x)*gamma+beta: dx (fp32), and dgamma / dbeta ACCUMULATED into the given [D] buffers
+ * (zero them first).  x is the LayerNorm input saved by the forward. */
+int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
+                       float* dgamma, float* dbeta, void* stream);
+
+/* Weight / bias gradient of Y = X W^T (+ b): dW[N,K] += dY[M,N]^T X[M,K], db[N] += column sums of dY (db may be
+ * NULL).  Accumulating (fp32 atomics over row chunks): zero or pre-load dW / db.  The input gradient dX = dY W is
+ * lamp_gemm_planes on the transposed weight planes. */
+int lamp_gemm_tn_acc(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t M, int N, int K, float* dW,
+                     float* db, void* stream);
+
 /* out = LayerNorm(y (+ add[row % add_mod or row])) * gamma + beta  (torch.nn.LayerNorm semantics, eps inside the
  * sqrt; lamp/SubLayers.py:117,141).  Writes fp32 and/or planes (any may be NULL).  D % 4 == 0, D <= 4096. */
 int lamp_layernorm(const float* y, const float* add, int add_mod, const float* gamma, const float* beta, float eps,
@@ -184,6 +195,11 @@ int lamp_zero_guard_rows(void* hi, void* lo, int64_t ld, int cols, const int32_t
 /* logits[b,l] = <x[b,l,:], W[l,:]> (+bias[l]) : the diagonal of the [B,L,L] projection, lamp/Models.py:124-126. */
 int lamp_diag_proj(const float* x, const float* W, const float* bias, int64_t B, int L, int D, float* logits,
                    void* stream);
+
+/* Backward of lamp_diag_proj: dx[b,l,:] = g[b,l] W[l,:] (dx may be NULL), dW[l,:] = sum_b g[b,l] x[b,l,:] and
+ * dbias[l] = sum_b g[b,l] (dW / dbias may be NULL; they are WRITTEN, not accumulated). */
+int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B, int L, int D, float* dx, float* dW,
+                       float* dbias, void* stream);
 
 /* ---------------------------------------------------------------- level 2: reference-shaped ops ----------- */
 

@@ -67,6 +67,9 @@ class LAMP(nn.Module):
         lin = self.tgt_word_proj.linear
         if fused and self.proj_share_weight:
             return ops.diag_proj(x, lin.weight, lin.bias)
+        if (self.proj_share_weight and ops.NATIVE_TRAINING and x.is_cuda and x.dtype == torch.float32
+                and x.shape[-1] % 4 == 0):
+            return ops.DiagProjFunction.apply(x, lin.weight, lin.bias)  # training: row dots instead of [B, L, L]
         return torch.diagonal(self.tgt_word_proj(x), 0, 1, 2)
 
     def forward(self, src, adj, tgt_seq, binary_tgt, return_attns=False, int_preds=False):

@@ -4,8 +4,10 @@ signatures / return tuples and ``state_dict`` keys -- with the arithmetic execut
 * inference (``torch.no_grad()`` or ``module.eval()``): the fused kernel path
   (``lamp_b200.ops`` -> ``liblamp_b200.so``);
 * training (``module.train()`` with grad enabled): the attention core runs on the native kernels in both directions
-  (``ops.SDPAFunction``: forward with in-kernel dropout, ``lamp_attn_core_bwd``); projections, FFN and LayerNorm are
-  a differentiable composition of torch CUDA ops with identical semantics (their native backward is "next" in DESIGN.md).
+  (``ops.SDPAFunction``: forward with in-kernel dropout, ``lamp_attn_core_bwd``), and so do the projections, both FFN
+  contractions and the LayerNorms (``ops.LinearFunction`` / ``ops.LayerNormFunction``: tcgen05 GEMM for y and dx,
+  ``lamp_gemm_tn_acc`` for dW / db, ``lamp_layernorm_bwd``); head split/merge, ReLU, residual adds and the two
+  element-wise dropouts are torch glue.
 
 There is no CPU path: CPU tensors raise.  Reference rough edges fixed at the boundary: masks may be
 ``bool`` or ``uint8``; nothing calls ``.cuda()`` unconditionally.
@@ -127,17 +129,18 @@ class MultiHeadAttention(nn.Module):
         sz_b, len_q, _ = q.size()
         len_k, len_v = k.size(1), v.size(1)
         residual = q
-        qh = self.w_qs(q).view(sz_b, len_q, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_q, d_k)
-        kh = self.w_ks(k).view(sz_b, len_k, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_k, d_k)
-        vh = self.w_vs(v).view(sz_b, len_v, n_head, d_v).permute(2, 0, 1, 3).reshape(-1, len_v, d_v)
+        lin = ops.linear_train  # native GEMMs (forward, dx, dW) when the shape allows, torch otherwise
+        qh = lin(q, self.w_qs.weight, None).view(sz_b, len_q, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_q, d_k)
+        kh = lin(k, self.w_ks.weight, None).view(sz_b, len_k, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_k, d_k)
+        vh = lin(v, self.w_vs.weight, None).view(sz_b, len_v, n_head, d_v).permute(2, 0, 1, 3).reshape(-1, len_v, d_v)
         if attn_mask is not None:
             attn_mask = attn_mask.bool().repeat(n_head, 1, 1)
         out, attn = self.attention.train_core(qh, kh, vh, attn_mask)  # native forward + backward of the core
         out = out.view(n_head, sz_b, len_q, d_v).permute(1, 2, 0, 3).reshape(sz_b, len_q, -1)
         if hasattr(self, 'fc'):
-            out = self.fc(out)
+            out = lin(out, self.fc.weight, None)
         out = self.dropout(out)
-        return self.layer_norm(out + residual), attn
+        return ops.layernorm_train(out + residual, self.layer_norm), attn
 
     # ------------------------------------------------------------------ fused path on Act objects
     def fused_ok(self) -> bool:
@@ -220,9 +223,9 @@ class PositionwiseFeedForward(nn.Module):
     def _composed(self, x):
         # Conv1d(k=1) == per-position linear map; F.linear keeps the training path in true fp32 (cuDNN convolutions
         # default to TF32, which would put 1e-3-level noise into the gradients)
-        h = F.relu(F.linear(x, self.w_1.weight.squeeze(-1), self.w_1.bias))
-        out = F.linear(h, self.w_2.weight.squeeze(-1), self.w_2.bias)
-        return self.layer_norm(self.dropout(out) + x)
+        h = F.relu(ops.linear_train(x, self.w_1.weight, self.w_1.bias))
+        out = ops.linear_train(h, self.w_2.weight, self.w_2.bias)
+        return ops.layernorm_train(self.dropout(out) + x, self.layer_norm)
 
     def fused_ok(self) -> bool:
         return self.w_1.in_channels % 8 == 0 and self.w_1.out_channels % 8 == 0

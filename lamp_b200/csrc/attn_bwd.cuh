@@ -298,4 +298,111 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_dkv_kernel(const Attn
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- probabilities
+// Attention probabilities of the training forward (and of `return_attns=True`): P = exp2(q.k * scale - max) / sum from
+// the operand planes and the row statistics the attention core saved, on the tensor cores (the warp-per-row
+// attn_probs_kernel recomputes q.k with scalar FMAs and took 80 % of a training step).  One CTA per (h, b, 64-row q
+// tile), loop over 64-key tiles; writes `probs` (after dropout, what the reference returns) and optionally
+// `probs_pre` (before dropout, saved for the backward), both [H*B, Lq, Lk] head-major.
+struct ProbsMmaParams {
+  int B, H, Lq, Lk, d;
+  float scale_log2;
+  const __nv_bfloat16 *q_hi, *q_lo, *kv_hi, *kv_lo;  // lo nullable (bf16 mode)
+  int ldq, ldkv, q_col0, k_col0, q_bcast;
+  const uint8_t* mask;
+  long long msb, msq, msk;
+  const float *row_max, *row_sum;
+  float* probs;
+  float* probs_pre;
+  uint32_t drop_thresh;
+  float drop_scale;
+  unsigned long long drop_seed;
+};
+
+// bf16 plane tile [rows x cols] (cols % 2 == 0, rows beyond rows_valid read as 0) -> smem (leading dim lds)
+__device__ __forceinline__ void bwd_stage_planes(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                                 long long ld, int rows_valid, int rows, int cols, __nv_bfloat16* dhi,
+                                                 __nv_bfloat16* dlo, int lds) {
+  for (int idx = threadIdx.x; idx < rows * (cols >> 1); idx += BWD_THREADS) {
+    const int r = idx / (cols >> 1), c = (idx % (cols >> 1)) << 1;
+    uint32_t h = 0u, l = 0u;
+    if (r < rows_valid) {
+      h = *reinterpret_cast<const uint32_t*>(hi + r * ld + c);
+      if (lo != nullptr) l = *reinterpret_cast<const uint32_t*>(lo + r * ld + c);
+    }
+    *reinterpret_cast<uint32_t*>(dhi + r * lds + c) = h;
+    *reinterpret_cast<uint32_t*>(dlo + r * lds + c) = l;
+  }
+}
+
+__host__ __device__ constexpr size_t attn_probs_smem_bytes(int d) {
+  return static_cast<size_t>(2) * 2 * BWD_TILE * bwd_dp(d) * 2 + BWD_TILE * (BWD_TILE + 4) * 4 + 2 * BWD_TILE * 4 + 128;
+}
+
+__global__ void __launch_bounds__(BWD_THREADS) attn_probs_mma_kernel(const ProbsMmaParams p) {
+  using namespace nvcuda;
+  extern __shared__ __align__(128) uint8_t bsm[];
+  const int DP = bwd_dp(p.d), FP = BWD_TILE + 4;
+  __nv_bfloat16* Q_hi = reinterpret_cast<__nv_bfloat16*>(bsm);
+  __nv_bfloat16* Q_lo = Q_hi + BWD_TILE * DP;
+  __nv_bfloat16* K_hi = Q_lo + BWD_TILE * DP;
+  __nv_bfloat16* K_lo = K_hi + BWD_TILE * DP;
+  float* S = reinterpret_cast<float*>(K_lo + BWD_TILE * DP);
+  float* rmx = S + BWD_TILE * FP;
+  float* rinv = rmx + BWD_TILE;
+
+  const int num_qt = (p.Lq + BWD_TILE - 1) / BWD_TILE;
+  const int qt = blockIdx.x % num_qt;
+  const int hb = blockIdx.x / num_qt;          // h * B + b (head-major)
+  const int b = hb % p.B, h = hb / p.B;
+  const int q0 = qt * BWD_TILE;
+  const int qrows = min(BWD_TILE, p.Lq - q0);
+  const int warp = threadIdx.x >> 5;
+  const int wr = (warp & 3) * 16, wh = warp >> 2;
+  const long long qrow0 = (p.q_bcast ? 0LL : static_cast<long long>(b) * p.Lq) + q0;
+  bwd_stage_planes(p.q_hi + qrow0 * p.ldq + p.q_col0 + h * p.d, p.q_lo ? p.q_lo + qrow0 * p.ldq + p.q_col0 + h * p.d : nullptr,
+                   p.ldq, qrows, BWD_TILE, p.d, Q_hi, Q_lo, DP);
+  const long long stat0 = static_cast<long long>(hb) * p.Lq + q0;
+  for (int r = threadIdx.x; r < BWD_TILE; r += BWD_THREADS) {
+    rmx[r] = r < qrows ? p.row_max[stat0 + r] : 0.0f;
+    rinv[r] = r < qrows ? 1.0f / p.row_sum[stat0 + r] : 0.0f;
+  }
+  const int num_kt = (p.Lk + BWD_TILE - 1) / BWD_TILE;
+  for (int kt = 0; kt < num_kt; ++kt) {
+    const int k0 = kt * BWD_TILE;
+    const int krows = min(BWD_TILE, p.Lk - k0);
+    __syncthreads();
+    const long long krow0 = static_cast<long long>(b) * p.Lk + k0;
+    bwd_stage_planes(p.kv_hi + krow0 * p.ldkv + p.k_col0 + h * p.d,
+                     p.kv_lo ? p.kv_lo + krow0 * p.ldkv + p.k_col0 + h * p.d : nullptr, p.ldkv, krows, BWD_TILE, p.d, K_hi,
+                     K_lo, DP);
+    __syncthreads();
+    FragC acc[2];
+    wmma::fill_fragment(acc[0], 0.0f);
+    wmma::fill_fragment(acc[1], 0.0f);
+    bwd_mma<2, false, true>(acc, Q_hi, Q_lo, DP, wr, K_hi, K_lo, DP, 32 * wh, p.d);
+    wmma::store_matrix_sync(S + wr * FP + 32 * wh, acc[0], FP, wmma::mem_row_major);
+    wmma::store_matrix_sync(S + wr * FP + 32 * wh + 16, acc[1], FP, wmma::mem_row_major);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < BWD_TILE * BWD_TILE; idx += BWD_THREADS) {
+      const int r = idx >> 6, c = idx & 63;
+      if (r < qrows && c < krows) {
+        const int i = q0 + r, j = k0 + c;
+        bool masked = false;
+        if (p.mask != nullptr)
+          masked = p.mask[static_cast<long long>(b) * p.msb + static_cast<long long>(i) * p.msq +
+                          static_cast<long long>(j) * p.msk] != 0;
+        float pr = masked ? (0.0f * rinv[r]) : exp2f(S[r * FP + c] * p.scale_log2 - rmx[r]) * rinv[r];
+        const long long g = (stat0 + r) * p.Lk + j;
+        if (p.probs_pre != nullptr) p.probs_pre[g] = pr;
+        if (p.drop_thresh) {
+          const uint32_t rh = drop_rowhash(p.drop_seed, static_cast<unsigned long long>(stat0 + r));
+          pr = drop_keep(rh, static_cast<uint32_t>(j), p.drop_thresh) ? pr * p.drop_scale : 0.0f;
+        }
+        p.probs[g] = pr;
+      }
+    }
+  }
+}
+
 }  // namespace lamp

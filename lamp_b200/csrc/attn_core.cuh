@@ -72,19 +72,6 @@ struct AttnParams {
   unsigned long long drop_seed;
 };
 
-__device__ __forceinline__ uint32_t drop_rowhash(unsigned long long seed, unsigned long long rowkey) {
-  unsigned long long z = seed + rowkey * 0x9E3779B97F4A7C15ull;  // splitmix64
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<uint32_t>(z >> 32);
-}
-__device__ __forceinline__ bool drop_keep(uint32_t rowhash, uint32_t col, uint32_t thresh) {
-  uint32_t h = rowhash ^ (col * 0x9E3779B9u);  // murmur3 finaliser
-  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-  return h >= thresh;
-}
-
 #ifdef LAMP_ATTN_TRACE
 // Debug build only (scripts/attn_trace.py): clock64() stamps of CTA 0's pipeline events, [event][unit].
 __device__ unsigned long long g_attn_trace[16 + 48][64];  // rows 16..: per softmax warp (16 warps x {S seen, max bar, P stored})
@@ -680,62 +667,6 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, ATTN_TMEM_COLS);
-  }
-}
-
-// Attention probabilities for `return_attns=True` (diagnostic path; lamp/SubLayers.py:121 returns them to the
-// caller).  Recomputes s = q.k from the planes with fp32 FMAs and normalises with the row statistics saved by
-// attn_core_kernel:  P[h*B+b, i, j] = exp2(s*scale - max_i) / sum_i  (head-major batch, lamp/SubLayers.py:96-98).
-struct ProbsParams {
-  int B, H, Lq, Lk, d;
-  float scale_log2;
-  const __nv_bfloat16 *q_hi, *q_lo, *kv_hi, *kv_lo;  // lo nullable
-  int ldq, ldkv, q_col0, k_col0, q_bcast;
-  const uint8_t* mask;
-  long long msb, msq, msk;
-  const float *row_max, *row_sum;
-  float* probs;      // [H*B, Lq, Lk] (after dropout when drop_thresh != 0: what the reference returns as `attn`)
-  float* probs_pre;  // optional: the probabilities before dropout (saved for the backward)
-  uint32_t drop_thresh;
-  float drop_scale;
-  unsigned long long drop_seed;
-};
-
-__global__ void attn_probs_kernel(const ProbsParams p) {
-  // one warp per (h, b, i) row; lanes stride over keys
-  const long long warp_g = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long nrows = static_cast<long long>(p.H) * p.B * p.Lq;
-  if (warp_g >= nrows) return;
-  const int i = static_cast<int>(warp_g % p.Lq);
-  const int b = static_cast<int>((warp_g / p.Lq) % p.B);
-  const int h = static_cast<int>(warp_g / (static_cast<long long>(p.Lq) * p.B));
-  const size_t qrow = (p.q_bcast ? 0 : static_cast<size_t>(b) * p.Lq) + i;
-  const __nv_bfloat16* qh = p.q_hi + qrow * p.ldq + p.q_col0 + h * p.d;
-  const __nv_bfloat16* ql = p.q_lo ? p.q_lo + qrow * p.ldq + p.q_col0 + h * p.d : nullptr;
-  const float mx = p.row_max[warp_g], inv = 1.0f / p.row_sum[warp_g];
-  float* out = p.probs + warp_g * p.Lk;
-  const uint32_t rh = p.drop_thresh ? drop_rowhash(p.drop_seed, static_cast<unsigned long long>(warp_g)) : 0u;
-  for (int j = lane; j < p.Lk; j += 32) {
-    const size_t krow = static_cast<size_t>(b) * p.Lk + j;
-    const __nv_bfloat16* kh = p.kv_hi + krow * p.ldkv + p.k_col0 + h * p.d;
-    const __nv_bfloat16* kl = p.kv_lo ? p.kv_lo + krow * p.ldkv + p.k_col0 + h * p.d : nullptr;
-    float s = 0.0f;
-    for (int c = 0; c < p.d; ++c) {
-      const float qa = __bfloat162float(qh[c]), ka = __bfloat162float(kh[c]);
-      float t = qa * ka;
-      if (ql != nullptr) t += qa * __bfloat162float(kl[c]) + __bfloat162float(ql[c]) * ka;
-      s += t;
-    }
-    bool masked = false;
-    if (p.mask != nullptr)
-      masked = p.mask[static_cast<long long>(b) * p.msb + static_cast<long long>(i) * p.msq +
-                      static_cast<long long>(j) * p.msk] != 0;
-    float pr = masked ? (0.0f * inv) : exp2f(s * p.scale_log2 - mx) * inv;
-    if (p.probs_pre != nullptr) p.probs_pre[warp_g * p.Lk + j] = pr;
-    if (p.drop_thresh && !drop_keep(rh, static_cast<uint32_t>(j), p.drop_thresh)) pr = 0.0f;
-    else if (p.drop_thresh) pr *= p.drop_scale;
-    out[j] = pr;
   }
 }
 

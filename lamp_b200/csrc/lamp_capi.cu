@@ -15,6 +15,7 @@
 #include "attn_core.cuh"
 #include "elementwise.cuh"
 #include "gemm_planes.cuh"
+#include "train_bwd.cuh"
 
 using namespace lamp;
 
@@ -586,7 +587,8 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
     rc = three ? launch_attn_plan<64, 3>(tm, p, can_stage, st) : launch_attn_plan<64, 1>(tm, p, can_stage, st);
   if (rc != LAMP_OK) return rc;
   if (probs) {
-    ProbsParams pp;
+    // probabilities from the operand planes and the saved row statistics, on the tensor cores
+    ProbsMmaParams pp;
     pp.B = B; pp.H = H; pp.Lq = Lq; pp.Lk = Lk; pp.d = d; pp.scale_log2 = p.scale_log2;
     pp.q_hi = static_cast<const __nv_bfloat16*>(q_hi);
     pp.q_lo = three ? static_cast<const __nv_bfloat16*>(q_lo) : nullptr;
@@ -596,9 +598,13 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
     pp.mask = mask; pp.msb = msb; pp.msq = msq; pp.msk = msk;
     pp.row_max = row_max; pp.row_sum = row_sum; pp.probs = probs;
     pp.probs_pre = probs_pre; pp.drop_thresh = p.drop_thresh; pp.drop_scale = p.drop_scale; pp.drop_seed = seed;
-    const long long nrows = (long long)H * B * Lq;
-    const long long blocks = (nrows * 32 + 255) / 256;
-    attn_probs_kernel<<<(unsigned)blocks, 256, 0, st>>>(pp);
+    static std::once_flag once;
+    static int once_rc = LAMP_OK;
+    std::call_once(once, [] { once_rc = set_smem(attn_probs_mma_kernel, (uint32_t)attn_probs_smem_bytes(BWD_DMAX)); });
+    if (once_rc != LAMP_OK) return once_rc;
+    const long long grid = (long long)H * B * ((Lq + BWD_TILE - 1) / BWD_TILE);
+    REQUIRE(grid < (1LL << 31), "attn: probability grid too large");
+    attn_probs_mma_kernel<<<(unsigned)grid, BWD_THREADS, (uint32_t)attn_probs_smem_bytes(d), st>>>(pp);
     rc = launch_check();
   }
   return rc;
@@ -636,6 +642,74 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
   if (int rc = launch_check()) return rc;
   attn_bwd_dkv_kernel<<<(unsigned)gk, BWD_THREADS, smem, st>>>(p);
   return launch_check();
+}
+
+int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
+                       float* dgamma, float* dbeta, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(x && dy && gamma && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
+  REQUIRE(D % 4 == 0 && D > 0 && D <= 4096, "layernorm_bwd: D=%d must be a multiple of 4, <= 4096", D);
+  REQUIRE(aligned16(x) && aligned16(dy) && aligned16(gamma) && aligned16(dx), "layernorm_bwd: alignment");
+  if (rows == 0) return LAMP_OK;
+  long long blocks = (rows * 32 + 255) / 256;
+  const long long cap = 4LL * sm_count_cached();  // grid-stride: few, long-lived blocks keep the atomic count low
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t red = (size_t)2 * D * sizeof(float);
+  if (D <= 512)
+    layernorm_bwd_kernel<4><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta);
+  else if (D <= 1024)
+    layernorm_bwd_kernel<8><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta);
+  else
+    layernorm_bwd_kernel<32><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta);
+  return launch_check();
+}
+
+int lamp_gemm_tn_acc(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t M, int N, int K, float* dW,
+                     float* db, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(dY && X && dW && M >= 0 && N > 0 && K > 0, "gemm_tn: bad arguments");
+  REQUIRE(ldy >= N && ldx >= K, "gemm_tn: leading dimensions");
+  if (M == 0) return LAMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tiles = (long long)((N + BWD_TILE - 1) / BWD_TILE) * ((K + BWD_TILE - 1) / BWD_TILE);
+  // split the M rows so that ~4 CTAs per SM exist; chunks are multiples of the 64-row staging tile
+  long long splits = (4LL * sm_count_cached() + tiles - 1) / tiles;
+  const long long max_splits = (M + BWD_TILE - 1) / BWD_TILE;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long chunk = ((M + splits - 1) / splits + BWD_TILE - 1) / BWD_TILE * BWD_TILE;
+  splits = (M + chunk - 1) / chunk;
+  REQUIRE(tiles * splits < (1LL << 31), "gemm_tn: grid too large");
+  gemm_tn_kernel<<<(unsigned)(tiles * splits), BWD_THREADS, 0, st>>>(dY, ldy, X, ldx, M, N, K, chunk, dW);
+  if (int rc = launch_check()) return rc;
+  if (db != nullptr) {
+    long long rb = (M + 511) / 512;
+    dim3 grid((unsigned)rb, (unsigned)((N + 127) / 128));
+    colsum_kernel<<<grid, 128, 0, st>>>(dY, ldy, M, N, 512, db);
+    return launch_check();
+  }
+  return LAMP_OK;
+}
+
+int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B, int L, int D, float* dx, float* dW,
+                       float* dbias, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(g && x && W && (dx || dW), "diag_proj_bwd: null pointer");
+  REQUIRE(D % 4 == 0 && aligned16(W) && (!dx || aligned16(dx)), "diag_proj_bwd: D multiple of 4 and 16-byte alignment required");
+  const long long rows = B * L;
+  if (rows == 0) return LAMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx != nullptr) {
+    const long long blocks = (rows * 32 + 255) / 256;
+    diag_proj_bwd_dx_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, W, rows, L, D, dx);
+    if (int rc = launch_check()) return rc;
+  }
+  if (dW != nullptr) {
+    diag_proj_bwd_dw_kernel<<<(unsigned)L, 256, 0, st>>>(g, x, B, L, D, dW, dbias);
+    return launch_check();
+  }
+  return LAMP_OK;
 }
 
 #ifdef LAMP_ATTN_TRACE

@@ -307,6 +307,21 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// Counter-based dropout decision (training forward of the attention core): a pure function of (seed, head-major row,
+// key), shared by the attention kernel and the probability kernel.  splitmix64 per row, murmur3 finaliser per key.
+__device__ __forceinline__ uint32_t drop_rowhash(unsigned long long seed, unsigned long long rowkey) {
+  unsigned long long z = seed + rowkey * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<uint32_t>(z >> 32);
+}
+__device__ __forceinline__ bool drop_keep(uint32_t rowhash, uint32_t col, uint32_t thresh) {
+  uint32_t h = rowhash ^ (col * 0x9E3779B9u);
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h >= thresh;
+}
+
 // Named barrier among a subset of warps (id 1..15; 0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

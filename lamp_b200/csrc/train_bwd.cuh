@@ -1,0 +1,210 @@
+// Backward kernels of the dense stages of the training path: LayerNorm backward and the
+// weight-gradient contraction dW = dY^T X (+ bias gradient).  The input gradient dX = dY W runs on the forward's
+// tcgen05 GEMM (gemm_planes.cuh) with transposed weight planes.  Correctness-first versions (warp-level MMA, fp32
+// atomics for the split-M reduction); same 3-term split-bf16 products as everywhere else.
+#pragma once
+#include "attn_bwd.cuh"
+
+namespace lamp {
+
+// y = LayerNorm(x) * gamma + beta (torch.nn.LayerNorm; lamp/SubLayers.py:117,141).  Given x and dy:
+//   xhat = (x - mean) * rstd;  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat));
+//   dgamma += sum_rows dy * xhat;  dbeta += sum_rows dy   (accumulated with fp32 atomics: zero them first).
+// One warp per row (grid-stride), the row and the warp's dgamma / dbeta partials live in registers (D <= 128 * MAXV).
+template <int MAXV>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                     const float* __restrict__ gamma, float eps, long long rows, int D,
+                                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int d4 = D >> 2;
+  float4 gsum[MAXV], bsum[MAXV], gam[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    gsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bsum[i] = gsum[i];
+    const int idx = lane + 32 * i;
+    gam[i] = idx < d4 ? __ldg(reinterpret_cast<const float4*>(gamma) + idx) : gsum[i];
+  }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const float4* dr = reinterpret_cast<const float4*>(dy + row * D);
+    float4 xv[MAXV], dv[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < d4) {
+        xv[i] = xr[idx];
+        dv[i] = dr[idx];
+        s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    const float mean = s / D;
+    float qv = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < d4) {
+        const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+        qv += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(0xFFFFFFFFu, qv, o);
+    const float rstd = rsqrtf(qv / D + eps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < d4) {
+        // xhat overwrites xv, g = dy * gamma overwrites nothing (dv is still needed for dgamma / dbeta)
+        xv[i].x = (xv[i].x - mean) * rstd; xv[i].y = (xv[i].y - mean) * rstd;
+        xv[i].z = (xv[i].z - mean) * rstd; xv[i].w = (xv[i].w - mean) * rstd;
+        const float g0 = dv[i].x * gam[i].x, g1 = dv[i].y * gam[i].y, g2 = dv[i].z * gam[i].z, g3 = dv[i].w * gam[i].w;
+        c1 += (g0 + g1) + (g2 + g3);
+        c2 += (g0 * xv[i].x + g1 * xv[i].y) + (g2 * xv[i].z + g3 * xv[i].w);
+        gsum[i].x += dv[i].x * xv[i].x; gsum[i].y += dv[i].y * xv[i].y;
+        gsum[i].z += dv[i].z * xv[i].z; gsum[i].w += dv[i].w * xv[i].w;
+        bsum[i].x += dv[i].x; bsum[i].y += dv[i].y; bsum[i].z += dv[i].z; bsum[i].w += dv[i].w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+      c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+    }
+    c1 /= D;
+    c2 /= D;
+    float4* outr = reinterpret_cast<float4*>(dx + row * D);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < d4) {
+        float4 o;
+        o.x = rstd * (dv[i].x * gam[i].x - c1 - xv[i].x * c2);
+        o.y = rstd * (dv[i].y * gam[i].y - c1 - xv[i].y * c2);
+        o.z = rstd * (dv[i].z * gam[i].z - c1 - xv[i].z * c2);
+        o.w = rstd * (dv[i].w * gam[i].w - c1 - xv[i].w * c2);
+        outr[idx] = o;
+      }
+    }
+  }
+  // block-level reduction in shared memory (the block's 8 warps add into one [2][D] buffer), then one global atomic
+  // per column and block
+  extern __shared__ float lnb_red[];  // [2 * D]
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) lnb_red[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < d4) {
+      atomicAdd(lnb_red + 4 * idx + 0, gsum[i].x); atomicAdd(lnb_red + 4 * idx + 1, gsum[i].y);
+      atomicAdd(lnb_red + 4 * idx + 2, gsum[i].z); atomicAdd(lnb_red + 4 * idx + 3, gsum[i].w);
+      atomicAdd(lnb_red + D + 4 * idx + 0, bsum[i].x); atomicAdd(lnb_red + D + 4 * idx + 1, bsum[i].y);
+      atomicAdd(lnb_red + D + 4 * idx + 2, bsum[i].z); atomicAdd(lnb_red + D + 4 * idx + 3, bsum[i].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(dgamma + c, lnb_red[c]);
+    atomicAdd(dbeta + c, lnb_red[D + c]);
+  }
+}
+
+// dW[N, K] += dY[M, N]^T X[M, K]  -- the weight gradient of Y = X W^T (nn.Linear / Conv1d(k=1): lamp/SubLayers.py:
+// 91-93,110,133).  CTA = one 64 x 64 tile of dW and one chunk of the M rows (split-M: `chunk` rows per CTA, partial
+// tiles are added with fp32 atomics); dY and X tiles are split to hi/lo planes while they are staged into smem, dY is
+// consumed transposed (col-major fragment loads).
+__global__ void __launch_bounds__(BWD_THREADS) gemm_tn_kernel(const float* __restrict__ dY, long long ldy,
+                                                              const float* __restrict__ X, long long ldx, long long M,
+                                                              int N, int K, long long chunk, float* __restrict__ dW) {
+  using namespace nvcuda;
+  constexpr int TP = BWD_TILE + 8;
+  __shared__ __align__(128) __nv_bfloat16 sm[4 * BWD_TILE * TP];
+  __shared__ __align__(128) float stage_all[8 * 16 * 20];
+  __nv_bfloat16* Y_hi = sm;
+  __nv_bfloat16* Y_lo = Y_hi + BWD_TILE * TP;
+  __nv_bfloat16* X_hi = Y_lo + BWD_TILE * TP;
+  __nv_bfloat16* X_lo = X_hi + BWD_TILE * TP;
+  const int tiles_k = (K + BWD_TILE - 1) / BWD_TILE, tiles_n = (N + BWD_TILE - 1) / BWD_TILE;
+  const int tile = blockIdx.x % (tiles_k * tiles_n);
+  const long long split = blockIdx.x / (tiles_k * tiles_n);
+  const int n0 = (tile / tiles_k) * BWD_TILE, k0 = (tile % tiles_k) * BWD_TILE;
+  const int ncols = min(BWD_TILE, N - n0), kcols = min(BWD_TILE, K - k0);
+  const long long m_begin = split * chunk, m_end = min(M, m_begin + chunk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = (warp & 3) * 16, wh = warp >> 2;
+  FragC acc[2];
+  wmma::fill_fragment(acc[0], 0.0f);
+  wmma::fill_fragment(acc[1], 0.0f);
+  for (long long m0 = m_begin; m0 < m_end; m0 += BWD_TILE) {
+    const long long mleft = m_end - m0;
+    const int mrows = mleft < BWD_TILE ? static_cast<int>(mleft) : BWD_TILE;
+    __syncthreads();
+    bwd_stage_tile(dY + m0 * ldy + n0, ldy, mrows, ncols, BWD_TILE, BWD_TILE, Y_hi, Y_lo, TP);
+    bwd_stage_tile(X + m0 * ldx + k0, ldx, mrows, kcols, BWD_TILE, BWD_TILE, X_hi, X_lo, TP);
+    __syncthreads();
+    bwd_mma<2, true, false>(acc, Y_hi, Y_lo, TP, wr, X_hi, X_lo, TP, 32 * wh, BWD_TILE);
+  }
+  float* stage = stage_all + warp * (16 * 20);
+  for (int f = 0; f < 2; ++f) {
+    wmma::store_matrix_sync(stage, acc[f], 20, wmma::mem_row_major);
+    __syncwarp();
+    for (int e = lane; e < 256; e += 32) {
+      const int r = e >> 4, c = e & 15;
+      const int n = wr + r, k = 32 * wh + 16 * f + c;
+      if (n < ncols && k < kcols) atomicAdd(dW + static_cast<long long>(n0 + n) * K + k0 + k, stage[r * 20 + c]);
+    }
+    __syncwarp();
+  }
+}
+
+// db[n] += sum_m dY[m, n]: thread per column, `chunk` rows per block, one atomic per thread.
+__global__ void colsum_kernel(const float* __restrict__ dY, long long ldy, long long M, int N, long long chunk,
+                              float* __restrict__ db) {
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long m_begin = blockIdx.x * chunk, m_end = min(M, m_begin + chunk);
+  float s = 0.f;
+  for (long long m = m_begin; m < m_end; ++m) s += dY[m * ldy + n];
+  atomicAdd(db + n, s);
+}
+
+// Backward of the diagonal label projection logits[b, l] = <x[b, l, :], W[l, :]> (+ bias[l]) (lamp/Models.py:124-126):
+//   dx[b, l, :] = g[b, l] * W[l, :]                       (one warp per (b, l) row)
+//   dW[l, :]    = sum_b g[b, l] * x[b, l, :],  dbias[l] = sum_b g[b, l]   (one block per label, threads over D)
+__global__ void diag_proj_bwd_dx_kernel(const float* __restrict__ g, const float* __restrict__ W, long long rows, int L,
+                                        int D, float* __restrict__ dx) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float gv = g[row];
+  const float4* wr = reinterpret_cast<const float4*>(W + static_cast<long long>(row % L) * D);
+  float4* o = reinterpret_cast<float4*>(dx + row * D);
+  for (int idx = lane; idx < (D >> 2); idx += 32) {
+    const float4 w = __ldg(wr + idx);
+    o[idx] = make_float4(gv * w.x, gv * w.y, gv * w.z, gv * w.w);
+  }
+}
+__global__ void diag_proj_bwd_dw_kernel(const float* __restrict__ g, const float* __restrict__ x, long long B, int L,
+                                        int D, float* __restrict__ dW, float* __restrict__ dbias) {
+  const int l = blockIdx.x;
+  float gs = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+    gs = 0.f;
+    for (long long b = 0; b < B; ++b) {
+      const float gv = g[b * L + l];
+      s = fmaf(gv, x[(b * L + l) * D + c], s);
+      gs += gv;
+    }
+    dW[static_cast<long long>(l) * D + c] = s;
+  }
+  if (dbias != nullptr && threadIdx.x == 0) dbias[l] = gs;  // thread 0 always owns column 0: its gs is the full sum
+}
+
+}  // namespace lamp

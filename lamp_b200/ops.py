@@ -562,6 +562,127 @@ class SDPAFunction(torch.autograd.Function):
         return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None, None, None
 
 
+# ------------------------------------------------------------------ training path: dense stages
+NATIVE_TRAINING = os.environ.get('LAMP_NATIVE_TRAIN', '1') != '0'  # Linear / LayerNorm of the training path on the native kernels
+
+
+class LinearFunction(torch.autograd.Function):
+    """``y = x W^T (+ b)`` for the training path (nn.Linear / Conv1d(k=1) of lamp/SubLayers.py:91-93,110,133).
+    forward and ``dx = dy W`` run on the tcgen05 GEMM (3-term split-bf16), ``dW = dy^T x`` and ``db`` on
+    ``lamp_gemm_tn_acc``.  x: [..., K] fp32, W: [N, K] (a Conv1d weight [N, K, 1] is viewed as such)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, prec):
+        w2 = W.reshape(W.shape[0], -1)
+        N, K = w2.shape
+        x2 = x.reshape(-1, K).contiguous().float()
+        M = x2.shape[0]
+        a_hi, a_lo = split(x2, prec)
+        w_hi, w_lo = split(w2.detach().contiguous().float(), prec)
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        gemm(a_hi, a_lo, K, w_hi, w_lo, K, M, N, K, prec, bias=None if b is None else b.detach().float().contiguous(),
+             out_f32=y, ldo=N)
+        ctx.save_for_backward(x2, W, b if b is not None else x2.new_empty(0))
+        ctx.prec, ctx.has_bias, ctx.x_shape = prec, b is not None, tuple(x.shape)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, b = ctx.saved_tensors
+        prec = ctx.prec
+        w2 = W.reshape(W.shape[0], -1)
+        N, K = w2.shape
+        dy2 = dy.reshape(-1, N).contiguous().float()
+        M = dy2.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            d_hi, d_lo = split(dy2, prec)
+            wt_hi, wt_lo = split(w2.detach().t().contiguous().float(), prec)  # [K, N]: dx = dy (W^T)^T
+            dx2 = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+            gemm(d_hi, d_lo, N, wt_hi, wt_lo, N, M, K, N, prec, out_f32=dx2, ldo=K)
+            dx = dx2.view(ctx.x_shape)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW2 = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
+            db = torch.zeros((N,), dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            STATS.call('gemm_tn', 2 if db is not None else 1, nat.lib().lamp_gemm_tn_acc,
+                       (dy2.data_ptr(), N, x2.data_ptr(), K, M, N, K, dW2.data_ptr(), nat.ptr(db), nat.stream()),
+                       flops=2.0 * M * N * K)
+            dW = dW2.view(W.shape).to(W.dtype)
+            if db is not None:
+                db = db.to(b.dtype)
+        return dx, dW, db, None
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """torch.nn.LayerNorm over the last dimension on the native kernels (forward ``lamp_layernorm``, backward
+    ``lamp_layernorm_bwd``) -- lamp/SubLayers.py:117,141 in the training path."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, prec):
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D).contiguous().float()
+        out = layernorm(x2, gamma.detach().float().contiguous(), beta.detach().float().contiguous(), eps, prec,
+                        want_planes=False).f32
+        ctx.save_for_backward(x2, gamma)
+        ctx.eps, ctx.shape = eps, tuple(x.shape)
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma = ctx.saved_tensors
+        rows, D = x2.shape
+        dy2 = dy.reshape(rows, D).contiguous().float()
+        dx = torch.empty_like(x2)
+        dg = torch.zeros((D,), dtype=torch.float32, device=dy.device)
+        db = torch.zeros_like(dg)
+        STATS.call('layernorm_bwd', 1, nat.lib().lamp_layernorm_bwd,
+                   (x2.data_ptr(), dy2.data_ptr(), gamma.detach().float().contiguous().data_ptr(), float(ctx.eps), rows, D,
+                    dx.data_ptr(), dg.data_ptr(), db.data_ptr(), nat.stream()), nbytes=rows * D * 12)
+        return dx.view(ctx.shape), dg.to(gamma.dtype), db.to(gamma.dtype), None, None
+
+
+class DiagProjFunction(torch.autograd.Function):
+    """Differentiable diagonal label projection (lamp/Models.py:124-126: the reference builds the [B, L, L] product
+    and keeps its diagonal): forward ``lamp_diag_proj``, backward ``lamp_diag_proj_bwd``."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        x = x.contiguous().float()
+        ctx.save_for_backward(x, W, bias if bias is not None else x.new_empty(0))
+        ctx.has_bias = bias is not None
+        return diag_proj(x, W.detach().float().contiguous(), None if bias is None else bias.detach().float().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W, bias = ctx.saved_tensors
+        B, L, D = x.shape
+        g = g.contiguous().float()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = torch.empty((L, D), dtype=torch.float32, device=x.device)
+        db = torch.empty((L,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        STATS.call('diag_proj_bwd', 2, nat.lib().lamp_diag_proj_bwd,
+                   (g.data_ptr(), x.data_ptr(), W.detach().float().contiguous().data_ptr(), B, L, D, nat.ptr(dx),
+                    dW.data_ptr(), nat.ptr(db), nat.stream()), nbytes=B * L * D * 8)
+        return dx, dW.to(W.dtype), (db.to(bias.dtype) if db is not None else None)
+
+
+def linear_train(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor], prec: Optional[int] = None) -> torch.Tensor:
+    """Differentiable ``x W^T (+b)`` of the training path: native when the shape allows, torch otherwise."""
+    w2 = W.reshape(W.shape[0], -1)
+    N, K = w2.shape
+    if NATIVE_TRAINING and x.is_cuda and x.dtype == torch.float32 and N % 8 == 0 and K % 8 == 0 and x.numel() > 0:
+        return LinearFunction.apply(x, W, b, default_precision() if prec is None else prec)
+    return torch.nn.functional.linear(x, w2, b)
+
+
+def layernorm_train(x: torch.Tensor, ln: torch.nn.LayerNorm, prec: Optional[int] = None) -> torch.Tensor:
+    D = x.shape[-1]
+    if NATIVE_TRAINING and x.is_cuda and x.dtype == torch.float32 and D % 4 == 0 and D <= 4096 and x.numel() > 0 \
+            and ln.elementwise_affine and tuple(ln.normalized_shape) == (D,):
+        return LayerNormFunction.apply(x, ln.weight, ln.bias, ln.eps, default_precision() if prec is None else prec)
+    return ln(x)
+
+
 def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor, pos_emb: Optional[torch.Tensor],
           prec: int, want_f32: bool = True, row_index=None, m_dev=None) -> Act:
     nat.require_cuda(seq, word_emb)

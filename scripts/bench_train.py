@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Training-step timing of the label-graph model (forward + BCE loss + backward, the reference's train.py:28-48 minus
+the optimizer) with the native training path (attention core, contractions, LayerNorm, label projection on lamp_b200
+kernels in both directions) vs the all-torch composed path.  cfg-1 dims (L=103, T=300, D=512, H=4, 2+2 layers),
+dropout 0.2 as in the reference's README command.  usage: python scripts/bench_train.py [--batch 32] [--steps 10]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lamp_b200 import ops  # noqa: E402
+from lamp_b200 import synthetic as syn  # noqa: E402
+from lamp_b200.Models import LAMP  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--batch', type=int, nargs='+', default=[32, 256])
+ap.add_argument('--steps', type=int, default=10)
+args = ap.parse_args()
+c = dict(L=103, T=300, V=20000, D=512, d_inner=512, H=4, n_enc=2, n_dec=2)
+dev = 'cuda'
+for B in args.batch:
+    params = syn.lamp_params(c['V'] + 4, c['L'], c['T'], c['D'], c['d_inner'], c['H'], c['n_enc'], c['n_dec'], seed=0)
+    adj = syn.prior_adjacency(syn.make_label_sets(c['L'], seed=0), c['L'])
+    src_seq, src_pos = syn.make_tokens(B, c['T'], c['V'], 1)
+    src = (src_seq.to(dev), src_pos.to(dev))
+    tgt = (torch.rand(B, c['L'], device=dev) < 0.05).float()
+    for native in (True, False):
+        ops.NATIVE_ATTENTION_BACKWARD = ops.NATIVE_TRAINING = native
+        d = c['D'] // c['H']
+        model = LAMP(c['V'] + 4, c['L'], c['T'], c['L'], n_layers_enc=c['n_enc'], n_layers_dec=c['n_dec'], n_head=c['H'],
+                     n_head2=c['H'], d_word_vec=c['D'], d_model=c['D'], d_inner_hid=c['d_inner'], d_k=d, d_v=d, dropout=0.2,
+                     dec_dropout=0.2, dec_dropout2=False, proj_share_weight=True, encoder='graph', decoder='graph',
+                     label_adj_matrix=adj, label_mask='prior')
+        model.load_state_dict(params, strict=True)
+        model = model.to(dev).train()
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            logits, _, _ = model(src, None, None, None)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, tgt)
+            loss.backward()
+            return loss
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ops.STATS.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        per_kernel = {}
+        if native:  # one more step with a CUDA-event pair around every native call
+            with ops.STATS.timed():
+                step()
+                per_kernel = {k: round(v['ms'], 2) for k, v in ops.STATS.stop_timing().items()}
+        print(json.dumps(dict(what='train step (fwd + BCE + bwd)', native=native, batch=B, ms_per_step=ms,
+                              native_kernel_ms=per_kernel,
+                              samples_per_s=B / ms * 1e3, loss=float(loss.detach()),
+                              native_launches_per_step=ops.STATS.launches / args.steps,
+                              kernels={k: v // args.steps for k, v in ops.STATS.by_kernel.items()})), flush=True)
+    ops.NATIVE_ATTENTION_BACKWARD = ops.NATIVE_TRAINING = True

@@ -649,3 +649,69 @@ def test_attn_core_training_forward_dropout_and_backward(N, Lq, Lk, d, pdrop):
         e = rel_err(x.detach(), y)
         print(f'attn train p={pdrop} N={N} Lq={Lq} Lk={Lk} d={d} {name}: {e:.2e}')
         assert e < 5e-5, name
+
+
+@pytest.mark.parametrize('M,N,K,bias', [(3296, 512, 512, True), (1000, 1536, 512, False), (777, 264, 72, True),
+                                         (130, 64, 1024, True), (9600, 512, 512, False)])
+def test_linear_function_grads(M, N, K, bias):
+    """ops.LinearFunction: y, dx on the tcgen05 GEMM, dW / db on lamp_gemm_tn_acc -- vs fp64 autograd."""
+    from lamp_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(DEV).requires_grad_(True)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(DEV).requires_grad_(True) if bias else None
+    go = torch.randn(M, N, generator=g).to(DEV)
+    y = ops.LinearFunction.apply(x, W, b, 0)
+    y.backward(go)
+    xd, Wd = x.detach().double().requires_grad_(True), W.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    ref = torch.nn.functional.linear(xd, Wd, bd)
+    ref.backward(go.double())
+    pairs = [('y', y.detach(), ref.detach()), ('dx', x.grad, xd.grad), ('dW', W.grad, Wd.grad)]
+    if bias:
+        pairs.append(('db', b.grad, bd.grad))
+    for name, a, r in pairs:
+        e = rel_err(a, r)
+        print(f'linear {M}x{N}x{K} {name}: {e:.2e}')
+        assert e < 3e-5, name
+
+
+@pytest.mark.parametrize('rows,D', [(3296, 512), (1000, 1024), (37, 64), (5000, 2048), (1, 512)])
+def test_layernorm_function_grads(rows, D):
+    from lamp_b200 import ops
+    g = torch.Generator().manual_seed(rows + D)
+    x = (torch.randn(rows, D, generator=g) * 2 + 0.5).to(DEV).requires_grad_(True)
+    gam = (1 + 0.3 * torch.randn(D, generator=g)).to(DEV).requires_grad_(True)
+    bet = torch.randn(D, generator=g).to(DEV).requires_grad_(True)
+    go = torch.randn(rows, D, generator=g).to(DEV)
+    y = ops.LayerNormFunction.apply(x, gam, bet, 1e-5, 0)
+    y.backward(go)
+    xd, gd, bd = (t.detach().double().requires_grad_(True) for t in (x, gam, bet))
+    ref = torch.nn.functional.layer_norm(xd, (D,), gd, bd, 1e-5)
+    ref.backward(go.double())
+    for name, a, r in (('y', y.detach(), ref.detach()), ('dx', x.grad, xd.grad), ('dgamma', gam.grad, gd.grad),
+                       ('dbeta', bet.grad, bd.grad)):
+        e = rel_err(a, r)
+        print(f'layernorm {rows}x{D} {name}: {e:.2e}')
+        assert e < 2e-5, name
+
+
+@pytest.mark.parametrize('B,L,D,bias', [(32, 103, 512, False), (5, 983, 512, True), (3, 7, 64, True)])
+def test_diag_proj_function_grads(B, L, D, bias):
+    from lamp_b200 import ops
+    g = torch.Generator().manual_seed(B + L + D)
+    x = torch.randn(B, L, D, generator=g).to(DEV).requires_grad_(True)
+    W = torch.randn(L, D, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(L, generator=g).to(DEV).requires_grad_(True) if bias else None
+    go = torch.randn(B, L, generator=g).to(DEV)
+    y = ops.DiagProjFunction.apply(x, W, b)
+    y.backward(go)
+    xd, Wd = x.detach().double().requires_grad_(True), W.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    ref = torch.diagonal(torch.nn.functional.linear(xd, Wd, bd), 0, 1, 2)   # lamp/Models.py:124-126
+    ref.backward(go.double())
+    pairs = [('y', y.detach(), ref.detach()), ('dx', x.grad, xd.grad), ('dW', W.grad, Wd.grad)]
+    if bias:
+        pairs.append(('db', b.grad, bd.grad))
+    for name, a, r in pairs:
+        assert rel_err(a, r) < 1e-5, name

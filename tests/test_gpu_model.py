@@ -105,15 +105,16 @@ def test_training_path_is_differentiable_and_matches_oracle_without_dropout():
 
 
 def test_training_gradients_native_attention_core_equals_composed_path():
-    """Training step with the attention core native in both directions (ops.SDPAFunction) vs the all-torch composed
-    path: same logits and the same gradient for every parameter (dropout off so that both are deterministic)."""
+    """Training step with the attention core, the projections / FFN contractions and the LayerNorms native in both
+    directions (ops.SDPAFunction, LinearFunction, LayerNormFunction) vs the all-torch composed path: same logits and
+    the same gradient for every parameter (dropout off so that both are deterministic)."""
     from lamp_b200 import ops
     c = dict(cases.MODEL_CASES['lamp_L37_none'])
     p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
     src = (src_seq.to(DEV), src_pos.to(DEV))
     res = {}
     for native in (True, False):
-        ops.NATIVE_ATTENTION_BACKWARD = native
+        ops.NATIVE_ATTENTION_BACKWARD = ops.NATIVE_TRAINING = native
         try:
             model = build_model(c, p, adj)
             model.train()
@@ -128,8 +129,10 @@ def test_training_gradients_native_attention_core_equals_composed_path():
             res[native] = (logits.detach(), {n: q.grad.clone() for n, q in model.named_parameters() if q.grad is not None},
                            dict(ops.STATS.by_kernel))
         finally:
-            ops.NATIVE_ATTENTION_BACKWARD = True
+            ops.NATIVE_ATTENTION_BACKWARD = ops.NATIVE_TRAINING = True
     assert res[True][2].get('attn_core_bwd', 0) > 0 and res[False][2].get('attn_core_bwd', 0) == 0
+    assert res[True][2].get('gemm_tn', 0) > 0 and res[True][2].get('layernorm_bwd', 0) > 0
+    assert res[False][2].get('gemm_tn', 0) == 0 and res[False][2].get('layernorm_bwd', 0) == 0
     assert rel_err(res[True][0], res[False][0]) < 1e-4
     assert res[True][1].keys() == res[False][1].keys()
     worst = max((rel_err(res[True][1][n], res[False][1][n]), n) for n in res[True][1])
