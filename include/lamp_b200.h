@@ -168,10 +168,11 @@ int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, floa
                        float* dgamma, float* dbeta, void* stream);
 
 /* Weight / bias gradient of Y = X W^T (+ b): dW[N,K] += dY[M,N]^T X[M,K], db[N] += column sums of dY (db may be
- * NULL).  Accumulating (fp32 atomics over row chunks): zero or pre-load dW / db.  The input gradient dX = dY W is
- * lamp_gemm_planes on the transposed weight planes. */
-int lamp_gemm_tn_acc(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t M, int N, int K, float* dW,
-                     float* db, void* stream);
+ * NULL).  dY and X are given as split-bf16 planes (lo planes NULL in bf16 mode).  Accumulating (fp32 atomics over row
+ * chunks): zero or pre-load dW / db.  N % 8 == 0, K % 8 == 0.  The input gradient dX = dY W is lamp_gemm_planes on
+ * the transposed weight planes. */
+int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx,
+                     int64_t M, int N, int K, float* dW, float* db, void* stream);
 
 /* out = LayerNorm(y (+ add[row % add_mod or row])) * gamma + beta  (torch.nn.LayerNorm semantics, eps inside the
  * sqrt; lamp/SubLayers.py:117,141).  Writes fp32 and/or planes (any may be NULL).  D % 4 == 0, D <= 4096. */

@@ -49,7 +49,7 @@ _SIGNATURES = {
                                      _i64, _vp, _vp, _i64, _vp, _i64, _vp], _i),
     'lamp_attn_core_bwd': ([_vp] * 11 + [_i, _i, _i, _i, _f, _f, _vp], _i),
     'lamp_layernorm_bwd': ([_vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp], _i),
-    'lamp_gemm_tn_acc': ([_vp, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp], _i),
+    'lamp_gemm_tn_acc': ([_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp], _i),
     'lamp_diag_proj_bwd': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp], _i),
     'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp, _vp], _i),
     'lamp_embed': ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),

@@ -665,28 +665,36 @@ int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, floa
   return launch_check();
 }
 
-int lamp_gemm_tn_acc(const float* dY, int64_t ldy, const float* X, int64_t ldx, int64_t M, int N, int K, float* dW,
-                     float* db, void* stream) {
+int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx,
+                     int64_t M, int N, int K, float* dW, float* db, void* stream) {
   if (int rc = arch_check()) return rc;
-  REQUIRE(dY && X && dW && M >= 0 && N > 0 && K > 0, "gemm_tn: bad arguments");
-  REQUIRE(ldy >= N && ldx >= K, "gemm_tn: leading dimensions");
+  REQUIRE(dy_hi && x_hi && dW && M >= 0 && N > 0 && K > 0, "gemm_tn: bad arguments");
+  REQUIRE(N % 8 == 0 && K % 8 == 0 && ldy % 8 == 0 && ldx % 8 == 0 && ldy >= N && ldx >= K, "gemm_tn: N, K and the leading dimensions must be multiples of 8");
+  REQUIRE(aligned16(dy_hi) && aligned16(x_hi) && (!dy_lo || aligned16(dy_lo)) && (!x_lo || aligned16(x_lo)), "gemm_tn: alignment");
   if (M == 0) return LAMP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long tiles = (long long)((N + BWD_TILE - 1) / BWD_TILE) * ((K + BWD_TILE - 1) / BWD_TILE);
-  // split the M rows so that ~4 CTAs per SM exist; chunks are multiples of the 64-row staging tile
-  long long splits = (4LL * sm_count_cached() + tiles - 1) / tiles;
+  static std::once_flag once;
+  static int once_rc = LAMP_OK;
+  std::call_once(once, [] { once_rc = set_smem(gemm_tn_kernel, (uint32_t)gemm_tn_smem_bytes()); });
+  if (once_rc != LAMP_OK) return once_rc;
+  const long long tiles = (long long)((N + TN_TILE - 1) / TN_TILE) * ((K + TN_TILE - 1) / TN_TILE);
+  // split the M rows so that ~3 CTAs per SM exist; chunks are multiples of the 64-row staging tile
+  long long splits = (3LL * sm_count_cached() + tiles - 1) / tiles;
   const long long max_splits = (M + BWD_TILE - 1) / BWD_TILE;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   long long chunk = ((M + splits - 1) / splits + BWD_TILE - 1) / BWD_TILE * BWD_TILE;
   splits = (M + chunk - 1) / chunk;
   REQUIRE(tiles * splits < (1LL << 31), "gemm_tn: grid too large");
-  gemm_tn_kernel<<<(unsigned)(tiles * splits), BWD_THREADS, 0, st>>>(dY, ldy, X, ldx, M, N, K, chunk, dW);
+  gemm_tn_kernel<<<(unsigned)(tiles * splits), BWD_THREADS, (uint32_t)gemm_tn_smem_bytes(), st>>>(
+      static_cast<const __nv_bfloat16*>(dy_hi), static_cast<const __nv_bfloat16*>(dy_lo), ldy,
+      static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), ldx, M, N, K, chunk, dW);
   if (int rc = launch_check()) return rc;
   if (db != nullptr) {
     long long rb = (M + 511) / 512;
     dim3 grid((unsigned)rb, (unsigned)((N + 127) / 128));
-    colsum_kernel<<<grid, 128, 0, st>>>(dY, ldy, M, N, 512, db);
+    colsum_planes_kernel<<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(dy_hi),
+                                               static_cast<const __nv_bfloat16*>(dy_lo), ldy, M, N, 512, db);
     return launch_check();
   }
   return LAMP_OK;

@@ -116,61 +116,91 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
 }
 
 // dW[N, K] += dY[M, N]^T X[M, K]  -- the weight gradient of Y = X W^T (nn.Linear / Conv1d(k=1): lamp/SubLayers.py:
-// 91-93,110,133).  CTA = one 64 x 64 tile of dW and one chunk of the M rows (split-M: `chunk` rows per CTA, partial
-// tiles are added with fp32 atomics); dY and X tiles are split to hi/lo planes while they are staged into smem, dY is
-// consumed transposed (col-major fragment loads).
-__global__ void __launch_bounds__(BWD_THREADS) gemm_tn_kernel(const float* __restrict__ dY, long long ldy,
-                                                              const float* __restrict__ X, long long ldx, long long M,
-                                                              int N, int K, long long chunk, float* __restrict__ dW) {
+// 91-93,110,133).  Operands are the split-bf16 planes that already exist (x: split for the forward GEMM, dy: split for
+// the dx GEMM).  CTA = one 128 x 128 tile of dW and one chunk of the M rows (split-M: partial tiles are added with fp32
+// atomics); per 64-row step the dY [64 x 128] and X [64 x 128] plane tiles are copied to smem and dY is consumed
+// transposed (col-major fragment loads).  8 warps: warp -> 32 rows (n) x 64 columns (k) of the tile.
+constexpr int TN_TILE = 128;
+__host__ __device__ constexpr size_t gemm_tn_smem_bytes() { return static_cast<size_t>(4) * BWD_TILE * (TN_TILE + 8) * 2 + 8 * 16 * 20 * 4; }
+
+__global__ void __launch_bounds__(BWD_THREADS) gemm_tn_kernel(const __nv_bfloat16* __restrict__ dy_hi,
+                                                              const __nv_bfloat16* __restrict__ dy_lo, long long ldy,
+                                                              const __nv_bfloat16* __restrict__ x_hi,
+                                                              const __nv_bfloat16* __restrict__ x_lo, long long ldx,
+                                                              long long M, int N, int K, long long chunk,
+                                                              float* __restrict__ dW) {
   using namespace nvcuda;
-  constexpr int TP = BWD_TILE + 8;
-  __shared__ __align__(128) __nv_bfloat16 sm[4 * BWD_TILE * TP];
-  __shared__ __align__(128) float stage_all[8 * 16 * 20];
-  __nv_bfloat16* Y_hi = sm;
+  constexpr int TP = TN_TILE + 8;
+  extern __shared__ __align__(128) uint8_t tsm[];
+  __nv_bfloat16* Y_hi = reinterpret_cast<__nv_bfloat16*>(tsm);
   __nv_bfloat16* Y_lo = Y_hi + BWD_TILE * TP;
   __nv_bfloat16* X_hi = Y_lo + BWD_TILE * TP;
   __nv_bfloat16* X_lo = X_hi + BWD_TILE * TP;
-  const int tiles_k = (K + BWD_TILE - 1) / BWD_TILE, tiles_n = (N + BWD_TILE - 1) / BWD_TILE;
+  float* stage_all = reinterpret_cast<float*>(X_lo + BWD_TILE * TP);
+  const int tiles_k = (K + TN_TILE - 1) / TN_TILE, tiles_n = (N + TN_TILE - 1) / TN_TILE;
   const int tile = blockIdx.x % (tiles_k * tiles_n);
   const long long split = blockIdx.x / (tiles_k * tiles_n);
-  const int n0 = (tile / tiles_k) * BWD_TILE, k0 = (tile % tiles_k) * BWD_TILE;
-  const int ncols = min(BWD_TILE, N - n0), kcols = min(BWD_TILE, K - k0);
+  const int n0 = (tile / tiles_k) * TN_TILE, k0 = (tile % tiles_k) * TN_TILE;
+  const int ncols = min(TN_TILE, N - n0), kcols = min(TN_TILE, K - k0);
   const long long m_begin = split * chunk, m_end = min(M, m_begin + chunk);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = (warp & 3) * 16, wh = warp >> 2;
-  FragC acc[2];
-  wmma::fill_fragment(acc[0], 0.0f);
-  wmma::fill_fragment(acc[1], 0.0f);
+  const int wr = (warp & 3) * 32, wc = (warp >> 2) * 64;
+  FragC acc0[4], acc1[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    wmma::fill_fragment(acc0[f], 0.0f);
+    wmma::fill_fragment(acc1[f], 0.0f);
+  }
+  // plane tile [64 rows x `cols` valid of 128] -> smem, zero beyond the valid rows / columns (cols are even: N, K % 8 == 0)
+  auto stage = [&](const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long ld, int rows_valid, int cols_valid,
+                   __nv_bfloat16* dhi, __nv_bfloat16* dlo) {
+    for (int idx = threadIdx.x; idx < BWD_TILE * (TN_TILE >> 3); idx += BWD_THREADS) {
+      const int r = idx / (TN_TILE >> 3), c = (idx % (TN_TILE >> 3)) << 3;
+      uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+      if (r < rows_valid && c < cols_valid) {  // 8-element groups are all in or all out
+        h = *reinterpret_cast<const uint4*>(hi + r * ld + c);
+        if (lo != nullptr) l = *reinterpret_cast<const uint4*>(lo + r * ld + c);
+      }
+      *reinterpret_cast<uint4*>(dhi + r * TP + c) = h;
+      *reinterpret_cast<uint4*>(dlo + r * TP + c) = l;
+    }
+  };
   for (long long m0 = m_begin; m0 < m_end; m0 += BWD_TILE) {
     const long long mleft = m_end - m0;
     const int mrows = mleft < BWD_TILE ? static_cast<int>(mleft) : BWD_TILE;
     __syncthreads();
-    bwd_stage_tile(dY + m0 * ldy + n0, ldy, mrows, ncols, BWD_TILE, BWD_TILE, Y_hi, Y_lo, TP);
-    bwd_stage_tile(X + m0 * ldx + k0, ldx, mrows, kcols, BWD_TILE, BWD_TILE, X_hi, X_lo, TP);
+    stage(dy_hi + m0 * ldy + n0, dy_lo ? dy_lo + m0 * ldy + n0 : nullptr, ldy, mrows, ncols, Y_hi, Y_lo);
+    stage(x_hi + m0 * ldx + k0, x_lo ? x_lo + m0 * ldx + k0 : nullptr, ldx, mrows, kcols, X_hi, X_lo);
     __syncthreads();
-    bwd_mma<2, true, false>(acc, Y_hi, Y_lo, TP, wr, X_hi, X_lo, TP, 32 * wh, BWD_TILE);
+    bwd_mma<4, true, false>(acc0, Y_hi, Y_lo, TP, wr, X_hi, X_lo, TP, wc, BWD_TILE);
+    bwd_mma<4, true, false>(acc1, Y_hi, Y_lo, TP, wr + 16, X_hi, X_lo, TP, wc, BWD_TILE);
   }
-  float* stage = stage_all + warp * (16 * 20);
-  for (int f = 0; f < 2; ++f) {
-    wmma::store_matrix_sync(stage, acc[f], 20, wmma::mem_row_major);
-    __syncwarp();
-    for (int e = lane; e < 256; e += 32) {
-      const int r = e >> 4, c = e & 15;
-      const int n = wr + r, k = 32 * wh + 16 * f + c;
-      if (n < ncols && k < kcols) atomicAdd(dW + static_cast<long long>(n0 + n) * K + k0 + k, stage[r * 20 + c]);
+  float* stg = stage_all + warp * (16 * 20);
+  for (int half = 0; half < 2; ++half) {
+    for (int f = 0; f < 4; ++f) {
+      wmma::store_matrix_sync(stg, half ? acc1[f] : acc0[f], 20, wmma::mem_row_major);
+      __syncwarp();
+      for (int e = lane; e < 256; e += 32) {
+        const int r = e >> 4, c = e & 15;
+        const int n = wr + 16 * half + r, k = wc + 16 * f + c;
+        if (n < ncols && k < kcols) atomicAdd(dW + static_cast<long long>(n0 + n) * K + k0 + k, stg[r * 20 + c]);
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
-// db[n] += sum_m dY[m, n]: thread per column, `chunk` rows per block, one atomic per thread.
-__global__ void colsum_kernel(const float* __restrict__ dY, long long ldy, long long M, int N, long long chunk,
-                              float* __restrict__ db) {
+// db[n] += sum_m dY[m, n] (dY given as planes): thread per column, `chunk` rows per block, one atomic per thread.
+__global__ void colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                     long long ldy, long long M, int N, long long chunk, float* __restrict__ db) {
   const int n = blockIdx.y * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const long long m_begin = blockIdx.x * chunk, m_end = min(M, m_begin + chunk);
   float s = 0.f;
-  for (long long m = m_begin; m < m_end; ++m) s += dY[m * ldy + n];
+  for (long long m = m_begin; m < m_end; ++m) {
+    s += __bfloat162float(hi[m * ldy + n]);
+    if (lo != nullptr) s += __bfloat162float(lo[m * ldy + n]);
+  }
   atomicAdd(db + n, s);
 }
 

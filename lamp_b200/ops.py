@@ -582,21 +582,24 @@ class LinearFunction(torch.autograd.Function):
         y = torch.empty((M, N), dtype=torch.float32, device=x.device)
         gemm(a_hi, a_lo, K, w_hi, w_lo, K, M, N, K, prec, bias=None if b is None else b.detach().float().contiguous(),
              out_f32=y, ldo=N)
-        ctx.save_for_backward(x2, W, b if b is not None else x2.new_empty(0))
+        # the operand planes of x are what the weight-gradient contraction consumes: keep them instead of x
+        ctx.save_for_backward(a_hi, a_lo if a_lo is not None else a_hi.new_empty(0), W,
+                              b if b is not None else x2.new_empty(0))
         ctx.prec, ctx.has_bias, ctx.x_shape = prec, b is not None, tuple(x.shape)
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, W, b = ctx.saved_tensors
+        a_hi, a_lo, W, b = ctx.saved_tensors
+        a_lo = a_lo if a_lo.numel() else None
         prec = ctx.prec
         w2 = W.reshape(W.shape[0], -1)
         N, K = w2.shape
         dy2 = dy.reshape(-1, N).contiguous().float()
         M = dy2.shape[0]
         dx = dW = db = None
+        d_hi, d_lo = split(dy2, prec)
         if ctx.needs_input_grad[0]:
-            d_hi, d_lo = split(dy2, prec)
             wt_hi, wt_lo = split(w2.detach().t().contiguous().float(), prec)  # [K, N]: dx = dy (W^T)^T
             dx2 = torch.empty((M, K), dtype=torch.float32, device=dy.device)
             gemm(d_hi, d_lo, N, wt_hi, wt_lo, N, M, K, N, prec, out_f32=dx2, ldo=K)
@@ -605,8 +608,8 @@ class LinearFunction(torch.autograd.Function):
             dW2 = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
             db = torch.zeros((N,), dtype=torch.float32, device=dy.device) if ctx.has_bias else None
             STATS.call('gemm_tn', 2 if db is not None else 1, nat.lib().lamp_gemm_tn_acc,
-                       (dy2.data_ptr(), N, x2.data_ptr(), K, M, N, K, dW2.data_ptr(), nat.ptr(db), nat.stream()),
-                       flops=2.0 * M * N * K)
+                       (d_hi.data_ptr(), nat.ptr(d_lo), N, a_hi.data_ptr(), nat.ptr(a_lo), K, M, N, K, dW2.data_ptr(),
+                        nat.ptr(db), nat.stream()), flops=2.0 * M * N * K)
             dW = dW2.view(W.shape).to(W.dtype)
             if db is not None:
                 db = db.to(b.dtype)
