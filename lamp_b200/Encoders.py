@@ -86,7 +86,12 @@ class GraphEncoder(nn.Module):
         attns = []
         out = enc_input
         for layer in self.layer_stack:
-            out, attn = layer(out, slf_attn_mask=mask)
+            if return_attns or not ops.ELIDE_DEAD_ENCODER_ATTENTION:
+                out, attn = layer(out, slf_attn_mask=mask)
+            else:
+                # lamp/Layers.py:16-18: the layer output is pos_ffn(enc_input); the self-attention result is discarded
+                # and its parameters never receive gradients, so it is only evaluated when its map is asked for
+                out, attn = layer.pos_ffn(out), None
             attns.append(attn)
         return self._pool(out, src_seq, src_seq.size(0)), attns
 

@@ -337,6 +337,7 @@ def linear_residual_deferred(x: Act, w_hi, w_lo, N: int, prec: int, residual: Ac
 
 
 NATIVE_ATTENTION_BACKWARD = os.environ.get('LAMP_NATIVE_ATTN_BWD', '1') != '0'  # training: attention core fwd+bwd native
+ELIDE_DEAD_ENCODER_ATTENTION = True  # training / composed path: skip the encoder self-attention whose output is discarded
 PADDING_AWARE = True  # GraphEncoder/GraphDecoder compute only non-PAD token rows (results identical, see Encoders.py)
 # fc / w_2 GEMMs emit pre-norm planes + row statistics and the LayerNorm is applied by the consumers (no LayerNorm
 # kernels inside the stack).  LAMP_DEFER_LN=0/1 overrides the default (benchmarking aid; results agree to fp32 rounding).
