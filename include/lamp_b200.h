@@ -49,6 +49,7 @@ int lamp_sm_count(void);
 #define LAMP_TUNE_ATTN_COMPACT 3  /* 1 (default: tile rows follow L, deepest K/V staging that fits) or 0 (128-row tiles) */
 #define LAMP_TUNE_ATTN_STAGE 4    /* 1 (default: attention output planes leave through smem staging + TMA stores) or 0 */
 #define LAMP_TUNE_ATTN_PV_SPLIT 5  /* 0 (default) or 1: O += P V as two interleaved N = 64 accumulation chains (d == 128) */
+#define LAMP_TUNE_GEMM_TN_TC 6     /* 1 (default): weight gradient dY^T X on tcgen05 (MN-major operands), 0: warp-MMA version */
 #define LAMP_TUNE_GEMM_CTA_PAIR 2 /* 1 (default: tcgen05 cta_group::2 pairs for 256-wide tiles) or 0 (single CTAs) */
 int lamp_set_tuning(int key, int value);
 

@@ -15,6 +15,7 @@
 #include "attn_core.cuh"
 #include "elementwise.cuh"
 #include "gemm_planes.cuh"
+#include "gemm_tn_tc.cuh"
 #include "train_bwd.cuh"
 
 using namespace lamp;
@@ -175,6 +176,7 @@ std::atomic<int> g_gemm_block_k{0};   // tuning knob (lamp_set_tuning): 32 -> 64
 std::atomic<int> g_attn_compact{1};   // tuning knob: 1 -> L-dependent tile rows + deepest K/V staging that fits, 0 -> full 128-row tiles, 1 stage
 std::atomic<int> g_attn_stage{1};     // tuning knob: 1 -> O planes leave through the smem staging tile + TMA stores when it fits
 std::atomic<int> g_attn_pv_split{0};  // tuning knob: 1 -> PV product as two interleaved N = 64 chains when d == 128
+std::atomic<int> g_gemm_tn_tc{1};     // tuning knob: 1 -> weight gradient on tcgen05 (gemm_tn_tc.cuh), 0 -> warp-MMA version
 std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group::2) for the 256-wide tiles, 0 -> single CTAs
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB: the sm_100 per-CTA opt-in maximum
@@ -253,6 +255,10 @@ int lamp_set_tuning(int key, int value) {
   }
   if (key == LAMP_TUNE_ATTN_PV_SPLIT && (value == 0 || value == 1)) {
     g_attn_pv_split.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_GEMM_TN_TC && (value == 0 || value == 1)) {
+    g_gemm_tn_tc.store(value);
     return LAMP_OK;
   }
   if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
@@ -673,6 +679,50 @@ int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const vo
   REQUIRE(aligned16(dy_hi) && aligned16(x_hi) && (!dy_lo || aligned16(dy_lo)) && (!x_lo || aligned16(x_lo)), "gemm_tn: alignment");
   if (M == 0) return LAMP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_gemm_tn_tc.load() != 0) {
+    // tcgen05 path: dY and X read MN-major straight from their row-major planes
+    const bool three = dy_lo != nullptr && x_lo != nullptr;
+    CUtensorMap ty_hi, ty_lo, tx_hi, tx_lo;
+    if (int rc = make_tmap(&ty_hi, dy_hi, (uint64_t)N, (uint64_t)M, 1, (uint64_t)ldy, TNC_BM, false)) return rc;
+    if (int rc = make_tmap(&tx_hi, x_hi, (uint64_t)K, (uint64_t)M, 1, (uint64_t)ldx, TNC_BM, false)) return rc;
+    if (three) {
+      if (int rc = make_tmap(&ty_lo, dy_lo, (uint64_t)N, (uint64_t)M, 1, (uint64_t)ldy, TNC_BM, false)) return rc;
+      if (int rc = make_tmap(&tx_lo, x_lo, (uint64_t)K, (uint64_t)M, 1, (uint64_t)ldx, TNC_BM, false)) return rc;
+    } else {
+      ty_lo = ty_hi;
+      tx_lo = tx_hi;
+    }
+    static std::once_flag once_tc;
+    static int once_tc_rc = LAMP_OK;
+    std::call_once(once_tc, [] {
+      once_tc_rc = set_smem(gemm_tn_tc_kernel<3>, tnc_smem_bytes(2));
+      if (once_tc_rc == LAMP_OK) once_tc_rc = set_smem(gemm_tn_tc_kernel<1>, tnc_smem_bytes(1));
+    });
+    if (once_tc_rc != LAMP_OK) return once_tc_rc;
+    const long long tiles = (long long)((N + TNC_TILE_N - 1) / TNC_TILE_N) * ((K + TNC_TILE_K - 1) / TNC_TILE_K);
+    long long splits = (sm_count_cached() + tiles - 1) / tiles;  // one CTA per SM (192 KB of smem each)
+    const long long max_splits = (M + TNC_BM - 1) / TNC_BM;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    GemmTnParams gp;
+    gp.M = M; gp.N = N; gp.K = K; gp.dW = dW;
+    gp.chunk = ((M + splits - 1) / splits + TNC_BM - 1) / TNC_BM * TNC_BM;
+    splits = (M + gp.chunk - 1) / gp.chunk;
+    REQUIRE(M < (1LL << 31), "gemm_tn: M too large for TMA coordinates");
+    if (three)
+      gemm_tn_tc_kernel<3><<<(unsigned)(tiles * splits), TNC_THREADS, tnc_smem_bytes(2), st>>>(ty_hi, ty_lo, tx_hi, tx_lo, gp);
+    else
+      gemm_tn_tc_kernel<1><<<(unsigned)(tiles * splits), TNC_THREADS, tnc_smem_bytes(1), st>>>(ty_hi, ty_lo, tx_hi, tx_lo, gp);
+    if (int rc = launch_check()) return rc;
+    if (db != nullptr) {
+      long long rb = (M + 511) / 512;
+      dim3 grid((unsigned)rb, (unsigned)((N + 127) / 128));
+      colsum_planes_kernel<<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(dy_hi),
+                                                 static_cast<const __nv_bfloat16*>(dy_lo), ldy, M, N, 512, db);
+      return launch_check();
+    }
+    return LAMP_OK;
+  }
   static std::once_flag once;
   static int once_rc = LAMP_OK;
   std::call_once(once, [] { once_rc = set_smem(gemm_tn_kernel, (uint32_t)gemm_tn_smem_bytes()); });

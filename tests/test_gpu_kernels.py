@@ -653,8 +653,19 @@ def test_attn_core_training_forward_dropout_and_backward(N, Lq, Lk, d, pdrop):
 
 @pytest.mark.parametrize('M,N,K,bias', [(3296, 512, 512, True), (1000, 1536, 512, False), (777, 264, 72, True),
                                          (130, 64, 1024, True), (9600, 512, 512, False)])
-def test_linear_function_grads(M, N, K, bias):
-    """ops.LinearFunction: y, dx on the tcgen05 GEMM, dW / db on lamp_gemm_tn_acc -- vs fp64 autograd."""
+@pytest.mark.parametrize('tn_tc', [1, 0])
+def test_linear_function_grads(M, N, K, bias, tn_tc):
+    """ops.LinearFunction: y, dx on the tcgen05 GEMM, dW / db on lamp_gemm_tn_acc (tcgen05 kernel with MN-major
+    operands, and the warp-MMA version behind LAMP_TUNE_GEMM_TN_TC=0) -- vs fp64 autograd."""
+    from lamp_b200 import ops
+    nat.check(nat.lib().lamp_set_tuning(6, tn_tc), 'tune')
+    try:
+        _linear_function_grads(M, N, K, bias)
+    finally:
+        nat.check(nat.lib().lamp_set_tuning(6, 1), 'tune')
+
+
+def _linear_function_grads(M, N, K, bias):
     from lamp_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).to(DEV).requires_grad_(True)
