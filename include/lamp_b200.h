@@ -50,6 +50,7 @@ int lamp_sm_count(void);
 #define LAMP_TUNE_ATTN_STAGE 4    /* 1 (default: attention output planes leave through smem staging + TMA stores) or 0 */
 #define LAMP_TUNE_ATTN_PV_SPLIT 5  /* 0 (default) or 1: O += P V as two interleaved N = 64 accumulation chains (d == 128) */
 #define LAMP_TUNE_GEMM_TN_TC 6     /* 1 (default): weight gradient dY^T X on tcgen05 (MN-major operands), 0: warp-MMA version */
+#define LAMP_TUNE_ATTN_BWD_TC 7    /* 1 (default): attention backward as batched tcgen05 products, 0: warp-MMA kernels */
 #define LAMP_TUNE_GEMM_CTA_PAIR 2 /* 1 (default: tcgen05 cta_group::2 pairs for 256-wide tiles) or 0 (single CTAs) */
 int lamp_set_tuning(int key, int value);
 
@@ -156,12 +157,15 @@ int lamp_attn_core_planes_mbits(const void* q_hi, const void* q_lo, int64_t ldq,
 
 /* Backward of the attention core (training path; lamp/SubLayers.py:27-43 differentiated):
  * given q [N,Lq,d], k,v [N,Lk,d], the forward's output O and probabilities P [N,Lq,Lk] (before dropout) and A (after
- * dropout; NULL = no dropout, A == P), and dO, computes dq, dk, dv (fp32, same shapes as q, k, v).  dS [N,Lq,Lk] is
- * caller-provided scratch.  p_drop is the dropout rate the forward used (scale 1/(1-p)); the kept set is read off A.
- * Masked entries need no mask here: their P is 0.  d % 16 == 0, d <= 128.  Deterministic (no atomics). */
+ * dropout; NULL = no dropout, A == P), and dO, computes dq, dk, dv (fp32, same shapes as q, k, v).  p_drop is the
+ * dropout rate the forward used (scale 1/(1-p)); the kept set is read off A.  Masked entries need no mask here: their
+ * P is 0.  d % 16 == 0, d <= 128.  Deterministic (no atomics).  Runs as four batched tcgen05 products
+ * (dA = dO V^T, dQ = dS K, dV = A^T dO, dK = dS^T Q; transposed operands are read MN-major in place) around one
+ * element-wise kernel; LAMP_TUNE_ATTN_BWD_TC = 0 selects the warp-MMA version. */
+size_t lamp_attn_core_bwd_workspace_bytes(int N, int Lq, int Lk, int d);
 int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const float* dO, const float* O, const float* P,
-                       const float* A, float* dS, float* dq, float* dk, float* dv, int N, int Lq, int Lk, int d,
-                       float temperature, float p_drop, void* stream);
+                       const float* A, float* dq, float* dk, float* dv, int N, int Lq, int Lk, int d, float temperature,
+                       float p_drop, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of out = LayerNorm(x)*gamma+beta: dx (fp32), and dgamma / dbeta ACCUMULATED into the given [D] buffers
  * (zero them first).  x is the LayerNorm input saved by the forward. */

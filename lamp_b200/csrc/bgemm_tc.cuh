@@ -1,0 +1,192 @@
+// Batched small GEMM on tcgen05 for the attention backward:  C_b[M, N] = opA(A_b) opB(B_b)  for b < batch, every
+// operand given as split-bf16 planes read in place by 3-D TMA maps {cols, rows, batch} (rows beyond the per-batch
+// bound are zero-filled, so ragged label counts need no padding).  Each operand is either K-major (the contraction
+// index is the contiguous one: [rows = M or N, cols = Kc]) or MN-major ([rows = Kc, cols = M or N]) -- the four
+// products of the backward differ only in that:
+//     dA = dO V^T     (A: dO K-major,  B: V  K-major)         dQ = dS K      (A: dS K-major,  B: K  MN-major)
+//     dV = A^T dO     (A: A  MN-major, B: dO MN-major)        dK = dS^T Q    (A: dS MN-major, B: Q  MN-major)
+// One CTA = one (batch, 128-row m tile, TN-column n tile); contraction in 64-wide chunks through a TMA ring;
+// 3-term split-bf16 products into one TMEM accumulator; epilogue: tcgen05.ld (lane == output row), scaled fp32 stores.
+#pragma once
+#include "sm100_primitives.cuh"
+
+namespace lamp {
+
+constexpr int BG_THREADS = 192;
+constexpr int BG_KC = 64;  // contraction chunk
+__host__ __device__ constexpr uint32_t bg_stage_bytes(int npl, int tn) { return npl * (128 + tn) * BG_KC * 2; }
+__host__ __device__ constexpr int bg_stages(int npl, int tn) { return (192 * 1024) / bg_stage_bytes(npl, tn); }
+__host__ __device__ constexpr uint32_t bg_smem_bytes(int npl, int tn) {
+  return (bg_stages(npl, tn) > 4 ? 4 : bg_stages(npl, tn)) * bg_stage_bytes(npl, tn) + 1024 + 256;
+}
+
+struct BgemmParams {
+  int batch, M, N, Kc;
+  float scale;      // C = scale * (A B)
+  float* C;         // [batch, M, ldc] fp32
+  long long ldc, stride_c;
+};
+
+template <bool A_MN, bool B_MN, int NTERMS, int TN>
+__global__ void __launch_bounds__(BG_THREADS, 1)
+bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const BgemmParams p) {
+  constexpr int NPL = (NTERMS == 3) ? 2 : 1;
+  constexpr int STAGES = bg_stages(NPL, TN) > 4 ? 4 : bg_stages(NPL, TN);
+  constexpr uint32_t A_BYTES = 128 * BG_KC * 2, B_BYTES = TN * BG_KC * 2;
+  constexpr uint32_t STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+  constexpr uint32_t BOX = 64 * 64 * 2;  // one [64 x 64] box of an MN-major operand
+  static_assert(STAGES >= 2, "ring too shallow");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  auto a_tile = [&](int s, int pl) { return smem + s * STAGE_BYTES + pl * (A_BYTES + B_BYTES); };
+  auto b_tile = [&](int s, int pl) { return smem + s * STAGE_BYTES + pl * (A_BYTES + B_BYTES) + A_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + 127) / 128, tiles_n = (p.N + TN - 1) / TN;
+  const int tile = blockIdx.x % (tiles_m * tiles_n);
+  const int b = blockIdx.x / (tiles_m * tiles_n);
+  const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * TN;
+  const int num_it = (p.Kc + BG_KC - 1) / BG_KC;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (NPL == 2) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TN);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+        const int kc0 = it * BG_KC;
+        for (int pl = 0; pl < NPL; ++pl) {
+          const CUtensorMap* ta = pl ? &tmA_lo : &tmA_hi;
+          const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
+          if (A_MN) {  // map {M cols, Kc rows, batch}, boxes {64, 64}
+            for (int bx = 0; bx < 2; ++bx) tma_load_3d(a_tile(stage, pl) + bx * BOX, ta, &full_bar[stage], m0 + 64 * bx, kc0, b);
+          } else {     // map {Kc cols, M rows, batch}, box {64, 128}
+            tma_load_3d(a_tile(stage, pl), ta, &full_bar[stage], kc0, m0, b);
+          }
+          if (B_MN) {
+            for (int bx = 0; bx < TN / 64; ++bx) tma_load_3d(b_tile(stage, pl) + bx * BOX, tb, &full_bar[stage], n0 + 64 * bx, kc0, b);
+          } else {
+            tma_load_3d(b_tile(stage, pl), tb, &full_bar[stage], kc0, n0, b);
+          }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, TN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int t = 0; t < BG_KC / 16; ++t) {
+          // K-major: 16 contraction elements = 32 B inside the swizzled 128 B row (SBO = 8 rows);
+          // MN-major: 16 contraction rows = 2 KB inside every [64 x 64] box (LBO = box stride, SBO = 8 rows)
+          auto desc = [&](uint8_t* base, bool mn) {
+            return mn ? umma_smem_desc(smem_u32(base) + t * 2048, BOX, 1024) : umma_smem_desc(smem_u32(base) + t * 32, 16, 1024);
+          };
+          const uint64_t da_hi = desc(a_tile(stage, 0), A_MN), db_hi = desc(b_tile(stage, 0), B_MN);
+          umma_bf16_ss(tmem_base, da_hi, db_hi, idesc, (it | t) != 0 ? 1u : 0u);
+          if (NTERMS == 3) {
+            const uint64_t da_lo = desc(a_tile(stage, 1), A_MN), db_lo = desc(b_tile(stage, 1), B_MN);
+            umma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1u);
+            umma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int wq = warp & 3;
+    const int m = m0 + wq * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tcgen05_fence_after();
+    float* row = p.C + static_cast<long long>(b) * p.stride_c + static_cast<long long>(m) * p.ldc + n0;
+    for (int c0 = 0; c0 < TN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + c0, r);
+      tmem_wait_ld();
+      if (m < p.M) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (n0 + c0 + e < p.N) row[c0 + e] = __uint_as_float(r[e]) * p.scale;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TN);
+  }
+}
+
+// dS = P o (dA * keep / (1 - p) - delta) / temperature  ->  split-bf16 planes [N*Lq, ld] (ld = Lk rounded up to 8; the
+// pad columns are written as 0), and A (attn after dropout) -> planes, both operands of the dQ / dK / dV products.
+// delta_i = <dO_i, O_i> is computed by the same block (one warp per row) before the row is swept.
+__global__ void attn_bwd_ds_kernel(const float* __restrict__ dA, const float* __restrict__ P, const float* __restrict__ A,
+                                   const float* __restrict__ dO, const float* __restrict__ O, long long rows, int Lk,
+                                   int d, int ld, float inv_temp, float drop_scale, __nv_bfloat16* __restrict__ dS_hi,
+                                   __nv_bfloat16* __restrict__ dS_lo, __nv_bfloat16* __restrict__ A_hi,
+                                   __nv_bfloat16* __restrict__ A_lo) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float delta = 0.f;
+  for (int c = lane; c < d; c += 32) delta += dO[row * d + c] * O[row * d + c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xFFFFFFFFu, delta, o);
+  for (int c = lane; c < ld; c += 32) {
+    float ds = 0.f, a = 0.f;
+    if (c < Lk) {
+      const long long g = row * Lk + c;
+      a = A[g];
+      const float keep = (a != 0.0f) ? drop_scale : 0.0f;
+      ds = P[g] * (dA[g] * keep - delta) * inv_temp;
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(ds);
+    dS_hi[row * ld + c] = h;
+    dS_lo[row * ld + c] = __float2bfloat16_rn(ds - __bfloat162float(h));
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a);
+    A_hi[row * ld + c] = ah;
+    A_lo[row * ld + c] = __float2bfloat16_rn(a - __bfloat162float(ah));
+  }
+}
+
+}  // namespace lamp

@@ -13,6 +13,7 @@
 
 #include "attn_bwd.cuh"
 #include "attn_core.cuh"
+#include "bgemm_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm_planes.cuh"
 #include "gemm_tn_tc.cuh"
@@ -177,6 +178,7 @@ std::atomic<int> g_attn_compact{1};   // tuning knob: 1 -> L-dependent tile rows
 std::atomic<int> g_attn_stage{1};     // tuning knob: 1 -> O planes leave through the smem staging tile + TMA stores when it fits
 std::atomic<int> g_attn_pv_split{0};  // tuning knob: 1 -> PV product as two interleaved N = 64 chains when d == 128
 std::atomic<int> g_gemm_tn_tc{1};     // tuning knob: 1 -> weight gradient on tcgen05 (gemm_tn_tc.cuh), 0 -> warp-MMA version
+std::atomic<int> g_attn_bwd_tc{1};    // tuning knob: 1 -> attention backward as batched tcgen05 products, 0 -> warp-MMA kernels
 std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group::2) for the 256-wide tiles, 0 -> single CTAs
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB: the sm_100 per-CTA opt-in maximum
@@ -259,6 +261,10 @@ int lamp_set_tuning(int key, int value) {
   }
   if (key == LAMP_TUNE_GEMM_TN_TC && (value == 0 || value == 1)) {
     g_gemm_tn_tc.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_ATTN_BWD_TC && (value == 0 || value == 1)) {
+    g_attn_bwd_tc.store(value);
     return LAMP_OK;
   }
   if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
@@ -616,38 +622,119 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
   return rc;
 }
 
+extern "C++" {
+namespace {
+struct AttnBwdPlan {
+  size_t qp, kp, vp, dop, dA, dSp, Ap, total;
+  int ld;
+};
+AttnBwdPlan attn_bwd_plan(int N, int Lq, int Lk, int d) {
+  AttnBwdPlan pl{};
+  pl.ld = (Lk + 7) / 8 * 8;
+  Carver c(nullptr);
+  const size_t nq = (size_t)N * Lq, nk = (size_t)N * Lk;
+  pl.qp = c.off;  c.take(nq * d * 4);
+  pl.kp = c.off;  c.take(nk * d * 4);
+  pl.vp = c.off;  c.take(nk * d * 4);
+  pl.dop = c.off; c.take(nq * d * 4);
+  pl.dA = c.off;  c.take(nq * Lk * 4);
+  pl.dSp = c.off; c.take(nq * pl.ld * 4);
+  pl.Ap = c.off;  c.take(nq * pl.ld * 4);
+  pl.total = c.off;
+  return pl;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_bgemm(const void* a_hi, const void* a_lo, uint64_t a_cols, uint64_t a_rows, uint64_t a_ld, const void* b_hi,
+                 const void* b_lo, uint64_t b_cols, uint64_t b_rows, uint64_t b_ld, int batch, int M, int N, int Kc,
+                 float scale, float* C, long long ldc, long long stride_c, cudaStream_t st) {
+  constexpr int TN = 128;
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  const uint32_t a_box_rows = A_MN ? 64 : 128, b_box_rows = B_MN ? 64 : TN;
+  if (int rc = make_tmap(&ta_hi, a_hi, a_cols, a_rows, (uint64_t)batch, a_ld, a_box_rows, true)) return rc;
+  if (int rc = make_tmap(&ta_lo, a_lo, a_cols, a_rows, (uint64_t)batch, a_ld, a_box_rows, true)) return rc;
+  if (int rc = make_tmap(&tb_hi, b_hi, b_cols, b_rows, (uint64_t)batch, b_ld, b_box_rows, true)) return rc;
+  if (int rc = make_tmap(&tb_lo, b_lo, b_cols, b_rows, (uint64_t)batch, b_ld, b_box_rows, true)) return rc;
+  auto kernel = bgemm_tc_kernel<A_MN, B_MN, 3, TN>;
+  static std::once_flag once;
+  static int once_rc = LAMP_OK;
+  std::call_once(once, [kernel] { once_rc = set_smem(kernel, bg_smem_bytes(2, TN)); });
+  if (once_rc != LAMP_OK) return once_rc;
+  BgemmParams p;
+  p.batch = batch; p.M = M; p.N = N; p.Kc = Kc; p.scale = scale; p.C = C; p.ldc = ldc; p.stride_c = stride_c;
+  const long long grid = (long long)batch * ((M + 127) / 128) * ((N + TN - 1) / TN);
+  if (grid >= (1LL << 31)) return fail(LAMP_EINVAL, "bgemm: grid too large");
+  kernel<<<(unsigned)grid, BG_THREADS, bg_smem_bytes(2, TN), st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  return launch_check();
+}
+}  // namespace
+}  // extern "C++"
+
+size_t lamp_attn_core_bwd_workspace_bytes(int N, int Lq, int Lk, int d) { return attn_bwd_plan(N, Lq, Lk, d).total; }
+
 int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const float* dO, const float* O, const float* P,
-                       const float* A, float* dS, float* dq, float* dk, float* dv, int N, int Lq, int Lk, int d,
-                       float temperature, float p_drop, void* stream) {
+                       const float* A, float* dq, float* dk, float* dv, int N, int Lq, int Lk, int d, float temperature,
+                       float p_drop, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = arch_check()) return rc;
-  REQUIRE(q && k && v && dO && O && P && dS && dq && dk && dv, "attn_bwd: null pointer");
+  REQUIRE(q && k && v && dO && O && P && dq && dk && dv, "attn_bwd: null pointer");
   REQUIRE(N >= 0 && Lq > 0 && Lk > 0, "attn_bwd: bad shape N=%d Lq=%d Lk=%d", N, Lq, Lk);
   REQUIRE(d % 16 == 0 && d >= 16 && d <= BWD_DMAX, "attn_bwd: head width %d must be a multiple of 16 in [16,128]", d);
   REQUIRE(temperature > 0.0f && p_drop >= 0.0f && p_drop < 1.0f, "attn_bwd: bad temperature / dropout rate");
   REQUIRE((long long)N * Lq * Lk < (1LL << 40), "attn_bwd: probability tensor too large");
+  const AttnBwdPlan pl = attn_bwd_plan(N, Lq, Lk, d);
+  if (!workspace || workspace_bytes < pl.total) return fail(LAMP_EWORKSPACE, "attn_bwd: workspace too small");
   if (N == 0) return LAMP_OK;
-  AttnBwdParams p;
-  p.N = N; p.Lq = Lq; p.Lk = Lk; p.d = d;
-  p.inv_temp = 1.0f / temperature;
-  p.drop_scale = 1.0f / (1.0f - p_drop);
-  p.q = q; p.k = k; p.v = v; p.dO = dO; p.O = O; p.P = P; p.A = A ? A : P;
-  p.dS = dS; p.dq = dq; p.dk = dk; p.dv = dv;
-  const uint32_t smem = (uint32_t)attn_bwd_smem_bytes(d);
-  static std::once_flag once;
-  static int once_rc = LAMP_OK;
-  std::call_once(once, [] {
-    once_rc = set_smem(attn_bwd_dq_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
-    if (once_rc == LAMP_OK) once_rc = set_smem(attn_bwd_dkv_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
-  });
-  if (once_rc != LAMP_OK) return once_rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long gq = (long long)N * ((Lq + BWD_TILE - 1) / BWD_TILE);
-  const long long gk = (long long)N * ((Lk + BWD_TILE - 1) / BWD_TILE);
-  REQUIRE(gq < (1LL << 31) && gk < (1LL << 31), "attn_bwd: grid too large");
-  attn_bwd_dq_kernel<<<(unsigned)gq, BWD_THREADS, smem, st>>>(p);
-  if (int rc = launch_check()) return rc;
-  attn_bwd_dkv_kernel<<<(unsigned)gk, BWD_THREADS, smem, st>>>(p);
-  return launch_check();
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t nq = (size_t)N * Lq, nk = (size_t)N * Lk;
+  if (g_attn_bwd_tc.load() == 0) {
+    // warp-MMA version (attn_bwd.cuh): fp32 operands, dS through the dA slot of the workspace
+    AttnBwdParams p;
+    p.N = N; p.Lq = Lq; p.Lk = Lk; p.d = d;
+    p.inv_temp = 1.0f / temperature;
+    p.drop_scale = 1.0f / (1.0f - p_drop);
+    p.q = q; p.k = k; p.v = v; p.dO = dO; p.O = O; p.P = P; p.A = A ? A : P;
+    p.dS = reinterpret_cast<float*>(ws + pl.dA); p.dq = dq; p.dk = dk; p.dv = dv;
+    const uint32_t smem = (uint32_t)attn_bwd_smem_bytes(d);
+    static std::once_flag once;
+    static int once_rc = LAMP_OK;
+    std::call_once(once, [] {
+      once_rc = set_smem(attn_bwd_dq_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
+      if (once_rc == LAMP_OK) once_rc = set_smem(attn_bwd_dkv_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
+    });
+    if (once_rc != LAMP_OK) return once_rc;
+    const long long gq = (long long)N * ((Lq + BWD_TILE - 1) / BWD_TILE);
+    const long long gk = (long long)N * ((Lk + BWD_TILE - 1) / BWD_TILE);
+    REQUIRE(gq < (1LL << 31) && gk < (1LL << 31), "attn_bwd: grid too large");
+    attn_bwd_dq_kernel<<<(unsigned)gq, BWD_THREADS, smem, st>>>(p);
+    if (int rc = launch_check()) return rc;
+    attn_bwd_dkv_kernel<<<(unsigned)gk, BWD_THREADS, smem, st>>>(p);
+    return launch_check();
+  }
+  // tcgen05 version: four batched products on the operand planes + one element-wise kernel
+  auto hi = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+  __nv_bfloat16 *qh = hi(pl.qp), *ql = qh + nq * d, *kh = hi(pl.kp), *kl = kh + nk * d, *vh = hi(pl.vp), *vl = vh + nk * d;
+  __nv_bfloat16 *gh = hi(pl.dop), *gl = gh + nq * d;
+  __nv_bfloat16 *sh = hi(pl.dSp), *sl = sh + nq * pl.ld, *ah = hi(pl.Ap), *al = ah + nq * pl.ld;
+  float* dA = reinterpret_cast<float*>(ws + pl.dA);
+  if (int rc = lamp_split_planes(q, (int64_t)nq, d, d, qh, ql, d, stream)) return rc;
+  if (int rc = lamp_split_planes(k, (int64_t)nk, d, d, kh, kl, d, stream)) return rc;
+  if (int rc = lamp_split_planes(v, (int64_t)nk, d, d, vh, vl, d, stream)) return rc;
+  if (int rc = lamp_split_planes(dO, (int64_t)nq, d, d, gh, gl, d, stream)) return rc;
+  // dA = dO V^T  [N, Lq, Lk]
+  if (int rc = launch_bgemm<false, false>(gh, gl, d, Lq, d, vh, vl, d, Lk, d, N, Lq, Lk, d, 1.0f, dA, Lk, (long long)Lq * Lk, st)) return rc;
+  // dS (scaled by 1/temperature) and A as planes [N*Lq, ld]
+  {
+    const long long blocks = ((long long)nq * 32 + 255) / 256;
+    attn_bwd_ds_kernel<<<(unsigned)blocks, 256, 0, st>>>(dA, P, A ? A : P, dO, O, (long long)nq, Lk, d, pl.ld,
+                                                         1.0f / temperature, 1.0f / (1.0f - p_drop), sh, sl, ah, al);
+    if (int rc = launch_check()) return rc;
+  }
+  // dQ = dS K   (A: dS K-major, B: K MN-major)
+  if (int rc = launch_bgemm<false, true>(sh, sl, Lk, Lq, pl.ld, kh, kl, d, Lk, d, N, Lq, d, Lk, 1.0f, dq, d, (long long)Lq * d, st)) return rc;
+  // dV = A^T dO, dK = dS^T Q   (both operands MN-major: contraction over the q rows)
+  if (int rc = launch_bgemm<true, true>(ah, al, Lk, Lq, pl.ld, gh, gl, d, Lq, d, N, Lk, d, Lq, 1.0f, dv, d, (long long)Lk * d, st)) return rc;
+  return launch_bgemm<true, true>(sh, sl, Lk, Lq, pl.ld, qh, ql, d, Lq, d, N, Lk, d, Lq, 1.0f, dk, d, (long long)Lk * d, st);
 }
 
 int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,

@@ -512,12 +512,13 @@ def sdpa_backward(q, k, v, out, probs, attn, grad_out, temperature: float, p_dro
     N, Lq, d = q.shape
     Lk = k.shape[1]
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    dS = torch.empty_like(probs)
+    L = nat.lib()
+    ws = torch.empty((max(L.lamp_attn_core_bwd_workspace_bytes(N, Lq, Lk, d), 16),), dtype=torch.uint8, device=q.device)
     a = None if attn is None or attn is probs else attn.contiguous().float()
-    STATS.call('attn_core_bwd', 2, nat.lib().lamp_attn_core_bwd,
+    STATS.call('attn_core_bwd', 10, L.lamp_attn_core_bwd,
                (q.data_ptr(), k.data_ptr(), v.data_ptr(), grad_out.data_ptr(), out.data_ptr(), probs.data_ptr(),
-                nat.ptr(a), dS.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), N, Lq, Lk, d,
-                float(temperature), float(p_drop), nat.stream()), flops=10.0 * N * Lq * Lk * d)
+                nat.ptr(a), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), N, Lq, Lk, d, float(temperature), float(p_drop),
+                ws.data_ptr(), ws.numel(), nat.stream()), flops=10.0 * N * Lq * Lk * d)
     return dq, dk, dv
 
 

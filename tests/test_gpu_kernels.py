@@ -572,9 +572,19 @@ def test_attn_core_packed_mask_equals_byte_mask(B, H, Lq, Lk, d, per_sample):
                                                  (5, 159, 159, 64, 'none'), (3, 70, 45, 32, 'label'),
                                                  (2, 200, 130, 48, 'pad'), (2, 33, 17, 16, 'none'),
                                                  (2, 260, 257, 112, 'label')])
-def test_attn_core_backward_vs_autograd(N, Lq, Lk, d, maskkind):
+@pytest.mark.parametrize('bwd_tc', [1, 0])
+def test_attn_core_backward_vs_autograd(N, Lq, Lk, d, maskkind, bwd_tc):
     """lamp_attn_core_bwd (dq, dk, dv of softmax(mask(q k^T / T)) v) against fp64 torch autograd of the same function,
-    through ops.SDPAFunction (native forward + native backward)."""
+    through ops.SDPAFunction (native forward + native backward): the batched tcgen05 version and the warp-MMA
+    version (LAMP_TUNE_ATTN_BWD_TC = 0)."""
+    nat.check(nat.lib().lamp_set_tuning(7, bwd_tc), 'tune')
+    try:
+        _attn_core_backward_vs_autograd(N, Lq, Lk, d, maskkind)
+    finally:
+        nat.check(nat.lib().lamp_set_tuning(7, 1), 'tune')
+
+
+def _attn_core_backward_vs_autograd(N, Lq, Lk, d, maskkind):
     from lamp_b200 import ops
     g = torch.Generator().manual_seed(N + Lq + Lk + d)
     q = torch.randn(N, Lq, d, generator=g).to(DEV).requires_grad_(True)
