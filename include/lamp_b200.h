@@ -219,11 +219,12 @@ int lamp_sdpa_fwd(const float* q, const float* k, const float* v, const uint8_t*
 /* Training forward of the same op: dropout with rate p_drop on the probabilities (lamp/SubLayers.py:40) inside the
  * kernel.  The kept set is a pure function of (seed, row, key) -- a counter-based hash, no state -- so `attn` (after
  * dropout, what the reference returns) and `probs_pre` (before dropout, saved for lamp_attn_core_bwd; may be NULL when
- * p_drop == 0) describe exactly what the PV product consumed. */
+ * p_drop == 0) describe exactly what the PV product consumed.  seed_dev (nullable, device uint64): a counter added to
+ * `seed` on the device -- a CUDA-graph replay of a training step bakes `seed` into the graph and advances the counter. */
 int lamp_sdpa_fwd_train(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
                         int64_t msk, float* out, float* attn, float* probs_pre, int N, int Lq, int Lk, int d,
-                        float temperature, int precision, float p_drop, uint64_t seed, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        float temperature, int precision, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* MultiHeadAttention.forward (lamp/SubLayers.py:77-121), eval mode (dropout = identity).
  * q [B,Lq,D]; kv [B,Lk,D] or NULL for self-attention (k = v = q); Wq,Wk,Wv [H*d, D]; Wfc [D, H*d] or NULL iff

@@ -9,7 +9,7 @@ from . import utils  # noqa: F401
 from . import ops  # noqa: F401
 from . import SubLayers, Layers, Encoders, Decoders, Models  # noqa: F401
 from .ops import set_default_precision  # noqa: F401
-from .graphs import GraphedForward  # noqa: F401
+from .graphs import GraphedForward, GraphedTrainStep  # noqa: F401
 
 __all__ = ['Constants', 'utils', 'ops', 'SubLayers', 'Layers', 'Encoders', 'Decoders', 'Models',
-           'set_default_precision', 'GraphedForward']
+           'set_default_precision', 'GraphedForward', 'GraphedTrainStep']

@@ -317,6 +317,7 @@ struct ProbsMmaParams {
   uint32_t drop_thresh;
   float drop_scale;
   unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;  // see AttnParams
 };
 
 // bf16 plane tile [rows x cols] (cols % 2 == 0, rows beyond rows_valid read as 0) -> smem (leading dim lds)
@@ -396,7 +397,8 @@ __global__ void __launch_bounds__(BWD_THREADS) attn_probs_mma_kernel(const Probs
         const long long g = (stat0 + r) * p.Lk + j;
         if (p.probs_pre != nullptr) p.probs_pre[g] = pr;
         if (p.drop_thresh) {
-          const uint32_t rh = drop_rowhash(p.drop_seed, static_cast<unsigned long long>(stat0 + r));
+          const uint32_t rh = drop_rowhash(p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0ull),
+                                           static_cast<unsigned long long>(stat0 + r));
           pr = drop_keep(rh, static_cast<uint32_t>(j), p.drop_thresh) ? pr * p.drop_scale : 0.0f;
         }
         p.probs[g] = pr;

@@ -70,6 +70,8 @@ struct AttnParams {
   uint32_t drop_thresh;  // 0: off; else an element is dropped iff hash < drop_thresh (= p * 2^32)
   float drop_scale;      // 1 / (1 - p)
   unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;  // optional device-side counter ADDED to drop_seed (CUDA-graph replays of a
+                                            // training step: the host seed is baked into the graph, the counter moves)
 };
 
 #ifdef LAMP_ATTN_TRACE
@@ -618,8 +620,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         const float mb2 = m_use * p.scale_log2;
         uint32_t ph_[16], pl_[16];
         const uint32_t rh = p.drop_thresh
-                                ? drop_rowhash(p.drop_seed, (static_cast<unsigned long long>(h) * p.B + b) * p.Lq +
-                                                                qt * ATTN_BLOCK_M + row)
+                                ? drop_rowhash(p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0ull),
+                                               (static_cast<unsigned long long>(h) * p.B + b) * p.Lq + qt * ATTN_BLOCK_M + row)
                                 : 0u;
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {

@@ -487,7 +487,7 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
                      void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
                      int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
                      const int32_t* kv_len, int64_t kv_rows, void* stream, float p_drop = 0.0f, uint64_t seed = 0,
-                     float* probs_pre = nullptr);
+                     float* probs_pre = nullptr, const uint64_t* seed_dev = nullptr);
 
 int lamp_attn_core_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
                           const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H,
@@ -518,7 +518,7 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
                      void* o_hi, void* o_lo, int64_t ldo, float* o_f32,
                      int64_t ldof, float* row_max, float* row_sum, float* probs, const int32_t* kv_start,
                      const int32_t* kv_len, int64_t kv_rows, void* stream, float p_drop, uint64_t seed,
-                     float* probs_pre) {
+                     float* probs_pre, const uint64_t* seed_dev) {
   if (int rc = arch_check()) return rc;
   REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "attn: dropout rate %f outside [0, 1)", (double)p_drop);
   REQUIRE(p_drop == 0.0f || (!kv_len && !mask_bits), "attn: dropout is a training-path feature (dense keys, byte mask)");
@@ -591,6 +591,7 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
   if (p_drop > 0.0f && p.drop_thresh == 0u) p.drop_thresh = 1u;
   p.drop_scale = 1.0f / (1.0f - p_drop);
   p.drop_seed = seed;
+  p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (block_kv == 128)
@@ -610,6 +611,7 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
     pp.mask = mask; pp.msb = msb; pp.msq = msq; pp.msk = msk;
     pp.row_max = row_max; pp.row_sum = row_sum; pp.probs = probs;
     pp.probs_pre = probs_pre; pp.drop_thresh = p.drop_thresh; pp.drop_scale = p.drop_scale; pp.drop_seed = seed;
+    pp.drop_seed_dev = p.drop_seed_dev;
     static std::once_flag once;
     static int once_rc = LAMP_OK;
     std::call_once(once, [] { once_rc = set_smem(attn_probs_mma_kernel, (uint32_t)attn_probs_smem_bytes(BWD_DMAX)); });
@@ -946,30 +948,30 @@ size_t lamp_sdpa_workspace_bytes(int N, int Lq, int Lk, int d) {
 
 static int sdpa_impl(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
                      int64_t msk, float* out, float* attn, float* probs_pre, int N, int Lq, int Lk, int d,
-                     float temperature, int precision, float p_drop, uint64_t seed, void* workspace,
-                     size_t workspace_bytes, void* stream);
+                     float temperature, int precision, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 int lamp_sdpa_fwd(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
                   int64_t msk, float* out, float* attn, int N, int Lq, int Lk, int d, float temperature,
                   int precision, void* workspace, size_t workspace_bytes, void* stream) {
   return sdpa_impl(q, k, v, mask, msb, msq, msk, out, attn, nullptr, N, Lq, Lk, d, temperature, precision, 0.0f, 0,
-                   workspace, workspace_bytes, stream);
+                   nullptr, workspace, workspace_bytes, stream);
 }
 
 int lamp_sdpa_fwd_train(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
                         int64_t msk, float* out, float* attn, float* probs_pre, int N, int Lq, int Lk, int d,
-                        float temperature, int precision, float p_drop, uint64_t seed, void* workspace,
-                        size_t workspace_bytes, void* stream) {
+                        float temperature, int precision, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   REQUIRE(attn != nullptr, "sdpa_train: the attention map is part of the training forward");
   REQUIRE(p_drop == 0.0f || probs_pre != nullptr, "sdpa_train: probs_pre is required when dropout is active");
   return sdpa_impl(q, k, v, mask, msb, msq, msk, out, attn, probs_pre, N, Lq, Lk, d, temperature, precision, p_drop,
-                   seed, workspace, workspace_bytes, stream);
+                   seed, seed_dev, workspace, workspace_bytes, stream);
 }
 
 static int sdpa_impl(const float* q, const float* k, const float* v, const uint8_t* mask, int64_t msb, int64_t msq,
                      int64_t msk, float* out, float* attn, float* probs_pre, int N, int Lq, int Lk, int d,
-                     float temperature, int precision, float p_drop, uint64_t seed, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+                     float temperature, int precision, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* workspace, size_t workspace_bytes, void* stream) {
   REQUIRE(q && k && v && out, "sdpa: null pointer");
   REQUIRE(N >= 0 && Lq > 0 && Lk > 0 && d > 0, "sdpa: bad shape");
   if (!workspace || workspace_bytes < lamp_sdpa_workspace_bytes(N, Lq, Lk, d))
@@ -988,7 +990,7 @@ static int sdpa_impl(const float* q, const float* k, const float* v, const uint8
   if (int rc = lamp_split_planes(v, (int64_t)N * Lk, d, d, kvp + d, three ? kvlo + d : nullptr, 2 * d, stream)) return rc;
   return attn_impl(qp, qlo, d, 0, 0, kvp, kvlo, 2 * d, 0, d, N, 1, Lq, Lk, d, temperature, precision, mask, msb, msq, msk,
                    nullptr, 0, 0, nullptr, nullptr, 0, out, d, stats, stats + (size_t)N * Lq, attn, nullptr, nullptr, 0,
-                   stream, p_drop, seed, probs_pre);
+                   stream, p_drop, seed, probs_pre, seed_dev);
 }
 
 namespace {

@@ -70,3 +70,76 @@ class GraphedForward:
     def __call__(self, src_seq: torch.Tensor, src_pos: torch.Tensor):
         self.load(src_seq, src_pos)
         return self.replay()
+
+
+class GraphedTrainStep:
+    """CUDA-graph replay of one training step of the label-graph model: ``zero_grad -> LAMP.forward -> loss ->
+    backward`` (train.py:28-48 without the data loading), optimizer step outside the graph.
+
+    A training step at the reference's batch size (32) is ~350 native kernel launches plus torch glue for ~6 ms of
+    GPU work: launched from Python it is host-bound.  The step is shape-static for a fixed ``(batch, seq_len)``, and
+    the one thing that must change between replays -- the dropout masks -- is handled on the device: the attention
+    kernels add a device-side counter (``ops.TRAIN_SEED_DEV``, advanced inside the graph) to their baked-in seeds,
+    torch's own dropouts use the graph-safe Philox offsets of the CUDA generator.
+
+        step = lamp_b200.GraphedTrainStep(model, loss_fn, batch=32, seq_len=300)
+        for src_seq, src_pos, target in loader:
+            loss = step(src_seq, src_pos, target)      # gradients are in p.grad (static tensors)
+            optimizer.step()
+
+    ``loss_fn(logits, target) -> scalar``.  Parameter ``.grad`` tensors are allocated inside the graph's memory pool
+    and overwritten by every replay."""
+
+    def __init__(self, model, loss_fn, batch: int, seq_len: int, device=None, warmup: int = 3, example=None):
+        from . import ops
+        if not model.training:
+            raise RuntimeError('GraphedTrainStep captures the training step: call model.train() first')
+        p = next(model.parameters())
+        nat.require_cuda(p)
+        self.model, self.loss_fn = model, loss_fn
+        self.device = torch.device(device) if device is not None else p.device
+        self.batch, self.seq_len = batch, seq_len
+        n_labels = model.decoder.n_tgt_vocab
+        self.src_seq = torch.empty((batch, seq_len), dtype=torch.int64, device=self.device)
+        self.src_pos = torch.empty((batch, seq_len), dtype=torch.int64, device=self.device)
+        self.target = torch.zeros((batch, n_labels), dtype=torch.float32, device=self.device)
+        if example is not None:
+            self.src_seq.copy_(example[0])
+            self.src_pos.copy_(example[1])
+            if len(example) > 2:
+                self.target.copy_(example[2])
+        else:
+            self.src_seq.fill_(4)
+            self.src_pos.copy_(torch.arange(1, seq_len + 1, device=self.device).expand(batch, seq_len))
+        self.seed_dev = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        ops.TRAIN_SEED_DEV = self.seed_dev
+
+        def body():
+            self.seed_dev.add_(1)
+            model.zero_grad(set_to_none=True)
+            logits, _, _ = model((self.src_seq, self.src_pos), None, None, None)
+            loss = loss_fn(logits, self.target)
+            loss.backward()
+            return loss.detach()
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.STATS.launches
+        with torch.cuda.graph(self.graph):
+            self.loss = body()
+        self.kernels_per_replay = ops.STATS.launches - n0
+
+    def __call__(self, src_seq: torch.Tensor, src_pos: torch.Tensor, target: torch.Tensor):
+        self.src_seq.copy_(src_seq, non_blocking=True)
+        self.src_pos.copy_(src_pos, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        self.graph.replay()
+        from . import ops
+        ops.STATS.launches += self.kernels_per_replay
+        return self.loss

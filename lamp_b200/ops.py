@@ -522,6 +522,11 @@ def sdpa_backward(q, k, v, out, probs, attn, grad_out, temperature: float, p_dro
     return dq, dk, dv
 
 
+# Device-side dropout counter (int64 [1]) added to every attention-dropout seed; set by graphs.GraphedTrainStep so that
+# replays of a captured training step draw fresh masks.  None in eager training (host seeds vary per call).
+TRAIN_SEED_DEV: Optional[torch.Tensor] = None
+
+
 def sdpa_train(q, k, v, mask, temperature: float, prec: int, p_drop: float, seed: int):
     """Training forward of the attention core (dropout inside the kernel) -> (out, attn after dropout, probabilities
     before dropout -- the same tensor as attn when p_drop == 0)."""
@@ -537,8 +542,8 @@ def sdpa_train(q, k, v, mask, temperature: float, prec: int, p_drop: float, seed
     keep, mptr, sb, sq, sk = mask_args(mask, N, Lq, Lk)
     STATS.call('sdpa_fwd_train', 5, L.lamp_sdpa_fwd_train,
                (q.data_ptr(), k.data_ptr(), v.data_ptr(), mptr, sb, sq, sk, out.data_ptr(), attn.data_ptr(), nat.ptr(pre),
-                N, Lq, Lk, d, float(temperature), prec, float(p_drop), int(seed), ws.data_ptr(), ws.numel(),
-                nat.stream()), flops=4.0 * N * Lq * Lk * d)
+                N, Lq, Lk, d, float(temperature), prec, float(p_drop), int(seed), nat.ptr(TRAIN_SEED_DEV), ws.data_ptr(),
+                ws.numel(), nat.stream()), flops=4.0 * N * Lq * Lk * d)
     del keep
     return out, attn, (attn if pre is None else pre)
 

@@ -67,3 +67,27 @@ for B in args.batch:
                               native_launches_per_step=ops.STATS.launches / args.steps,
                               kernels={k: v // args.steps for k, v in ops.STATS.by_kernel.items()})), flush=True)
     ops.NATIVE_ATTENTION_BACKWARD = ops.NATIVE_TRAINING = True
+    # the same native step replayed as one CUDA graph (lamp_b200.GraphedTrainStep)
+    import lamp_b200
+    model = LAMP(c['V'] + 4, c['L'], c['T'], c['L'], n_layers_enc=c['n_enc'], n_layers_dec=c['n_dec'], n_head=c['H'],
+                 n_head2=c['H'], d_word_vec=c['D'], d_model=c['D'], d_inner_hid=c['d_inner'], d_k=c['D'] // c['H'],
+                 d_v=c['D'] // c['H'], dropout=0.2, dec_dropout=0.2, dec_dropout2=False, proj_share_weight=True,
+                 encoder='graph', decoder='graph', label_adj_matrix=adj, label_mask='prior')
+    model.load_state_dict(params, strict=True)
+    model = model.to(dev).train()
+    gstep = lamp_b200.GraphedTrainStep(model, torch.nn.functional.binary_cross_entropy_with_logits, B, c['T'],
+                                       example=(src[0], src[1], tgt))
+    for _ in range(3):
+        gstep(src[0], src[1], tgt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = gstep(src[0], src[1], tgt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps(dict(what='train step (fwd + BCE + bwd), CUDA-graph replay', native=True, batch=B, ms_per_step=ms,
+                          samples_per_s=B / ms * 1e3, loss=float(loss), native_launches_per_step=gstep.kernels_per_replay)),
+          flush=True)
+    ops.TRAIN_SEED_DEV = None

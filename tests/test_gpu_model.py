@@ -353,6 +353,48 @@ def test_deferred_layernorm_equals_explicit_layernorm_and_oracle(name):
     assert rel_err(outs[True][1], outs[False][1]) < 1e-4
 
 
+def test_graphed_train_step_equals_eager_and_redraws_dropout():
+    """lamp_b200.GraphedTrainStep: (i) without dropout a replay produces the eager step's loss and gradients for new
+    inputs, (ii) with dropout successive replays on the same batch draw different attention-dropout masks (the
+    device-side seed counter advances inside the graph) and stay finite."""
+    from lamp_b200 import ops
+    c = dict(cases.MODEL_CASES['lamp_L37_none'])
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    B, T = src_seq.shape
+    tgt = (torch.arange(B * c['L']).view(B, c['L']) % 4 == 0).float()
+    loss_fn = torch.nn.functional.binary_cross_entropy_with_logits
+    try:
+        model = build_model(c, p, adj)
+        model.train()
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        step = lamp_b200.GraphedTrainStep(model, loss_fn, B, T)
+        assert step.kernels_per_replay > 50
+        # new inputs after capture: a permutation of the batch
+        perm = torch.arange(B - 1, -1, -1)
+        loss = step(src_seq[perm], src_pos[perm], tgt[perm]).clone()
+        g_graph = {n: q.grad.clone() for n, q in model.named_parameters() if q.grad is not None}
+        ops.TRAIN_SEED_DEV = None
+        model.zero_grad(set_to_none=True)
+        logits, _, _ = model((src_seq[perm].to(DEV), src_pos[perm].to(DEV)), None, None, None)
+        l2 = loss_fn(logits, tgt[perm].to(DEV))
+        l2.backward()
+        assert abs(float(loss) - float(l2)) < 1e-6
+        for n, q in model.named_parameters():
+            if q.grad is not None:
+                assert rel_err(g_graph[n], q.grad) < 1e-5, n
+        # dropout: replays differ
+        model2 = build_model(c, p, adj)
+        model2.train()
+        step2 = lamp_b200.GraphedTrainStep(model2, loss_fn, B, T, example=(src_seq, src_pos, tgt))
+        losses = [float(step2(src_seq, src_pos, tgt)) for _ in range(4)]
+        assert len(set(losses)) == 4, losses
+        assert all(torch.isfinite(q.grad).all() for q in model2.parameters() if q.grad is not None)
+    finally:
+        ops.TRAIN_SEED_DEV = None
+
+
 def test_graphed_forward_replays_equal_eager_for_new_batches():
     """GraphedForward (CUDA-graph replay of LAMP.forward): replaying with NEW token ids -- different padding, hence a
     different device-side packed row count -- gives bit-identical logits / enc_output to the eager call."""
