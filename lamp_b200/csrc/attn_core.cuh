@@ -198,6 +198,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();  // PDL: nothing above touches global memory
 
   const int num_qt = (p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M;
   const int num_kv = (p.Lk + BLOCK_KV - 1) / BLOCK_KV;  // upper bound; per item: item_keys()

@@ -31,6 +31,8 @@ __global__ void layernorm_kernel(const float* __restrict__ y, const float* __res
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                  long long rows, int D, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
                                  __nv_bfloat16* __restrict__ out_lo, const int* __restrict__ m_dev) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (m_dev != nullptr && rows > __ldg(m_dev)) rows = __ldg(m_dev);  // device-side row count (padding-aware runs)
@@ -100,6 +102,8 @@ __global__ void embed_kernel(const long long* __restrict__ seq, const long long*
                              int D, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
                              __nv_bfloat16* __restrict__ out_lo, const long long* __restrict__ row_index,
                              const int* __restrict__ m_dev) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (m_dev != nullptr && rows > __ldg(m_dev)) rows = __ldg(m_dev);
@@ -128,6 +132,8 @@ __global__ void embed_kernel(const long long* __restrict__ seq, const long long*
 // representative PAD row being replicated to every PAD position).  One warp per output row.
 __global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ index, long long rows,
                                    int D, float* __restrict__ out) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -158,6 +164,8 @@ __global__ void zero_guard_rows_kernel(__nv_bfloat16* __restrict__ hi, __nv_bflo
 __global__ void diag_proj_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                  const float* __restrict__ bias, long long rows, int L, int D,
                                  float* __restrict__ logits) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;

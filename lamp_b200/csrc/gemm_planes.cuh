@@ -194,6 +194,8 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();
+  griddep_wait();  // PDL: nothing above touches global memory
 
   const int M = (p.m_dev != nullptr) ? min(p.M, __ldg(p.m_dev)) : p.M;
   const int num_m = (M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP);

@@ -122,6 +122,8 @@ int launch_check() {
   return LAMP_OK;
 }
 
+std::atomic<int> g_pdl{0};  // tuning knob: 1 -> programmatic dependent launch for the inference-path kernels
+
 template <int BLOCK_N, int NTERMS, int BLOCK_K, int EPI, int CTA_GROUP>
 int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                     const GemmParams& p, cudaStream_t st) {
@@ -140,13 +142,15 @@ int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUte
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTA_GROUP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl.load() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, a_hi, a_lo, w_hi, w_lo, p);
   if (e != cudaSuccess) return fail(LAMP_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
   return launch_check();
@@ -183,6 +187,22 @@ std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group:
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB: the sm_100 per-CTA opt-in maximum
 
+// <<<>>> replacement that can request programmatic dependent launch (only for kernels that call griddep_wait())
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <int BLOCK_KV, int NTERMS>
 int launch_attn(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st) {
   auto kernel = attn_core_kernel<BLOCK_KV, NTERMS>;
@@ -192,7 +212,9 @@ int launch_attn(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_b
   if (once_rc != LAMP_OK) return once_rc;
   const int items = p.B * p.H * ((p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M);
   const int grid = items < sm_count_cached() ? items : sm_count_cached();
-  kernel<<<grid, attn_threads(BLOCK_KV), smem_bytes, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], p);
+  cudaError_t e = launch_k(kernel, (unsigned)grid, (unsigned)attn_threads(BLOCK_KV), smem_bytes, st, tm[0], tm[1], tm[2], tm[3],
+                           tm[4], tm[5], tm[6], tm[7], p);
+  if (e != cudaSuccess) return fail(LAMP_ECUDA, "attn launch: %s", cudaGetErrorString(e));
   return launch_check();
 }
 
@@ -265,6 +287,10 @@ int lamp_set_tuning(int key, int value) {
   }
   if (key == LAMP_TUNE_ATTN_BWD_TC && (value == 0 || value == 1)) {
     g_attn_bwd_tc.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_PDL && (value == 0 || value == 1)) {
+    g_pdl.store(value);
     return LAMP_OK;
   }
   if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
@@ -878,12 +904,15 @@ int lamp_layernorm(const float* y, const float* add, int add_mod, const float* g
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(out_hi);
   __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(out_lo);
+  const long long rows_ll = rows;
+  cudaError_t e;
   if (D <= 512)
-    layernorm_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo, m_dev);
+    e = launch_k(layernorm_kernel<4>, (unsigned)blocks, 256u, 0, st, y, add, add_mod, gamma, beta, eps, rows_ll, D, out, hi, lo, m_dev);
   else if (D <= 1024)
-    layernorm_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo, m_dev);
+    e = launch_k(layernorm_kernel<8>, (unsigned)blocks, 256u, 0, st, y, add, add_mod, gamma, beta, eps, rows_ll, D, out, hi, lo, m_dev);
   else
-    layernorm_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(y, add, add_mod, gamma, beta, eps, rows, D, out, hi, lo, m_dev);
+    e = launch_k(layernorm_kernel<32>, (unsigned)blocks, 256u, 0, st, y, add, add_mod, gamma, beta, eps, rows_ll, D, out, hi, lo, m_dev);
+  if (e != cudaSuccess) return fail(LAMP_ECUDA, "layernorm launch: %s", cudaGetErrorString(e));
   return launch_check();
 }
 
@@ -896,10 +925,11 @@ int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, co
   REQUIRE(D % 4 == 0, "embed: D must be a multiple of 4");
   if (rows == 0) return LAMP_OK;
   const long long blocks = (rows * 32 + 255) / 256;
-  embed_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const long long*>(seq), reinterpret_cast<const long long*>(pos), word_emb, pos_emb, rows, D,
-      out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
-      reinterpret_cast<const long long*>(row_index), m_dev);
+  cudaError_t e = launch_k(embed_kernel, (unsigned)blocks, 256u, 0, (cudaStream_t)stream,
+                           reinterpret_cast<const long long*>(seq), reinterpret_cast<const long long*>(pos), word_emb, pos_emb,
+                           (long long)rows, D, out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
+                           reinterpret_cast<const long long*>(row_index), m_dev);
+  if (e != cudaSuccess) return fail(LAMP_ECUDA, "embed launch: %s", cudaGetErrorString(e));
   return launch_check();
 }
 
@@ -909,8 +939,9 @@ int lamp_gather_rows(const float* src, const int64_t* index, int64_t rows, int D
   REQUIRE(D % 4 == 0 && aligned16(src) && aligned16(out), "gather_rows: D multiple of 4 and 16-byte alignment required");
   if (rows == 0) return LAMP_OK;
   const long long blocks = (rows * 32 + 255) / 256;
-  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<const long long*>(index),
-                                                                          rows, D, out);
+  cudaError_t e = launch_k(gather_rows_kernel, (unsigned)blocks, 256u, 0, (cudaStream_t)stream, src,
+                           reinterpret_cast<const long long*>(index), (long long)rows, D, out);
+  if (e != cudaSuccess) return fail(LAMP_ECUDA, "gather_rows launch: %s", cudaGetErrorString(e));
   return launch_check();
 }
 
@@ -932,7 +963,8 @@ int lamp_diag_proj(const float* x, const float* W, const float* bias, int64_t B,
   const long long rows = B * L;
   if (rows == 0) return LAMP_OK;
   const long long blocks = (rows * 32 + 255) / 256;
-  diag_proj_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, W, bias, rows, L, D, logits);
+  cudaError_t e = launch_k(diag_proj_kernel, (unsigned)blocks, 256u, 0, (cudaStream_t)stream, x, W, bias, rows, L, D, logits);
+  if (e != cudaSuccess) return fail(LAMP_ECUDA, "diag_proj launch: %s", cudaGetErrorString(e));
   return launch_check();
 }
 

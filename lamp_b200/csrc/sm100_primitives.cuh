@@ -307,6 +307,13 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still draining; everything before griddep_wait() (barrier
+// init, TMEM allocation, descriptor prefetch) then overlaps the predecessor's tail.  griddep_wait() returns once the
+// predecessor grid has completed and its memory is visible; without the launch attribute both are no-ops.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Counter-based dropout decision (training forward of the attention core): a pure function of (seed, head-major row,
 // key), shared by the attention kernel and the probability kernel.  splitmix64 per row, murmur3 finaliser per key.
 __device__ __forceinline__ uint32_t drop_rowhash(unsigned long long seed, unsigned long long rowkey) {
