@@ -59,32 +59,34 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], world: Optional[in
     world = dist.get_world_size(group) if (world is None and dist.is_initialized()) else (world or 1)
     dev = params[0].device
     sizes = [p.numel() for p in params]
-    flat = torch.zeros(sum(sizes) + len(params), dtype=torch.float32, device=dev)
-    off = 0
-    for p in params:
-        if p.grad is not None:
-            flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-        off += p.numel()
-    # trailing flags: did any rank produce a gradient for parameter i?
-    flags = flat[off:]
-    for i, p in enumerate(params):
-        if p.grad is not None:
-            flags[i] = 1.0
+    total = sum(sizes)
+    have = [p.grad is not None for p in params]
+    # one flat buffer: gradients (zeros where this rank has none) + one "some rank has a gradient" flag per parameter
+    pieces = [p.grad.reshape(-1).float() if h else torch.zeros(n, dtype=torch.float32, device=dev)
+              for p, h, n in zip(params, have, sizes)]
+    pieces.append(torch.tensor([1.0 if h else 0.0 for h in have], dtype=torch.float32, device=dev))
+    flat = torch.cat(pieces)
     if local_weight != 1.0:
-        flat[:off].mul_(local_weight)
+        flat[:total].mul_(local_weight)
     if world > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat[:off].div_(world)
-    off = 0
-    for i, p in enumerate(params):
-        if flags[i].item() > 0:
-            g = flat[off:off + p.numel()].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-        off += p.numel()
-    return sum(sizes)
+        flat[:total].div_(world)
+        any_rank = flat[total:].tolist()  # the only host synchronisation of the step
+    else:
+        any_rank = [1.0 if h else 0.0 for h in have]
+    views = torch.split(flat[:total], sizes)
+    dst, src = [], []
+    for p, h, flag, v in zip(params, have, any_rank, views):
+        if flag <= 0:
+            continue
+        if h:
+            dst.append(p.grad)
+            src.append(v.view_as(p).to(p.grad.dtype))
+        else:
+            p.grad = v.view_as(p).to(p.dtype).clone()
+    if dst:
+        torch._foreach_copy_(dst, src)
+    return total
 
 
 def data_parallel_step(model, optimizer, loss_fn, batch, world: Optional[int] = None, group=None) -> float:
