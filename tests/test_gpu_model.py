@@ -140,6 +140,54 @@ def test_training_gradients_native_attention_core_equals_composed_path():
     assert worst[0] < 1e-3, worst
 
 
+@pytest.mark.parametrize('name', ['lamp_L37_none', 'lamp_L103_prior'])
+def test_training_gradients_match_oracle_autograd_fp64(name):
+    """Parameter gradients of one native training step (dropout off) against autograd through the CPU oracle in fp64
+    -- the oracle being pinned to the reference, this anchors the backward to the reference's own arithmetic.
+    The model has ReLU kinks: a pre-activation that is 0 to within the forward's rounding error (a handful out of 1e5)
+    can land on the other side in fp32, which changes the gradient of that FFN's w_1 / b_1 (and, diluted, everything
+    upstream) by a rank-1 term -- 0.9 % in max-norm for `lamp_L103_prior`, independent of the kernels
+    (scripts/probes/grad_debug3.py: every tensor before that ReLU agrees to 1e-5).  Bars: `lamp_L37_none` (no such
+    pre-activation) 1e-3 in max-norm for every gradient; `lamp_L103_prior` 5e-3 in Frobenius norm for every gradient,
+    median below 1e-3 and 90 % below 5e-3 in max-norm."""
+    from lamp_b200 import ops
+    c = dict(cases.MODEL_CASES[name])
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    B = src_seq.shape[0]
+    tgt = (torch.arange(B * c['L']).view(B, c['L']) % 5 == 0).float()
+    model = build_model(c, p, adj)
+    model.train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    ops.STATS.reset()
+    logits, _, _ = model((src_seq.to(DEV), src_pos.to(DEV)), None, None, None)
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, tgt.to(DEV)).backward()
+    assert ops.STATS.by_kernel.get('attn_core_bwd', 0) > 0 and ops.STATS.by_kernel.get('gemm_tn', 0) > 0
+    pd = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in p.items()}
+    lm = orc.label_mask_from(c['L'], adj, c['mask'])
+    ref_logits, _ = orc.lamp_forward(pd, cfg, src_seq, src_pos, lm)
+    torch.nn.functional.binary_cross_entropy_with_logits(ref_logits, tgt.double()).backward()
+    assert rel_err(logits.detach(), ref_logits.detach()) < TOL
+    mx, fro = [], []
+    for n, q in model.named_parameters():
+        ref = pd[n].grad if n in pd else None
+        if q.grad is None or ref is None or float(ref.abs().max()) == 0.0:
+            continue
+        g = q.grad.double().cpu()
+        mx.append((rel_err(g, ref), n))
+        fro.append((float((g - ref).norm() / ref.norm()), n))
+    assert len(mx) > 40
+    mx.sort()
+    print(f'{name}: {len(mx)} gradients vs oracle fp64 autograd: max-norm median {mx[len(mx) // 2][0]:.1e}, '
+          f'90th pct {mx[int(len(mx) * 0.9)][0]:.1e}, worst {mx[-1]}; Frobenius worst {max(fro)}')
+    if name == 'lamp_L37_none':       # no pre-activation within rounding error of 0 in this case: tight everywhere
+        assert mx[-1][0] < TOL, mx[-5:]
+    else:                             # one kink flip in the last decoder layer's first FFN (see the docstring)
+        assert max(fro)[0] < 5e-3, max(fro)
+        assert mx[int(len(mx) * 0.9)][0] < 5e-3 and mx[len(mx) // 2][0] < TOL, mx[-5:]
+
+
 def test_training_with_dropout_runs_native_core_and_is_seeded():
     """model.train() with the reference's dropout rates: the native core applies dropout to the probabilities, two
     steps with the same torch seed give identical losses and gradients, another seed gives different ones."""
