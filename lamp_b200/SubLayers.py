@@ -130,9 +130,20 @@ class MultiHeadAttention(nn.Module):
         len_k, len_v = k.size(1), v.size(1)
         residual = q
         lin = ops.linear_train  # native GEMMs (forward, dx, dW) when the shape allows, torch otherwise
-        qh = lin(q, self.w_qs.weight, None).view(sz_b, len_q, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_q, d_k)
-        kh = lin(k, self.w_ks.weight, None).view(sz_b, len_k, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_k, d_k)
-        vh = lin(v, self.w_vs.weight, None).view(sz_b, len_v, n_head, d_v).permute(2, 0, 1, 3).reshape(-1, len_v, d_v)
+        if q is k and k is v:
+            # self-attention: one [3*H*d, D] contraction for Q | K | V (one GEMM forward, one dx and one dW backward)
+            qkv = lin(q, torch.cat((self.w_qs.weight, self.w_ks.weight, self.w_vs.weight), dim=0), None)
+            qp, kp, vp = qkv.split((n_head * d_k, n_head * d_k, n_head * d_v), dim=-1)
+        else:
+            qp = lin(q, self.w_qs.weight, None)
+            if k is v:
+                kv = lin(k, torch.cat((self.w_ks.weight, self.w_vs.weight), dim=0), None)
+                kp, vp = kv.split((n_head * d_k, n_head * d_v), dim=-1)
+            else:
+                kp, vp = lin(k, self.w_ks.weight, None), lin(v, self.w_vs.weight, None)
+        qh = qp.reshape(sz_b, len_q, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_q, d_k)
+        kh = kp.reshape(sz_b, len_k, n_head, d_k).permute(2, 0, 1, 3).reshape(-1, len_k, d_k)
+        vh = vp.reshape(sz_b, len_v, n_head, d_v).permute(2, 0, 1, 3).reshape(-1, len_v, d_v)
         if attn_mask is not None:
             attn_mask = attn_mask.bool().repeat(n_head, 1, 1)
         out, attn = self.attention.train_core(qh, kh, vh, attn_mask)  # native forward + backward of the core
