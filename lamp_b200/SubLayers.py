@@ -73,6 +73,10 @@ class ScaledDotProductAttention(nn.Module):
         the kernel, seeded from torch's CPU generator) and native backward (``ops.SDPAFunction``); the composed torch
         ops remain for shapes the kernels do not cover and when ``ops.NATIVE_ATTENTION_BACKWARD`` is off."""
         if not (ops.NATIVE_ATTENTION_BACKWARD and self._kernel_ok(q, k, v) and q.dtype == torch.float32):
+            if ops.NATIVE_ATTENTION_BACKWARD:
+                ops.warn_torch_fallback('the attention core of the training path',
+                                        f'needs softmax attention, fp32, head width % 16 == 0 and <= 128; got '
+                                        f'{self.attn_kind}, {q.dtype}, d={q.shape[-1]}')
             return self._composed(q, k, v, attn_mask)
         p = float(self.dropout.p) if self.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0

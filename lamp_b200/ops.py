@@ -676,12 +676,27 @@ class DiagProjFunction(torch.autograd.Function):
         return dx, dW.to(W.dtype), (db.to(bias.dtype) if db is not None else None)
 
 
+_WARNED: set = set()
+
+
+def warn_torch_fallback(what: str, why: str) -> None:
+    """The training path never falls back silently: the first time a stage runs as torch ops although the native
+    training path is enabled, say so (once per stage / reason)."""
+    if (what, why) not in _WARNED:
+        _WARNED.add((what, why))
+        import warnings
+        warnings.warn(f'lamp_b200: {what} runs as torch ops, not on the native kernels ({why})', RuntimeWarning, stacklevel=3)
+
+
 def linear_train(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor], prec: Optional[int] = None) -> torch.Tensor:
     """Differentiable ``x W^T (+b)`` of the training path: native when the shape allows, torch otherwise."""
     w2 = W.reshape(W.shape[0], -1)
     N, K = w2.shape
     if NATIVE_TRAINING and x.is_cuda and x.dtype == torch.float32 and N % 8 == 0 and K % 8 == 0 and x.numel() > 0:
         return LinearFunction.apply(x, W, b, default_precision() if prec is None else prec)
+    if NATIVE_TRAINING and x.numel() > 0:
+        warn_torch_fallback('a linear projection of the training path',
+                            f'needs fp32 CUDA input and feature counts that are multiples of 8; got {x.dtype}, N={N}, K={K}')
     return torch.nn.functional.linear(x, w2, b)
 
 
@@ -690,6 +705,8 @@ def layernorm_train(x: torch.Tensor, ln: torch.nn.LayerNorm, prec: Optional[int]
     if NATIVE_TRAINING and x.is_cuda and x.dtype == torch.float32 and D % 4 == 0 and D <= 4096 and x.numel() > 0 \
             and ln.elementwise_affine and tuple(ln.normalized_shape) == (D,):
         return LayerNormFunction.apply(x, ln.weight, ln.bias, ln.eps, default_precision() if prec is None else prec)
+    if NATIVE_TRAINING and x.numel() > 0:
+        warn_torch_fallback('a LayerNorm of the training path', f'needs fp32 CUDA input with D % 4 == 0, D <= 4096; got {x.dtype}, D={D}')
     return ln(x)
 
 
