@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liblamp_b200.so')
+LIB_PATH = os.environ.get('LAMP_B200_LIB') or os.path.join(_HERE, 'liblamp_b200.so')  # env: A/B builds of the library
 
 PREC_FP32 = 0   # 3-term split-bf16 tensor-core products, fp32-grade results
 PREC_BF16 = 1   # plain bf16 operands

@@ -113,7 +113,9 @@ __host__ __device__ constexpr uint32_t attn_smem_bytes(uint32_t q_bytes, uint32_
   return q_bytes * (staged ? 2 : 1) + slots * slot_bytes + ATTN_RED_BYTES + 1024 /*align*/ + ATTN_BAR_BYTES;
 }
 
-template <int BLOCK_KV, int NTERMS>
+// DROP: training forward (dropout on the probabilities); a compile-time switch so that the inference kernel carries
+// none of it (as a run-time branch inside the exp loop it cost the d = 64 / bf16 shapes 29 %).
+template <int BLOCK_KV, int NTERMS, bool DROP>
 __global__ void __launch_bounds__(attn_threads(BLOCK_KV), 1)
 attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_constant__ CUtensorMap tmQ_lo,
                  const __grid_constant__ CUtensorMap tmK_hi, const __grid_constant__ CUtensorMap tmK_lo,
@@ -621,7 +623,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         float sum = 0.0f;
         const float mb2 = m_use * p.scale_log2;
         uint32_t ph_[16], pl_[16];
-        const uint32_t rh = p.drop_thresh
+        const uint32_t rh = DROP
                                 ? drop_rowhash(p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0ull),
                                                (static_cast<unsigned long long>(h) * p.B + b) * p.Lq + qt * ATTN_BLOCK_M + row)
                                 : 0u;
@@ -630,7 +632,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
           float x0 = ex2_approx(fmaf(__uint_as_float(r[e]), p.scale_log2, -mb2));      // 2^(-inf) = 0 for masked
           float x1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), p.scale_log2, -mb2));
           sum += x0 + x1;  // the softmax denominator is taken before dropout
-          if (p.drop_thresh) {
+          if (DROP) {
             x0 = drop_keep(rh, static_cast<uint32_t>(k0 + e), p.drop_thresh) ? x0 * p.drop_scale : 0.0f;
             x1 = drop_keep(rh, static_cast<uint32_t>(k0 + e + 1), p.drop_thresh) ? x1 * p.drop_scale : 0.0f;
           }

@@ -203,9 +203,18 @@ cudaError_t launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, si
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+template <int BLOCK_KV, int NTERMS, bool DROP>
+int launch_attn_k(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st);
+
 template <int BLOCK_KV, int NTERMS>
 int launch_attn(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st) {
-  auto kernel = attn_core_kernel<BLOCK_KV, NTERMS>;
+  return p.drop_thresh ? launch_attn_k<BLOCK_KV, NTERMS, true>(tm, p, smem_bytes, st)
+                       : launch_attn_k<BLOCK_KV, NTERMS, false>(tm, p, smem_bytes, st);
+}
+
+template <int BLOCK_KV, int NTERMS, bool DROP>
+int launch_attn_k(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st) {
+  auto kernel = attn_core_kernel<BLOCK_KV, NTERMS, DROP>;
   static std::once_flag once;
   static int once_rc = LAMP_OK;
   std::call_once(once, [kernel] { once_rc = set_smem(kernel, kMaxDynSmem); });
