@@ -10,7 +10,9 @@
  *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns immediately;
  *  - return value: 0 on success, a negative LAMP_E* code otherwise; lamp_last_error() gives a thread-local
  *    human-readable message.  Nothing throws, nothing calls exit();
- *  - re-entrant / thread-safe: one process per GPU or several host threads may call concurrently.
+ *  - re-entrant / thread-safe: one process per GPU or several host threads may call concurrently;
+ *  - results are bit-reproducible run to run except for the two accumulating backward entry points
+ *    (lamp_gemm_tn_acc, lamp_layernorm_bwd's dgamma / dbeta), which sum partial results with fp32 atomics.
  *
  * Number formats
  *  - LAMP_PREC_FP32 : fp32 in / fp32 out; contractions run on the tcgen05 tensor cores as 3-term split-bf16

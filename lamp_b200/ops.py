@@ -4,6 +4,10 @@ Activations travel between kernels as :class:`Act`: an fp32 matrix ``[rows, D]``
 its split-bf16 planes (tensor-core operand form).  Producers (LayerNorm, embedding, GEMM epilogues) emit the planes
 directly, so no separate conversion pass runs inside a layer.  Weights are split once and cached per parameter
 version.  Everything is enqueued on torch's current CUDA stream; torch only provides memory and streams.
+
+The training path lives here as autograd Functions over the same kernels: ``SDPAFunction``
+(attention core with in-kernel dropout / ``lamp_attn_core_bwd``), ``LinearFunction`` (tcgen05 GEMMs for y, dx and dW),
+``LayerNormFunction``, ``DiagProjFunction``; see DESIGN.md section 4b.
 """
 from __future__ import annotations
 
