@@ -85,12 +85,16 @@ class GraphedTrainStep:
         step = lamp_b200.GraphedTrainStep(model, loss_fn, batch=32, seq_len=300)
         for src_seq, src_pos, target in loader:
             loss = step(src_seq, src_pos, target)      # gradients are in p.grad (static tensors)
-            optimizer.step()
+            optimizer.step()                           # (or pass a capturable optimizer to put it inside the graph)
 
     ``loss_fn(logits, target) -> scalar``.  Parameter ``.grad`` tensors are allocated inside the graph's memory pool
     and overwritten by every replay."""
 
-    def __init__(self, model, loss_fn, batch: int, seq_len: int, device=None, warmup: int = 3, example=None):
+    def __init__(self, model, loss_fn, batch: int, seq_len: int, device=None, warmup: int = 3, example=None,
+                 optimizer=None):
+        """``optimizer`` (optional): a graph-capturable optimizer -- e.g. ``torch.optim.Adam(..., capturable=True)`` --
+        whose ``step()`` is then part of the captured graph, so that a whole training iteration is one launch.  The
+        warm-up iterations before the capture DO update the parameters in that case."""
         from . import ops
         if not model.training:
             raise RuntimeError('GraphedTrainStep captures the training step: call model.train() first')
@@ -120,6 +124,8 @@ class GraphedTrainStep:
             logits, _, _ = model((self.src_seq, self.src_pos), None, None, None)
             loss = loss_fn(logits, self.target)
             loss.backward()
+            if optimizer is not None:
+                optimizer.step()
             return loss.detach()
 
         side = torch.cuda.Stream(device=self.device)
