@@ -48,6 +48,43 @@ def test_library_exports_every_header_symbol(built):
     assert nat.lib().lamp_version() >= 100
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/lamp_b200.h against the ctypes argtypes of lamp_b200/_native.py: same argument
+    count, and pointer / integer / float / size_t arguments in the same positions (a mismatch here only shows up as a
+    crash or garbage on the GPU box)."""
+    import ctypes as C
+    text = open(os.path.join(ROOT, 'include', 'lamp_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = re.findall(r'\b(?:int|size_t|const char\*)\s+(lamp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S)
+    assert len(protos) == len(nat.EXPORTED_SYMBOLS)
+
+    def kind_of_c(arg: str) -> str:
+        arg = ' '.join(arg.split())
+        if '*' in arg:
+            return 'ptr'
+        if arg.startswith('float'):
+            return 'float'
+        if arg.startswith('size_t'):
+            return 'size'
+        if arg.startswith('uint64_t') or arg.startswith('int64_t'):
+            return 'i64'
+        if arg.startswith('int'):
+            return 'int'
+        raise AssertionError(f'unrecognised C argument: {arg}')
+
+    def kind_of_ct(t) -> str:
+        return {C.c_void_p: 'ptr', C.c_char_p: 'ptr', C.c_float: 'float', C.c_size_t: 'size', C.c_int64: 'i64',
+                C.c_uint64: 'i64', C.c_int: 'int'}[t]
+
+    for name, args in protos:
+        args = args.strip()
+        c_kinds = [] if args in ('', 'void') else [kind_of_c(a) for a in args.split(',')]
+        ct_kinds = [kind_of_ct(t) for t in nat._SIGNATURES[name][0]]
+        # size_t and 64-bit integers share a register class on this ABI; everything else must agree exactly
+        norm = lambda ks: ['i64' if k == 'size' else k for k in ks]
+        assert norm(c_kinds) == norm(ct_kinds), f'{name}: header {c_kinds} vs ctypes {ct_kinds}'
+
+
 def test_library_is_built_for_sm100a_with_tcgen05_and_tma(built):
     out = subprocess.run(['cuobjdump', '-lelf', built], capture_output=True, text=True).stdout
     assert 'sm_100a' in out
