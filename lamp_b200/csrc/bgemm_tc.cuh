@@ -5,8 +5,11 @@
 // products of the backward differ only in that:
 //     dA = dO V^T     (A: dO K-major,  B: V  K-major)         dQ = dS K      (A: dS K-major,  B: K  MN-major)
 //     dV = A^T dO     (A: A  MN-major, B: dO MN-major)        dK = dS^T Q    (A: dS MN-major, B: Q  MN-major)
-// One CTA = one (batch, 128-row m tile, TN-column n tile); contraction in 64-wide chunks through a TMA ring;
-// 3-term split-bf16 products into one TMEM accumulator; epilogue: tcgen05.ld (lane == output row), scaled fp32 stores.
+// Persistent: one CTA per SM walks (batch, 128-row m tile, TN-column n tile) work items; contraction in 64-wide chunks
+// through a TMA ring that keeps running across items; 3-term split-bf16 products into one of two TMEM accumulators,
+// so the epilogue of an item (tcgen05.ld, lane == output row, scaled fp32 stores) overlaps the MMAs of the next one.
+// (The first version launched one CTA per item: with 2 chunks of work each, TMEM allocation and barrier set-up
+// dominated -- tensor pipe 7-8 % active.)
 #pragma once
 #include "sm100_primitives.cuh"
 
@@ -16,8 +19,9 @@ constexpr int BG_THREADS = 192;
 constexpr int BG_KC = 64;  // contraction chunk
 __host__ __device__ constexpr uint32_t bg_stage_bytes(int npl, int tn) { return npl * (128 + tn) * BG_KC * 2; }
 __host__ __device__ constexpr int bg_stages(int npl, int tn) { return (192 * 1024) / bg_stage_bytes(npl, tn); }
+constexpr uint32_t BG_EPI_STAGING = 4 * 32 * 33 * 4;  // per epilogue warp: a [32 x 32] fp32 chunk, row pitch 33 words
 __host__ __device__ constexpr uint32_t bg_smem_bytes(int npl, int tn) {
-  return (bg_stages(npl, tn) > 4 ? 4 : bg_stages(npl, tn)) * bg_stage_bytes(npl, tn) + 1024 + 256;
+  return (bg_stages(npl, tn) > 4 ? 4 : bg_stages(npl, tn)) * bg_stage_bytes(npl, tn) + BG_EPI_STAGING + 1024 + 256;
 }
 
 struct BgemmParams {
@@ -40,19 +44,20 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   static_assert(STAGES >= 2, "ring too shallow");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BG_EPI_STAGING);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
-  uint64_t* acc_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* acc_full = bars + 2 * STAGES;       // [2]
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2], count 128 (the epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   auto a_tile = [&](int s, int pl) { return smem + s * STAGE_BYTES + pl * (A_BYTES + B_BYTES); };
   auto b_tile = [&](int s, int pl) { return smem + s * STAGE_BYTES + pl * (A_BYTES + B_BYTES) + A_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + 127) / 128, tiles_n = (p.N + TN - 1) / TN;
-  const int tile = blockIdx.x % (tiles_m * tiles_n);
-  const int b = blockIdx.x / (tiles_m * tiles_n);
-  const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * TN;
+  const int per_batch = tiles_m * tiles_n;
+  const long long num_items = static_cast<long long>(p.batch) * per_batch;
   const int num_it = (p.Kc + BG_KC - 1) / BG_KC;
 
   if (warp == 0 && lane == 0) {
@@ -66,11 +71,14 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TN);
+    tmem_alloc(tmem_slot, 2 * TN);
     tmem_relinquish();
   }
   tcgen05_fence_before();
@@ -82,78 +90,103 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < num_it; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-        const int kc0 = it * BG_KC;
-        for (int pl = 0; pl < NPL; ++pl) {
-          const CUtensorMap* ta = pl ? &tmA_lo : &tmA_hi;
-          const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
-          if (A_MN) {  // map {M cols, Kc rows, batch}, boxes {64, 64}
-            for (int bx = 0; bx < 2; ++bx) tma_load_3d(a_tile(stage, pl) + bx * BOX, ta, &full_bar[stage], m0 + 64 * bx, kc0, b);
-          } else {     // map {Kc cols, M rows, batch}, box {64, 128}
-            tma_load_3d(a_tile(stage, pl), ta, &full_bar[stage], kc0, m0, b);
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int b = static_cast<int>(item / per_batch), tile = static_cast<int>(item % per_batch);
+        const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * TN;
+        for (int it = 0; it < num_it; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int kc0 = it * BG_KC;
+          for (int pl = 0; pl < NPL; ++pl) {
+            const CUtensorMap* ta = pl ? &tmA_lo : &tmA_hi;
+            const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
+            if (A_MN) {  // map {M cols, Kc rows, batch}, boxes {64, 64}
+              for (int bx = 0; bx < 2; ++bx) tma_load_3d(a_tile(stage, pl) + bx * BOX, ta, &full_bar[stage], m0 + 64 * bx, kc0, b);
+            } else {     // map {Kc cols, M rows, batch}, box {64, 128}
+              tma_load_3d(a_tile(stage, pl), ta, &full_bar[stage], kc0, m0, b);
+            }
+            if (B_MN) {
+              for (int bx = 0; bx < TN / 64; ++bx) tma_load_3d(b_tile(stage, pl) + bx * BOX, tb, &full_bar[stage], n0 + 64 * bx, kc0, b);
+            } else {
+              tma_load_3d(b_tile(stage, pl), tb, &full_bar[stage], kc0, n0, b);
+            }
           }
-          if (B_MN) {
-            for (int bx = 0; bx < TN / 64; ++bx) tma_load_3d(b_tile(stage, pl) + bx * BOX, tb, &full_bar[stage], n0 + 64 * bx, kc0, b);
-          } else {
-            tma_load_3d(b_tile(stage, pl), tb, &full_bar[stage], kc0, n0, b);
-          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, TN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < num_it; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+      uint32_t phase = 0, t = 0;
+      for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
+        const uint32_t acc = t & 1, use = t >> 1;
+        mbar_wait(&acc_empty[acc], (use & 1) ^ 1);  // the epilogue has drained this accumulator
         tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TN;
+        for (int it = 0; it < num_it; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
 #pragma unroll
-        for (int t = 0; t < BG_KC / 16; ++t) {
-          // K-major: 16 contraction elements = 32 B inside the swizzled 128 B row (SBO = 8 rows);
-          // MN-major: 16 contraction rows = 2 KB inside every [64 x 64] box (LBO = box stride, SBO = 8 rows)
-          auto desc = [&](uint8_t* base, bool mn) {
-            return mn ? umma_smem_desc(smem_u32(base) + t * 2048, BOX, 1024) : umma_smem_desc(smem_u32(base) + t * 32, 16, 1024);
-          };
-          const uint64_t da_hi = desc(a_tile(stage, 0), A_MN), db_hi = desc(b_tile(stage, 0), B_MN);
-          umma_bf16_ss(tmem_base, da_hi, db_hi, idesc, (it | t) != 0 ? 1u : 0u);
-          if (NTERMS == 3) {
-            const uint64_t da_lo = desc(a_tile(stage, 1), A_MN), db_lo = desc(b_tile(stage, 1), B_MN);
-            umma_bf16_ss(tmem_base, da_hi, db_lo, idesc, 1u);
-            umma_bf16_ss(tmem_base, da_lo, db_hi, idesc, 1u);
+          for (int k = 0; k < BG_KC / 16; ++k) {
+            // K-major: 16 contraction elements = 32 B inside the swizzled 128 B row (SBO = 8 rows);
+            // MN-major: 16 contraction rows = 2 KB inside every [64 x 64] box (LBO = box stride, SBO = 8 rows)
+            auto desc = [&](uint8_t* base, bool mn) {
+              return mn ? umma_smem_desc(smem_u32(base) + k * 2048, BOX, 1024) : umma_smem_desc(smem_u32(base) + k * 32, 16, 1024);
+            };
+            const uint64_t da_hi = desc(a_tile(stage, 0), A_MN), db_hi = desc(b_tile(stage, 0), B_MN);
+            umma_bf16_ss(d_tmem, da_hi, db_hi, idesc, (it | k) != 0 ? 1u : 0u);
+            if (NTERMS == 3) {
+              const uint64_t da_lo = desc(a_tile(stage, 1), A_MN), db_lo = desc(b_tile(stage, 1), B_MN);
+              umma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
           }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&acc_full[acc]);
       }
-      umma_commit(acc_full);
     }
   } else {
     const int wq = warp & 3;
-    const int m = m0 + wq * 32 + lane;
-    mbar_wait(acc_full, 0);
-    tcgen05_fence_after();
-    float* row = p.C + static_cast<long long>(b) * p.stride_c + static_cast<long long>(m) * p.ldc + n0;
-    for (int c0 = 0; c0 < TN; c0 += 32) {
-      if (n0 + c0 >= p.N) break;
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + c0, r);
-      tmem_wait_ld();
-      if (m < p.M) {
+    uint32_t t = 0;
+    for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
+      const int b = static_cast<int>(item / per_batch), tile = static_cast<int>(item % per_batch);
+      const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * TN;
+      const uint32_t acc = t & 1, use = t >> 1;
+      const int m = m0 + wq * 32 + lane;
+      mbar_wait(&acc_full[acc], use & 1);
+      tcgen05_fence_after();
+      // registers (lane == row) -> per-warp smem chunk -> row-contiguous global stores: every store instruction writes
+      // one 128 B segment of one output row (lane == column) instead of 32 scattered words
+      float* stg = epi_stage + (warp - 2) * (32 * 33);
+      float* base = p.C + static_cast<long long>(b) * p.stride_c + static_cast<long long>(m0 + wq * 32) * p.ldc + n0;
+      const int rows_valid = p.M - (m0 + wq * 32);  // rows of this warp's 32 that exist
+      (void)m;
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + acc * TN + (static_cast<uint32_t>(wq * 32) << 16) + c0, r);
+        tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (n0 + c0 + e < p.N) row[c0 + e] = __uint_as_float(r[e]) * p.scale;
+        for (int e = 0; e < 32; ++e) stg[lane * 33 + e] = __uint_as_float(r[e]) * p.scale;
+        __syncwarp();
+        const bool col_ok = n0 + c0 + lane < p.N;
+        for (int rr = 0; rr < 32; ++rr)
+          if (rr < rows_valid && col_ok) base[static_cast<long long>(rr) * p.ldc + c0 + lane] = stg[rr * 33 + lane];
+        __syncwarp();
       }
+      tcgen05_fence_before();
+      mbar_arrive(&acc_empty[acc]);
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TN);
+    tmem_dealloc(tmem_base, 2 * TN);
   }
 }
 

@@ -709,8 +709,8 @@ int launch_bgemm(const void* a_hi, const void* a_lo, uint64_t a_cols, uint64_t a
   if (once_rc != LAMP_OK) return once_rc;
   BgemmParams p;
   p.batch = batch; p.M = M; p.N = N; p.Kc = Kc; p.scale = scale; p.C = C; p.ldc = ldc; p.stride_c = stride_c;
-  const long long grid = (long long)batch * ((M + 127) / 128) * ((N + TN - 1) / TN);
-  if (grid >= (1LL << 31)) return fail(LAMP_EINVAL, "bgemm: grid too large");
+  const long long items = (long long)batch * ((M + 127) / 128) * ((N + TN - 1) / TN);
+  const long long grid = items < sm_count_cached() ? items : sm_count_cached();  // persistent: one CTA per SM
   kernel<<<(unsigned)grid, BG_THREADS, bg_smem_bytes(2, TN), st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   return launch_check();
 }
