@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from . import _native as nat
+from . import graphs
 from . import ops
 from .Decoders import GraphDecoder
 from .Encoders import GraphEncoder
@@ -73,8 +74,25 @@ class LAMP(nn.Module):
         return torch.diagonal(self.tgt_word_proj(x), 0, 1, 2)
 
     def forward(self, src, adj, tgt_seq, binary_tgt, return_attns=False, int_preds=False):
+        """lamp/Models.py:110-137.  Eval-mode calls of the plain ``(logits, enc_output, None)`` form -- what the
+        reference's test loop makes (test.py:41) -- are served from a shape-keyed cache of CUDA graphs of this same
+        forward (``graphs.EvalGraphCache``; ``LAMP_EVAL_GRAPHS=0`` turns it off): the second call with a given
+        (batch, padded length) captures, later ones replay with one launch.  Results are identical to the eager
+        launch sequence; the returned tensors are fresh copies, not the graph's static buffers."""
         src_seq, src_pos = src
         nat.require_cuda(src_seq, src_pos)
+        if (graphs.EVAL_GRAPHS and not return_attns and not int_preds and not adj and not _needs_autograd(self)
+                and not getattr(self, '_is_replica', False) and not torch.cuda.is_current_stream_capturing()
+                and self.proj_share_weight and self.encoder.fused_ok(adj) and self.decoder.fused_ok()):
+            cache = self.__dict__.get('_eval_graphs')
+            if cache is None:
+                cache = self.__dict__['_eval_graphs'] = graphs.EvalGraphCache(self)
+            seq_logit, enc_output = cache.run(src_seq, src_pos)
+            return seq_logit, enc_output, None
+        return self._forward_impl(src, adj, tgt_seq, binary_tgt, return_attns, int_preds)
+
+    def _forward_impl(self, src, adj, tgt_seq, binary_tgt, return_attns=False, int_preds=False):
+        src_seq, src_pos = src
         batch_size = src_seq.size(0)
         fused = not _needs_autograd(self)
         enc_output, *enc_self_attns = self.encoder(src_seq, adj, src_pos, return_attns=return_attns)

@@ -7,13 +7,30 @@ rebinds those names inside the reference's ``lamp`` package to the ``lamp_b200``
 outside the label-graph path; ``python -m lamp_b200.run_main /path/to/reference <main.py args>`` then runs the
 reference's byte-identical ``main.py``.
 """
-import functools
 import importlib
+import os
 import sys
 
 import torch
 
 _PATCHED = False
+
+
+def _scoped_torch_load(reference_dir):
+    """torch >= 2.6 defaults ``torch.load(weights_only=True)``; main.py:23 / :118 load pickled dicts.
+    Only calls made FROM files of the reference tree get ``weights_only=False``; every other caller in the process keeps
+    torch's safe default."""
+    orig = torch.load
+    root = os.path.realpath(reference_dir) + os.sep if reference_dir else None
+
+    def load(*args, **kwargs):
+        if 'weights_only' not in kwargs:
+            caller = os.path.realpath(sys._getframe(1).f_code.co_filename)
+            if root is None or caller.startswith(root):
+                kwargs['weights_only'] = False
+        return orig(*args, **kwargs)
+    load.__wrapped__ = orig
+    return load
 
 
 def patch_reference(reference_dir=None):
@@ -22,8 +39,7 @@ def patch_reference(reference_dir=None):
     if reference_dir is not None and reference_dir not in sys.path:
         sys.path.insert(0, reference_dir)
     if not _PATCHED:
-        # torch >= 2.6 defaults torch.load(weights_only=True); main.py:23 loads a pickled dict
-        torch.load = functools.partial(torch.load, weights_only=False)
+        torch.load = _scoped_torch_load(reference_dir)
         _PATCHED = True
     import lamp_b200
     ref = importlib.import_module('lamp')

@@ -85,29 +85,59 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, ui
   return LAMP_OK;
 }
 
-int sm_count_cached() {
-  static std::atomic<int> n{0};
-  int v = n.load();
-  if (v) return v;
+// Per-device host state.  One process may drive several GPUs (nn.DataParallel threads as in the reference's
+// main.py:106-108, a model moved to cuda:1, tests switching devices): the >48 KB dynamic-shared-memory opt-in
+// (cudaFuncSetAttribute) is a per-device attribute and SM counts / architectures are per device, so everything that is
+// cached is cached per device ordinal of the calling thread's current device.
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
+int sm_count_cached() {
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return 0;
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v) return v;
   if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  n.store(v);
+  n[dev].store(v, std::memory_order_relaxed);
   return v;
 }
 
 int arch_check() {
-  static std::atomic<int> ok{0};  // 0 unknown, 1 ok, -1 bad
-  int v = ok.load();
+  static std::atomic<int> ok[kMaxDevices];  // 0 unknown, 1 ok, -1 bad
+  const int dev = current_device();
+  if (dev < 0) return fail(LAMP_ECUDA, "no CUDA device");
+  int v = ok[dev].load(std::memory_order_relaxed);
   if (v == 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
       return fail(LAMP_ECUDA, "no CUDA device");
     v = (major == 10) ? 1 : -1;
-    ok.store(v);
+    ok[dev].store(v, std::memory_order_relaxed);
   }
   if (v < 0) return fail(LAMP_EARCH, "lamp_b200 kernels are built for sm_100a only");
   return LAMP_OK;
+}
+
+// "once per device" for the function attributes: `init` may run twice under a race between two threads on the same
+// device, which is harmless (cudaFuncSetAttribute is idempotent).
+struct PerDeviceOnce {
+  std::atomic<int> done[kMaxDevices];
+};
+
+template <typename F>
+int per_device_once(PerDeviceOnce& o, F&& init) {
+  const int dev = current_device();
+  if (dev < 0) return fail(LAMP_ECUDA, "no CUDA device");
+  if (o.done[dev].load(std::memory_order_acquire)) return LAMP_OK;
+  const int rc = init();
+  if (rc == LAMP_OK) o.done[dev].store(1, std::memory_order_release);
+  return rc;
 }
 
 template <typename K>
@@ -137,10 +167,8 @@ int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUte
                     const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BLOCK_N, NTERMS, BLOCK_K, CTA_GROUP>;
   auto kernel = gemm_planes_kernel<BLOCK_N, NTERMS, BLOCK_K, EPI, CTA_GROUP>;
-  static std::once_flag once;
-  static int once_rc = LAMP_OK;
-  std::call_once(once, [kernel] { once_rc = set_smem(kernel, Cfg::SMEM_BYTES); });
-  if (once_rc != LAMP_OK) return once_rc;
+  static PerDeviceOnce once;
+  if (int once_rc = per_device_once(once, [kernel] { int rc_ = set_smem(kernel, Cfg::SMEM_BYTES); return rc_; })) return once_rc;
   const int m_tiles = (p.M + GEMM_BLOCK_M * CTA_GROUP - 1) / (GEMM_BLOCK_M * CTA_GROUP);
   const int tiles = (EPI == EPI_LN) ? m_tiles : m_tiles * ((p.N + BLOCK_N - 1) / BLOCK_N);
   const int max_groups = sm_count_cached() / CTA_GROUP;
@@ -224,10 +252,8 @@ int launch_attn(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_b
 template <int BLOCK_KV, int NTERMS, bool DROP>
 int launch_attn_k(const CUtensorMap (&tm)[8], const AttnParams& p, uint32_t smem_bytes, cudaStream_t st) {
   auto kernel = attn_core_kernel<BLOCK_KV, NTERMS, DROP>;
-  static std::once_flag once;
-  static int once_rc = LAMP_OK;
-  std::call_once(once, [kernel] { once_rc = set_smem(kernel, kMaxDynSmem); });
-  if (once_rc != LAMP_OK) return once_rc;
+  static PerDeviceOnce once;
+  if (int once_rc = per_device_once(once, [kernel] { int rc_ = set_smem(kernel, kMaxDynSmem); return rc_; })) return once_rc;
   const int items = p.B * p.H * ((p.Lq + ATTN_BLOCK_M - 1) / ATTN_BLOCK_M);
   const int grid = items < sm_count_cached() ? items : sm_count_cached();
   cudaError_t e = launch_k(kernel, (unsigned)grid, (unsigned)attn_threads(BLOCK_KV), smem_bytes, st,
@@ -657,10 +683,8 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
     pp.row_max = row_max; pp.row_sum = row_sum; pp.probs = probs;
     pp.probs_pre = probs_pre; pp.drop_thresh = p.drop_thresh; pp.drop_scale = p.drop_scale; pp.drop_seed = seed;
     pp.drop_seed_dev = p.drop_seed_dev;
-    static std::once_flag once;
-    static int once_rc = LAMP_OK;
-    std::call_once(once, [] { once_rc = set_smem(attn_probs_mma_kernel, (uint32_t)attn_probs_smem_bytes(BWD_DMAX)); });
-    if (once_rc != LAMP_OK) return once_rc;
+    static PerDeviceOnce once;
+    if (int once_rc = per_device_once(once, [] { int rc_ = set_smem(attn_probs_mma_kernel, (uint32_t)attn_probs_smem_bytes(BWD_DMAX)); return rc_; })) return once_rc;
     const long long grid = (long long)H * B * ((Lq + BWD_TILE - 1) / BWD_TILE);
     REQUIRE(grid < (1LL << 31), "attn: probability grid too large");
     attn_probs_mma_kernel<<<(unsigned)grid, BWD_THREADS, (uint32_t)attn_probs_smem_bytes(d), st>>>(pp);
@@ -703,10 +727,8 @@ int launch_bgemm(const void* a_hi, const void* a_lo, uint64_t a_cols, uint64_t a
   if (int rc = make_tmap(&tb_hi, b_hi, b_cols, b_rows, (uint64_t)batch, b_ld, b_box_rows, true)) return rc;
   if (int rc = make_tmap(&tb_lo, b_lo, b_cols, b_rows, (uint64_t)batch, b_ld, b_box_rows, true)) return rc;
   auto kernel = bgemm_tc_kernel<A_MN, B_MN, 3, TN>;
-  static std::once_flag once;
-  static int once_rc = LAMP_OK;
-  std::call_once(once, [kernel] { once_rc = set_smem(kernel, bg_smem_bytes(2, TN)); });
-  if (once_rc != LAMP_OK) return once_rc;
+  static PerDeviceOnce once;
+  if (int once_rc = per_device_once(once, [kernel] { int rc_ = set_smem(kernel, bg_smem_bytes(2, TN)); return rc_; })) return once_rc;
   BgemmParams p;
   p.batch = batch; p.M = M; p.N = N; p.Kc = Kc; p.scale = scale; p.C = C; p.ldc = ldc; p.stride_c = stride_c;
   const long long items = (long long)batch * ((M + 127) / 128) * ((N + TN - 1) / TN);
@@ -743,13 +765,9 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
     p.q = q; p.k = k; p.v = v; p.dO = dO; p.O = O; p.P = P; p.A = A ? A : P;
     p.dS = reinterpret_cast<float*>(ws + pl.dA); p.dq = dq; p.dk = dk; p.dv = dv;
     const uint32_t smem = (uint32_t)attn_bwd_smem_bytes(d);
-    static std::once_flag once;
-    static int once_rc = LAMP_OK;
-    std::call_once(once, [] {
-      once_rc = set_smem(attn_bwd_dq_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
-      if (once_rc == LAMP_OK) once_rc = set_smem(attn_bwd_dkv_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
-    });
-    if (once_rc != LAMP_OK) return once_rc;
+    static PerDeviceOnce once;
+    if (int once_rc = per_device_once(once, [] { int rc_ = set_smem(attn_bwd_dq_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX));
+      if (rc_ == LAMP_OK) rc_ = set_smem(attn_bwd_dkv_kernel, (uint32_t)attn_bwd_smem_bytes(BWD_DMAX)); return rc_; })) return once_rc;
     const long long gq = (long long)N * ((Lq + BWD_TILE - 1) / BWD_TILE);
     const long long gk = (long long)N * ((Lk + BWD_TILE - 1) / BWD_TILE);
     REQUIRE(gq < (1LL << 31) && gk < (1LL << 31), "attn_bwd: grid too large");
@@ -826,13 +844,9 @@ int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const vo
       ty_lo = ty_hi;
       tx_lo = tx_hi;
     }
-    static std::once_flag once_tc;
-    static int once_tc_rc = LAMP_OK;
-    std::call_once(once_tc, [] {
-      once_tc_rc = set_smem(gemm_tn_tc_kernel<3>, tnc_smem_bytes(2));
-      if (once_tc_rc == LAMP_OK) once_tc_rc = set_smem(gemm_tn_tc_kernel<1>, tnc_smem_bytes(1));
-    });
-    if (once_tc_rc != LAMP_OK) return once_tc_rc;
+    static PerDeviceOnce once_tc;
+    if (int once_tc_rc = per_device_once(once_tc, [] { int rc_ = set_smem(gemm_tn_tc_kernel<3>, tnc_smem_bytes(2));
+      if (rc_ == LAMP_OK) rc_ = set_smem(gemm_tn_tc_kernel<1>, tnc_smem_bytes(1)); return rc_; })) return once_tc_rc;
     const long long tiles = (long long)((N + TNC_TILE_N - 1) / TNC_TILE_N) * ((K + TNC_TILE_K - 1) / TNC_TILE_K);
     long long splits = (sm_count_cached() + tiles - 1) / tiles;  // one CTA per SM (192 KB of smem each)
     const long long max_splits = (M + TNC_BM - 1) / TNC_BM;
@@ -857,10 +871,8 @@ int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const vo
     }
     return LAMP_OK;
   }
-  static std::once_flag once;
-  static int once_rc = LAMP_OK;
-  std::call_once(once, [] { once_rc = set_smem(gemm_tn_kernel, (uint32_t)gemm_tn_smem_bytes()); });
-  if (once_rc != LAMP_OK) return once_rc;
+  static PerDeviceOnce once;
+  if (int once_rc = per_device_once(once, [] { int rc_ = set_smem(gemm_tn_kernel, (uint32_t)gemm_tn_smem_bytes()); return rc_; })) return once_rc;
   const long long tiles = (long long)((N + TN_TILE - 1) / TN_TILE) * ((K + TN_TILE - 1) / TN_TILE);
   // split the M rows so that ~3 CTAs per SM exist; chunks are multiples of the 64-row staging tile
   long long splits = (3LL * sm_count_cached() + tiles - 1) / tiles;

@@ -14,9 +14,20 @@ to keep them).  The captured forward is the module's own fused path, so results 
 """
 from __future__ import annotations
 
+import os
+from collections import OrderedDict
+
 import torch
 
 from . import _native as nat
+
+# LAMP.forward serves plain eval calls from a shape-keyed cache of CUDA graphs (EvalGraphCache); LAMP_EVAL_GRAPHS=0: off
+EVAL_GRAPHS = os.environ.get('LAMP_EVAL_GRAPHS', '1') != '0'
+
+
+def _plain_forward(model):
+    """The model's forward WITHOUT the eval graph cache (what a capture must record)."""
+    return getattr(model, '_forward_impl', model)
 
 
 class GraphedForward:
@@ -42,14 +53,14 @@ class GraphedForward:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.no_grad(), torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):  # weight planes, smem attributes, allocator pools: all outside the graph
-                model((self.src_seq, self.src_pos), None, None, None)
+                _plain_forward(model)((self.src_seq, self.src_pos), None, None, None)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
         from . import ops
         n0 = ops.STATS.launches
         with torch.no_grad(), torch.cuda.graph(self.graph):
-            logits, enc_output, *_ = model((self.src_seq, self.src_pos), None, None, None)
+            logits, enc_output, *_ = _plain_forward(model)((self.src_seq, self.src_pos), None, None, None)
         self.kernels_per_replay = ops.STATS.launches - n0   # native kernel launches captured in the graph
         self.logits, self.enc_output = logits, enc_output
 
@@ -62,14 +73,101 @@ class GraphedForward:
         self.src_pos.copy_(src_pos, non_blocking=True)
 
     def replay(self):
-        self.graph.replay()
+        """The graph reads the weight PLANES, not the parameters: they are brought up to date (in place, same buffers)
+        first, so a replay after ``optimizer.step()`` / ``load_state_dict`` sees the new weights."""
         from . import ops
+        ops.refresh_weight_planes(self.model)
+        self.graph.replay()
         ops.STATS.launches += self.kernels_per_replay
         return self.logits, self.enc_output
 
     def __call__(self, src_seq: torch.Tensor, src_pos: torch.Tensor):
         self.load(src_seq, src_pos)
         return self.replay()
+
+
+class EvalGraphCache:
+    """Shape-keyed cache of CUDA graphs of the fused eval forward, used by ``LAMP.forward`` itself so that the
+    reference's own eval loop (test.py:41: ``model(src, adj, None, None)`` batch after batch) gets graph-replay launch
+    cost without calling any extra API.
+
+    * key: (batch, padded length, device, precision / path switches).  The reference's loader pads every batch to its
+      longest document (utils/data_loader.py:261-279), so the token length varies from batch to batch: it is rounded up
+      to a multiple of ``t_bucket`` with PAD tokens (id 0, position 0).  Those are exactly the rows the padding-aware
+      encoder drops and the decoder never attends to, so the logits are unchanged; ``enc_output`` is cut back to T.
+    * the first call with a key runs eagerly (one-off shapes are never captured), the second captures, later ones replay.
+    * weights: planes are refreshed in place before every replay (``ops.refresh_weight_planes``), so an eval epoch
+      after a training epoch sees the trained weights; everything else the kernels read (LayerNorm affine, biases,
+      embedding tables) is read from the parameters themselves.
+    * all graphs share one memory pool (replays are stream-ordered and the outputs handed out are copies), LRU-bounded."""
+
+    def __init__(self, model, max_graphs: int = 16, t_bucket: int = 32):
+        self.model = model
+        self.max_graphs, self.t_bucket = max_graphs, t_bucket
+        self.entries: 'OrderedDict[tuple, dict]' = OrderedDict()
+        self.seen: dict = {}
+        self.pool = None
+        self.replays = self.captures = self.eager_calls = 0
+
+    def _key(self, B: int, Tb: int, dev) -> tuple:
+        from . import ops
+        return (B, Tb, dev.index, ops.default_precision(), ops.PADDING_AWARE, ops.DEFER_LAYERNORM, ops.FUSE_LAYERNORM)
+
+    def _capture(self, key, B: int, Tb: int, dev, src_seq, src_pos, T: int) -> dict:
+        from . import ops
+        s_seq = torch.zeros((B, Tb), dtype=torch.int64, device=dev)
+        s_pos = torch.zeros((B, Tb), dtype=torch.int64, device=dev)
+        s_seq[:, :T].copy_(src_seq)
+        s_pos[:, :T].copy_(src_pos)
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.STATS.launches
+        torch.cuda.synchronize(dev)
+        with torch.no_grad(), torch.cuda.graph(graph, pool=self.pool):
+            logits, enc_output, _ = self.model._forward_impl((s_seq, s_pos), None, None, None)
+        e = dict(graph=graph, seq=s_seq, pos=s_pos, logits=logits, enc=enc_output, kernels=ops.STATS.launches - n0, T=T)
+        self.entries[key] = e
+        self.captures += 1
+        while len(self.entries) > self.max_graphs:
+            self.entries.popitem(last=False)
+        return e
+
+    def run(self, src_seq: torch.Tensor, src_pos: torch.Tensor):
+        from . import ops
+        B, T = src_seq.shape
+        dev = src_seq.device
+        tb = self.t_bucket
+        Tb = (T + tb - 1) // tb * tb
+        key = self._key(B, Tb, dev)
+        e = self.entries.get(key)
+        if e is None:
+            n = self.seen.get(key, 0)
+            self.seen[key] = n + 1
+            if n == 0 or src_seq.dtype != torch.int64 or src_pos.dtype != torch.int64:
+                self.eager_calls += 1
+                logits, enc_output, _ = self.model._forward_impl((src_seq, src_pos), None, None, None)
+                return logits, enc_output
+            ops.refresh_weight_planes(self.model)
+            e = self._capture(key, B, Tb, dev, src_seq, src_pos, T)
+        else:
+            self.entries.move_to_end(key)
+            ops.refresh_weight_planes(self.model)
+            if T == Tb:
+                e['seq'].copy_(src_seq, non_blocking=True)
+                e['pos'].copy_(src_pos, non_blocking=True)
+            else:
+                e['seq'][:, :T].copy_(src_seq, non_blocking=True)
+                e['pos'][:, :T].copy_(src_pos, non_blocking=True)
+                if T < e['T']:  # the previous batch of this bucket was longer: blank its tail
+                    e['seq'][:, T:].zero_()
+                    e['pos'][:, T:].zero_()
+            e['T'] = T
+        e['graph'].replay()
+        self.replays += 1
+        ops.STATS.launches += e['kernels']
+        enc = e['enc']
+        return e['logits'].clone(), (enc.clone() if T == Tb else enc[:, :T].clone())
 
 
 class GraphedTrainStep:
@@ -101,6 +199,7 @@ class GraphedTrainStep:
         p = next(model.parameters())
         nat.require_cuda(p)
         self.model, self.loss_fn = model, loss_fn
+        self.optimizer_in_graph = optimizer is not None
         self.device = torch.device(device) if device is not None else p.device
         self.batch, self.seq_len = batch, seq_len
         n_labels = model.decoder.n_tgt_vocab
@@ -148,4 +247,8 @@ class GraphedTrainStep:
         self.graph.replay()
         from . import ops
         ops.STATS.launches += self.kernels_per_replay
+        if self.optimizer_in_graph:
+            # the replay changed the parameters without touching their tensor versions: invalidate every cached
+            # weight-plane signature so that the next eval forward (eager or captured) re-splits the new weights
+            ops.bump_weights_epoch()
         return self.loss

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 import os
+import threading
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -138,13 +139,14 @@ def _empty_planes(rows: int, cols: int, prec: int, device) -> Tuple[torch.Tensor
     return hi, lo
 
 
-def split(x: torch.Tensor, prec: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """fp32 ``[..., cols]`` (contiguous) -> planes ``[rows, cols]``."""
+def split(x: torch.Tensor, prec: int, out=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """fp32 ``[..., cols]`` (contiguous) -> planes ``[rows, cols]``.  ``out``: existing ``(hi, lo)`` buffers of that
+    shape to overwrite (weight planes refreshed in place keep the addresses captured CUDA graphs hold)."""
     nat.require_cuda(x)
     x = x.contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
-    hi, lo = _empty_planes(rows, cols, prec, x.device)
+    hi, lo = _empty_planes(rows, cols, prec, x.device) if out is None else out
     STATS.call('split_planes', 1, nat.lib().lamp_split_planes,
                (x.data_ptr(), rows, cols, cols, hi.data_ptr(), nat.ptr(lo), cols, nat.stream()),
                nbytes=rows * cols * (4 + (4 if lo is not None else 2)))
@@ -174,47 +176,123 @@ def stash_planes(x: torch.Tensor, act: Act, prec: int) -> torch.Tensor:
     return x
 
 
+# Bumped by whatever changes parameters WITHOUT advancing their tensor ``_version`` -- replays of a CUDA graph that
+# contains an optimizer step (graphs.GraphedTrainStep with a capturable optimizer).  Part of every weight-plane signature.
+WEIGHTS_EPOCH = 0
+
+
+def bump_weights_epoch() -> None:
+    global WEIGHTS_EPOCH
+    WEIGHTS_EPOCH += 1
+
+
+class _PlaneEntry:
+    __slots__ = ('sig', 'deps', 'build', 'bufs')
+
+    def __init__(self, sig, deps, build, bufs):
+        self.sig, self.deps, self.build, self.bufs = sig, deps, build, bufs
+
+
 class WeightPlanes:
-    """Split-bf16 planes of (a concatenation of) 2-D weights, cached against the parameters' versions."""
+    """Split-bf16 planes of (a concatenation of) 2-D weights, cached against the parameters' versions.
+
+    * A stale entry is refreshed IN PLACE (same buffers): CUDA graphs that captured a forward keep pointing at valid,
+      up-to-date planes after an optimizer step / ``load_state_dict`` (see :func:`refresh_weight_planes`).
+    * Entries are keyed by device as well: ``nn.DataParallel`` replicas (the reference's multi-GPU mode, main.py:106-108)
+      are shallow copies that share this object, each thread works on its own device's entry under a lock.
+    * An entry keeps its parameters alive, so a signature (address, version, shape) can never be recycled."""
 
     def __init__(self):
-        self._cache: Dict[tuple, tuple] = {}
+        self._cache: Dict[tuple, _PlaneEntry] = {}
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _sig(deps, extra) -> tuple:
+        return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in deps) + extra + (WEIGHTS_EPOCH,)
+
+    def _lookup(self, ck: tuple, deps: tuple, extra: tuple, build):
+        sig = self._sig(deps, extra)
+        hit = self._cache.get(ck)
+        if hit is not None and hit.sig == sig:
+            return hit.bufs
+        with self._lock:
+            hit = self._cache.get(ck)
+            if hit is not None and hit.sig == sig:
+                return hit.bufs
+            with torch.no_grad():
+                bufs = build(deps, None if hit is None else hit.bufs)
+            self._cache[ck] = _PlaneEntry(sig, deps, build, bufs)  # replaced as a whole: readers never see a torn entry
+            return bufs
+
+    def refresh(self) -> int:
+        """Re-split every entry whose parameters changed (in place).  -> number of entries refreshed."""
+        n = 0
+        for ck, e in list(self._cache.items()):
+            extra = e.sig[len(e.deps):-1]
+            if e.sig != self._sig(e.deps, extra):
+                self._lookup(ck, e.deps, extra, e.build)
+                n += 1
+        return n
+
+    @staticmethod
+    def _cat(params) -> torch.Tensor:
+        mats = [p.detach().reshape(p.shape[0], -1).float() for p in params]  # Conv1d [out,in,1] -> [out,in]
+        return mats[0] if len(mats) == 1 else torch.cat(mats, dim=0)
 
     def get(self, key: str, params, prec: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-        sig = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params) + (prec,)
-        hit = self._cache.get(key)
-        if hit is not None and hit[0] == sig:
-            return hit[1], hit[2]
-        with torch.no_grad():
-            mats = [p.detach().reshape(p.shape[0], -1).float() for p in params]  # Conv1d [out,in,1] -> [out,in]
-            w = mats[0] if len(mats) == 1 else torch.cat(mats, dim=0)
-            hi, lo = split(w, prec)
-        self._cache[key] = (sig, hi, lo)
-        return hi, lo
+        params = tuple(params)
+
+        def build(deps, old):
+            w = self._cat(deps)
+            if old is not None and old[0].shape == w.shape and old[0].device == w.device:
+                return split(w, prec, out=old)
+            return split(w, prec)
+        return self._lookup((key, params[0].device.index, prec), params, (prec,), build)
 
     def get_folded(self, key: str, params, ln: 'DeferredLN', bias, prec: int):
         """Weights of a GEMM whose A operand is a deferred LayerNorm (gamma, beta):
         ``LN(y) W^T + bias = rstd * (y (W*gamma)^T - mean * colsum) + (bias + W beta)``.
         -> (planes of W*diag(gamma), colsum [N] fp32, folded bias [N] fp32), cached per parameter versions."""
-        deps = tuple(params) + (ln.gamma, ln.beta) + ((bias,) if bias is not None else ())
-        sig = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in deps) + (prec, bias is None)
-        ck = key + '@ln'
-        hit = self._cache.get(ck)
-        if hit is not None and hit[0] == sig:
-            return hit[1:]
-        with torch.no_grad():
-            mats = [p.detach().reshape(p.shape[0], -1).float() for p in params]
-            w = mats[0] if len(mats) == 1 else torch.cat(mats, dim=0)
-            wg = (w * ln.gamma.detach().float().unsqueeze(0)).contiguous()
-            hi, lo = split(wg, prec)
+        params = tuple(params)
+        n = len(params)
+        deps = params + (ln.gamma, ln.beta) + ((bias,) if bias is not None else ())
+
+        def build(deps, old):
+            w = self._cat(deps[:n])
+            gamma, beta = deps[n], deps[n + 1]
+            b = deps[n + 2] if len(deps) > n + 2 else None
+            wg = (w * gamma.detach().float().unsqueeze(0)).contiguous()
+            reuse = old is not None and old[0].shape == wg.shape and old[0].device == wg.device
+            hi, lo = split(wg, prec, out=(old[0], old[1]) if reuse else None)
             # colsum from the operand planes themselves, so that `y Wg^T - mean * colsum` cancels exactly
             colsum = (hi.float() if lo is None else hi.float() + lo.float()).sum(dim=1).contiguous()
-            biasf = w.double() @ ln.beta.detach().double()
-            if bias is not None:
-                biasf = biasf + bias.detach().double()
+            biasf = w.double() @ beta.detach().double()
+            if b is not None:
+                biasf = biasf + b.detach().double()
             biasf = biasf.float().contiguous()
-        self._cache[ck] = (sig, hi, lo, colsum, biasf)
-        return hi, lo, colsum, biasf
+            if reuse:
+                old[2].copy_(colsum)
+                old[3].copy_(biasf)
+                return old
+            return hi, lo, colsum, biasf
+        return self._lookup((key + '@ln', params[0].device.index, prec), deps, (prec, bias is None), build)
+
+
+def refresh_weight_planes(model: torch.nn.Module) -> int:
+    """Bring every cached weight-plane buffer of ``model`` up to date with its parameters, in place.  Called before a
+    captured forward is replayed (graphs.GraphedForward, the eval graph cache of ``LAMP.forward``): the graph reads the
+    plane buffers, not the parameters.  A quick (version, address) check makes the common no-change case ~15 us."""
+    state = model.__dict__.get('_lamp_planes_state')
+    if state is None:
+        plist = list(model.parameters())
+        holders = [m._wp for m in model.modules() if isinstance(getattr(m, '_wp', None), WeightPlanes)]
+        state = model.__dict__['_lamp_planes_state'] = dict(params=plist, holders=holders, stamp=None)
+    stamp = (WEIGHTS_EPOCH,) + tuple((p._version, p.data_ptr()) for p in state['params'])
+    if stamp == state['stamp']:
+        return 0
+    n = sum(h.refresh() for h in state['holders'])
+    state['stamp'] = stamp
+    return n
 
 
 def gemm(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, prec: int, *, bias=None, relu=False,
