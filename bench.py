@@ -412,6 +412,17 @@ def main():
         barrier()
         dropin_ms = max_over_ranks(e0.elapsed_time(e1))
         cache = model.__dict__.get('_eval_graphs')
+        # (A') region A once more: the board is power-capped (SM clocks sag over the first few hundred ms of tensor
+        # work), so the drop-in call is compared with a graph replay timed in the SAME thermal state
+        replay_after_ms = None
+        if runner is not None:
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                runner.replay()
+            e1.record()
+            barrier()
+            replay_after_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         # ---------------- (B) the same K steps launched kernel by kernel with a CUDA-event pair around every native
         #                  call: per-kernel durations for the roofline figures (and the eager-launch step time)
         barrier()
@@ -492,6 +503,7 @@ def main():
                  api='model((src_seq, src_pos), None, None, None) -- the reference-facing LAMP.forward call'),
         dropin=dict(value=total_samples / (dropin_ms * 1e-3), unit='samples/s', ms_per_step=dropin_ms / args.steps,
                     api='LAMP.forward (eval graph cache)', enabled=graphs.EVAL_GRAPHS,
+                    graph_replay_ms_per_step_timed_right_after=replay_after_ms,
                     replays=None if cache is None else cache.replays,
                     captures=None if cache is None else cache.captures),
         gpu_launches=launches, clocks=clocks,

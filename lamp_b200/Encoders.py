@@ -138,10 +138,17 @@ class GraphEncoder(nn.Module):
         n = len(self.layer_stack)
         for i, layer in enumerate(self.layer_stack):
             x, _ = layer.forward_act(x, B, T, None, False, want_f32=(i == n - 1) and not ops.DEFER_LAYERNORM)
+        unpack = None
         if x.ln is not None:
             # the last LayerNorm is still pending: apply it while un-packing into the dense API tensor; the decoder's
             # K|V projection consumes the deferred packed activation directly
             out = ops.materialize(x, prec, want_f32=True, want_planes=False, index=src_row).f32
+        elif ops.DEFER_UNPACK and self.enc_transform == '':
+            # forward being captured by graphs.EvalGraphCache: the dense [B, T, D] API tensor is written AFTER each
+            # replay, straight into a fresh tensor (no copy out of a static buffer); inside the graph enc_output is
+            # only a shape carrier -- the decoder consumes the packed rows
+            unpack = (ops.act_f32(x), src_row)
+            out = unpack[0].new_empty(1).expand(R, self.d_model)
         else:
             out = ops.gather_rows(ops.act_f32(x), src_row, self.d_model)
         out = out.view(B, T, self.d_model)
@@ -150,7 +157,7 @@ class GraphEncoder(nn.Module):
             kv_start = torch.cumsum(kv_len, 0) - kv_len
             out._lamp_packed = dict(act=x, kv_start=kv_start.to(torch.int32), kv_len=kv_len.to(torch.int32),
                                     key_is_pad=is_pad[order].to(torch.uint8), version=out._version, prec=prec,
-                                    shape=(B, T, self.d_model))
+                                    shape=(B, T, self.d_model), unpack=unpack)
         return self._pool(out, src_seq, B)
 
     def forward(self, src_seq, adj, src_pos, return_attns=False):

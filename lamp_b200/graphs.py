@@ -124,9 +124,16 @@ class EvalGraphCache:
         graph = torch.cuda.CUDAGraph()
         n0 = ops.STATS.launches
         torch.cuda.synchronize(dev)
-        with torch.no_grad(), torch.cuda.graph(graph, pool=self.pool):
-            logits, enc_output, _ = self.model._forward_impl((s_seq, s_pos), None, None, None)
-        e = dict(graph=graph, seq=s_seq, pos=s_pos, logits=logits, enc=enc_output, kernels=ops.STATS.launches - n0, T=T)
+        ops.DEFER_UNPACK = True
+        try:
+            with torch.no_grad(), torch.cuda.graph(graph, pool=self.pool):
+                logits, enc_output, _ = self.model._forward_impl((s_seq, s_pos), None, None, None)
+        finally:
+            ops.DEFER_UNPACK = False
+        packed = getattr(enc_output, '_lamp_packed', None)
+        unpack = None if packed is None else packed.get('unpack')
+        e = dict(graph=graph, seq=s_seq, pos=s_pos, logits=logits, enc=enc_output, unpack=unpack,
+                 kernels=ops.STATS.launches - n0, T=T)
         self.entries[key] = e
         self.captures += 1
         while len(self.entries) > self.max_graphs:
@@ -166,8 +173,15 @@ class EvalGraphCache:
         e['graph'].replay()
         self.replays += 1
         ops.STATS.launches += e['kernels']
-        enc = e['enc']
-        return e['logits'].clone(), (enc.clone() if T == Tb else enc[:, :T].clone())
+        if e['unpack'] is not None:
+            # padding-aware encoder: un-pack the packed rows the replay left in its static buffer into a FRESH dense
+            # [B, T, D] tensor (the same gather the eager forward ends with -- no copy out of a static buffer)
+            x32, src_row = e['unpack']
+            idx = src_row if T == Tb else src_row.view(B, Tb)[:, :T].reshape(-1)
+            enc = ops.gather_rows(x32, idx, x32.shape[1]).view(B, T, x32.shape[1])
+        else:
+            enc = e['enc'].clone() if T == Tb else e['enc'][:, :T].clone()
+        return e['logits'].clone(), enc
 
 
 class GraphedTrainStep:

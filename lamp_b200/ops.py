@@ -420,6 +420,7 @@ def linear_residual_deferred(x: Act, w_hi, w_lo, N: int, prec: int, residual: Ac
 
 NATIVE_ATTENTION_BACKWARD = os.environ.get('LAMP_NATIVE_ATTN_BWD', '1') != '0'  # training: attention core fwd+bwd native
 ELIDE_DEAD_ENCODER_ATTENTION = True  # training / composed path: skip the encoder self-attention whose output is discarded
+DEFER_UNPACK = False  # set by graphs.EvalGraphCache while it captures: the encoder leaves the un-packing gather to the cache
 PADDING_AWARE = True  # GraphEncoder/GraphDecoder compute only non-PAD token rows (results identical, see Encoders.py)
 # fc / w_2 GEMMs emit pre-norm planes + row statistics and the LayerNorm is applied by the consumers (no LayerNorm
 # kernels inside the stack).  LAMP_DEFER_LN=0/1 overrides the default (benchmarking aid; results agree to fp32 rounding).
@@ -465,11 +466,11 @@ def layernorm(y: torch.Tensor, gamma, beta, eps: float, prec: int, *, add: Optio
     add_t, add_mod = (None, 0)
     if add is not None:
         add_t, add_mod = act_f32(add), (add.rows if add.bcast_rows else 0)
+    el_bytes = 4 + (4 if want_f32 else 0) + (0 if hi is None else (4 if lo is not None else 2))  # (no tensors in the lambda)
     STATS.call('layernorm', 1, nat.lib().lamp_layernorm,
                (y.data_ptr(), nat.ptr(add_t), add_mod, gamma.data_ptr(), beta.data_ptr(), float(eps), rows, D,
                 nat.ptr(out), nat.ptr(hi), nat.ptr(lo), nat.ptr(m_dev), nat.stream()),
-               nbytes=lambda m: (rows if m is None else min(rows, m)) * D *
-               (4 + (4 if want_f32 else 0) + (0 if hi is None else (4 if lo is not None else 2))), rows_dev=m_dev)
+               nbytes=lambda m: (rows if m is None else min(rows, m)) * D * el_bytes, rows_dev=m_dev)
     return Act(out, hi, lo, rows, D, 0, m_dev)
 
 
@@ -802,11 +803,11 @@ def embed(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb: torch.Tensor
     hi, lo = _empty_planes(rows, D, prec, seq.device)
     if pos_emb is not None:
         pos = pos.contiguous().long()
+    el_bytes = 4 + (4 if want_f32 else 0) + (4 if lo is not None else 2)
     STATS.call('embed', 1, nat.lib().lamp_embed,
                (seq.data_ptr(), nat.ptr(pos) if pos_emb is not None else None, word_emb.data_ptr(), nat.ptr(pos_emb),
                 rows, D, nat.ptr(out), hi.data_ptr(), nat.ptr(lo), nat.ptr(row_index), nat.ptr(m_dev), nat.stream()),
-               nbytes=lambda m: (rows if m is None else min(rows, m)) * D *
-               (4 + (4 if want_f32 else 0) + (4 if lo is not None else 2)), rows_dev=m_dev)
+               nbytes=lambda m: (rows if m is None else min(rows, m)) * D * el_bytes, rows_dev=m_dev)
     return Act(out, hi, lo, rows, D, 0, m_dev)
 
 

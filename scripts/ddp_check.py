@@ -62,13 +62,31 @@ def main():
         assert (q.grad is None) == (r.grad is None)
         if r.grad is not None:
             worst = max(worst, float((q.grad - r.grad).abs().max() / r.grad.abs().max().clamp_min(1e-20)))
+    # 3. the bucketed, backward-overlapped reducer (flat buffer, p.grad views): three steps vs single-process gradients
+    model2 = build(c, p, adj, dev).train()
+    plist = list(model2.get_trainable_parameters())
+    red = D.GradientReducer(plist, world=world, bucket_mb=0.25)
+    red.local_weight = (b - a) * world / c['B']
+    worst_red = 0.0
+    for step in range(3):
+        red.zero_grad()
+        lg, _, _ = model2((s_seq.to(dev), s_pos.to(dev)), None, None, None)
+        torch.nn.functional.binary_cross_entropy_with_logits(lg, s_gold).backward()
+        red.finish()
+        for q, r in zip(plist, ref.get_trainable_parameters()):
+            assert (q.grad is None) == (r.grad is None)
+            if r.grad is not None:
+                worst_red = max(worst_red, float((q.grad - r.grad).abs().max() / r.grad.abs().max().clamp_min(1e-20)))
+    worst = max(worst, worst_red)
+    red_stats = dict(red.stats)
     res = torch.tensor([float(fwd_equal), worst], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MIN if False else dist.ReduceOp.MAX)
     ok = torch.tensor([float(fwd_equal)], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f'ddp_check world={world}: forward shard == full rows: {bool(ok.item())}; flat all-reduce of {nel} grads, '
-              f'{n_none} params with grad None; max rel grad diff vs single process: {res[1].item():.2e}')
+              f'{n_none} params with grad None; max rel grad diff vs single process: {res[1].item():.2e}; '
+              f'GradientReducer (3 steps): {red_stats}')
         assert ok.item() == 1.0 and res[1].item() < 1e-4
     dist.destroy_process_group()
 

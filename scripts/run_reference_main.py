@@ -47,6 +47,7 @@ def main():
     ap.add_argument('--no-cuda', action='store_true', help='pass -no_cuda (CPU check of the reference arm)')
     ap.add_argument('--gpus', default=None, help='CUDA_VISIBLE_DEVICES for the child runs (default: inherit)')
     args = ap.parse_args()
+    args.out = os.path.abspath(args.out)   # the child runs chdir into the reference tree
     os.makedirs(args.out, exist_ok=True)
     ref = os.path.join(ROOT, 'baseline', '_ref')
     if not os.path.exists(os.path.join(ref, 'main.py')):
