@@ -213,8 +213,10 @@ def test_data_parallel_replicas_match_single_gpu(tmp_path):
         loss_fn(single(src, None, None, gold)[0], gold).backward()
         loss_fn(dp(src, None, None, gold)[0], gold).backward()
         for (n, a), (_, b) in zip(dp.module.named_parameters(), single.named_parameters()):
-            assert (a.grad is None) == (b.grad is None), n
-            if a.grad is not None:
+            if b.grad is None:
+                # dead parameters: DataParallel's Broadcast backward hands back zeros where a single GPU leaves None
+                assert a.grad is None or float(a.grad.abs().max()) == 0.0, n
+            else:
                 assert rel_err(a.grad, b.grad) < 1e-4, (it, n)
     # ... and the whole main.py epoch through DataParallel
     s, r = _run_main_epoch(tmp_path, 'dropin', gpus='0,1')
