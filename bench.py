@@ -254,15 +254,24 @@ def train_block(c, name, batch, steps, warmup, rank, world, dev, barrier, max_ov
     model = build_model(c, params, adj, dev).train()
     torch.manual_seed(1000 + rank)  # per-rank dropout streams
     seq, pos = src_seq.to(dev), src_pos.to(dev)
-    gold = (torch.rand(batch, c['L'], device=dev) < 0.03).float()
+    # label-id rows as train.py receives them (tgt[:, 1:]: ids + 4, EOS, PAD): the multi-hot targets are built on the
+    # device every step (ops.gold_binary, the kernel behind the drop-in utils.get_gold_binary), as train.py:34 does
+    from lamp_b200 import synthetic as syn
+    rows = syn.make_label_sets(c['L'], n_docs=batch, seed=700 + rank)
+    width = max(len(r) for r in rows) - 1
+    gold_rows = torch.zeros((batch, width), dtype=torch.int64)
+    for i, r in enumerate(rows):
+        gold_rows[i, :len(r) - 1] = torch.tensor(r[1:])
+    gold_rows = gold_rows.to(dev)
     plist = list(model.get_trainable_parameters())
     opt = torch.optim.Adam(plist, betas=(0.9, 0.98), lr=2e-4, fused=True)
     red = lds.GradientReducer(plist, world=world)
 
     def step():
         red.zero_grad()
+        gold = ops.gold_binary(gold_rows, c['L'])
         logits, _, _ = model((seq, pos), None, None, gold)
-        loss = F.binary_cross_entropy_with_logits(logits, gold)
+        loss = ops.bce_with_logits(logits, gold)   # value + gradient in one kernel (train.py:38)
         loss.backward()
         red.finish()
         opt.step()

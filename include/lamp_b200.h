@@ -210,6 +210,21 @@ int lamp_diag_proj(const float* x, const float* W, const float* bias, int64_t B,
 int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B, int L, int D, float* dx, float* dW,
                        float* dbias, void* stream);
 
+/* Device-side training targets (replaces the per-row CPU loop of utils/utils.py:205-216 `get_gold_binary`, called from
+ * train.py:34 and test.py:47): gold [B, W] int64 label ids (+`skip` = 4 special tokens), EOS-terminated, PAD = 0 padded.
+ * Per row: entries > 0 minus the LAST of them (the EOS) -> out[b, id - skip] = 1, everything else 0.  out [B, L] fp32 is
+ * written completely. */
+int lamp_gold_binary(const int64_t* gold, int64_t B, int W, int L, int skip, float* out, void* stream);
+
+/* F.binary_cross_entropy_with_logits(logits, target, reduction='mean') (train.py:38) and its gradient in ONE pass:
+ * *loss = mean(max(x,0) - x y + log1p(exp(-|x|))), dlogits = (sigmoid(x) - y) / n (dlogits may be NULL).  Deterministic
+ * (fixed-order block partials).  workspace: lamp_bce_logits_workspace_bytes() bytes, zeroed ONCE by the caller before
+ * the first use (the kernel re-arms it, so CUDA-graph replays can reuse it). */
+#define LAMP_BCE_MAX_BLOCKS 256
+size_t lamp_bce_logits_workspace_bytes(void);
+int lamp_bce_logits(const float* logits, const float* target, int64_t n, float* loss, float* dlogits, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- level 2: reference-shaped ops ----------- */
 
 /* ScaledDotProductAttention.forward (lamp/SubLayers.py:27-43), eval mode.

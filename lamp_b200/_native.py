@@ -52,6 +52,9 @@ _SIGNATURES = {
     'lamp_layernorm_bwd': ([_vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp], _i),
     'lamp_gemm_tn_acc': ([_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp], _i),
     'lamp_diag_proj_bwd': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp], _i),
+    'lamp_gold_binary': ([_vp, _i64, _i, _i, _i, _vp, _vp], _i),
+    'lamp_bce_logits_workspace_bytes': ([], _sz),
+    'lamp_bce_logits': ([_vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp], _i),
     'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp, _vp], _i),
     'lamp_embed': ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     'lamp_gather_rows': ([_vp, _vp, _i64, _i, _vp, _vp], _i),

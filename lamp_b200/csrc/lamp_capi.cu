@@ -916,6 +916,33 @@ int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B
   return LAMP_OK;
 }
 
+int lamp_gold_binary(const int64_t* gold, int64_t B, int W, int L, int skip, float* out, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(gold && out && B >= 0 && W > 0 && L > 0 && skip >= 0, "gold_binary: bad arguments");
+  if (B == 0) return LAMP_OK;
+  const long long blocks = (B * 32 + 255) / 256;
+  gold_binary_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(gold), B, W, L,
+                                                                         skip, out);
+  return launch_check();
+}
+
+size_t lamp_bce_logits_workspace_bytes(void) { return (LAMP_BCE_MAX_BLOCKS + 4) * sizeof(float); }
+
+int lamp_bce_logits(const float* logits, const float* target, int64_t n, float* loss, float* dlogits, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(logits && target && loss && workspace && n > 0, "bce_logits: bad arguments");
+  REQUIRE(workspace_bytes >= lamp_bce_logits_workspace_bytes() && aligned16(workspace), "bce_logits: workspace too small");
+  // workspace: [0] ticket counter (zero on first use: the caller clears the workspace ONCE; the kernel re-arms it),
+  // [4 ..] per-block partial sums
+  long long blocks = (n + BCE_THREADS * 4 - 1) / (BCE_THREADS * 4);
+  if (blocks > LAMP_BCE_MAX_BLOCKS) blocks = LAMP_BCE_MAX_BLOCKS;
+  float* ws = static_cast<float*>(workspace);
+  bce_logits_kernel<<<(unsigned)blocks, BCE_THREADS, 0, (cudaStream_t)stream>>>(
+      logits, target, n, 1.0f / static_cast<float>(n), dlogits, ws + 4, reinterpret_cast<unsigned int*>(ws), loss);
+  return launch_check();
+}
+
 #ifdef LAMP_ATTN_TRACE
 /* debug build only: copies the [64][64] clock64() stamps of CTA 0 of the last attention launch to the host */
 int lamp_debug_attn_trace(unsigned long long* out) {

@@ -237,4 +237,74 @@ __global__ void diag_proj_bwd_dw_kernel(const float* __restrict__ g, const float
   if (dbias != nullptr && threadIdx.x == 0) dbias[l] = gs;  // thread 0 always owns column 0: its gs is the full sum
 }
 
+// ---- device-side training targets and loss (train.py:34-38; utils/utils.py:205-216) --------------------------------
+// get_gold_binary: `gold` [B, W] int64 holds each document's label ids (+4 for the special tokens), terminated by EOS
+// and padded with PAD = 0.  Per row the reference keeps the entries > 0, DROPS THE LAST ONE of them (the EOS), sets
+// out[b, id] = 1 in a [B, L + 4] matrix and cuts its first `skip` = 4 columns.  One warp per row; `out` is fully
+// written (zeros included), so the caller does not clear it.  Ids whose column falls outside [0, L) are ignored.
+__global__ void gold_binary_kernel(const long long* __restrict__ gold, long long B, int W, int L, int skip,
+                                   float* __restrict__ out) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const long long* g = gold + row * W;
+  float* o = out + row * L;
+  for (int c = lane; c < L; c += 32) o[c] = 0.0f;
+  int last = -1;  // position of the last entry > 0
+  for (int j = lane; j < W; j += 32)
+    if (g[j] > 0) last = j;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, off));
+  __syncwarp();  // the zeros above are ordered before the ones below (same warp, same row)
+  for (int j = lane; j < W; j += 32) {
+    const long long id = g[j];
+    if (id > 0 && j != last) {
+      const long long c = id - skip;
+      if (c >= 0 && c < L) o[c] = 1.0f;
+    }
+  }
+}
+
+// F.binary_cross_entropy_with_logits(x, y, reduction='mean') and its gradient in one pass:
+//   loss = mean( max(x, 0) - x y + log(1 + exp(-|x|)) ),  dx = (sigmoid(x) - y) / n.
+// Deterministic: every block writes one partial sum, the LAST block to finish (ticket counter) adds them in index order.
+constexpr int BCE_THREADS = 256;
+__global__ void __launch_bounds__(BCE_THREADS)
+bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float inv_n,
+                  float* __restrict__ dx, float* __restrict__ partials, unsigned int* __restrict__ ticket,
+                  float* __restrict__ loss) {
+  __shared__ float red[BCE_THREADS / 32];
+  __shared__ bool is_last;
+  float s = 0.0f;
+  for (long long i = static_cast<long long>(blockIdx.x) * BCE_THREADS + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * BCE_THREADS) {
+    const float xv = x[i], yv = y[i];
+    const float e = __expf(-fabsf(xv));
+    s += fmaxf(xv, 0.0f) - xv * yv + log1pf(e);
+    if (dx != nullptr) {
+      const float sig = xv >= 0.0f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+      dx[i] = (sig - yv) * inv_n;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < BCE_THREADS / 32; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.0f;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile float*>(partials)[b];
+    *loss = t * inv_n;
+    *ticket = 0u;  // ready for the next launch (CUDA-graph replays reuse the workspace)
+  }
+}
+
 }  // namespace lamp

@@ -759,6 +759,56 @@ class DiagProjFunction(torch.autograd.Function):
         return dx, dW.to(W.dtype), (db.to(bias.dtype) if db is not None else None)
 
 
+def gold_binary(gold: torch.Tensor, n_labels: int, skip: int = 4) -> torch.Tensor:
+    """Device-side ``utils.get_gold_binary`` (utils/utils.py:205-216, called every step from train.py:34 / test.py:47):
+    ``gold`` [B, W] int64 label-id rows (ids offset by the 4 special tokens, EOS-terminated, PAD-padded) -> multi-hot
+    targets [B, n_labels] fp32 on the device, without the reference's per-row Python loop on the host."""
+    nat.require_cuda(gold)
+    gold = gold.contiguous().long()
+    B, W = gold.shape
+    out = torch.empty((B, n_labels), dtype=torch.float32, device=gold.device)
+    STATS.call('gold_binary', 1, nat.lib().lamp_gold_binary,
+               (gold.data_ptr(), B, W, n_labels, skip, out.data_ptr(), nat.stream()), nbytes=B * (W * 8 + n_labels * 4))
+    return out
+
+
+_BCE_WS: Dict[int, torch.Tensor] = {}  # per device: ticket + block partials, zeroed once (the kernel re-arms it)
+
+
+class BCEWithLogitsFunction(torch.autograd.Function):
+    """``F.binary_cross_entropy_with_logits(logits, target, reduction='mean')`` (train.py:38) with the gradient produced
+    in the same pass (``lamp_bce_logits``): one kernel instead of torch's forward + backward element-wise chains."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        nat.require_cuda(logits, target)
+        x = logits.contiguous().float()
+        y = target.contiguous().float()
+        dev = x.device
+        ws = _BCE_WS.get(dev.index)
+        if ws is None:
+            ws = _BCE_WS[dev.index] = torch.zeros(nat.lib().lamp_bce_logits_workspace_bytes() // 4, dtype=torch.float32,
+                                                  device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        STATS.call('bce_logits', 1, nat.lib().lamp_bce_logits,
+                   (x.data_ptr(), y.data_ptr(), x.numel(), loss.data_ptr(), nat.ptr(dx), ws.data_ptr(), ws.numel() * 4,
+                    nat.stream()), nbytes=x.numel() * 12)
+        ctx.save_for_backward(dx if dx is not None else x.new_empty(0))
+        ctx.shape = tuple(logits.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return (dx * g).view(ctx.shape) if dx.numel() else None, None
+
+
+def bce_with_logits(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Mean BCE-with-logits on the native kernel (loss + gradient in one pass); same value as torch's."""
+    return BCEWithLogitsFunction.apply(logits, target)
+
+
 _WARNED: set = set()
 
 

@@ -43,3 +43,21 @@ def get_attn_subsequent_mask(seq):
 def swap_0_1(tensor, on_zero, on_non_zero):
     """Elementwise: zeros -> ``on_zero``, everything else -> ``on_non_zero`` -- lamp/utils.py:46-50."""
     return torch.where(tensor == 0, torch.full_like(tensor, on_zero), torch.full_like(tensor, on_non_zero))
+
+
+def get_gold_binary(gold, tgt_vocab_size):
+    """Drop-in for ``utils.utils.get_gold_binary`` (utils/utils.py:205-216; train.py:34, test.py:47) that builds the
+    multi-hot target matrix ON THE DEVICE with one kernel instead of a per-row Python loop on the host.  ``gold`` may be
+    the CPU copy the reference's loops pass (``gold.data.cpu()``) or a CUDA tensor; the result is a CUDA tensor, so the
+    ``.cuda()`` the reference appends is a no-op.  Without a CUDA device the reference semantics run on the host."""
+    import torch
+    if torch.cuda.is_available():
+        from . import ops
+        g = gold if gold.is_cuda else gold.cuda(non_blocking=True)
+        return ops.gold_binary(g, tgt_vocab_size)
+    out = torch.zeros(gold.size(0), tgt_vocab_size + 4)
+    for i in range(gold.size(0)):
+        idx = gold[i][gold[i] > 0][0:-1]
+        if len(idx) > 0:
+            out[i].index_fill_(0, idx, 1)
+    return out[:, 4:]

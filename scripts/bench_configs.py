@@ -9,7 +9,11 @@ For each: U1 = label<-label attention core (Q,K,V -> O), U2 = one self-attention
 GraphDecoder stack over T=300 token encodings (random enc_output, padded lengths U{T/3..T}).  Per unit: samples/s and
 the algorithmic GB/s and TFLOP/s of SURVEY.md 8d next to the measured peaks, naming the binding roofline.
 CUDA events, inputs resident, >= 3 warm-ups; one JSON line per (config, unit).
-usage: python scripts/bench_configs.py [cfg2] [cfg3] [cfg4] [cfg5] [--iters N]"""
+usage: python scripts/bench_configs.py [cfg2] [cfg3] [cfg4] [cfg5] [--iters N]
+Multi-GPU (BASELINE cfg-4 "batch-sharded 4xB200", cfg-5 "8xB200 sweep"): launch under torchrun, one rank per GPU --
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/bench_configs.py cfg5
+every rank runs the same per-GPU batch on its own shard (weights and label graph replicated, no forward collective:
+weak scaling), times are the max over ranks between barriers, rank 0 prints whole-job samples/s and per-GPU rooflines."""
 import json
 import os
 import sys
@@ -28,6 +32,14 @@ from lamp_b200 import synthetic as syn  # noqa: E402
 from lamp_b200.Decoders import GraphDecoder  # noqa: E402
 from lamp_b200.SubLayers import MultiHeadAttention  # noqa: E402
 
+RANK = int(os.environ.get('RANK', '0'))
+WORLD = int(os.environ.get('WORLD_SIZE', '1'))
+LOCAL_RANK = int(os.environ.get('LOCAL_RANK', '0'))
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+torch.cuda.set_device(LOCAL_RANK)
+if WORLD > 1:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=torch.device('cuda', LOCAL_RANK))
 DEV = 'cuda'
 
 
@@ -42,14 +54,23 @@ def peaks():
 def timeit(fn, iters, warm=3):
     for _ in range(warm):
         fn()
+    if WORLD > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
         fn()
     e1.record()
+    if WORLD > 1:
+        dist.barrier()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e-3
+    ms = e0.elapsed_time(e1)
+    if WORLD > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=DEV)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / iters * 1e-3
 
 
 def report(cfg, unit, B, sec, flops, nbytes, extra=None):
@@ -57,12 +78,14 @@ def report(cfg, unit, B, sec, flops, nbytes, extra=None):
     gbs, tfs = nbytes / sec / 1e9, flops / sec / 1e12
     t_hbm, t_tensor = nbytes / (hbm * 1e9), flops / (tf * 1e12)
     bound = 'hbm' if t_hbm >= t_tensor else 'tensor'
-    line = dict(config=cfg, unit=unit, batch=B, ms=sec * 1e3, samples_per_s=B / sec, alg_gbs=gbs, alg_tflops=tfs,
+    line = dict(config=cfg, unit=unit, n_gpus=WORLD, batch_per_gpu=B, ms=sec * 1e3, samples_per_s=B * WORLD / sec,
+                per_gpu=True, alg_gbs=gbs, alg_tflops=tfs,
                 frac_hbm=gbs / hbm, frac_tensor_bf16=tfs / tf, binding=bound,
                 frac_of_binding=(gbs / hbm if bound == 'hbm' else tfs / tf), peaks=dict(hbm_gbs=hbm, bf16_tflops=tf, src=src))
     if extra:
         line.update(extra)
-    print(json.dumps(line), flush=True)
+    if RANK == 0:
+        print(json.dumps(line), flush=True)
 
 
 def run_config(name, L, D, H, n_layers, mask_kind, prec_name, B, T=300, d_inner=None, iters=10, units=('U1', 'U2', 'U3')):
@@ -71,7 +94,7 @@ def run_config(name, L, D, H, n_layers, mask_kind, prec_name, B, T=300, d_inner=
     prec = nat.PREC_FP32 if prec_name == 'fp32' else nat.PREC_BF16
     e = 4 if prec_name == 'fp32' else 2   # bytes per element of the operand form (plane pair / bf16)
     lamp_b200.set_default_precision(prec_name)
-    rs = np.random.RandomState(1)
+    rs = np.random.RandomState(1 + RANK)
     adj = cases.label_adj('prior', L, 1) if mask_kind == 'prior' else None
     cfg = f'{name} L={L} D={D} H={H} mask={mask_kind} {prec_name}'
     try:
@@ -92,7 +115,7 @@ def run_config(name, L, D, H, n_layers, mask_kind, prec_name, B, T=300, d_inner=
             by = B * 2.0 * L * D * e + 4.0 * D * D * e
             report(cfg, 'U2 MultiHeadAttention (self)', B, sec, fl, by)
         if 'U3' in units:
-            src_seq, _ = syn.make_tokens(B, T, 1000, 2, min_len=T // 3)
+            src_seq, _ = syn.make_tokens(B, T, 1000, 2 + RANK, min_len=T // 3)
             src_seq = src_seq.to(DEV)
             enc = torch.randn(B, T, D, device=DEV)
             keys = int((src_seq != 0).sum().item())
@@ -114,7 +137,7 @@ if __name__ == '__main__':
     args = [a for a in sys.argv[1:] if not a.startswith('--')]
     iters = int(sys.argv[sys.argv.index('--iters') + 1]) if '--iters' in sys.argv else 10
     what = args or ['cfg2', 'cfg3', 'cfg4', 'cfg5']
-    torch.manual_seed(0)
+    torch.manual_seed(RANK)
     if 'cfg2' in what:
         for B in (32, 1024, 8192):
             run_config('cfg-2', 103, 512, 4, 2, 'prior', 'fp32', B, iters=iters, units=('U1', 'U2') if B == 8192 else ('U1', 'U2', 'U3'))
@@ -125,3 +148,5 @@ if __name__ == '__main__':
     if 'cfg5' in what:
         for L in (512, 1024, 2048, 4096):
             run_config('cfg-5', L, 1024, 16, 2, 'none', 'bf16', max(4, 16384 // L), iters=max(3, iters // 2))
+    if WORLD > 1:
+        dist.destroy_process_group()

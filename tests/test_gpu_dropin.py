@@ -222,3 +222,48 @@ def test_data_parallel_replicas_match_single_gpu(tmp_path):
     s, r = _run_main_epoch(tmp_path, 'dropin', gpus='0,1')
     assert s['dropin']['returncode'] == 0 and s['dropin']['data_parallel'], s['dropin'].get('error_tail')
     assert np.isfinite(s['dropin']['testing_bce_per_doc'])
+
+
+def _gold_rows(B, W, L, seed):
+    """Rows as the reference loader builds them after `tgt[:, 1:]`: label ids + 4, then EOS = 3, then PAD = 0."""
+    rs = np.random.RandomState(seed)
+    g = np.zeros((B, W), dtype=np.int64)
+    for b in range(B):
+        k = rs.randint(0, min(W - 1, 6) + 1)
+        labs = rs.choice(L, size=k, replace=False) + 4
+        g[b, :k] = labs
+        g[b, k] = 3
+    g[0, :] = 0                       # a row with nothing at all
+    g[1, :] = 0
+    g[1, 0] = 3                       # only the EOS
+    g[2, :3] = [7, 7, 3]              # a repeated label
+    return torch.from_numpy(g)
+
+
+def test_gold_binary_kernel_matches_reference_loop():
+    """utils/utils.py:205-216 restated inline (entries > 0, minus the last one, index_fill, drop 4 columns)."""
+    for (B, W, L) in ((37, 9, 103), (5, 40, 12), (300, 64, 983)):
+        gold = _gold_rows(B, W, L, seed=B)
+        want = torch.zeros(B, L + 4)
+        for i in range(B):
+            idx = gold[i][gold[i] > 0][0:-1]
+            if len(idx) > 0:
+                want[i].index_fill_(0, idx, 1)
+        want = want[:, 4:]
+        got = ops.gold_binary(gold.to(DEV), L)
+        assert got.shape == (B, L) and torch.equal(got.cpu(), want), (B, W, L)
+        assert torch.equal(lamp_b200.utils.get_gold_binary(gold, L).cpu(), want)   # the drop-in entry point (CPU input)
+
+
+def test_bce_with_logits_kernel_matches_torch_value_and_gradient():
+    g = torch.Generator().manual_seed(5)
+    for shape in ((32, 103), (256, 103), (7, 983), (1100, 103)):
+        x = (torch.randn(shape, generator=g) * 4).to(DEV).requires_grad_(True)
+        y = (torch.rand(shape, generator=g) < 0.1).float().to(DEV)
+        want = torch.nn.functional.binary_cross_entropy_with_logits(x.double(), y.double())
+        (gw,) = torch.autograd.grad(want, x)
+        for _ in range(2):   # second call: the ticket counter was re-armed by the kernel
+            got = ops.bce_with_logits(x, y)
+            (gg,) = torch.autograd.grad(got * 3.0, x)
+            assert abs(float(got) - float(want)) < 1e-6 * max(1.0, abs(float(want))), shape
+            assert rel_err(gg, gw * 3.0) < 1e-5, shape

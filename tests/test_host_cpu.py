@@ -303,3 +303,41 @@ def test_bench_reference_arm_contract():
     assert d['cpu_baseline']['kind'] == ('reference' if have_ref else 'port')
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config']
+
+
+def test_get_gold_binary_host_semantics_equal_the_reference():
+    """lamp_b200.utils.get_gold_binary (device kernel on a GPU box; this host restatement elsewhere) against the
+    reference's own utils.utils.get_gold_binary (utils/utils.py:205-216) on rows incl. empty / EOS-only ones."""
+    import importlib
+    import numpy as np
+    ref = None
+    for d in (os.path.join(ROOT, 'baseline', '_ref'), '/root/reference'):
+        if os.path.exists(os.path.join(d, 'utils', 'utils.py')):
+            ref = d
+            break
+    if ref is None:
+        pytest.skip('reference tree not present')
+    if torch.cuda.is_available():
+        pytest.skip('host semantics are exercised on the GPU-less container; the GPU suite checks the kernel')
+    sys.path.insert(0, ref)
+    try:
+        for m in [k for k in sys.modules if k == 'utils' or k.startswith('utils.')]:
+            del sys.modules[m]
+        ru = importlib.import_module('utils.utils')
+        from lamp_b200 import utils as lu
+        rs = np.random.RandomState(0)
+        B, W, L = 24, 9, 30
+        g = np.zeros((B, W), dtype=np.int64)
+        for b in range(B):
+            k = rs.randint(0, 6)
+            g[b, :k] = rs.choice(L, size=k, replace=False) + 4
+            g[b, k] = 3
+        g[0, :] = 0
+        g[1, :] = 0
+        g[1, 0] = 3
+        g = torch.from_numpy(g)
+        assert torch.equal(ru.get_gold_binary(g, L), lu.get_gold_binary(g, L))
+    finally:
+        sys.path.remove(ref)
+        for m in [k for k in sys.modules if k == 'utils' or k.startswith('utils.')]:
+            del sys.modules[m]
