@@ -210,6 +210,46 @@ int lamp_diag_proj(const float* x, const float* W, const float* bias, int64_t B,
 int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B, int L, int D, float* dx, float* dW,
                        float* dbias, void* stream);
 
+/* ---- fused training sub-layers (second pass): everything stays in the projection GEMMs' layouts ---- */
+
+/* Training forward of the attention core (lamp/SubLayers.py:27-43 with the dropout of :40 inside the kernel) on operand
+ * planes: like lamp_attn_core_planes plus p_drop / seed (+ optional device-side counter added to the seed, so CUDA-graph
+ * replays draw fresh masks), and the probability tensors the backward consumes: attn [H*B, Lq, Lk] (after dropout; the
+ * reference's return value, head-major) and probs_pre (before dropout; NULL iff p_drop == 0).  row_max / row_sum:
+ * [H*B*Lq] scratch. */
+int lamp_attn_core_planes_train(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast, const void* kv_hi,
+                                const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H, int Lq, int Lk, int d,
+                                float temperature, int precision, const uint8_t* mask, int64_t msb, int64_t msq,
+                                int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* row_max, float* row_sum,
+                                float* attn, float* probs_pre, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                                void* stream);
+
+/* Backward of the attention core with every operand in place: Q / K / V / dO / O are split-bf16 planes, head h = column
+ * slice [col0 + h*d, col0 + (h+1)*d) of a [B*L, ld] matrix (dO and O: [B*Lq, ldo], col0 = 0); P / A: the fp32 head-major
+ * [H*B, Lq, Lk] tensors of the training forward (A may be NULL or == P without dropout).  dQ -> planes [B*Lq, lddq] at
+ * dq_col0 + h*d; dK / dV -> planes [B*Lk, lddkv] at dk_col0 / dv_col0 + h*d.  Four batched tcgen05 products around one
+ * element-wise kernel; no permute / contiguous copies, no fp32 round trips. */
+size_t lamp_attn_bwd_planes_workspace_bytes(int B, int H, int Lq, int Lk);
+int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, const void* kv_hi, const void* kv_lo,
+                         int64_t ldkv, int k_col0, int v_col0, const void* do_hi, const void* do_lo, const void* o_hi,
+                         const void* o_lo, int64_t ldo, const float* P, const float* A, void* dq_hi, void* dq_lo,
+                         int64_t lddq, int dq_col0, void* dkv_hi, void* dkv_lo, int64_t lddkv, int dk_col0, int dv_col0,
+                         int B, int H, int Lq, int Lk, int d, float temperature, float p_drop, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* y = dropout(y0) + x (lamp/SubLayers.py:113-119 / :139-141): keep(row, col) is a counter hash of (seed [+ *seed_dev],
+ * row, col), kept values are scaled by 1/(1-p); x row index is row % x_mod when x_mod > 0 (broadcast residual). */
+int lamp_dropout_add(const float* y0, const float* x, int64_t rows, int D, int x_mod, float p_drop, uint64_t seed,
+                     const uint64_t* seed_dev, float* y, void* stream);
+
+/* planes(dropout-backward(dy)): the same mask recomputed, result written as split-bf16 planes [rows, D] (p_drop == 0: a
+ * plain split). */
+int lamp_dropout_split(const float* dy, int64_t rows, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                       void* hi, void* lo, void* stream);
+
+/* ReLU backward on operand planes, in place: g = 0 where the forward activation (its hi plane) is <= 0.  n % 8 == 0. */
+int lamp_relu_mask_planes(void* g_hi, void* g_lo, const void* h_hi, int64_t n, void* stream);
+
 /* Device-side training targets (replaces the per-row CPU loop of utils/utils.py:205-216 `get_gold_binary`, called from
  * train.py:34 and test.py:47): gold [B, W] int64 label ids (+`skip` = 4 special tokens), EOS-terminated, PAD = 0 padded.
  * Per row: entries > 0 minus the LAST of them (the EOS) -> out[b, id - skip] = 1, everything else 0.  out [B, L] fp32 is

@@ -128,7 +128,15 @@ class MultiHeadAttention(nn.Module):
         self._wp = ops.WeightPlanes()
 
     # ------------------------------------------------------------------ composed (autograd) path
+    def _fused_train_ok(self, q, k, v) -> bool:
+        return (ops.FUSED_TRAINING and ops.NATIVE_TRAINING and ops.NATIVE_ATTENTION_BACKWARD and k is v and self.fused_ok()
+                and self.n_head > 1 and q.is_cuda and q.dtype == torch.float32 and k.dtype == torch.float32
+                and q.dim() == 3 and self._prec() == nat.PREC_FP32 and q.numel() > 0 and k.numel() > 0)
+
     def _composed(self, q, k, v, attn_mask):
+        if self._fused_train_ok(q, k, v):
+            # one autograd node for the whole sub-layer, everything in the tensor-core operand layouts (ops.MHATrainFunction)
+            return ops.mha_train(q, None if k is q else k, attn_mask, self)
         d_k, d_v, n_head = self.d_k, self.d_v, self.n_head
         sz_b, len_q, _ = q.size()
         len_k, len_v = k.size(1), v.size(1)
@@ -236,6 +244,10 @@ class PositionwiseFeedForward(nn.Module):
         self._wp = ops.WeightPlanes()
 
     def _composed(self, x):
+        prec = ops.default_precision() if self.precision is None else self.precision
+        if (ops.FUSED_TRAINING and ops.NATIVE_TRAINING and self.fused_ok() and x.is_cuda and x.dtype == torch.float32
+                and x.numel() > 0 and prec == nat.PREC_FP32):
+            return ops.ffn_train(x, self)   # one autograd node for the whole sub-layer (ops.FFNTrainFunction)
         # Conv1d(k=1) == per-position linear map; F.linear keeps the training path in true fp32 (cuDNN convolutions
         # default to TF32, which would put 1e-3-level noise into the gradients)
         h = F.relu(ops.linear_train(x, self.w_1.weight, self.w_1.bias))

@@ -52,6 +52,14 @@ _SIGNATURES = {
     'lamp_layernorm_bwd': ([_vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp], _i),
     'lamp_gemm_tn_acc': ([_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp], _i),
     'lamp_diag_proj_bwd': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp], _i),
+    'lamp_attn_core_planes_train': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,
+                                     _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f, C.c_uint64, _vp, _vp], _i),
+    'lamp_attn_bwd_planes_workspace_bytes': ([_i, _i, _i, _i], _sz),
+    'lamp_attn_bwd_planes': ([_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
+                              _i64, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _sz, _vp], _i),
+    'lamp_dropout_add': ([_vp, _vp, _i64, _i, _i, _f, C.c_uint64, _vp, _vp, _vp], _i),
+    'lamp_dropout_split': ([_vp, _i64, _i, _f, C.c_uint64, _vp, _vp, _vp, _vp], _i),
+    'lamp_relu_mask_planes': ([_vp, _vp, _vp, _i64, _vp], _i),
     'lamp_gold_binary': ([_vp, _i64, _i, _i, _i, _vp, _vp], _i),
     'lamp_bce_logits_workspace_bytes': ([], _sz),
     'lamp_bce_logits': ([_vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp], _i),

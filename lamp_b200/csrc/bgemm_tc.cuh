@@ -1,6 +1,9 @@
 // Batched small GEMM on tcgen05 for the attention backward:  C_b[M, N] = opA(A_b) opB(B_b)  for b < batch, every
-// operand given as split-bf16 planes read in place by 3-D TMA maps {cols, rows, batch} (rows beyond the per-batch
-// bound are zero-filled, so ragged label counts need no padding).  Each operand is either K-major (the contraction
+// operand given as split-bf16 planes read in place by 4-D TMA maps {cols, rows, head, sample} (rows beyond the
+// per-batch bound are zero-filled, so ragged label counts need no padding).  The batch index is two-level,
+// batch = sample * H + head, with independent element strides for the two coordinates: the same kernel reads
+// head-major [H*B, L, d] tensors (the reference's attention layout) and head COLUMN SLICES of the [B*L, H*d] plane
+// matrices the projection GEMMs produce / consume -- so the training path needs no permute / contiguous copies.  Each operand is either K-major (the contraction
 // index is the contiguous one: [rows = M or N, cols = Kc]) or MN-major ([rows = Kc, cols = M or N]) -- the four
 // products of the backward differ only in that:
 //     dA = dO V^T     (A: dO K-major,  B: V  K-major)         dQ = dS K      (A: dS K-major,  B: K  MN-major)
@@ -25,10 +28,12 @@ __host__ __device__ constexpr uint32_t bg_smem_bytes(int npl, int tn) {
 }
 
 struct BgemmParams {
-  int batch, M, N, Kc;
-  float scale;      // C = scale * (A B)
-  float* C;         // [batch, M, ldc] fp32
-  long long ldc, stride_c;
+  int batch, H, M, N, Kc;   // batch = samples * H; item -> (sample = batch / H, head = batch % H)
+  float scale;              // C = scale * (A B)
+  float* C;                 // fp32 output (nullable): element (sample, head, m, n) at C[sample*stride_c + head*stride_ch + m*ldc + n]
+  __nv_bfloat16* C_hi;      // split-bf16 plane output (nullable), same indexing
+  __nv_bfloat16* C_lo;
+  long long ldc, stride_c, stride_ch;
 };
 
 template <bool A_MN, bool B_MN, int NTERMS, int TN>
@@ -91,7 +96,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (long long item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int b = static_cast<int>(item / per_batch), tile = static_cast<int>(item % per_batch);
+        const int bh = static_cast<int>(item / per_batch), tile = static_cast<int>(item % per_batch);
+        const int b = bh / p.H, h = bh % p.H;
         const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * TN;
         for (int it = 0; it < num_it; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -100,15 +106,15 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           for (int pl = 0; pl < NPL; ++pl) {
             const CUtensorMap* ta = pl ? &tmA_lo : &tmA_hi;
             const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
-            if (A_MN) {  // map {M cols, Kc rows, batch}, boxes {64, 64}
-              for (int bx = 0; bx < 2; ++bx) tma_load_3d(a_tile(stage, pl) + bx * BOX, ta, &full_bar[stage], m0 + 64 * bx, kc0, b);
-            } else {     // map {Kc cols, M rows, batch}, box {64, 128}
-              tma_load_3d(a_tile(stage, pl), ta, &full_bar[stage], kc0, m0, b);
+            if (A_MN) {  // map {M cols, Kc rows, head, sample}, boxes {64, 64}
+              for (int bx = 0; bx < 2; ++bx) tma_load_4d(a_tile(stage, pl) + bx * BOX, ta, &full_bar[stage], m0 + 64 * bx, kc0, h, b);
+            } else {     // map {Kc cols, M rows, head, sample}, box {64, 128}
+              tma_load_4d(a_tile(stage, pl), ta, &full_bar[stage], kc0, m0, h, b);
             }
             if (B_MN) {
-              for (int bx = 0; bx < TN / 64; ++bx) tma_load_3d(b_tile(stage, pl) + bx * BOX, tb, &full_bar[stage], n0 + 64 * bx, kc0, b);
+              for (int bx = 0; bx < TN / 64; ++bx) tma_load_4d(b_tile(stage, pl) + bx * BOX, tb, &full_bar[stage], n0 + 64 * bx, kc0, h, b);
             } else {
-              tma_load_3d(b_tile(stage, pl), tb, &full_bar[stage], kc0, n0, b);
+              tma_load_4d(b_tile(stage, pl), tb, &full_bar[stage], kc0, n0, h, b);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -153,18 +159,18 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int wq = warp & 3;
     uint32_t t = 0;
     for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
-      const int b = static_cast<int>(item / per_batch), tile = static_cast<int>(item % per_batch);
+      const int bh = static_cast<int>(item / per_batch), tile = static_cast<int>(item % per_batch);
+      const int b = bh / p.H, h = bh % p.H;
       const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * TN;
       const uint32_t acc = t & 1, use = t >> 1;
-      const int m = m0 + wq * 32 + lane;
       mbar_wait(&acc_full[acc], use & 1);
       tcgen05_fence_after();
       // registers (lane == row) -> per-warp smem chunk -> row-contiguous global stores: every store instruction writes
-      // one 128 B segment of one output row (lane == column) instead of 32 scattered words
+      // one contiguous segment of one output row (lane == column) instead of 32 scattered words
       float* stg = epi_stage + (warp - 2) * (32 * 33);
-      float* base = p.C + static_cast<long long>(b) * p.stride_c + static_cast<long long>(m0 + wq * 32) * p.ldc + n0;
+      const long long off0 = static_cast<long long>(b) * p.stride_c + static_cast<long long>(h) * p.stride_ch +
+                             static_cast<long long>(m0 + wq * 32) * p.ldc + n0;
       const int rows_valid = p.M - (m0 + wq * 32);  // rows of this warp's 32 that exist
-      (void)m;
       for (int c0 = 0; c0 < TN; c0 += 32) {
         if (n0 + c0 >= p.N) break;
         uint32_t r[32];
@@ -174,8 +180,21 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         for (int e = 0; e < 32; ++e) stg[lane * 33 + e] = __uint_as_float(r[e]) * p.scale;
         __syncwarp();
         const bool col_ok = n0 + c0 + lane < p.N;
-        for (int rr = 0; rr < 32; ++rr)
-          if (rr < rows_valid && col_ok) base[static_cast<long long>(rr) * p.ldc + c0 + lane] = stg[rr * 33 + lane];
+        if (p.C != nullptr) {
+          float* base = p.C + off0;
+          for (int rr = 0; rr < 32; ++rr)
+            if (rr < rows_valid && col_ok) base[static_cast<long long>(rr) * p.ldc + c0 + lane] = stg[rr * 33 + lane];
+        }
+        if (p.C_hi != nullptr) {
+          for (int rr = 0; rr < 32; ++rr)
+            if (rr < rows_valid && col_ok) {
+              const float v = stg[rr * 33 + lane];
+              const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+              const long long o = off0 + static_cast<long long>(rr) * p.ldc + c0 + lane;
+              p.C_hi[o] = hi;
+              if (p.C_lo != nullptr) p.C_lo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
+            }
+        }
         __syncwarp();
       }
       tcgen05_fence_before();
@@ -216,6 +235,50 @@ __global__ void attn_bwd_ds_kernel(const float* __restrict__ dA, const float* __
     const __nv_bfloat16 h = __float2bfloat16_rn(ds);
     dS_hi[row * ld + c] = h;
     dS_lo[row * ld + c] = __float2bfloat16_rn(ds - __bfloat162float(h));
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a);
+    A_hi[row * ld + c] = ah;
+    A_lo[row * ld + c] = __float2bfloat16_rn(a - __bfloat162float(ah));
+  }
+}
+
+// The same for the training path that keeps everything in the projection GEMMs' layouts: dO and O are split-bf16 planes
+// [B*Lq, ld_o] whose head h lives in columns [h*d, (h+1)*d); P / A / dA stay head-major [H*B, Lq, Lk] (row index
+// (h*B + b)*Lq + i), which is also the layout of the dS / A planes written here.
+__global__ void attn_bwd_ds_planes_kernel(const float* __restrict__ dA, const float* __restrict__ P,
+                                          const float* __restrict__ A, const __nv_bfloat16* __restrict__ dO_hi,
+                                          const __nv_bfloat16* __restrict__ dO_lo, const __nv_bfloat16* __restrict__ O_hi,
+                                          const __nv_bfloat16* __restrict__ O_lo, long long ld_o, int B, int H, int Lq,
+                                          int Lk, int d, int ld, float inv_temp, float drop_scale,
+                                          __nv_bfloat16* __restrict__ dS_hi, __nv_bfloat16* __restrict__ dS_lo,
+                                          __nv_bfloat16* __restrict__ A_hi, __nv_bfloat16* __restrict__ A_lo) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = static_cast<long long>(H) * B * Lq;
+  if (row >= rows) return;
+  const int i = static_cast<int>(row % Lq);
+  const long long n = row / Lq;
+  const int b = static_cast<int>(n % B), h = static_cast<int>(n / B);
+  const long long orow = (static_cast<long long>(b) * Lq + i) * ld_o + static_cast<long long>(h) * d;
+  float delta = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    float g = __bfloat162float(dO_hi[orow + c]), o = __bfloat162float(O_hi[orow + c]);
+    if (dO_lo != nullptr) g += __bfloat162float(dO_lo[orow + c]);
+    if (O_lo != nullptr) o += __bfloat162float(O_lo[orow + c]);
+    delta = fmaf(g, o, delta);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xFFFFFFFFu, delta, o);
+  for (int c = lane; c < ld; c += 32) {
+    float ds = 0.f, a = 0.f;
+    if (c < Lk) {
+      const long long g = row * Lk + c;
+      a = A[g];
+      const float keep = (a != 0.0f) ? drop_scale : 0.0f;
+      ds = P[g] * (dA[g] * keep - delta) * inv_temp;
+    }
+    const __nv_bfloat16 hh = __float2bfloat16_rn(ds);
+    dS_hi[row * ld + c] = hh;
+    dS_lo[row * ld + c] = __float2bfloat16_rn(ds - __bfloat162float(hh));
     const __nv_bfloat16 ah = __float2bfloat16_rn(a);
     A_hi[row * ld + c] = ah;
     A_lo[row * ld + c] = __float2bfloat16_rn(a - __bfloat162float(ah));

@@ -97,6 +97,28 @@ inline int current_device() {
   return dev;
 }
 
+// bf16 tensor viewed as {cols, rows, heads, samples} with independent element strides for rows / heads / samples;
+// box = {64 cols, box_rows, 1, 1}, 128B swizzle, zero OOB fill.  Used by the batched attention-backward products, whose
+// operands are either head-major [H*B, L, d] tensors or head column slices of [B*L, H*d] plane matrices.
+int make_tmap4(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t heads, uint64_t samples,
+               uint64_t ld_elems, uint64_t head_stride, uint64_t sample_stride, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!aligned16(base)) return fail(LAMP_EINVAL, "TMA base pointer not 16-byte aligned");
+  if ((ld_elems * 2) % 16 != 0 || (head_stride * 2) % 16 != 0 || (sample_stride * 2) % 16 != 0)
+    return fail(LAMP_EINVAL, "TMA strides (%llu, %llu, %llu elements) must be multiples of 8 elements",
+                (unsigned long long)ld_elems, (unsigned long long)head_stride, (unsigned long long)sample_stride);
+  cuuint64_t dims[4] = {cols, rows, heads, samples};
+  cuuint64_t strides[3] = {ld_elems * 2, head_stride * 2, sample_stride * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled (4-D) failed with CUresult %d", (int)r);
+  return LAMP_OK;
+}
+
 int sm_count_cached() {
   static std::atomic<int> n[kMaxDevices];
   const int dev = current_device();
@@ -715,23 +737,53 @@ AttnBwdPlan attn_bwd_plan(int N, int Lq, int Lk, int d) {
   return pl;
 }
 
+// One operand of a batched product: planes + (cols, rows) of ONE (sample, head) matrix and the element strides of the
+// row / head / sample coordinates.
+struct BgOperand {
+  const void* hi;
+  const void* lo;
+  uint64_t cols, rows, ld, head_stride, sample_stride;
+};
+// head-major contiguous [N, rows, ld] tensor: N plain batches (H = 1)
+inline BgOperand bg_headmajor(const void* hi, const void* lo, uint64_t cols, uint64_t rows, uint64_t ld) {
+  return BgOperand{hi, lo, cols, rows, ld, rows * ld, rows * ld};
+}
+// head column slice of a [B*rows, ld] plane matrix: head h at column col0 + h*d
+inline BgOperand bg_slices(const void* hi, const void* lo, uint64_t col0, uint64_t d, uint64_t rows, uint64_t ld) {
+  return BgOperand{static_cast<const __nv_bfloat16*>(hi) + col0,
+                   lo ? static_cast<const void*>(static_cast<const __nv_bfloat16*>(lo) + col0) : nullptr, d, rows, ld, d,
+                   rows * ld};
+}
+
+// C (fp32 and/or planes): element (sample, head, m, n) at [sample*stride_c + head*stride_ch + m*ldc + n]
+struct BgOutput {
+  float* f32;
+  void* hi;
+  void* lo;
+  long long ldc, stride_c, stride_ch;
+};
+
 template <bool A_MN, bool B_MN>
-int launch_bgemm(const void* a_hi, const void* a_lo, uint64_t a_cols, uint64_t a_rows, uint64_t a_ld, const void* b_hi,
-                 const void* b_lo, uint64_t b_cols, uint64_t b_rows, uint64_t b_ld, int batch, int M, int N, int Kc,
-                 float scale, float* C, long long ldc, long long stride_c, cudaStream_t st) {
+int launch_bgemm(const BgOperand& a, const BgOperand& b, int samples, int H, int M, int N, int Kc, float scale,
+                 const BgOutput& c, cudaStream_t st) {
   constexpr int TN = 128;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const uint32_t a_box_rows = A_MN ? 64 : 128, b_box_rows = B_MN ? 64 : TN;
-  if (int rc = make_tmap(&ta_hi, a_hi, a_cols, a_rows, (uint64_t)batch, a_ld, a_box_rows, true)) return rc;
-  if (int rc = make_tmap(&ta_lo, a_lo, a_cols, a_rows, (uint64_t)batch, a_ld, a_box_rows, true)) return rc;
-  if (int rc = make_tmap(&tb_hi, b_hi, b_cols, b_rows, (uint64_t)batch, b_ld, b_box_rows, true)) return rc;
-  if (int rc = make_tmap(&tb_lo, b_lo, b_cols, b_rows, (uint64_t)batch, b_ld, b_box_rows, true)) return rc;
+  auto mk = [&](CUtensorMap* m, const void* base, const BgOperand& o, uint32_t box_rows) {
+    return make_tmap4(m, base, o.cols, o.rows, (uint64_t)H, (uint64_t)samples, o.ld, o.head_stride, o.sample_stride, box_rows);
+  };
+  if (int rc = mk(&ta_hi, a.hi, a, a_box_rows)) return rc;
+  if (int rc = mk(&ta_lo, a.lo ? a.lo : a.hi, a, a_box_rows)) return rc;
+  if (int rc = mk(&tb_hi, b.hi, b, b_box_rows)) return rc;
+  if (int rc = mk(&tb_lo, b.lo ? b.lo : b.hi, b, b_box_rows)) return rc;
   auto kernel = bgemm_tc_kernel<A_MN, B_MN, 3, TN>;
   static PerDeviceOnce once;
   if (int once_rc = per_device_once(once, [kernel] { int rc_ = set_smem(kernel, bg_smem_bytes(2, TN)); return rc_; })) return once_rc;
   BgemmParams p;
-  p.batch = batch; p.M = M; p.N = N; p.Kc = Kc; p.scale = scale; p.C = C; p.ldc = ldc; p.stride_c = stride_c;
-  const long long items = (long long)batch * ((M + 127) / 128) * ((N + TN - 1) / TN);
+  p.batch = samples * H; p.H = H; p.M = M; p.N = N; p.Kc = Kc; p.scale = scale;
+  p.C = c.f32; p.C_hi = static_cast<__nv_bfloat16*>(c.hi); p.C_lo = static_cast<__nv_bfloat16*>(c.lo);
+  p.ldc = c.ldc; p.stride_c = c.stride_c; p.stride_ch = c.stride_ch;
+  const long long items = (long long)p.batch * ((M + 127) / 128) * ((N + TN - 1) / TN);
   const long long grid = items < sm_count_cached() ? items : sm_count_cached();  // persistent: one CTA per SM
   kernel<<<(unsigned)grid, BG_THREADS, bg_smem_bytes(2, TN), st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   return launch_check();
@@ -787,7 +839,8 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
   if (int rc = lamp_split_planes(v, (int64_t)nk, d, d, vh, vl, d, stream)) return rc;
   if (int rc = lamp_split_planes(dO, (int64_t)nq, d, d, gh, gl, d, stream)) return rc;
   // dA = dO V^T  [N, Lq, Lk]
-  if (int rc = launch_bgemm<false, false>(gh, gl, d, Lq, d, vh, vl, d, Lk, d, N, Lq, Lk, d, 1.0f, dA, Lk, (long long)Lq * Lk, st)) return rc;
+  if (int rc = launch_bgemm<false, false>(bg_headmajor(gh, gl, d, Lq, d), bg_headmajor(vh, vl, d, Lk, d), N, 1, Lq, Lk, d, 1.0f,
+                                          BgOutput{dA, nullptr, nullptr, Lk, (long long)Lq * Lk, 0}, st)) return rc;
   // dS (scaled by 1/temperature) and A as planes [N*Lq, ld]
   {
     const long long blocks = ((long long)nq * 32 + 255) / 256;
@@ -796,10 +849,76 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
     if (int rc = launch_check()) return rc;
   }
   // dQ = dS K   (A: dS K-major, B: K MN-major)
-  if (int rc = launch_bgemm<false, true>(sh, sl, Lk, Lq, pl.ld, kh, kl, d, Lk, d, N, Lq, d, Lk, 1.0f, dq, d, (long long)Lq * d, st)) return rc;
+  if (int rc = launch_bgemm<false, true>(bg_headmajor(sh, sl, Lk, Lq, pl.ld), bg_headmajor(kh, kl, d, Lk, d), N, 1, Lq, d, Lk, 1.0f,
+                                         BgOutput{dq, nullptr, nullptr, d, (long long)Lq * d, 0}, st)) return rc;
   // dV = A^T dO, dK = dS^T Q   (both operands MN-major: contraction over the q rows)
-  if (int rc = launch_bgemm<true, true>(ah, al, Lk, Lq, pl.ld, gh, gl, d, Lq, d, N, Lk, d, Lq, 1.0f, dv, d, (long long)Lk * d, st)) return rc;
-  return launch_bgemm<true, true>(sh, sl, Lk, Lq, pl.ld, qh, ql, d, Lq, d, N, Lk, d, Lq, 1.0f, dk, d, (long long)Lk * d, st);
+  if (int rc = launch_bgemm<true, true>(bg_headmajor(ah, al, Lk, Lq, pl.ld), bg_headmajor(gh, gl, d, Lq, d), N, 1, Lk, d, Lq, 1.0f,
+                                        BgOutput{dv, nullptr, nullptr, d, (long long)Lk * d, 0}, st)) return rc;
+  return launch_bgemm<true, true>(bg_headmajor(sh, sl, Lk, Lq, pl.ld), bg_headmajor(qh, ql, d, Lq, d), N, 1, Lk, d, Lq, 1.0f,
+                                  BgOutput{dk, nullptr, nullptr, d, (long long)Lk * d, 0}, st);
+}
+
+/* Attention backward in the layouts of the projection GEMMs (training path; no head-major copies, no fp32 round trips):
+ * Q / K / V / dO / O are split-bf16 planes whose head h is the column slice [col0 + h*d, col0 + (h+1)*d) of a
+ * [B*L, ld] matrix; P (softmax before dropout) and A (after dropout; may equal P) are the head-major fp32
+ * [H*B, Lq, Lk] tensors the training forward wrote.  dQ / dK / dV leave as planes in the same slice layout. */
+size_t lamp_attn_bwd_planes_workspace_bytes(int B, int H, int Lq, int Lk) {
+  const size_t nq = (size_t)B * H * Lq, ld = (size_t)(Lk + 7) / 8 * 8;
+  return align_up(nq * Lk * 4) + 2 * align_up(nq * ld * 4);
+}
+
+int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, const void* kv_hi, const void* kv_lo,
+                         int64_t ldkv, int k_col0, int v_col0, const void* do_hi, const void* do_lo, const void* o_hi,
+                         const void* o_lo, int64_t ldo, const float* P, const float* A, void* dq_hi, void* dq_lo,
+                         int64_t lddq, int dq_col0, void* dkv_hi, void* dkv_lo, int64_t lddkv, int dk_col0, int dv_col0,
+                         int B, int H, int Lq, int Lk, int d, float temperature, float p_drop, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(q_hi && q_lo && kv_hi && kv_lo && do_hi && do_lo && o_hi && o_lo && P && dq_hi && dq_lo && dkv_hi && dkv_lo,
+          "attn_bwd_planes: null pointer (3-term planes required)");
+  REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "attn_bwd_planes: bad shape");
+  REQUIRE(d % 16 == 0 && d >= 16 && d <= 128, "attn_bwd_planes: head width %d must be a multiple of 16 in [16,128]", d);
+  REQUIRE(temperature > 0.0f && p_drop >= 0.0f && p_drop < 1.0f, "attn_bwd_planes: bad temperature / dropout rate");
+  REQUIRE(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0 && dq_col0 % 8 == 0 && dk_col0 % 8 == 0 && dv_col0 % 8 == 0,
+          "attn_bwd_planes: column offsets must be multiples of 8");
+  if (!workspace || workspace_bytes < lamp_attn_bwd_planes_workspace_bytes(B, H, Lq, Lk))
+    return fail(LAMP_EWORKSPACE, "attn_bwd_planes: workspace too small");
+  if (B == 0) return LAMP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nq = (size_t)B * H * Lq;
+  const int ld = (Lk + 7) / 8 * 8;
+  Carver cv(workspace);
+  float* dA = static_cast<float*>(cv.take(nq * Lk * 4));
+  __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(cv.take(nq * ld * 4));
+  __nv_bfloat16* sl = sh + nq * ld;
+  __nv_bfloat16* ah = static_cast<__nv_bfloat16*>(cv.take(nq * ld * 4));
+  __nv_bfloat16* al = ah + nq * ld;
+  const BgOperand Q = bg_slices(q_hi, q_lo, q_col0, d, Lq, ldq), K = bg_slices(kv_hi, kv_lo, k_col0, d, Lk, ldkv),
+                  V = bg_slices(kv_hi, kv_lo, v_col0, d, Lk, ldkv), G = bg_slices(do_hi, do_lo, 0, d, Lq, ldo);
+  // head-major [H*B, Lq, .] tensors: sample stride Lq*ld, head stride B*Lq*ld
+  auto hm = [&](const void* hi, const void* lo, uint64_t cols, uint64_t pitch) {
+    return BgOperand{hi, lo, cols, (uint64_t)Lq, pitch, (uint64_t)B * Lq * pitch, (uint64_t)Lq * pitch};
+  };
+  // dA = dO V^T   [H*B, Lq, Lk] fp32
+  if (int rc = launch_bgemm<false, false>(G, V, B, H, Lq, Lk, d, 1.0f,
+                                          BgOutput{dA, nullptr, nullptr, Lk, (long long)Lq * Lk, (long long)B * Lq * Lk}, st)) return rc;
+  {
+    const long long blocks = ((long long)nq * 32 + 255) / 256;
+    attn_bwd_ds_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        dA, P, A ? A : P, static_cast<const __nv_bfloat16*>(do_hi), static_cast<const __nv_bfloat16*>(do_lo),
+        static_cast<const __nv_bfloat16*>(o_hi), static_cast<const __nv_bfloat16*>(o_lo), ldo, B, H, Lq, Lk, d, ld,
+        1.0f / temperature, 1.0f / (1.0f - p_drop), sh, sl, ah, al);
+    if (int rc = launch_check()) return rc;
+  }
+  const BgOperand dS = hm(sh, sl, Lk, ld), Ap = hm(ah, al, Lk, ld);
+  auto out = [&](void* hi, void* lo, int col0, int64_t ldc, int rows) {
+    return BgOutput{nullptr, static_cast<__nv_bfloat16*>(hi) + col0, static_cast<__nv_bfloat16*>(lo) + col0, (long long)ldc,
+                    (long long)rows * ldc, (long long)d};
+  };
+  // dQ = dS K (K MN-major), dV = A^T dO, dK = dS^T Q (both operands MN-major)
+  if (int rc = launch_bgemm<false, true>(dS, K, B, H, Lq, d, Lk, 1.0f, out(dq_hi, dq_lo, dq_col0, lddq, Lq), st)) return rc;
+  if (int rc = launch_bgemm<true, true>(Ap, G, B, H, Lk, d, Lq, 1.0f, out(dkv_hi, dkv_lo, dv_col0, lddkv, Lk), st)) return rc;
+  return launch_bgemm<true, true>(dS, Q, B, H, Lk, d, Lq, 1.0f, out(dkv_hi, dkv_lo, dk_col0, lddkv, Lk), st);
 }
 
 int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
@@ -914,6 +1033,63 @@ int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B
     return launch_check();
   }
   return LAMP_OK;
+}
+
+/* Training forward of the attention core on operand planes (the layouts of the projection GEMMs): like
+ * lamp_attn_core_planes, plus dropout on the probabilities inside the kernel and the two probability tensors the
+ * backward consumes (attn: after dropout -- the reference's return value; probs_pre: before dropout, NULL when
+ * p_drop == 0).  row_max / row_sum: [H*B*Lq] scratch. */
+int lamp_attn_core_planes_train(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast, const void* kv_hi,
+                                const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H, int Lq, int Lk, int d,
+                                float temperature, int precision, const uint8_t* mask, int64_t msb, int64_t msq,
+                                int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* row_max, float* row_sum,
+                                float* attn, float* probs_pre, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                                void* stream) {
+  REQUIRE(attn != nullptr && row_max && row_sum, "attn_train: attn / row statistics buffers are required");
+  REQUIRE(p_drop == 0.0f || probs_pre != nullptr, "attn_train: probs_pre is required when dropout is active");
+  return attn_impl(q_hi, q_lo, ldq, q_col0, q_bcast, kv_hi, kv_lo, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature,
+                   precision, mask, msb, msq, msk, nullptr, 0, 0, o_hi, o_lo, ldo, nullptr, 0, row_max, row_sum, attn,
+                   nullptr, nullptr, 0, stream, p_drop, seed, probs_pre, seed_dev);
+}
+
+int lamp_dropout_add(const float* y0, const float* x, int64_t rows, int D, int x_mod, float p_drop, uint64_t seed,
+                     const uint64_t* seed_dev, float* y, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(y0 && x && y && rows >= 0 && D > 0 && D % 4 == 0, "dropout_add: bad arguments");
+  REQUIRE(aligned16(y0) && aligned16(x) && aligned16(y), "dropout_add: alignment");
+  REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "dropout_add: rate outside [0, 1)");
+  if (rows == 0) return LAMP_OK;
+  const uint32_t thresh = p_drop > 0.0f ? (uint32_t)((double)p_drop * 4294967296.0) : 0u;
+  const long long blocks = (rows * 32 + 255) / 256;
+  dropout_add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      y0, x, rows, D, x_mod, thresh, 1.0f / (1.0f - p_drop), seed, reinterpret_cast<const unsigned long long*>(seed_dev), y);
+  return launch_check();
+}
+
+int lamp_dropout_split(const float* dy, int64_t rows, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                       void* hi, void* lo, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(dy && hi && lo && rows >= 0 && D > 0 && D % 4 == 0, "dropout_split: bad arguments");
+  REQUIRE(aligned16(dy) && aligned16(hi) && aligned16(lo), "dropout_split: alignment");
+  REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "dropout_split: rate outside [0, 1)");
+  if (rows == 0) return LAMP_OK;
+  const uint32_t thresh = p_drop > 0.0f ? (uint32_t)((double)p_drop * 4294967296.0) : 0u;
+  const long long blocks = (rows * 32 + 255) / 256;
+  dropout_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      dy, rows, D, thresh, 1.0f / (1.0f - p_drop), seed, reinterpret_cast<const unsigned long long*>(seed_dev),
+      static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
+  return launch_check();
+}
+
+int lamp_relu_mask_planes(void* g_hi, void* g_lo, const void* h_hi, int64_t n, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(g_hi && g_lo && h_hi && n >= 0 && n % 8 == 0, "relu_mask_planes: element count must be a multiple of 8");
+  REQUIRE(aligned16(g_hi) && aligned16(g_lo) && aligned16(h_hi), "relu_mask_planes: alignment");
+  if (n == 0) return LAMP_OK;
+  const long long n8 = n / 8, blocks = (n8 + 255) / 256;
+  relu_mask_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      static_cast<__nv_bfloat16*>(g_hi), static_cast<__nv_bfloat16*>(g_lo), static_cast<const __nv_bfloat16*>(h_hi), n8);
+  return launch_check();
 }
 
 int lamp_gold_binary(const int64_t* gold, int64_t B, int W, int L, int skip, float* out, void* stream) {

@@ -307,4 +307,75 @@ bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ y, long
   }
 }
 
+// ---- element-wise pieces of the fused training sub-layers (lamp/SubLayers.py:113-119,136-141) -----------------------
+// The element-wise dropout after fc / w_2 uses the same counter hash as the attention dropout: keep(row, col) is a pure
+// function of (seed, row, col), so the backward recomputes the mask instead of storing it.
+//   y = keep * y0 / (1 - p) + x           (x: residual; row index modulo `x_mod` when the residual is broadcast)
+__global__ void dropout_add_kernel(const float* __restrict__ y0, const float* __restrict__ x, long long rows, int D,
+                                   int x_mod, uint32_t thresh, float scale, unsigned long long seed,
+                                   const unsigned long long* __restrict__ seed_dev, float* __restrict__ y) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint32_t rh = drop_rowhash(seed + (seed_dev ? __ldg(seed_dev) : 0ull), static_cast<unsigned long long>(row));
+  const float4* a = reinterpret_cast<const float4*>(y0 + row * D);
+  const float4* r = reinterpret_cast<const float4*>(x + (x_mod ? row % x_mod : row) * D);
+  float4* o = reinterpret_cast<float4*>(y + row * D);
+  for (int c = lane; c < (D >> 2); c += 32) {
+    float4 v = a[c];
+    const float4 rv = __ldg(r + c);
+    const uint32_t col = 4u * c;
+    v.x = (thresh && !drop_keep(rh, col, thresh) ? 0.f : v.x * scale) + rv.x;
+    v.y = (thresh && !drop_keep(rh, col + 1, thresh) ? 0.f : v.y * scale) + rv.y;
+    v.z = (thresh && !drop_keep(rh, col + 2, thresh) ? 0.f : v.z * scale) + rv.z;
+    v.w = (thresh && !drop_keep(rh, col + 3, thresh) ? 0.f : v.w * scale) + rv.w;
+    o[c] = v;
+  }
+}
+//   planes(keep * dy / (1 - p)): the gradient of the dropped branch, directly as the tensor-core operand of the dW / dx
+//   products (thresh == 0: a plain split)
+__global__ void dropout_split_kernel(const float* __restrict__ dy, long long rows, int D, uint32_t thresh, float scale,
+                                     unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint32_t rh = drop_rowhash(seed + (seed_dev ? __ldg(seed_dev) : 0ull), static_cast<unsigned long long>(row));
+  const float4* a = reinterpret_cast<const float4*>(dy + row * D);
+  uint2* oh = reinterpret_cast<uint2*>(hi + row * D);
+  uint2* ol = reinterpret_cast<uint2*>(lo + row * D);
+  for (int c = lane; c < (D >> 2); c += 32) {
+    float4 v = a[c];
+    const uint32_t col = 4u * c;
+    v.x = (thresh && !drop_keep(rh, col, thresh)) ? 0.f : v.x * scale;
+    v.y = (thresh && !drop_keep(rh, col + 1, thresh)) ? 0.f : v.y * scale;
+    v.z = (thresh && !drop_keep(rh, col + 2, thresh)) ? 0.f : v.z * scale;
+    v.w = (thresh && !drop_keep(rh, col + 3, thresh)) ? 0.f : v.w * scale;
+    uint2 h, l;
+    split_bf16x2(v.x, v.y, h.x, l.x);
+    split_bf16x2(v.z, v.w, h.y, l.y);
+    oh[c] = h;
+    ol[c] = l;
+  }
+}
+//   ReLU backward on operand planes, in place: dh = 0 where the forward activation h (its hi plane decides: h > 0 iff
+//   hi > 0, the split keeps the sign) was clipped
+__global__ void relu_mask_planes_kernel(__nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo,
+                                        const __nv_bfloat16* __restrict__ h_hi, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(h_hi) + i);
+  uint4 a = reinterpret_cast<uint4*>(g_hi)[i], b = reinterpret_cast<uint4*>(g_lo)[i];
+  auto keep = [](uint32_t hv) -> uint32_t {  // two bf16 per word: > 0 <=> sign clear and magnitude non-zero
+    const uint32_t lo = ((hv & 0x8000u) == 0u && (hv & 0x7FFFu) != 0u) ? 0x0000FFFFu : 0u;
+    const uint32_t hi = ((hv & 0x80000000u) == 0u && (hv & 0x7FFF0000u) != 0u) ? 0xFFFF0000u : 0u;
+    return lo | hi;
+  };
+  const uint32_t k0 = keep(h.x), k1 = keep(h.y), k2 = keep(h.z), k3 = keep(h.w);
+  a.x &= k0; a.y &= k1; a.z &= k2; a.w &= k3;
+  b.x &= k0; b.y &= k1; b.z &= k2; b.w &= k3;
+  reinterpret_cast<uint4*>(g_hi)[i] = a;
+  reinterpret_cast<uint4*>(g_lo)[i] = b;
+}
+
 }  // namespace lamp

@@ -759,6 +759,281 @@ class DiagProjFunction(torch.autograd.Function):
         return dx, dW.to(W.dtype), (db.to(bias.dtype) if db is not None else None)
 
 
+# ------------------------------------------------------------------ fused training sub-layers (N4, second pass)
+# One autograd Function per reference sub-layer (PositionwiseFeedForward, MultiHeadAttention).  Inside a Function every
+# tensor stays in the layout the tensor-core kernels consume (split-bf16 planes, heads as column slices): no head
+# split / merge copies, no fp32 -> planes re-splits of activations that a previous kernel already produced as planes, no
+# stored dropout masks (counter-hash masks are recomputed in the backward), ReLU / bias / residual in GEMM epilogues.
+FUSED_TRAINING = os.environ.get('LAMP_FUSED_TRAIN', '1') != '0'
+
+
+def planes_of(x: torch.Tensor, prec: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Operand planes of an fp32 activation [..., D]: the ones stashed on the tensor by the lamp_b200 sub-layer that
+    produced it (still valid: same version), else a split pass."""
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    stash = getattr(x, '_lamp_planes', None)
+    if stash is not None:
+        hi, lo, ver, sprec = stash
+        if ver == x._version and sprec == prec and hi.shape == (rows, cols):
+            return hi, lo
+    return split(x.detach().reshape(rows, cols).float(), prec)
+
+
+def _wplanes(W: torch.Tensor, prec: int, transpose: bool = False):
+    w2 = W.detach().reshape(W.shape[0], -1).float()
+    return split(w2.t().contiguous() if transpose else w2.contiguous(), prec)
+
+
+def _seed_dev_ptr():
+    return nat.ptr(TRAIN_SEED_DEV)
+
+
+def dropout_add(y0: torch.Tensor, x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+    """y = dropout(y0) + x on [rows, D] fp32 (counter-hash mask, see lamp_dropout_add)."""
+    rows, D = y0.shape
+    y = torch.empty_like(y0)
+    STATS.call('dropout_add', 1, nat.lib().lamp_dropout_add,
+               (y0.data_ptr(), x.data_ptr(), rows, D, 0, float(p), int(seed), _seed_dev_ptr(), y.data_ptr(), nat.stream()),
+               nbytes=rows * D * 12)
+    return y
+
+
+def dropout_split(dy: torch.Tensor, p: float, seed: int):
+    """planes(dropout-backward(dy)) for [rows, D] fp32 (the mask of ``dropout_add`` recomputed)."""
+    rows, D = dy.shape
+    hi, lo = _empty_planes(rows, D, nat.PREC_FP32, dy.device)
+    STATS.call('dropout_split', 1, nat.lib().lamp_dropout_split,
+               (dy.data_ptr(), rows, D, float(p), int(seed), _seed_dev_ptr(), hi.data_ptr(), lo.data_ptr(), nat.stream()),
+               nbytes=rows * D * 8)
+    return hi, lo
+
+
+def _layernorm_bwd(y: torch.Tensor, g: torch.Tensor, gamma: torch.Tensor, eps: float):
+    rows, D = y.shape
+    dy = torch.empty_like(y)
+    dg = torch.zeros((D,), dtype=torch.float32, device=y.device)
+    db = torch.zeros_like(dg)
+    STATS.call('layernorm_bwd', 1, nat.lib().lamp_layernorm_bwd,
+               (y.data_ptr(), g.data_ptr(), gamma.detach().float().contiguous().data_ptr(), float(eps), rows, D,
+                dy.data_ptr(), dg.data_ptr(), db.data_ptr(), nat.stream()), nbytes=rows * D * 12)
+    return dy, dg, db
+
+
+def _gemm_tn(d_hi, d_lo, N: int, a_hi, a_lo, K: int, M: int, want_bias: bool):
+    """dW [N, K] = dy^T x and db [N] = column sums of dy, both from operand planes."""
+    dW = torch.zeros((N, K), dtype=torch.float32, device=d_hi.device)
+    db = torch.zeros((N,), dtype=torch.float32, device=d_hi.device) if want_bias else None
+    STATS.call('gemm_tn', 2 if want_bias else 1, nat.lib().lamp_gemm_tn_acc,
+               (d_hi.data_ptr(), nat.ptr(d_lo), N, a_hi.data_ptr(), nat.ptr(a_lo), K, M, N, K, dW.data_ptr(), nat.ptr(db),
+                nat.stream()), flops=2.0 * M * N * K)
+    return dW, db
+
+
+class FFNTrainFunction(torch.autograd.Function):
+    """PositionwiseFeedForward of the training path (lamp/SubLayers.py:125-142) as ONE autograd node:
+    forward  GEMM(+b1, ReLU -> planes) -> GEMM(+b2 [+x]) -> dropout + residual -> LayerNorm (fp32 + planes);
+    backward LayerNorm bwd -> planes of the dropped gradient -> dW2 | dh (ReLU mask) -> dW1 | dx (+ residual grad)."""
+
+    @staticmethod
+    def forward(ctx, x, x_hi, x_lo, W1, b1, W2, b2, gamma, beta, eps, p_drop, seed):
+        prec = nat.PREC_FP32
+        D = x.shape[-1]
+        x2 = x.detach().reshape(-1, D).float().contiguous()
+        M, dh = x2.shape[0], W1.shape[0]
+        if x_hi is None:
+            x_hi, x_lo = split(x2, prec)
+        w1h, w1l = _wplanes(W1, prec)
+        w2h, w2l = _wplanes(W2, prec)
+        h_hi, h_lo = _empty_planes(M, dh, prec, x.device)
+        gemm(x_hi, x_lo, D, w1h, w1l, D, M, dh, D, prec, bias=b1.detach().float().contiguous(), relu=True, out_hi=h_hi,
+             out_lo=h_lo, ldp=dh)
+        y = torch.empty((M, D), dtype=torch.float32, device=x.device)
+        b2f = b2.detach().float().contiguous()
+        if p_drop > 0:
+            y0 = torch.empty_like(y)
+            gemm(h_hi, h_lo, dh, w2h, w2l, dh, M, D, dh, prec, bias=b2f, out_f32=y0, ldo=D)
+            y = dropout_add(y0, x2, p_drop, seed)
+        else:
+            gemm(h_hi, h_lo, dh, w2h, w2l, dh, M, D, dh, prec, bias=b2f, residual=x2, ldr=D, out_f32=y, ldo=D)
+        out = layernorm(y, gamma.detach().float().contiguous(), beta.detach().float().contiguous(), eps, prec)
+        ctx.save_for_backward(x_hi, x_lo, h_hi, h_lo, y, W1, W2, gamma)
+        ctx.eps, ctx.p_drop, ctx.seed, ctx.x_shape = eps, p_drop, seed, tuple(x.shape)
+        ctx.mark_non_differentiable(out.hi, out.lo)
+        return out.f32.view(x.shape), out.hi, out.lo
+
+    @staticmethod
+    def backward(ctx, g, _ghi, _glo):
+        x_hi, x_lo, h_hi, h_lo, y, W1, W2, gamma = ctx.saved_tensors
+        prec = nat.PREC_FP32
+        M, D = y.shape
+        dh = W1.shape[0]
+        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(M, D).float().contiguous(), gamma, ctx.eps)
+        d_hi, d_lo = dropout_split(dy, ctx.p_drop, ctx.seed)
+        dW2, db2 = _gemm_tn(d_hi, d_lo, D, h_hi, h_lo, dh, M, True)
+        w2t_hi, w2t_lo = _wplanes(W2, prec, transpose=True)          # [dh, D]: dh = d W2
+        g_hi, g_lo = _empty_planes(M, dh, prec, y.device)
+        gemm(d_hi, d_lo, D, w2t_hi, w2t_lo, D, M, dh, D, prec, out_hi=g_hi, out_lo=g_lo, ldp=dh)
+        STATS.call('relu_mask', 1, nat.lib().lamp_relu_mask_planes,
+                   (g_hi.data_ptr(), g_lo.data_ptr(), h_hi.data_ptr(), M * dh, nat.stream()), nbytes=M * dh * 10)
+        dW1, db1 = _gemm_tn(g_hi, g_lo, dh, x_hi, x_lo, D, M, True)
+        w1t_hi, w1t_lo = _wplanes(W1, prec, transpose=True)          # [D, dh]: dx = dh W1 (+ the residual branch)
+        dx = torch.empty((M, D), dtype=torch.float32, device=y.device)
+        gemm(g_hi, g_lo, dh, w1t_hi, w1t_lo, dh, M, D, dh, prec, residual=dy, ldr=D, out_f32=dx, ldo=D)
+        return (dx.view(ctx.x_shape), None, None, dW1.view(W1.shape).to(W1.dtype), db1, dW2.view(W2.shape).to(W2.dtype), db2,
+                dgamma, dbeta, None, None, None)
+
+
+class MHATrainFunction(torch.autograd.Function):
+    """MultiHeadAttention of the training path (lamp/SubLayers.py:77-121) as ONE autograd node, self-attention
+    (``xkv is None``) or label<-input attention.  Q|K|V live in one [rows, 3*H*d] (or Q and K|V in [rows, H*d] /
+    [rows, 2*H*d]) plane matrix, heads are column slices for the attention core in both directions."""
+
+    @staticmethod
+    def forward(ctx, xq, xq_hi, xq_lo, xkv, xkv_hi, xkv_lo, Wq, Wk, Wv, Wfc, gamma, beta, eps, mask, H, d, temperature,
+                p_attn, p_out, seed_attn, seed_out):
+        prec = nat.PREC_FP32
+        L = nat.lib()
+        B, Lq, D = xq.shape
+        self_attn = xkv is None
+        Lk = Lq if self_attn else xkv.shape[1]
+        hd = H * d
+        dev = xq.device
+        x2 = xq.detach().reshape(-1, D).float().contiguous()
+        Mq, Mk = B * Lq, B * Lk
+        if xq_hi is None:
+            xq_hi, xq_lo = split(x2, prec)
+        if self_attn:
+            w_hi, w_lo = _wplanes(torch.cat((Wq.detach(), Wk.detach(), Wv.detach()), dim=0), prec)
+            qp = _empty_planes(Mq, 3 * hd, prec, dev)
+            gemm(xq_hi, xq_lo, D, w_hi, w_lo, D, Mq, 3 * hd, D, prec, out_hi=qp[0], out_lo=qp[1], ldp=3 * hd)
+            kvp, ldq, ldkv, k_col0, v_col0 = qp, 3 * hd, 3 * hd, hd, 2 * hd
+        else:
+            if xkv_hi is None:
+                xkv_hi, xkv_lo = split(xkv.detach().reshape(-1, D).float().contiguous(), prec)
+            wq_hi, wq_lo = _wplanes(Wq, prec)
+            wkv_hi, wkv_lo = _wplanes(torch.cat((Wk.detach(), Wv.detach()), dim=0), prec)
+            qp = _empty_planes(Mq, hd, prec, dev)
+            kvp = _empty_planes(Mk, 2 * hd, prec, dev)
+            gemm(xq_hi, xq_lo, D, wq_hi, wq_lo, D, Mq, hd, D, prec, out_hi=qp[0], out_lo=qp[1], ldp=hd)
+            gemm(xkv_hi, xkv_lo, D, wkv_hi, wkv_lo, D, Mk, 2 * hd, D, prec, out_hi=kvp[0], out_lo=kvp[1], ldp=2 * hd)
+            ldq, ldkv, k_col0, v_col0 = hd, 2 * hd, 0, hd
+        o_hi, o_lo = _empty_planes(Mq, hd, prec, dev)
+        attn = torch.empty((H * B, Lq, Lk), dtype=torch.float32, device=dev)
+        pre = torch.empty_like(attn) if p_attn > 0 else None
+        stats = torch.empty((2, H * B * Lq), dtype=torch.float32, device=dev)
+        keep, mptr, sb, sq, sk = mask_args(mask, B, Lq, Lk)
+        STATS.call('attn_core_train', 2, L.lamp_attn_core_planes_train,
+                   (qp[0].data_ptr(), qp[1].data_ptr(), ldq, 0, 0, kvp[0].data_ptr(), kvp[1].data_ptr(), ldkv, k_col0, v_col0,
+                    B, H, Lq, Lk, d, float(temperature), prec, mptr, sb, sq, sk, o_hi.data_ptr(), o_lo.data_ptr(), hd,
+                    stats[0].data_ptr(), stats[1].data_ptr(), attn.data_ptr(), nat.ptr(pre), float(p_attn), int(seed_attn),
+                    _seed_dev_ptr(), nat.stream()), flops=4.0 * H * Lq * d * B * Lk)
+        del keep
+        wfc_hi, wfc_lo = _wplanes(Wfc, prec)
+        y = torch.empty((Mq, D), dtype=torch.float32, device=dev)
+        if p_out > 0:
+            y0 = torch.empty_like(y)
+            gemm(o_hi, o_lo, hd, wfc_hi, wfc_lo, hd, Mq, D, hd, prec, out_f32=y0, ldo=D)
+            y = dropout_add(y0, x2, p_out, seed_out)
+        else:
+            gemm(o_hi, o_lo, hd, wfc_hi, wfc_lo, hd, Mq, D, hd, prec, residual=x2, ldr=D, out_f32=y, ldo=D)
+        out = layernorm(y, gamma.detach().float().contiguous(), beta.detach().float().contiguous(), eps, prec)
+        empty = xq_hi.new_empty(0)
+        ctx.save_for_backward(xq_hi, xq_lo, empty if self_attn else xkv_hi, empty if self_attn else xkv_lo, qp[0], qp[1],
+                              empty if self_attn else kvp[0], empty if self_attn else kvp[1], o_hi, o_lo, attn,
+                              pre if pre is not None else attn, y, Wq, Wk, Wv, Wfc, gamma)
+        ctx.cfg = (B, Lq, Lk, D, H, d, float(temperature), float(p_attn), float(p_out), int(seed_out), self_attn, eps,
+                   None if self_attn else tuple(xkv.shape))
+        ctx.mark_non_differentiable(out.hi, out.lo, attn)
+        return out.f32.view(B, Lq, D), out.hi, out.lo, attn
+
+    @staticmethod
+    def backward(ctx, g, _ghi, _glo, _gattn):
+        (xq_hi, xq_lo, xkv_hi, xkv_lo, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, attn, pre, y, Wq, Wk, Wv, Wfc,
+         gamma) = ctx.saved_tensors
+        B, Lq, Lk, D, H, d, temperature, p_attn, p_out, seed_out, self_attn, eps, kv_shape = ctx.cfg
+        prec = nat.PREC_FP32
+        L = nat.lib()
+        hd = H * d
+        Mq, Mk = B * Lq, B * Lk
+        dev = y.device
+        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(Mq, D).float().contiguous(), gamma, eps)
+        d_hi, d_lo = dropout_split(dy, p_out, seed_out)
+        dWfc, _ = _gemm_tn(d_hi, d_lo, D, o_hi, o_lo, hd, Mq, False)
+        wfct_hi, wfct_lo = _wplanes(Wfc, prec, transpose=True)       # [hd, D]: dO = d Wfc
+        do_hi, do_lo = _empty_planes(Mq, hd, prec, dev)
+        gemm(d_hi, d_lo, D, wfct_hi, wfct_lo, D, Mq, hd, D, prec, out_hi=do_hi, out_lo=do_lo, ldp=hd)
+        if self_attn:
+            dq = _empty_planes(Mq, 3 * hd, prec, dev)
+            dkv, kvp, lddq, lddkv, ldq, ldkv = dq, (q_hi, q_lo), 3 * hd, 3 * hd, 3 * hd, 3 * hd
+            k_col0, v_col0 = hd, 2 * hd
+        else:
+            dq = _empty_planes(Mq, hd, prec, dev)
+            dkv = _empty_planes(Mk, 2 * hd, prec, dev)
+            kvp, lddq, lddkv, ldq, ldkv = (kv_hi, kv_lo), hd, 2 * hd, hd, 2 * hd
+            k_col0, v_col0 = 0, hd
+        ws = torch.empty((max(L.lamp_attn_bwd_planes_workspace_bytes(B, H, Lq, Lk), 16),), dtype=torch.uint8, device=dev)
+        STATS.call('attn_core_bwd', 5, L.lamp_attn_bwd_planes,
+                   (q_hi.data_ptr(), q_lo.data_ptr(), ldq, 0, kvp[0].data_ptr(), kvp[1].data_ptr(), ldkv, k_col0, v_col0,
+                    do_hi.data_ptr(), do_lo.data_ptr(), o_hi.data_ptr(), o_lo.data_ptr(), hd, pre.data_ptr(),
+                    attn.data_ptr() if p_attn > 0 else None, dq[0].data_ptr(), dq[1].data_ptr(), lddq, 0,
+                    dkv[0].data_ptr(), dkv[1].data_ptr(), lddkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature, p_attn,
+                    ws.data_ptr(), ws.numel(), nat.stream()), flops=10.0 * H * B * Lq * Lk * d)
+        dxq = torch.empty((Mq, D), dtype=torch.float32, device=dev)
+        dxkv = None
+        if self_attn:
+            dW, _ = _gemm_tn(dq[0], dq[1], 3 * hd, xq_hi, xq_lo, D, Mq, False)
+            dWq, dWk, dWv = dW[:hd], dW[hd:2 * hd], dW[2 * hd:]
+            wt_hi, wt_lo = _wplanes(torch.cat((Wq.detach(), Wk.detach(), Wv.detach()), dim=0), prec, transpose=True)  # [D, 3hd]
+            gemm(dq[0], dq[1], 3 * hd, wt_hi, wt_lo, 3 * hd, Mq, D, 3 * hd, prec, residual=dy, ldr=D, out_f32=dxq, ldo=D)
+        else:
+            dWq, _ = _gemm_tn(dq[0], dq[1], hd, xq_hi, xq_lo, D, Mq, False)
+            wqt_hi, wqt_lo = _wplanes(Wq, prec, transpose=True)      # [D, hd]
+            gemm(dq[0], dq[1], hd, wqt_hi, wqt_lo, hd, Mq, D, hd, prec, residual=dy, ldr=D, out_f32=dxq, ldo=D)
+            dWkv, _ = _gemm_tn(dkv[0], dkv[1], 2 * hd, xkv_hi, xkv_lo, D, Mk, False)
+            dWk, dWv = dWkv[:hd], dWkv[hd:]
+            wkvt_hi, wkvt_lo = _wplanes(torch.cat((Wk.detach(), Wv.detach()), dim=0), prec, transpose=True)  # [D, 2hd]
+            dxkv = torch.empty((Mk, D), dtype=torch.float32, device=dev)
+            gemm(dkv[0], dkv[1], 2 * hd, wkvt_hi, wkvt_lo, 2 * hd, Mk, D, 2 * hd, prec, out_f32=dxkv, ldo=D)
+            dxkv = dxkv.view(kv_shape)
+        return (dxq.view(B, Lq, D), None, None, dxkv, None, None, dWq.to(Wq.dtype), dWk.to(Wk.dtype), dWv.to(Wv.dtype),
+                dWfc.to(Wfc.dtype), dgamma, dbeta, None, None, None, None, None, None, None, None, None)
+
+
+def _train_seed() -> int:
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def ffn_train(x: torch.Tensor, mod) -> torch.Tensor:
+    """PositionwiseFeedForward.forward in training mode through :class:`FFNTrainFunction`; the operand planes of the
+    result are stashed on the returned tensor for the next lamp_b200 sub-layer."""
+    p = float(mod.dropout.p) if mod.training else 0.0
+    prec = nat.PREC_FP32
+    x_hi, x_lo = planes_of(x, prec)
+    ln = mod.layer_norm
+    out, hi, lo = FFNTrainFunction.apply(x, x_hi, x_lo, mod.w_1.weight, mod.w_1.bias, mod.w_2.weight, mod.w_2.bias,
+                                         ln.weight, ln.bias, ln.eps, p, _train_seed() if p > 0 else 0)
+    out._lamp_planes = (hi, lo, out._version, prec)
+    return out
+
+
+def mha_train(q: torch.Tensor, kv: Optional[torch.Tensor], mask, mod):
+    """MultiHeadAttention.forward in training mode through :class:`MHATrainFunction` (``kv`` None: self-attention).
+    -> (out [B, Lq, D] with stashed planes, attn [H*B, Lq, Lk] after dropout, as the reference returns it)."""
+    prec = nat.PREC_FP32
+    p_attn = float(mod.attention.dropout.p) if mod.training else 0.0
+    p_out = float(mod.dropout.p) if mod.training else 0.0
+    q_hi, q_lo = planes_of(q, prec)
+    kv_hi, kv_lo = (None, None) if kv is None else planes_of(kv, prec)
+    ln = mod.layer_norm
+    out, hi, lo, attn = MHATrainFunction.apply(
+        q, q_hi, q_lo, kv, kv_hi, kv_lo, mod.w_qs.weight, mod.w_ks.weight, mod.w_vs.weight, mod.fc.weight, ln.weight,
+        ln.bias, ln.eps, mask, mod.n_head, mod.d_k, mod.attention.temperature, p_attn, p_out,
+        _train_seed() if p_attn > 0 else 0, _train_seed() if p_out > 0 else 0)
+    out._lamp_planes = (hi, lo, out._version, prec)
+    return out, attn
+
+
 def gold_binary(gold: torch.Tensor, n_labels: int, skip: int = 4) -> torch.Tensor:
     """Device-side ``utils.get_gold_binary`` (utils/utils.py:205-216, called every step from train.py:34 / test.py:47):
     ``gold`` [B, W] int64 label-id rows (ids offset by the 4 special tokens, EOS-terminated, PAD-padded) -> multi-hot

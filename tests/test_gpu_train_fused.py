@@ -1,0 +1,145 @@
+"""GPU tests of the fused training sub-layers (round 2; SURVEY.md 8f N4 second pass): ``ops.FFNTrainFunction`` and
+``ops.MHATrainFunction`` against fp64 autograd through the CPU oracle's sub-layers (lamp/SubLayers.py:77-142), the
+planes-native attention backward (``lamp_attn_bwd_planes``) and the counter-hash dropout kernels."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from lamp_b200 import _native as nat
+from lamp_b200 import ops
+from lamp_b200 import synthetic as syn
+from lamp_b200.SubLayers import MultiHeadAttention, PositionwiseFeedForward
+from oracle import lamp_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def set_dropout(mod, p):
+    for m in mod.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = p
+
+
+@pytest.mark.parametrize('B,L,D,dh', [(3, 37, 128, 256), (2, 103, 512, 512), (1, 300, 64, 128)])
+def test_ffn_train_function_matches_fp64_autograd(B, L, D, dh):
+    rs = np.random.RandomState(B * 1000 + L)
+    p = syn.ffn_params(rs, '', D, dh, random_ln=True)
+    mod = PositionwiseFeedForward(D, dh, dropout=0.0)
+    mod.load_state_dict(p, strict=True)
+    mod = mod.to(DEV).train()
+    x = torch.from_numpy(rs.standard_normal((B, L, D)).astype(np.float32))
+    w = torch.from_numpy(rs.standard_normal((B, L, D)).astype(np.float32))      # loss = <out, w>
+    xg = x.to(DEV).requires_grad_(True)
+    ops.STATS.reset()
+    out = mod(xg)
+    assert ops.STATS.by_kernel.get('gemm_planes', 0) == 2 and 'split_planes' in ops.STATS.by_kernel
+    assert getattr(out, '_lamp_planes', None) is not None          # planes travel with the activation
+    (out * w.to(DEV)).sum().backward()
+    assert ops.STATS.by_kernel.get('relu_mask', 0) == 1 and ops.STATS.by_kernel.get('gemm_tn', 0) == 4
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    x64 = x.double().requires_grad_(True)
+    ref = orc.ffn(p64, '', x64)
+    (ref * w.double()).sum().backward()
+    assert rel_err(out, ref) < 2e-5
+    assert rel_err(xg.grad, x64.grad) < 5e-5
+    for name, q in mod.named_parameters():
+        assert rel_err(q.grad, p64[name].grad) < 5e-5, name
+
+
+@pytest.mark.parametrize('case', ['self_prior', 'self_none', 'enc_pad', 'self_L159_H8'])
+def test_mha_train_function_matches_fp64_autograd(case):
+    cfg = dict(self_prior=dict(B=2, Lq=103, Lk=103, D=512, H=4, mask='prior', self_attn=True),
+               self_none=dict(B=3, Lq=37, Lk=37, D=128, H=8, mask='none', self_attn=True),
+               enc_pad=dict(B=3, Lq=53, Lk=90, D=256, H=4, mask='pad', self_attn=False),
+               self_L159_H8=dict(B=2, Lq=159, Lk=159, D=512, H=8, mask='none', self_attn=True))[case]
+    c = dict(cfg, seed=dict(self_prior=101, self_none=102, enc_pad=103, self_L159_H8=104)[case])
+    p, q, kv, mask = cases.mha_inputs(c)
+    rs = np.random.RandomState(7)
+    for k_ in p:
+        if 'layer_norm' in k_:   # non-trivial affine so that dgamma / dbeta are exercised
+            p[k_] = p[k_] + torch.from_numpy(0.1 * rs.standard_normal(p[k_].shape).astype(np.float32))
+    d = c['D'] // c['H']
+    mod = MultiHeadAttention(c['H'], c['D'], d, d, dropout=0.0)
+    mod.load_state_dict(p, strict=True)
+    mod = mod.to(DEV).train()
+    w = torch.from_numpy(rs.standard_normal(q.shape).astype(np.float32))
+    qg = q.to(DEV).requires_grad_(True)
+    kvg = qg if c['self_attn'] else kv.to(DEV).requires_grad_(True)
+    m_dev = None if mask is None else mask.to(DEV)
+    ops.STATS.reset()
+    out, attn = mod(qg, kvg, kvg, attn_mask=m_dev)
+    assert ops.STATS.by_kernel.get('attn_core_train', 0) == 2
+    (out * w.to(DEV)).sum().backward()
+    assert ops.STATS.by_kernel.get('attn_core_bwd', 0) == 5
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    q64 = q.double().requires_grad_(True)
+    kv64 = q64 if c['self_attn'] else kv.double().requires_grad_(True)
+    ref, ref_attn = orc.mha(p64, '', q64, kv64, kv64, mask, c['H'])
+    (ref * w.double()).sum().backward()
+    assert rel_err(out, ref) < 2e-5 and rel_err(attn, ref_attn) < 2e-5
+    assert rel_err(qg.grad, q64.grad) < 5e-5
+    if not c['self_attn']:
+        assert rel_err(kvg.grad, kv64.grad) < 5e-5
+    for name, prm in mod.named_parameters():
+        assert rel_err(prm.grad, p64[name].grad) < 5e-5, name
+
+
+def test_dropout_kernels_share_one_mask_and_scale():
+    rows, D, p = 517, 256, 0.3
+    y0 = torch.randn(rows, D, device=DEV) + 3.0          # no exact zeros
+    zero = torch.zeros(rows, D, device=DEV)
+    y = ops.dropout_add(y0, zero, p, seed=1234)
+    kept = y != 0
+    frac = float(kept.float().mean())
+    assert abs(frac - (1 - p)) < 0.01, frac
+    assert torch.allclose(y[kept], y0[kept] / (1 - p), rtol=1e-6)
+    hi, lo = ops.dropout_split(torch.ones(rows, D, device=DEV), p, seed=1234)
+    g = hi.float() + lo.float()
+    assert torch.equal(g != 0, kept) and torch.allclose(g[kept], torch.full_like(g[kept], 1 / (1 - p)), rtol=1e-5)
+    y2 = ops.dropout_add(y0, zero, p, seed=1235)
+    assert not torch.equal(y2 != 0, kept)
+    # p = 0: identity + residual / plain split
+    x = torch.randn(rows, D, device=DEV)
+    assert torch.equal(ops.dropout_add(y0, x, 0.0, 0), y0 + x)
+    hi, lo = ops.dropout_split(y0, 0.0, 0)
+    h2, l2 = ops.split(y0, nat.PREC_FP32)
+    assert torch.equal(hi, h2) and torch.equal(lo, l2)
+
+
+def test_fused_sublayers_with_dropout_are_consistent_between_forward_and_backward():
+    """With dropout the backward recomputes the masks from the seeds: check the FFN gradient against torch autograd
+    through an explicit re-statement that uses the SAME masks (read back from the forward's effect)."""
+    B, L, D, dh, p = 2, 40, 128, 256, 0.25
+    rs = np.random.RandomState(3)
+    prm = syn.ffn_params(rs, '', D, dh, random_ln=True)
+    mod = PositionwiseFeedForward(D, dh, dropout=p)
+    mod.load_state_dict(prm, strict=True)
+    mod = mod.to(DEV).train()
+    x = torch.randn(B, L, D, device=DEV)
+    w = torch.randn(B, L, D, device=DEV)
+    torch.manual_seed(11)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())     # the seed ffn_train is about to draw
+    torch.manual_seed(11)
+    xg = x.clone().requires_grad_(True)
+    out = mod(xg)
+    (out * w).sum().backward()
+    # explicit restatement with the same mask
+    hi, lo = ops.dropout_split(torch.ones(B * L, D, device=DEV), p, seed)
+    keep = (hi.float() + lo.float()).view(B, L, D).double()
+    p64 = {k: v.double().to(DEV).requires_grad_(True) for k, v in prm.items()}
+    x64 = x.double().requires_grad_(True)
+    h = torch.relu(torch.nn.functional.linear(x64, p64['w_1.weight'][:, :, 0], p64['w_1.bias']))
+    y = torch.nn.functional.linear(h, p64['w_2.weight'][:, :, 0], p64['w_2.bias']) * keep + x64
+    ref = torch.nn.functional.layer_norm(y, (D,), p64['layer_norm.weight'], p64['layer_norm.bias'], 1e-5)
+    (ref * w.double()).sum().backward()
+    assert rel_err(out, ref) < 2e-5
+    assert rel_err(xg.grad, x64.grad) < 5e-5
+    for name, q in mod.named_parameters():
+        assert rel_err(q.grad, p64[name].grad) < 5e-5, name
