@@ -214,9 +214,9 @@ int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B
 
 /* Training forward of the attention core (lamp/SubLayers.py:27-43 with the dropout of :40 inside the kernel) on operand
  * planes: like lamp_attn_core_planes plus p_drop / seed (+ optional device-side counter added to the seed, so CUDA-graph
- * replays draw fresh masks), and the probability tensors the backward consumes: attn [H*B, Lq, Lk] (after dropout; the
- * reference's return value, head-major) and probs_pre (before dropout; NULL iff p_drop == 0).  row_max / row_sum:
- * [H*B*Lq] scratch. */
+ * replays draw fresh masks), and optionally the probability tensors: attn [H*B, Lq, Lk] (after dropout; the reference's
+ * return value, head-major) and probs_pre (before dropout; NULL iff p_drop == 0).  attn == NULL: nothing of size Lq*Lk
+ * is written -- the backward recomputes P (lamp_attn_bwd_planes, recompute form) from row_max / row_sum [H*B*Lq]. */
 int lamp_attn_core_planes_train(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast, const void* kv_hi,
                                 const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B, int H, int Lq, int Lk, int d,
                                 float temperature, int precision, const uint8_t* mask, int64_t msb, int64_t msq,
@@ -228,14 +228,18 @@ int lamp_attn_core_planes_train(const void* q_hi, const void* q_lo, int64_t ldq,
  * slice [col0 + h*d, col0 + (h+1)*d) of a [B*L, ld] matrix (dO and O: [B*Lq, ldo], col0 = 0); P / A: the fp32 head-major
  * [H*B, Lq, Lk] tensors of the training forward (A may be NULL or == P without dropout).  dQ -> planes [B*Lq, lddq] at
  * dq_col0 + h*d; dK / dV -> planes [B*Lk, lddkv] at dk_col0 / dv_col0 + h*d.  Four batched tcgen05 products around one
- * element-wise kernel; no permute / contiguous copies, no fp32 round trips. */
+ * element-wise kernel; no permute / contiguous copies, no fp32 round trips.
+ * RECOMPUTE FORM (P == NULL): the forward kept no probability tensor at all (lamp_attn_core_planes_train with attn ==
+ * NULL); P is rebuilt from one more batched product S = Q K^T, the forward's row_max / row_sum, the mask (same pointer /
+ * strides as the forward) and the dropout counter hash of (seed [+ *seed_dev]). */
 size_t lamp_attn_bwd_planes_workspace_bytes(int B, int H, int Lq, int Lk);
 int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, const void* kv_hi, const void* kv_lo,
                          int64_t ldkv, int k_col0, int v_col0, const void* do_hi, const void* do_lo, const void* o_hi,
                          const void* o_lo, int64_t ldo, const float* P, const float* A, void* dq_hi, void* dq_lo,
                          int64_t lddq, int dq_col0, void* dkv_hi, void* dkv_lo, int64_t lddkv, int dk_col0, int dv_col0,
-                         int B, int H, int Lq, int Lk, int d, float temperature, float p_drop, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         int B, int H, int Lq, int Lk, int d, float temperature, float p_drop, const float* row_max,
+                         const float* row_sum, const uint8_t* mask, int64_t msb, int64_t msq, int64_t msk, uint64_t seed,
+                         const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, void* stream);
 
 /* y = dropout(y0) + x (lamp/SubLayers.py:113-119 / :139-141): keep(row, col) is a counter hash of (seed [+ *seed_dev],
  * row, col), kept values are scaled by 1/(1-p); x row index is row % x_mod when x_mod > 0 (broadcast residual). */

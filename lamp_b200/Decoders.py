@@ -80,7 +80,7 @@ class GraphDecoder(nn.Module):
         out = dec_input
         for layer in self.layer_stack:
             out, out_int, slf_attn, enc_attn = layer(out, enc_output, slf_attn_mask=slf_mask,
-                                                     dec_enc_attn_mask=pad_mask)
+                                                     dec_enc_attn_mask=pad_mask, return_attns=return_attns)
             if int_preds:
                 if out_int is not None:
                     int_outs.append(out_int)

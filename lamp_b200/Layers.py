@@ -76,11 +76,14 @@ class DecoderLayer(nn.Module):
     def forward(self, dec_input, enc_output, slf_attn_mask=None, dec_enc_attn_mask=None, return_attns=True):
         nat.require_cuda(dec_input, enc_output, slf_attn_mask, dec_enc_attn_mask)
         if _needs_autograd(self, dec_input, enc_output) or not self.fused_ok():
-            out, enc_attn = self.enc_attn(dec_input, enc_output, enc_output, attn_mask=dec_enc_attn_mask)
+            # training: the attention maps are only materialised when the caller wants them (the reference always
+            # returns them; GraphDecoder reads them for return_attns only) -- see ops.MHATrainFunction
+            ra = return_attns or not self.training
+            out, enc_attn = self.enc_attn(dec_input, enc_output, enc_output, attn_mask=dec_enc_attn_mask, return_attn=ra)
             out = self.pos_ffn1(out)
             if hasattr(self, 'slf_attn'):
                 out_int = out
-                out, slf_attn = self.slf_attn(out, out, out, attn_mask=slf_attn_mask, dec_self=True)
+                out, slf_attn = self.slf_attn(out, out, out, attn_mask=slf_attn_mask, dec_self=True, return_attn=ra)
             else:
                 out_int, slf_attn = None, None
             return self.pos_ffn2(out), out_int, slf_attn, enc_attn

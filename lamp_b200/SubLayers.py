@@ -133,10 +133,10 @@ class MultiHeadAttention(nn.Module):
                 and self.n_head > 1 and q.is_cuda and q.dtype == torch.float32 and k.dtype == torch.float32
                 and q.dim() == 3 and self._prec() == nat.PREC_FP32 and q.numel() > 0 and k.numel() > 0)
 
-    def _composed(self, q, k, v, attn_mask):
+    def _composed(self, q, k, v, attn_mask, want_attn=True):
         if self._fused_train_ok(q, k, v):
             # one autograd node for the whole sub-layer, everything in the tensor-core operand layouts (ops.MHATrainFunction)
-            return ops.mha_train(q, None if k is q else k, attn_mask, self)
+            return ops.mha_train(q, None if k is q else k, attn_mask, self, want_attn=want_attn)
         d_k, d_v, n_head = self.d_k, self.d_v, self.n_head
         sz_b, len_q, _ = q.size()
         len_k, len_v = k.size(1), v.size(1)
@@ -205,7 +205,9 @@ class MultiHeadAttention(nn.Module):
 
     def forward(self, q, k, v, attn_mask=None, dec_self=False, return_attn=True):
         nat.require_cuda(q, k, v, attn_mask)
-        if _needs_autograd(self, q, k, v) or not self.fused_ok():
+        if _needs_autograd(self, q, k, v):
+            return self._composed(q, k, v, attn_mask, want_attn=return_attn)
+        if not self.fused_ok():
             return self._composed(q, k, v, attn_mask)
         B, Lq, D = q.shape
         Lk = k.shape[1]

@@ -56,7 +56,8 @@ _SIGNATURES = {
                                      _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f, C.c_uint64, _vp, _vp], _i),
     'lamp_attn_bwd_planes_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'lamp_attn_bwd_planes': ([_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
-                              _i64, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _sz, _vp], _i),
+                              _i64, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _i64, _i64, _i64,
+                              C.c_uint64, _vp, _vp, _sz, _vp], _i),
     'lamp_dropout_add': ([_vp, _vp, _i64, _i, _i, _f, C.c_uint64, _vp, _vp, _vp], _i),
     'lamp_dropout_split': ([_vp, _i64, _i, _f, C.c_uint64, _vp, _vp, _vp, _vp], _i),
     'lamp_relu_mask_planes': ([_vp, _vp, _vp, _i64, _vp], _i),

@@ -285,4 +285,64 @@ __global__ void attn_bwd_ds_planes_kernel(const float* __restrict__ dA, const fl
   }
 }
 
+// Recompute form (no probability tensors kept by the forward): P is rebuilt from the raw scores S = Q K^T (one more
+// batched product), the row statistics the forward saved (reference maximum in the scaled log2 domain, denominator), the
+// mask and the dropout counter hash -- exactly the expression of the probability kernel (attn_probs_mma_kernel).
+struct DsRecomputeParams {
+  const float* S;        // [H*B, Lq, Lk] raw scores
+  const float* dA;       // [H*B, Lq, Lk]
+  const float* row_max;  // [H*B*Lq]
+  const float* row_sum;
+  const uint8_t* mask;   // nullable; element (b, i, j) at b*msb + i*msq + j*msk, non-zero = masked
+  long long msb, msq, msk;
+  float scale_log2, inv_temp, drop_scale;
+  uint32_t drop_thresh;
+  unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;
+  const __nv_bfloat16 *dO_hi, *dO_lo, *O_hi, *O_lo;
+  long long ld_o;
+  int B, H, Lq, Lk, d, ld;
+  __nv_bfloat16 *dS_hi, *dS_lo, *A_hi, *A_lo;
+};
+__global__ void attn_bwd_ds_recompute_kernel(const DsRecomputeParams p) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = static_cast<long long>(p.H) * p.B * p.Lq;
+  if (row >= rows) return;
+  const int i = static_cast<int>(row % p.Lq);
+  const long long n = row / p.Lq;
+  const int b = static_cast<int>(n % p.B), h = static_cast<int>(n / p.B);
+  const long long orow = (static_cast<long long>(b) * p.Lq + i) * p.ld_o + static_cast<long long>(h) * p.d;
+  float delta = 0.f;
+  for (int c = lane; c < p.d; c += 32) {
+    const float g = __bfloat162float(p.dO_hi[orow + c]) + __bfloat162float(p.dO_lo[orow + c]);
+    const float o = __bfloat162float(p.O_hi[orow + c]) + __bfloat162float(p.O_lo[orow + c]);
+    delta = fmaf(g, o, delta);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xFFFFFFFFu, delta, o);
+  const float rmx = p.row_max[row], rinv = 1.0f / p.row_sum[row];
+  const uint32_t rh = p.drop_thresh ? drop_rowhash(p.drop_seed + (p.drop_seed_dev ? __ldg(p.drop_seed_dev) : 0ull),
+                                                   static_cast<unsigned long long>(row))
+                                    : 0u;
+  const uint8_t* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.msb + static_cast<long long>(i) * p.msq : nullptr;
+  for (int c = lane; c < p.ld; c += 32) {
+    float ds = 0.f, a = 0.f;
+    if (c < p.Lk) {
+      const long long g = row * p.Lk + c;
+      const bool masked = mrow != nullptr && mrow[static_cast<long long>(c) * p.msk] != 0;
+      const float pr = masked ? (0.0f * rinv) : exp2f(p.S[g] * p.scale_log2 - rmx) * rinv;
+      const float keep = (!p.drop_thresh || drop_keep(rh, static_cast<uint32_t>(c), p.drop_thresh)) ? p.drop_scale : 0.0f;
+      a = pr * keep;
+      ds = pr * (p.dA[g] * keep - delta) * p.inv_temp;
+    }
+    const __nv_bfloat16 hh = __float2bfloat16_rn(ds);
+    p.dS_hi[row * p.ld + c] = hh;
+    p.dS_lo[row * p.ld + c] = __float2bfloat16_rn(ds - __bfloat162float(hh));
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a);
+    p.A_hi[row * p.ld + c] = ah;
+    p.A_lo[row * p.ld + c] = __float2bfloat16_rn(a - __bfloat162float(ah));
+  }
+}
+
 }  // namespace lamp

@@ -168,6 +168,14 @@ int set_smem(K kernel, uint32_t bytes) {
   return LAMP_OK;
 }
 
+// dropout rate -> 32-bit threshold of the counter hash (an element is dropped iff hash < threshold); one definition for
+// the attention kernels, the probability kernel, the element-wise dropouts and the recompute backward
+inline uint32_t drop_threshold(float p_drop) {
+  if (!(p_drop > 0.0f)) return 0u;
+  const uint32_t t = (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0);
+  return t == 0u ? 1u : t;
+}
+
 int launch_check() {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LAMP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
@@ -680,8 +688,7 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
   p.qrows = qrows; p.krows = krows; p.vrows = vrows;
   p.kv_start = kv_start; p.kv_len = kv_len;
   p.pv_split = (d == 128 && g_attn_pv_split.load() != 0) ? 1 : 0;
-  p.drop_thresh = p_drop > 0.0f ? (uint32_t)fmin((double)p_drop * 4294967296.0, 4294967295.0) : 0u;
-  if (p_drop > 0.0f && p.drop_thresh == 0u) p.drop_thresh = 1u;
+  p.drop_thresh = drop_threshold(p_drop);
   p.drop_scale = 1.0f / (1.0f - p_drop);
   p.drop_seed = seed;
   p.drop_seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
@@ -864,18 +871,20 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
  * [H*B, Lq, Lk] tensors the training forward wrote.  dQ / dK / dV leave as planes in the same slice layout. */
 size_t lamp_attn_bwd_planes_workspace_bytes(int B, int H, int Lq, int Lk) {
   const size_t nq = (size_t)B * H * Lq, ld = (size_t)(Lk + 7) / 8 * 8;
-  return align_up(nq * Lk * 4) + 2 * align_up(nq * ld * 4);
+  return 2 * align_up(nq * Lk * 4) + 2 * align_up(nq * ld * 4);  // dA, S (recompute form), dS planes, A planes
 }
 
 int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, const void* kv_hi, const void* kv_lo,
                          int64_t ldkv, int k_col0, int v_col0, const void* do_hi, const void* do_lo, const void* o_hi,
                          const void* o_lo, int64_t ldo, const float* P, const float* A, void* dq_hi, void* dq_lo,
                          int64_t lddq, int dq_col0, void* dkv_hi, void* dkv_lo, int64_t lddkv, int dk_col0, int dv_col0,
-                         int B, int H, int Lq, int Lk, int d, float temperature, float p_drop, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+                         int B, int H, int Lq, int Lk, int d, float temperature, float p_drop, const float* row_max,
+                         const float* row_sum, const uint8_t* mask, int64_t msb, int64_t msq, int64_t msk, uint64_t seed,
+                         const uint64_t* seed_dev, void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = arch_check()) return rc;
-  REQUIRE(q_hi && q_lo && kv_hi && kv_lo && do_hi && do_lo && o_hi && o_lo && P && dq_hi && dq_lo && dkv_hi && dkv_lo,
+  REQUIRE(q_hi && q_lo && kv_hi && kv_lo && do_hi && do_lo && o_hi && o_lo && dq_hi && dq_lo && dkv_hi && dkv_lo,
           "attn_bwd_planes: null pointer (3-term planes required)");
+  REQUIRE(P != nullptr || (row_max && row_sum), "attn_bwd_planes: give P (and A), or the forward's row statistics to recompute them");
   REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "attn_bwd_planes: bad shape");
   REQUIRE(d % 16 == 0 && d >= 16 && d <= 128, "attn_bwd_planes: head width %d must be a multiple of 16 in [16,128]", d);
   REQUIRE(temperature > 0.0f && p_drop >= 0.0f && p_drop < 1.0f, "attn_bwd_planes: bad temperature / dropout rate");
@@ -889,6 +898,7 @@ int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_
   const int ld = (Lk + 7) / 8 * 8;
   Carver cv(workspace);
   float* dA = static_cast<float*>(cv.take(nq * Lk * 4));
+  float* S = static_cast<float*>(cv.take(nq * Lk * 4));
   __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(cv.take(nq * ld * 4));
   __nv_bfloat16* sl = sh + nq * ld;
   __nv_bfloat16* ah = static_cast<__nv_bfloat16*>(cv.take(nq * ld * 4));
@@ -902,12 +912,29 @@ int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_
   // dA = dO V^T   [H*B, Lq, Lk] fp32
   if (int rc = launch_bgemm<false, false>(G, V, B, H, Lq, Lk, d, 1.0f,
                                           BgOutput{dA, nullptr, nullptr, Lk, (long long)Lq * Lk, (long long)B * Lq * Lk}, st)) return rc;
-  {
-    const long long blocks = ((long long)nq * 32 + 255) / 256;
-    attn_bwd_ds_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+  const long long ds_blocks = ((long long)nq * 32 + 255) / 256;
+  if (P != nullptr) {
+    attn_bwd_ds_planes_kernel<<<(unsigned)ds_blocks, 256, 0, st>>>(
         dA, P, A ? A : P, static_cast<const __nv_bfloat16*>(do_hi), static_cast<const __nv_bfloat16*>(do_lo),
         static_cast<const __nv_bfloat16*>(o_hi), static_cast<const __nv_bfloat16*>(o_lo), ldo, B, H, Lq, Lk, d, ld,
         1.0f / temperature, 1.0f / (1.0f - p_drop), sh, sl, ah, al);
+    if (int rc = launch_check()) return rc;
+  } else {
+    // recompute form: S = Q K^T once more, P rebuilt inside the element-wise kernel
+    if (int rc = launch_bgemm<false, false>(Q, K, B, H, Lq, Lk, d, 1.0f,
+                                            BgOutput{S, nullptr, nullptr, Lk, (long long)Lq * Lk, (long long)B * Lq * Lk}, st)) return rc;
+    DsRecomputeParams rp;
+    rp.S = S; rp.dA = dA; rp.row_max = row_max; rp.row_sum = row_sum;
+    rp.mask = mask; rp.msb = msb; rp.msq = msq; rp.msk = msk;
+    rp.scale_log2 = 1.4426950408889634f / temperature; rp.inv_temp = 1.0f / temperature;
+    rp.drop_scale = 1.0f / (1.0f - p_drop);
+    rp.drop_thresh = drop_threshold(p_drop);
+    rp.drop_seed = seed; rp.drop_seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+    rp.dO_hi = static_cast<const __nv_bfloat16*>(do_hi); rp.dO_lo = static_cast<const __nv_bfloat16*>(do_lo);
+    rp.O_hi = static_cast<const __nv_bfloat16*>(o_hi); rp.O_lo = static_cast<const __nv_bfloat16*>(o_lo);
+    rp.ld_o = ldo; rp.B = B; rp.H = H; rp.Lq = Lq; rp.Lk = Lk; rp.d = d; rp.ld = ld;
+    rp.dS_hi = sh; rp.dS_lo = sl; rp.A_hi = ah; rp.A_lo = al;
+    attn_bwd_ds_recompute_kernel<<<(unsigned)ds_blocks, 256, 0, st>>>(rp);
     if (int rc = launch_check()) return rc;
   }
   const BgOperand dS = hm(sh, sl, Lk, ld), Ap = hm(ah, al, Lk, ld);
@@ -1045,8 +1072,9 @@ int lamp_attn_core_planes_train(const void* q_hi, const void* q_lo, int64_t ldq,
                                 int64_t msk, void* o_hi, void* o_lo, int64_t ldo, float* row_max, float* row_sum,
                                 float* attn, float* probs_pre, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                                 void* stream) {
-  REQUIRE(attn != nullptr && row_max && row_sum, "attn_train: attn / row statistics buffers are required");
-  REQUIRE(p_drop == 0.0f || probs_pre != nullptr, "attn_train: probs_pre is required when dropout is active");
+  REQUIRE(row_max && row_sum, "attn_train: the row statistics buffers are required");
+  REQUIRE(attn == nullptr || p_drop == 0.0f || probs_pre != nullptr,
+          "attn_train: probs_pre is required next to attn when dropout is active");
   return attn_impl(q_hi, q_lo, ldq, q_col0, q_bcast, kv_hi, kv_lo, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature,
                    precision, mask, msb, msq, msk, nullptr, 0, 0, o_hi, o_lo, ldo, nullptr, 0, row_max, row_sum, attn,
                    nullptr, nullptr, 0, stream, p_drop, seed, probs_pre, seed_dev);
@@ -1059,7 +1087,7 @@ int lamp_dropout_add(const float* y0, const float* x, int64_t rows, int D, int x
   REQUIRE(aligned16(y0) && aligned16(x) && aligned16(y), "dropout_add: alignment");
   REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "dropout_add: rate outside [0, 1)");
   if (rows == 0) return LAMP_OK;
-  const uint32_t thresh = p_drop > 0.0f ? (uint32_t)((double)p_drop * 4294967296.0) : 0u;
+  const uint32_t thresh = drop_threshold(p_drop);
   const long long blocks = (rows * 32 + 255) / 256;
   dropout_add_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       y0, x, rows, D, x_mod, thresh, 1.0f / (1.0f - p_drop), seed, reinterpret_cast<const unsigned long long*>(seed_dev), y);
@@ -1073,7 +1101,7 @@ int lamp_dropout_split(const float* dy, int64_t rows, int D, float p_drop, uint6
   REQUIRE(aligned16(dy) && aligned16(hi) && aligned16(lo), "dropout_split: alignment");
   REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "dropout_split: rate outside [0, 1)");
   if (rows == 0) return LAMP_OK;
-  const uint32_t thresh = p_drop > 0.0f ? (uint32_t)((double)p_drop * 4294967296.0) : 0u;
+  const uint32_t thresh = drop_threshold(p_drop);
   const long long blocks = (rows * 32 + 255) / 256;
   dropout_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       dy, rows, D, thresh, 1.0f / (1.0f - p_drop), seed, reinterpret_cast<const unsigned long long*>(seed_dev),

@@ -891,7 +891,7 @@ class MHATrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xq, xq_hi, xq_lo, xkv, xkv_hi, xkv_lo, Wq, Wk, Wv, Wfc, gamma, beta, eps, mask, H, d, temperature,
-                p_attn, p_out, seed_attn, seed_out):
+                p_attn, p_out, seed_attn, seed_out, want_attn):
         prec = nat.PREC_FP32
         L = nat.lib()
         B, Lq, D = xq.shape
@@ -919,16 +919,17 @@ class MHATrainFunction(torch.autograd.Function):
             gemm(xkv_hi, xkv_lo, D, wkv_hi, wkv_lo, D, Mk, 2 * hd, D, prec, out_hi=kvp[0], out_lo=kvp[1], ldp=2 * hd)
             ldq, ldkv, k_col0, v_col0 = hd, 2 * hd, 0, hd
         o_hi, o_lo = _empty_planes(Mq, hd, prec, dev)
-        attn = torch.empty((H * B, Lq, Lk), dtype=torch.float32, device=dev)
-        pre = torch.empty_like(attn) if p_attn > 0 else None
+        # want_attn False (nobody reads the attention map: the reference's layers only return it): nothing of size
+        # Lq x Lk is written by the forward; the backward rebuilds P from the saved row statistics (recompute form)
+        attn = torch.empty((H * B, Lq, Lk), dtype=torch.float32, device=dev) if want_attn else None
+        pre = torch.empty_like(attn) if (want_attn and p_attn > 0) else None
         stats = torch.empty((2, H * B * Lq), dtype=torch.float32, device=dev)
         keep, mptr, sb, sq, sk = mask_args(mask, B, Lq, Lk)
-        STATS.call('attn_core_train', 2, L.lamp_attn_core_planes_train,
+        STATS.call('attn_core_train', 2 if want_attn else 1, L.lamp_attn_core_planes_train,
                    (qp[0].data_ptr(), qp[1].data_ptr(), ldq, 0, 0, kvp[0].data_ptr(), kvp[1].data_ptr(), ldkv, k_col0, v_col0,
                     B, H, Lq, Lk, d, float(temperature), prec, mptr, sb, sq, sk, o_hi.data_ptr(), o_lo.data_ptr(), hd,
-                    stats[0].data_ptr(), stats[1].data_ptr(), attn.data_ptr(), nat.ptr(pre), float(p_attn), int(seed_attn),
+                    stats[0].data_ptr(), stats[1].data_ptr(), nat.ptr(attn), nat.ptr(pre), float(p_attn), int(seed_attn),
                     _seed_dev_ptr(), nat.stream()), flops=4.0 * H * Lq * d * B * Lk)
-        del keep
         wfc_hi, wfc_lo = _wplanes(Wfc, prec)
         y = torch.empty((Mq, D), dtype=torch.float32, device=dev)
         if p_out > 0:
@@ -939,19 +940,27 @@ class MHATrainFunction(torch.autograd.Function):
             gemm(o_hi, o_lo, hd, wfc_hi, wfc_lo, hd, Mq, D, hd, prec, residual=x2, ldr=D, out_f32=y, ldo=D)
         out = layernorm(y, gamma.detach().float().contiguous(), beta.detach().float().contiguous(), eps, prec)
         empty = xq_hi.new_empty(0)
+        emptyf = y.new_empty(0)
         ctx.save_for_backward(xq_hi, xq_lo, empty if self_attn else xkv_hi, empty if self_attn else xkv_lo, qp[0], qp[1],
-                              empty if self_attn else kvp[0], empty if self_attn else kvp[1], o_hi, o_lo, attn,
-                              pre if pre is not None else attn, y, Wq, Wk, Wv, Wfc, gamma)
+                              empty if self_attn else kvp[0], empty if self_attn else kvp[1], o_hi, o_lo,
+                              attn if want_attn else emptyf, (pre if pre is not None else attn) if want_attn else emptyf, y,
+                              Wq, Wk, Wv, Wfc, gamma, stats, keep if keep is not None else empty)
         ctx.cfg = (B, Lq, Lk, D, H, d, float(temperature), float(p_attn), float(p_out), int(seed_out), self_attn, eps,
-                   None if self_attn else tuple(xkv.shape))
-        ctx.mark_non_differentiable(out.hi, out.lo, attn)
+                   None if self_attn else tuple(xkv.shape), bool(want_attn), int(seed_attn), (sb, sq, sk),
+                   TRAIN_SEED_DEV)
+        if want_attn:
+            ctx.mark_non_differentiable(out.hi, out.lo, attn)
+        else:
+            attn = emptyf
+            ctx.mark_non_differentiable(out.hi, out.lo, attn)
         return out.f32.view(B, Lq, D), out.hi, out.lo, attn
 
     @staticmethod
     def backward(ctx, g, _ghi, _glo, _gattn):
         (xq_hi, xq_lo, xkv_hi, xkv_lo, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, attn, pre, y, Wq, Wk, Wv, Wfc,
-         gamma) = ctx.saved_tensors
-        B, Lq, Lk, D, H, d, temperature, p_attn, p_out, seed_out, self_attn, eps, kv_shape = ctx.cfg
+         gamma, stats, keep) = ctx.saved_tensors
+        (B, Lq, Lk, D, H, d, temperature, p_attn, p_out, seed_out, self_attn, eps, kv_shape, want_attn, seed_attn,
+         (sb, sq, sk), seed_dev) = ctx.cfg
         prec = nat.PREC_FP32
         L = nat.lib()
         hd = H * d
@@ -975,10 +984,13 @@ class MHATrainFunction(torch.autograd.Function):
         ws = torch.empty((max(L.lamp_attn_bwd_planes_workspace_bytes(B, H, Lq, Lk), 16),), dtype=torch.uint8, device=dev)
         STATS.call('attn_core_bwd', 5, L.lamp_attn_bwd_planes,
                    (q_hi.data_ptr(), q_lo.data_ptr(), ldq, 0, kvp[0].data_ptr(), kvp[1].data_ptr(), ldkv, k_col0, v_col0,
-                    do_hi.data_ptr(), do_lo.data_ptr(), o_hi.data_ptr(), o_lo.data_ptr(), hd, pre.data_ptr(),
-                    attn.data_ptr() if p_attn > 0 else None, dq[0].data_ptr(), dq[1].data_ptr(), lddq, 0,
+                    do_hi.data_ptr(), do_lo.data_ptr(), o_hi.data_ptr(), o_lo.data_ptr(), hd,
+                    pre.data_ptr() if want_attn else None, attn.data_ptr() if (want_attn and p_attn > 0) else None,
+                    dq[0].data_ptr(), dq[1].data_ptr(), lddq, 0,
                     dkv[0].data_ptr(), dkv[1].data_ptr(), lddkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature, p_attn,
-                    ws.data_ptr(), ws.numel(), nat.stream()), flops=10.0 * H * B * Lq * Lk * d)
+                    stats[0].data_ptr(), stats[1].data_ptr(), keep.data_ptr() if keep.numel() else None, sb, sq, sk,
+                    seed_attn, nat.ptr(seed_dev), ws.data_ptr(), ws.numel(), nat.stream()),
+                   flops=(10.0 if want_attn else 12.0) * H * B * Lq * Lk * d)
         dxq = torch.empty((Mq, D), dtype=torch.float32, device=dev)
         dxkv = None
         if self_attn:
@@ -997,7 +1009,7 @@ class MHATrainFunction(torch.autograd.Function):
             gemm(dkv[0], dkv[1], 2 * hd, wkvt_hi, wkvt_lo, 2 * hd, Mk, D, 2 * hd, prec, out_f32=dxkv, ldo=D)
             dxkv = dxkv.view(kv_shape)
         return (dxq.view(B, Lq, D), None, None, dxkv, None, None, dWq.to(Wq.dtype), dWk.to(Wk.dtype), dWv.to(Wv.dtype),
-                dWfc.to(Wfc.dtype), dgamma, dbeta, None, None, None, None, None, None, None, None, None)
+                dWfc.to(Wfc.dtype), dgamma, dbeta, None, None, None, None, None, None, None, None, None, None)
 
 
 def _train_seed() -> int:
@@ -1017,9 +1029,10 @@ def ffn_train(x: torch.Tensor, mod) -> torch.Tensor:
     return out
 
 
-def mha_train(q: torch.Tensor, kv: Optional[torch.Tensor], mask, mod):
+def mha_train(q: torch.Tensor, kv: Optional[torch.Tensor], mask, mod, want_attn: bool = True):
     """MultiHeadAttention.forward in training mode through :class:`MHATrainFunction` (``kv`` None: self-attention).
-    -> (out [B, Lq, D] with stashed planes, attn [H*B, Lq, Lk] after dropout, as the reference returns it)."""
+    -> (out [B, Lq, D] with stashed planes, attn [H*B, Lq, Lk] after dropout as the reference returns it -- or None
+    with ``want_attn=False``, in which case no probability tensor is written at all and the backward recomputes P)."""
     prec = nat.PREC_FP32
     p_attn = float(mod.attention.dropout.p) if mod.training else 0.0
     p_out = float(mod.dropout.p) if mod.training else 0.0
@@ -1029,9 +1042,9 @@ def mha_train(q: torch.Tensor, kv: Optional[torch.Tensor], mask, mod):
     out, hi, lo, attn = MHATrainFunction.apply(
         q, q_hi, q_lo, kv, kv_hi, kv_lo, mod.w_qs.weight, mod.w_ks.weight, mod.w_vs.weight, mod.fc.weight, ln.weight,
         ln.bias, ln.eps, mask, mod.n_head, mod.d_k, mod.attention.temperature, p_attn, p_out,
-        _train_seed() if p_attn > 0 else 0, _train_seed() if p_out > 0 else 0)
+        _train_seed() if p_attn > 0 else 0, _train_seed() if p_out > 0 else 0, bool(want_attn))
     out._lamp_planes = (hi, lo, out._version, prec)
-    return out, attn
+    return out, (attn if want_attn else None)
 
 
 def gold_binary(gold: torch.Tensor, n_labels: int, skip: int = 4) -> torch.Tensor:

@@ -143,3 +143,52 @@ def test_fused_sublayers_with_dropout_are_consistent_between_forward_and_backwar
     assert rel_err(xg.grad, x64.grad) < 5e-5
     for name, q in mod.named_parameters():
         assert rel_err(q.grad, p64[name].grad) < 5e-5, name
+
+
+@pytest.mark.parametrize('case', ['self_prior', 'enc_pad'])
+def test_mha_train_recompute_form_matches_fp64_autograd_and_the_stored_form(case):
+    """return_attn=False in training: the forward writes no probability tensor, the backward rebuilds P from the saved
+    row statistics, the mask and the dropout hash (lamp_attn_bwd_planes, recompute form).  (i) without dropout: fp64
+    autograd of the oracle; (ii) with attention dropout 0.2 and the same seeds: identical to the stored-P form."""
+    cfg = dict(self_prior=dict(B=2, Lq=103, Lk=103, D=512, H=4, mask='prior', self_attn=True, seed=201),
+               enc_pad=dict(B=3, Lq=53, Lk=90, D=256, H=4, mask='pad', self_attn=False, seed=203))[case]
+    c = dict(cfg)
+    p, q, kv, mask = cases.mha_inputs(c)
+    d = c['D'] // c['H']
+    rs = np.random.RandomState(9)
+    w = torch.from_numpy(rs.standard_normal(q.shape).astype(np.float32)).to(DEV)
+    m_dev = None if mask is None else mask.to(DEV)
+
+    def run(p_drop, return_attn, seed):
+        mod = MultiHeadAttention(c['H'], c['D'], d, d, dropout=p_drop)
+        mod.load_state_dict(p, strict=True)
+        mod = mod.to(DEV).train()
+        qg = q.to(DEV).requires_grad_(True)
+        kvg = qg if c['self_attn'] else kv.to(DEV).requires_grad_(True)
+        torch.manual_seed(seed)
+        ops.STATS.reset()
+        out, attn = mod(qg, kvg, kvg, attn_mask=m_dev, return_attn=return_attn)
+        assert (attn is None) == (not return_attn)
+        assert ops.STATS.by_kernel.get('attn_core_train', 0) == (2 if return_attn else 1)
+        (out * w).sum().backward()
+        grads = {n: x.grad.clone() for n, x in mod.named_parameters()}
+        grads['q'] = qg.grad.clone()
+        if not c['self_attn']:
+            grads['kv'] = kvg.grad.clone()
+        return out.detach(), grads
+
+    out, grads = run(0.0, False, 1)
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    q64 = q.double().requires_grad_(True)
+    kv64 = q64 if c['self_attn'] else kv.double().requires_grad_(True)
+    ref, _ = orc.mha(p64, '', q64, kv64, kv64, mask, c['H'])
+    (ref * w.double().cpu()).sum().backward()
+    assert rel_err(out, ref) < 2e-5 and rel_err(grads['q'], q64.grad) < 5e-5
+    for name in p:
+        assert rel_err(grads[name], p64[name].grad) < 5e-5, name
+    # with dropout: stored-P form and recompute form see the same masks (same seeds) -> same results
+    out_a, g_a = run(0.2, True, 77)
+    out_b, g_b = run(0.2, False, 77)
+    assert rel_err(out_b, out_a) < 1e-6
+    for name in g_a:
+        assert rel_err(g_b[name], g_a[name]) < 2e-5, name
