@@ -95,6 +95,37 @@ class GraphEncoder(nn.Module):
             attns.append(attn)
         return self._pool(out, src_seq, src_seq.size(0)), attns
 
+    def _train_packed_ok(self, src_seq, adj, return_attns) -> bool:
+        return (ops.PACKED_TRAINING and ops.FUSED_TRAINING and ops.NATIVE_TRAINING and ops.ELIDE_DEAD_ENCODER_ATTENTION
+                and not return_attns and not adj and not self.onehot and self.enc_transform == '' and src_seq.is_cuda
+                and len(self.layer_stack) > 0 and ops.default_precision() == nat.PREC_FP32
+                and all(l.pos_ffn.fused_ok() and l.pos_ffn.precision is None for l in self.layer_stack)
+                and self.src_word_emb.weight.dtype == torch.float32 and not torch.cuda.is_current_stream_capturing())
+
+    def _forward_train_packed(self, src_seq, src_pos):
+        """Training forward on the PACKED non-PAD token rows.  The encoder is a per-row map (embedding, FFN, LayerNorm;
+        the token self-attention never reaches the output, lamp/Layers.py:16-18) and the decoder masks PAD keys
+        (lamp/Decoders.py:137-138), so PAD rows neither influence the logits nor receive gradients: the FFN stack runs
+        on the n non-PAD rows plus ONE PAD representative (so that the returned enc_output still holds the reference's
+        values at PAD positions).  One host read (the row count) per step."""
+        B, T = src_seq.shape
+        seq_flat, pos_flat = src_seq.reshape(-1), src_pos.reshape(-1)
+        keep = seq_flat.ne(Constants.PAD)
+        idx = torch.nonzero(keep).squeeze(1)                      # [n] packed row -> dense position (host sync)
+        n = idx.numel()
+        src_row = torch.where(keep, torch.cumsum(keep.to(torch.int64), 0) - 1, torch.full_like(seq_flat, n))
+        pad_tok = torch.zeros((1,), dtype=seq_flat.dtype, device=seq_flat.device)  # (PAD, position 0): the representative
+        seq_p = torch.cat((seq_flat.index_select(0, idx), pad_tok))
+        x = self.src_word_emb(seq_p)
+        if hasattr(self, 'position_enc'):
+            x = x + self.position_enc(torch.cat((pos_flat.index_select(0, idx), pad_tok)))
+        out = x.unsqueeze(0)                                      # [1, n + 1, D]
+        for layer in self.layer_stack:
+            out = layer.pos_ffn(out)                              # ops.FFNTrainFunction, planes stashed on the result
+        dense = out[0].index_select(0, src_row).view(B, T, self.d_model)   # API tensor (PAD rows = the representative)
+        dense._lamp_train_packed = dict(packed=out, src_row=src_row, idx=idx, version=dense._version)
+        return dense
+
     def _forward_fused(self, src_seq, src_pos, return_attns):
         B, T = src_seq.shape
         prec = ops.default_precision() if self.layer_stack[0].pos_ffn.precision is None \
@@ -162,7 +193,9 @@ class GraphEncoder(nn.Module):
 
     def forward(self, src_seq, adj, src_pos, return_attns=False):
         nat.require_cuda(src_seq, src_pos)
-        if _needs_autograd(self) or not self.fused_ok(adj):
+        if _needs_autograd(self) and self._train_packed_ok(src_seq, adj, return_attns):
+            out, attns = self._forward_train_packed(src_seq, src_pos), [None] * len(self.layer_stack)
+        elif _needs_autograd(self) or not self.fused_ok(adj):
             out, attns = self._forward_composed(src_seq, adj, src_pos, return_attns)
         else:
             out, attns = self._forward_fused(src_seq, src_pos, return_attns)

@@ -765,6 +765,8 @@ class DiagProjFunction(torch.autograd.Function):
 # split / merge copies, no fp32 -> planes re-splits of activations that a previous kernel already produced as planes, no
 # stored dropout masks (counter-hash masks are recomputed in the backward), ReLU / bias / residual in GEMM epilogues.
 FUSED_TRAINING = os.environ.get('LAMP_FUSED_TRAIN', '1') != '0'
+# training encoder on the packed non-PAD token rows (one host read of the row count per step; dense inside graph captures)
+PACKED_TRAINING = os.environ.get('LAMP_PACKED_TRAIN', '1') != '0'
 
 
 def planes_of(x: torch.Tensor, prec: int) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -891,12 +893,16 @@ class MHATrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xq, xq_hi, xq_lo, xkv, xkv_hi, xkv_lo, Wq, Wk, Wv, Wfc, gamma, beta, eps, mask, H, d, temperature,
-                p_attn, p_out, seed_attn, seed_out, want_attn):
+                p_attn, p_out, seed_attn, seed_out, want_attn, kv_map):
+        """``kv_map`` (label<-input attention over a padding-aware encoder output): ``xkv`` is then the PACKED
+        [1, n+1, D] encoder activation (non-PAD token rows + one PAD representative), ``kv_map = (src_row [B*T] int64:
+        dense position -> packed row, idx [n] int64: packed row -> dense position, T)``.  K|V are projected on the
+        packed rows only and scattered into the dense [B*T, 2*H*d] layout the attention core reads."""
         prec = nat.PREC_FP32
         L = nat.lib()
         B, Lq, D = xq.shape
         self_attn = xkv is None
-        Lk = Lq if self_attn else xkv.shape[1]
+        Lk = Lq if self_attn else (kv_map[2] if kv_map is not None else xkv.shape[1])
         hd = H * d
         dev = xq.device
         x2 = xq.detach().reshape(-1, D).float().contiguous()
@@ -914,9 +920,16 @@ class MHATrainFunction(torch.autograd.Function):
             wq_hi, wq_lo = _wplanes(Wq, prec)
             wkv_hi, wkv_lo = _wplanes(torch.cat((Wk.detach(), Wv.detach()), dim=0), prec)
             qp = _empty_planes(Mq, hd, prec, dev)
-            kvp = _empty_planes(Mk, 2 * hd, prec, dev)
             gemm(xq_hi, xq_lo, D, wq_hi, wq_lo, D, Mq, hd, D, prec, out_hi=qp[0], out_lo=qp[1], ldp=hd)
-            gemm(xkv_hi, xkv_lo, D, wkv_hi, wkv_lo, D, Mk, 2 * hd, D, prec, out_hi=kvp[0], out_lo=kvp[1], ldp=2 * hd)
+            if kv_map is None:
+                kvp = _empty_planes(Mk, 2 * hd, prec, dev)
+                gemm(xkv_hi, xkv_lo, D, wkv_hi, wkv_lo, D, Mk, 2 * hd, D, prec, out_hi=kvp[0], out_lo=kvp[1], ldp=2 * hd)
+            else:
+                n_rows = xkv_hi.shape[0]
+                kpk = _empty_planes(n_rows, 2 * hd, prec, dev)
+                gemm(xkv_hi, xkv_lo, D, wkv_hi, wkv_lo, D, n_rows, 2 * hd, D, prec, out_hi=kpk[0], out_lo=kpk[1], ldp=2 * hd)
+                kvp = (kpk[0].index_select(0, kv_map[0]), kpk[1].index_select(0, kv_map[0]))   # dense [B*T, 2hd]
+                del kpk
             ldq, ldkv, k_col0, v_col0 = hd, 2 * hd, 0, hd
         o_hi, o_lo = _empty_planes(Mq, hd, prec, dev)
         # want_attn False (nobody reads the attention map: the reference's layers only return it): nothing of size
@@ -947,7 +960,7 @@ class MHATrainFunction(torch.autograd.Function):
                               Wq, Wk, Wv, Wfc, gamma, stats, keep if keep is not None else empty)
         ctx.cfg = (B, Lq, Lk, D, H, d, float(temperature), float(p_attn), float(p_out), int(seed_out), self_attn, eps,
                    None if self_attn else tuple(xkv.shape), bool(want_attn), int(seed_attn), (sb, sq, sk),
-                   TRAIN_SEED_DEV)
+                   TRAIN_SEED_DEV, None if kv_map is None else kv_map[1])
         if want_attn:
             ctx.mark_non_differentiable(out.hi, out.lo, attn)
         else:
@@ -960,7 +973,7 @@ class MHATrainFunction(torch.autograd.Function):
         (xq_hi, xq_lo, xkv_hi, xkv_lo, q_hi, q_lo, kv_hi, kv_lo, o_hi, o_lo, attn, pre, y, Wq, Wk, Wv, Wfc,
          gamma, stats, keep) = ctx.saved_tensors
         (B, Lq, Lk, D, H, d, temperature, p_attn, p_out, seed_out, self_attn, eps, kv_shape, want_attn, seed_attn,
-         (sb, sq, sk), seed_dev) = ctx.cfg
+         (sb, sq, sk), seed_dev, kv_idx) = ctx.cfg
         prec = nat.PREC_FP32
         L = nat.lib()
         hd = H * d
@@ -1002,6 +1015,12 @@ class MHATrainFunction(torch.autograd.Function):
             dWq, _ = _gemm_tn(dq[0], dq[1], hd, xq_hi, xq_lo, D, Mq, False)
             wqt_hi, wqt_lo = _wplanes(Wq, prec, transpose=True)      # [D, hd]
             gemm(dq[0], dq[1], hd, wqt_hi, wqt_lo, hd, Mq, D, hd, prec, residual=dy, ldr=D, out_f32=dxq, ldo=D)
+            if kv_idx is not None:
+                # packed encoder rows: gather the key/value gradients of the non-PAD positions; the PAD representative
+                # (last packed row) gets exactly zero -- PAD keys are masked, their dK / dV are 0
+                zrow = dkv[0].new_zeros((1, 2 * hd))
+                dkv = (torch.cat((dkv[0].index_select(0, kv_idx), zrow)), torch.cat((dkv[1].index_select(0, kv_idx), zrow)))
+                Mk = dkv[0].shape[0]
             dWkv, _ = _gemm_tn(dkv[0], dkv[1], 2 * hd, xkv_hi, xkv_lo, D, Mk, False)
             dWk, dWv = dWkv[:hd], dWkv[hd:]
             wkvt_hi, wkvt_lo = _wplanes(torch.cat((Wk.detach(), Wv.detach()), dim=0), prec, transpose=True)  # [D, 2hd]
@@ -1009,7 +1028,7 @@ class MHATrainFunction(torch.autograd.Function):
             gemm(dkv[0], dkv[1], 2 * hd, wkvt_hi, wkvt_lo, 2 * hd, Mk, D, 2 * hd, prec, out_f32=dxkv, ldo=D)
             dxkv = dxkv.view(kv_shape)
         return (dxq.view(B, Lq, D), None, None, dxkv, None, None, dWq.to(Wq.dtype), dWk.to(Wk.dtype), dWv.to(Wv.dtype),
-                dWfc.to(Wfc.dtype), dgamma, dbeta, None, None, None, None, None, None, None, None, None, None)
+                dWfc.to(Wfc.dtype), dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def _train_seed() -> int:
@@ -1037,12 +1056,19 @@ def mha_train(q: torch.Tensor, kv: Optional[torch.Tensor], mask, mod, want_attn:
     p_attn = float(mod.attention.dropout.p) if mod.training else 0.0
     p_out = float(mod.dropout.p) if mod.training else 0.0
     q_hi, q_lo = planes_of(q, prec)
+    kv_map = None
+    if kv is not None:
+        pk = getattr(kv, '_lamp_train_packed', None)
+        if pk is not None and pk['version'] == kv._version and PACKED_TRAINING:
+            # padding-aware encoder output (Encoders.GraphEncoder, training): project K|V on the packed rows only
+            kv_map = (pk['src_row'], pk['idx'], kv.shape[1])
+            kv = pk['packed']
     kv_hi, kv_lo = (None, None) if kv is None else planes_of(kv, prec)
     ln = mod.layer_norm
     out, hi, lo, attn = MHATrainFunction.apply(
         q, q_hi, q_lo, kv, kv_hi, kv_lo, mod.w_qs.weight, mod.w_ks.weight, mod.w_vs.weight, mod.fc.weight, ln.weight,
         ln.bias, ln.eps, mask, mod.n_head, mod.d_k, mod.attention.temperature, p_attn, p_out,
-        _train_seed() if p_attn > 0 else 0, _train_seed() if p_out > 0 else 0, bool(want_attn))
+        _train_seed() if p_attn > 0 else 0, _train_seed() if p_out > 0 else 0, bool(want_attn), kv_map)
     out._lamp_planes = (hi, lo, out._version, prec)
     return out, (attn if want_attn else None)
 
