@@ -3,10 +3,10 @@
 // Both operands are consumed "MN-major": in dY [M, N] and X [M, K] (row-major planes) the contraction index m is the
 // slow dimension and the output indices n / k are contiguous, which is exactly the layout tcgen05 reads with the
 // a_major / b_major bits set -- no transposed copies of the activations are ever made.  TMA stages [64 rows x 64
-// columns] boxes (128B swizzle) of the hi / lo planes: two boxes form the 128-wide n tile of dY (operand A, M = 128),
+// columns] boxes (TNC_BM rows x 64 columns in general; 128B swizzle) of the hi / lo planes: two boxes form the 128-wide n tile of dY (operand A, M = 128),
 // four the 256-wide k tile of X (operand B, N = 256); one UMMA K-step consumes 16 rows.  3-term split-bf16 products.
-//   warp 0: TMA producer (2-stage ring of 96 KB stages)      warp 1: MMA issuer (accumulator: 256 TMEM columns)
-//   warps 2-5: epilogue -- tcgen05.ld (lane == n row) and fp32 red.global.add into dW: the M rows are split across
+//   warp 0: TMA producer (4-stage ring of 48 KB stages)      warp 1: MMA issuer (accumulator: 256 TMEM columns)
+//   warps 2-5: epilogue -- tcgen05.ld (lane == n row), smem transpose, 128-bit vector red.global.add into dW: the M rows are split across
 //              CTAs (split-K of this contraction), so that all SMs work on the few output tiles of a 512 x 512 weight.
 // One CTA = one (n tile, k tile, row chunk).
 #pragma once
@@ -14,13 +14,14 @@
 
 namespace lamp {
 
-constexpr int TNC_BM = 64;         // rows (contraction) per stage
+constexpr int TNC_BM = 32;         // rows (contraction) per stage: 48 KB stages, 4 in flight (64-row stages left only
+                                   // ONE 96 KB stage in flight while the other was consumed: load-latency bound)
 constexpr int TNC_TILE_N = 128;    // dW rows per CTA (UMMA M)
 constexpr int TNC_TILE_K = 256;    // dW columns per CTA (UMMA N)
 constexpr int TNC_THREADS = 192;
 constexpr uint32_t TNC_BOX_BYTES = TNC_BM * 128;  // one [64 x 64] bf16 box
 __host__ __device__ constexpr uint32_t tnc_stage_bytes(int npl) { return npl * (2 + 4) * TNC_BOX_BYTES; }
-__host__ __device__ constexpr int tnc_stages(int npl) { return npl == 2 ? 2 : 4; }
+__host__ __device__ constexpr int tnc_stages(int npl) { return npl == 2 ? 4 : 8; }
 __host__ __device__ constexpr uint32_t tnc_smem_bytes(int npl) { return tnc_stages(npl) * tnc_stage_bytes(npl) + 1024 + 256; }
 
 struct GemmTnParams {
@@ -126,22 +127,40 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_const
       umma_commit(acc_full);
     }
   } else {
-    // epilogue: TMEM lane == dW row inside the tile; 32 columns per tcgen05.ld, fp32 atomics into dW
+    // epilogue: TMEM lane == dW row inside the tile; 32 columns per tcgen05.ld.  The chunk is transposed through a
+    // per-warp smem slice (the operand ring is idle by now) so that the reductions into dW leave as 128-bit vector
+    // red.global.add over CONTIGUOUS row segments: 8 lanes cover the 32 columns of a row, one instruction 4 rows -- a
+    // scalar atomicAdd per (lane == row) element touched 32 different sectors per instruction and made the L2 atomic
+    // units the bottleneck of this split-K contraction.
     const int wq = warp & 3;
-    const int n = n0 + wq * 32 + lane;
     mbar_wait(acc_full, 0);
     tcgen05_fence_after();
     if (num_it > 0) {
-      float* row = p.dW + static_cast<long long>(n) * p.K + k0;
+      float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);  // [32 rows][36]: 16-byte aligned rows
+      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
       for (int c0 = 0; c0 < TNC_TILE_K; c0 += 32) {
+        if (k0 + c0 >= p.K) break;
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + c0, r);
         tmem_wait_ld();
-        if (n < p.N) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (k0 + c0 + e < p.K) atomicAdd(row + c0 + e, __uint_as_float(r[e]));
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + e) = make_float4(__uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                                                                        __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+        __syncwarp();
+        const bool col_ok = k0 + c0 + sub_c < p.K;  // K % 8 == 0: the 4 columns are all in or all out
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub_r;
+          const int n = n0 + wq * 32 + rr;
+          if (n < p.N && col_ok) {
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + sub_c);
+            float* dst = p.dW + static_cast<long long>(n) * p.K + k0 + c0 + sub_c;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
         }
+        __syncwarp();
       }
     }
   }

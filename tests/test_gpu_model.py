@@ -210,8 +210,10 @@ def test_training_with_dropout_runs_native_core_and_is_seeded():
     assert ops.STATS.by_kernel.get('attn_core_bwd', 0) > 0
     l2, g2 = step(5)
     l3, g3 = step(6)
-    assert l1 == l2 and torch.equal(g1, g2)
-    assert l1 != l3 and not torch.equal(g1, g3)
+    # same seed -> same dropout masks: identical loss; the gradients agree to fp32 summation order (the split-K weight
+    # gradient reduces its partial tiles with fp32 red.global.add, whose order is not fixed)
+    assert l1 == l2 and rel_err(g2, g1) < 1e-5
+    assert l1 != l3 and rel_err(g3, g1) > 1e-3
     assert torch.isfinite(g1).all()
 
 
