@@ -147,6 +147,9 @@ class GraphDecoder(nn.Module):
         LayerNorm is still pending, to be applied inside the label-projection kernel."""
         nat.require_cuda(src_seq, enc_output)
         if _needs_autograd(self, enc_output) or not self.fused_ok():
+            if not _needs_autograd(self, enc_output):
+                ops.warn_torch_fallback('GraphDecoder (eval)', 'a layer has a shape the kernels do not cover (see the '
+                                        'MultiHeadAttention / PositionwiseFeedForward conditions)')
             out, int_outs, slf_attns, enc_attns = self._forward_composed(src_seq, enc_output, return_attns, int_preds)
         else:
             out, int_outs, slf_attns, enc_attns = self._forward_fused(src_seq, enc_output, return_attns, int_preds,

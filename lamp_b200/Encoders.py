@@ -196,6 +196,9 @@ class GraphEncoder(nn.Module):
         if _needs_autograd(self) and self._train_packed_ok(src_seq, adj, return_attns):
             out, attns = self._forward_train_packed(src_seq, src_pos), [None] * len(self.layer_stack)
         elif _needs_autograd(self) or not self.fused_ok(adj):
+            if not _needs_autograd(self):
+                ops.warn_torch_fallback('GraphEncoder (eval)', 'the one-hot (genomics) front-end, per-sample adjacency masks '
+                                        '(sider) and feature counts that are not multiples of 8 run as torch ops')
             out, attns = self._forward_composed(src_seq, adj, src_pos, return_attns)
         else:
             out, attns = self._forward_fused(src_seq, src_pos, return_attns)

@@ -88,6 +88,9 @@ class ScaledDotProductAttention(nn.Module):
         if _needs_autograd(self, q, k, v):
             return self.train_core(q, k, v, attn_mask)
         if not self._kernel_ok(q, k, v):
+            ops.warn_torch_fallback('ScaledDotProductAttention (eval)',
+                                    f'the kernels need softmax attention and a head width that is a multiple of 16 and <= 128; '
+                                    f'got {self.attn_kind}, d={q.shape[-1]}')
             return self._composed(q, k, v, attn_mask)
         prec = ops.default_precision() if self.precision is None else self.precision
         return ops.sdpa(q, k, v, attn_mask, self.temperature, prec, want_attn=True)
@@ -208,6 +211,9 @@ class MultiHeadAttention(nn.Module):
         if _needs_autograd(self, q, k, v):
             return self._composed(q, k, v, attn_mask, want_attn=return_attn)
         if not self.fused_ok():
+            ops.warn_torch_fallback('MultiHeadAttention (eval)',
+                                    f'the kernels need softmax attention, d_k == d_v, d_k % 16 == 0, d_k <= 128 and d_model % 8 == 0; '
+                                    f'got {self.attn_kind}, d_k={self.d_k}, d_v={self.d_v}, d_model={self.d_model}')
             return self._composed(q, k, v, attn_mask)
         B, Lq, D = q.shape
         Lk = k.shape[1]
@@ -270,7 +276,10 @@ class PositionwiseFeedForward(nn.Module):
 
     def forward(self, x):
         nat.require_cuda(x)
-        if _needs_autograd(self, x) or not self.fused_ok():
+        if _needs_autograd(self, x):
+            return self._composed(x)
+        if not self.fused_ok():
+            ops.warn_torch_fallback('PositionwiseFeedForward (eval)', 'the kernels need d_in and d_hid to be multiples of 8')
             return self._composed(x)
         prec = ops.default_precision() if self.precision is None else self.precision
         out = self.forward_act(ops.act_from_tensor(x, prec))

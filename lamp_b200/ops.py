@@ -1127,8 +1127,9 @@ _WARNED: set = set()
 
 
 def warn_torch_fallback(what: str, why: str) -> None:
-    """The training path never falls back silently: the first time a stage runs as torch ops although the native
-    training path is enabled, say so (once per stage / reason)."""
+    """Nothing falls back silently: the first time a stage runs as torch ops (CUDA, eager) instead of the native
+    kernels -- a training stage while the native training path is enabled, or an eval call whose shape the kernels do
+    not cover -- say so (once per stage / reason).  There is never a CPU fallback."""
     if (what, why) not in _WARNED:
         _WARNED.add((what, why))
         import warnings
