@@ -19,6 +19,7 @@ from lamp_b200.Models import LAMP  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, nargs='+', default=[32, 256])
 ap.add_argument('--steps', type=int, default=10)
+ap.add_argument('--native-only', action='store_true', help='only the native eager step (profiling runs)')
 ap.add_argument('--ddp', action='store_true',
                 help='under torchrun: one process per GPU, per-rank batch, flat NCCL gradient all-reduce every step '
                      '(lamp_b200.distributed.allreduce_gradients); prints whole-job samples/s from rank 0')
@@ -79,7 +80,7 @@ for B in args.batch:
     src_seq, src_pos = syn.make_tokens(B, c['T'], c['V'], 1)
     src = (src_seq.to(dev), src_pos.to(dev))
     tgt = (torch.rand(B, c['L'], device=dev) < 0.05).float()
-    for native in (True, False):
+    for native in ((True,) if args.native_only else (True, False)):
         ops.NATIVE_ATTENTION_BACKWARD = ops.NATIVE_TRAINING = native
         d = c['D'] // c['H']
         model = LAMP(c['V'] + 4, c['L'], c['T'], c['L'], n_layers_enc=c['n_enc'], n_layers_dec=c['n_dec'], n_head=c['H'],
@@ -118,6 +119,8 @@ for B in args.batch:
                               native_launches_per_step=ops.STATS.launches / args.steps,
                               kernels={k: v // args.steps for k, v in ops.STATS.by_kernel.items()})), flush=True)
     ops.NATIVE_ATTENTION_BACKWARD = ops.NATIVE_TRAINING = True
+    if args.native_only:
+        continue
     # the same native step replayed as one CUDA graph (lamp_b200.GraphedTrainStep)
     import lamp_b200
     model = LAMP(c['V'] + 4, c['L'], c['T'], c['L'], n_layers_enc=c['n_enc'], n_layers_dec=c['n_dec'], n_head=c['H'],

@@ -1,10 +1,17 @@
 #!/usr/bin/env python
 """Turn an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv` launch log of
-bench.py into profiles/r01_traffic.json (average DRAM bytes per launch for each lamp_b200 kernel family)."""
+bench.py into profiles/r02_traffic.json (average DRAM bytes per launch for each lamp_b200 kernel family).  The file
+records the hash of the native sources it was captured with (bench.lib_source_hash); bench.py quotes it in
+`roofline.traffic` only while that hash matches the library it runs.
+usage: python scripts/ncu_traffic.py <launches.csv> <out.json> <batch> <precision>"""
 import collections
 import csv
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402  (lib_source_hash)
 
 log, out, batch, precision = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
 rows = [r for r in csv.reader(open(log)) if len(r) > 5]
@@ -44,7 +51,7 @@ for rec in per.values():
     a[0] += 1
     a[1] += rec.get('dram__bytes_read.sum', 0.0) + rec.get('dram__bytes_write.sum', 0.0)
     a[2] += rec.get('gpu__time_duration.sum', 0.0)
-res = dict(batch=batch, precision=precision, source=log,
+res = dict(batch=batch, precision=precision, source=log, lib_source_hash=bench.lib_source_hash(),
            avg_bytes_per_launch={k: v[1] / v[0] for k, v in agg.items()},
            launches={k: v[0] for k, v in agg.items()},
            avg_duration_us={k: v[2] / v[0] * 1e6 for k, v in agg.items()})
