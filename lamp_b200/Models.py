@@ -54,6 +54,13 @@ class LAMP(nn.Module):
         if int_preds:
             self.tgt_word_proj_copy = XavierLinear(d_model, n_tgt_vocab, bias=bias)
 
+    def __getstate__(self):
+        # run-time caches (CUDA graphs of the eval forward, the weight-plane freshness stamp) are not part of a copy
+        state = dict(super().__getstate__() if hasattr(super(), '__getstate__') else self.__dict__)
+        state.pop('_eval_graphs', None)
+        state.pop('_lamp_planes_state', None)
+        return state
+
     def get_trainable_parameters(self):
         """Everything except the frozen sinusoid table (and the one-hot table) -- lamp/Models.py:97-107."""
         frozen = set()

@@ -326,6 +326,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         umma_commit(&s_full[sb]);
         umma_commit(&kv_empty[ks]);
         if (x.j == x.nkv - 1) umma_commit(q_empty);
+        ATTN_TRACE(3, u);
       };
 
       // O(item parity) (+)= P(u) V_u
@@ -377,6 +378,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         umma_commit(&pv_done[sb]);
         umma_commit(&kv_empty[vs]);
         umma_commit(&s_free[sb]);  // the score / P buffer may be overwritten by S(u + 2)
+        ATTN_TRACE(5, u);
       };
 
       UnitIt si{static_cast<int>(blockIdx.x), 0, 1, 0, 0u, 0u};

@@ -109,6 +109,12 @@ class EvalGraphCache:
         self.pool = None
         self.replays = self.captures = self.eager_calls = 0
 
+    def __deepcopy__(self, memo):
+        return None   # a copied model (copy.deepcopy: train.py:45) builds its own cache on first use; graphs do not copy
+
+    def __reduce__(self):
+        return (type(None), ())   # ... and a pickled one carries none
+
     def _key(self, B: int, Tb: int, dev) -> tuple:
         from . import ops
         return (B, Tb, dev.index, ops.default_precision(), ops.PADDING_AWARE, ops.DEFER_LAYERNORM, ops.FUSE_LAYERNORM)

@@ -206,6 +206,17 @@ class WeightPlanes:
         self._cache: Dict[tuple, _PlaneEntry] = {}
         self._lock = threading.Lock()
 
+    # A copy of a module (copy.deepcopy(model) -- the reference does that at train.py:45 -- or pickling) starts with an
+    # empty cache of its own: plane buffers belong to the parameters they were split from, and locks do not copy.
+    def __deepcopy__(self, memo):
+        return WeightPlanes()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
     @staticmethod
     def _sig(deps, extra) -> tuple:
         return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in deps) + extra + (WEIGHTS_EPOCH,)

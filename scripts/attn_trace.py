@@ -24,14 +24,14 @@ nat.LIB_PATH = TRACE_LIB
 from lamp_b200 import ops  # noqa: E402
 
 DEV = 'cuda'
-NAMES = ['Kld', 'Qld', 'Vld', '-', 'Siss', '-', 'PViss', 'Sdone', 'maxbar', 'Pst', 'Odone', 'epiend', 'Pseen', 'Vland',
+NAMES = ['Kld', 'Qld', 'Vld', 'Send', 'Siss', 'PVend', 'PViss', 'Sdone', 'maxbar', 'Pst', 'Odone', 'epiend', 'Pseen', 'Vland',
          'Kland', 'Sfree']
 
 
 def main():
-    which = next((a for a in sys.argv[1:] if a in ('self', 'enc', 'l159', 'l983', 'l4096')), 'self')
+    which = next((a for a in sys.argv[1:] if a in ('self', 'enc', 'encp', 'l159', 'l983', 'l4096')), 'self')
     B, H, d, prec = 1100, 4, 128, 0
-    Lq, Lk = (103, 300) if which == 'enc' else (103, 103)
+    Lq, Lk = (103, 300) if which in ('enc', 'encp') else (103, 103)
     if which == 'l159':      # cfg-3: bibtex, H=8, bf16, fully connected
         B, H, d, prec, Lq, Lk = 1024, 8, 64, 1, 159, 159
     elif which == 'l983':    # cfg-4: delicious, prior mask
@@ -40,7 +40,8 @@ def main():
         B, H, d, prec, Lq, Lk = 4, 16, 64, 1, 4096, 4096
     hd = H * d
     torch.manual_seed(0)
-    if which != 'enc':
+    kv_start = kv_len = None
+    if which not in ('enc', 'encp'):
         qkv = ops.Act(None, *ops.split(torch.randn(B * Lq, 3 * hd, device=DEV), prec), B * Lq, 3 * hd)
         q = kv = qkv
         qc, kc, vc = 0, hd, 2 * hd
@@ -54,12 +55,18 @@ def main():
         qc, kc, vc = 0, 0, hd
         mask = (torch.rand(B, 1, Lk, device=DEV) < 0.3)
         mask[:, :, 0] = False
+        if which == 'encp':   # packed keys as in the bench: per-sample key counts U{20..300}, K|V rows packed back to back
+            lens = torch.randint(20, Lk + 1, (B,), device=DEV, dtype=torch.int32)
+            lens[0] = Lk
+            kv_len = lens
+            kv_start = (torch.cumsum(lens, 0) - lens).to(torch.int32)
+            mask = None
     for _ in range(300 if Lq < 200 else 30):  # long enough for the clocks to settle
-        ops.attention(q, qc, kv, kc, vc, B, H, Lq, Lk, d, prec, mask, False)
+        ops.attention(q, qc, kv, kc, vc, B, H, Lq, Lk, d, prec, mask, False, kv_start=kv_start, kv_len=kv_len)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.attention(q, qc, kv, kc, vc, B, H, Lq, Lk, d, prec, mask, False)
+    ops.attention(q, qc, kv, kc, vc, B, H, Lq, Lk, d, prec, mask, False, kv_start=kv_start, kv_len=kv_len)
     e1.record()
     torch.cuda.synchronize()
     print(f'{which}: launch {e0.elapsed_time(e1) * 1e3:.1f} us')
@@ -84,6 +91,8 @@ def main():
     print(f'K load issue -> Q load issue:           {gap(0, 1):.0f}')
     print(f'V load issue -> PV issue (same unit):   {gap(2, 6):.0f}')
     print(f'V load issue(u) -> K load issue(u+1):   {gap(2, 0, 1):.0f}')
+    print(f'S issue loop (issue -> end):            {gap(4, 3):.0f}')
+    print(f'PV issue loop (issue -> end):           {gap(6, 5):.0f}')
     print(f'S issued -> S complete seen:            {gap(4, 7):.0f}')
     print(f'S complete -> max barrier:              {gap(7, 8):.0f}')
     print(f'max barrier -> P stored:                {gap(8, 9):.0f}')

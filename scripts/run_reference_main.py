@@ -66,7 +66,8 @@ def main():
     flags = ['-dataroot', dataroot + '/', '-dataset', 'synth', '-batch_size', str(dims['batch']), '-d_model', str(dims['d']),
              '-d_inner_hid', str(dims['dh']), '-n_layers_enc', str(dims['layers']), '-n_layers_dec', str(dims['layers']),
              '-n_head', str(dims['heads']), '-epoch', str(args.epochs), '-dropout', '0.2', '-dec_dropout', '0.2',
-             '-lr', '0.0002', '-encoder', 'graph', '-decoder', 'graph', '-label_mask', 'prior', '-overwrite'] + (['-no_cuda'] if args.no_cuda else [])
+             '-lr', '0.0002', '-encoder', 'graph', '-decoder', 'graph', '-label_mask', 'prior', '-overwrite',
+             '-thresh1', '1']   # epoch == thresh1: train.py:45 deep-copies the model every step of that epoch + (['-no_cuda'] if args.no_cuda else [])
     env = dict(os.environ, PYTHONPATH=ROOT)
     if args.gpus is not None:
         env['CUDA_VISIBLE_DEVICES'] = args.gpus

@@ -267,3 +267,24 @@ def test_bce_with_logits_kernel_matches_torch_value_and_gradient():
             (gg,) = torch.autograd.grad(got * 3.0, x)
             assert abs(float(got) - float(want)) < 1e-6 * max(1.0, abs(float(want))), shape
             assert rel_err(gg, gw * 3.0) < 1e-5, shape
+
+
+def test_deepcopy_after_graph_capture_gives_an_independent_working_model():
+    """train.py:45 deep-copies the model mid-training; with captured eval graphs and filled weight-plane caches the copy
+    must work on its own (fresh caches) and follow ITS parameters."""
+    import copy
+    c = cases.MODEL_CASES['lamp_L37_none']
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    model = build_model(c, p, adj)
+    src = (src_seq.to(DEV), src_pos.to(DEV))
+    a = [model(src, None, None, None)[0] for _ in range(3)][-1]       # eager, capture, replay
+    twin = copy.deepcopy(model)
+    assert '_eval_graphs' not in twin.__dict__
+    b = [twin(src, None, None, None)[0] for _ in range(3)][-1]
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        for q in twin.parameters():
+            q.mul_(1.01)
+    b2 = twin(src, None, None, None)[0]
+    a2 = model(src, None, None, None)[0]
+    assert torch.equal(a2, a) and rel_err(b2, a) > 1e-4

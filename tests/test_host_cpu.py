@@ -341,3 +341,25 @@ def test_get_gold_binary_host_semantics_equal_the_reference():
         sys.path.remove(ref)
         for m in [k for k in sys.modules if k == 'utils' or k.startswith('utils.')]:
             del sys.modules[m]
+
+
+def test_model_deepcopy_and_pickle_drop_runtime_caches():
+    """train.py:45 runs copy.deepcopy(model) on every step of epoch `thresh1`: run-time caches (weight-plane caches with
+    their locks, the eval CUDA-graph cache) must not break it, and the copy must start with empty caches."""
+    import copy
+    import io
+    from lamp_b200 import ops
+    m = LAMP(54, 12, 20, 12, n_layers_enc=1, n_layers_dec=1, n_head=2, n_head2=2, d_word_vec=32, d_model=32,
+             d_inner_hid=32, d_k=16, d_v=16, encoder='graph', decoder='graph', label_mask='inveye')
+    m.__dict__['_eval_graphs'] = object()
+    m.__dict__['_lamp_planes_state'] = dict(stamp=1)
+    c = copy.deepcopy(m)
+    assert '_eval_graphs' not in c.__dict__ and '_lamp_planes_state' not in c.__dict__
+    assert isinstance(c.decoder._wp, ops.WeightPlanes) and c.decoder._wp is not m.decoder._wp
+    assert c.tgt_word_proj.weight is c.decoder.tgt_word_emb.weight            # the reference's alias survives the copy
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert list(r.state_dict()) == list(m.state_dict())
