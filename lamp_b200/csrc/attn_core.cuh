@@ -299,6 +299,19 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
       };
 
+      // Shared-memory descriptors are built ONCE: inside the issue loops a descriptor is the base plus a small offset in
+      // 16-byte units (the start-address field occupies the low 14 bits; all offsets stay below 256 KB).  The issuing
+      // thread is the serial resource of this kernel -- 36 tcgen05.mma per 64-key unit -- and rebuilding four
+      // descriptors per K-step from pointers cost it ~95 clocks per instruction against the ~55-64 the tensor pipe
+      // needs (scripts/probes/umma_probe.cu).
+      const uint64_t dQ0 = umma_smem_desc(smem_u32(sQ), 16, 1024);
+      const uint64_t dK0 = umma_smem_desc(smem_u32(sKV), 16, 1024);
+      const uint64_t dV0 = umma_smem_desc(smem_u32(sKV), p.vrows * 128, 1024);
+      const uint32_t q_kb16 = (p.qrows * 128) >> 4, q_pl16 = kb64 * q_kb16;   // 64-column block / plane strides
+      const uint32_t k_kb16 = (p.krows * 128) >> 4, k_pl16 = kb64 * k_kb16;
+      const uint32_t v_pl16 = kb64 * ((p.vrows * 128) >> 4);
+      const uint32_t slot16 = p.slot_bytes >> 4;
+
       // S(u) = Q K_u^T into score buffer u & 1 (N = the tile's key count rounded up to 16)
       auto issue_s = [&](const UnitIt& x) {
         const uint32_t u = x.u;
@@ -310,17 +323,15 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         ATTN_TRACE(4, u);
         tcgen05_fence_after();
         const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128;
+        const uint64_t dKs = dK0 + static_cast<uint32_t>(ks) * slot16;
         for (int t = 0; t < ksteps_d; ++t) {
-          const int kb = t >> 2;
-          const uint32_t koff = (t & 3) * 32;
-          const uint64_t dq_hi = umma_smem_desc(smem_u32(q_tile(0, kb)) + koff, 16, 1024);
-          const uint64_t dk_hi = umma_smem_desc(smem_u32(k_tile(ks, 0, kb)) + koff, 16, 1024);
+          const uint32_t kb = t >> 2, koff16 = (t & 3) * 2;  // 16 bf16 = 32 B inside the swizzled 128 B row
+          const uint64_t dq_hi = dQ0 + (kb * q_kb16 + koff16);
+          const uint64_t dk_hi = dKs + (kb * k_kb16 + koff16);
           umma_bf16_ss(tS, dq_hi, dk_hi, idesc_s, t != 0 ? 1u : 0u);
           if (NTERMS == 3) {
-            const uint64_t dq_lo = umma_smem_desc(smem_u32(q_tile(1, kb)) + koff, 16, 1024);
-            const uint64_t dk_lo = umma_smem_desc(smem_u32(k_tile(ks, 1, kb)) + koff, 16, 1024);
-            umma_bf16_ss(tS, dq_hi, dk_lo, idesc_s, 1u);
-            umma_bf16_ss(tS, dq_lo, dk_hi, idesc_s, 1u);
+            umma_bf16_ss(tS, dq_hi, dk_hi + k_pl16, idesc_s, 1u);
+            umma_bf16_ss(tS, dq_hi + q_pl16, dk_hi, idesc_s, 1u);
           }
         }
         umma_commit(&s_full[sb]);
@@ -360,19 +371,20 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
               umma_bf16_ts(tO + 64, pa + 16, dvh[1], idesc_h, 1u);
             }
           }
-        } else
-        for (int t = 0; t < ksteps_kv; ++t) {
-          // A = P from TMEM: keys 16t..16t+15 sit in 32-column chunk t/2: hi pairs at +8*(t&1), lo pairs 16 further.
-          // B = V MN-major: K (= key index) advances by 16 rows of 128 B, LBO = distance between the 64-wide d
-          // blocks, SBO = 8 key rows.
-          const uint32_t pa = tP + 32 * (t >> 1) + 8 * (t & 1);
-          const uint64_t dv_hi = umma_smem_desc(smem_u32(v_tile(vs, 0, 0)) + t * 2048, p.vrows * 128, 1024);
-          const uint32_t accum = (x.j != 0 || t != 0) ? 1u : 0u;
-          umma_bf16_ts(tO, pa, dv_hi, idesc_o, accum);
-          if (NTERMS == 3) {
-            const uint64_t dv_lo = umma_smem_desc(smem_u32(v_tile(vs, 1, 0)) + t * 2048, p.vrows * 128, 1024);
-            umma_bf16_ts(tO, pa, dv_lo, idesc_o, 1u);
-            umma_bf16_ts(tO, pa + 16, dv_hi, idesc_o, 1u);
+        } else {
+          const uint64_t dVs = dV0 + static_cast<uint32_t>(vs) * slot16;
+          for (int t = 0; t < ksteps_kv; ++t) {
+            // A = P from TMEM: keys 16t..16t+15 sit in 32-column chunk t/2: hi pairs at +8*(t&1), lo pairs 16 further.
+            // B = V MN-major: K (= key index) advances by 16 rows of 128 B (= 128 sixteen-byte units), LBO = distance
+            // between the 64-wide d blocks, SBO = 8 key rows.
+            const uint32_t pa = tP + 32 * (t >> 1) + 8 * (t & 1);
+            const uint64_t dv_hi = dVs + static_cast<uint32_t>(t) * 128u;
+            const uint32_t accum = (x.j != 0 || t != 0) ? 1u : 0u;
+            umma_bf16_ts(tO, pa, dv_hi, idesc_o, accum);
+            if (NTERMS == 3) {
+              umma_bf16_ts(tO, pa, dv_hi + v_pl16, idesc_o, 1u);
+              umma_bf16_ts(tO, pa + 16, dv_hi, idesc_o, 1u);
+            }
           }
         }
         umma_commit(&pv_done[sb]);
