@@ -1,5 +1,8 @@
+"""Launch-path probe: eval forward at B=1100 launched eagerly / with a CUDA-event pair per native call / as a graph replay /
+through the drop-in call, with allocator statistics (found the per-kernel timing mode holding activations alive).
+usage: python scripts/probes/eager_launch_probe.py [batch]"""
 import os, sys, time, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 import lamp_b200
