@@ -119,7 +119,8 @@ class GraphDecoder(nn.Module):
         for layer in self.layer_stack:
             kv_params += [layer.enc_attn.w_ks.weight, layer.enc_attn.w_vs.weight]
         hd = self.layer_stack[0].enc_attn.n_head * self.layer_stack[0].enc_attn.d_k
-        kv_all = ops.project(enc, self._wp, 'kv_all', tuple(kv_params), 2 * hd * len(self.layer_stack), prec)
+        kv_all = ops.project(enc, self._wp, 'kv_all', tuple(kv_params), 2 * hd * len(self.layer_stack), prec,
+                             ld_pad=ops.KV_LD_PAD)
         if kv_ranges is not None:
             ops.zero_guard_rows(kv_all)  # rows a KV tile may read past the packed keys must be finite
         int_outs, slf_attns, enc_attns = [], [], []

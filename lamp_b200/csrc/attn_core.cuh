@@ -10,14 +10,19 @@
 //              S = Q K^T retires (early in a unit), a V slot only after its PV product (late), so with separate rings
 //              and producers the K tiles run ahead by the ring depth instead of queueing behind the V loads -- with
 //              multi-tile rows (L = 983) the measured load-to-use latency is ~4400 clocks, i.e. 1.5 unit periods.
-//   warp 1   : MMA issuer   -- event driven: one thread polls (mbarrier.test_wait) the operands of the next S = Q K^T
-//              and of the next O (+)= P V and issues whichever is ready; S goes to one of two TMEM score buffers,
-//              O to one of two TMEM output buffers (item parity), so neither the next item's PV nor the next S ever
-//              waits for the epilogue.  P is read from TENSOR MEMORY (TS form), V is consumed MN-major straight from
-//              its natural [keys x d] layout (no transpose pass); 3-term split-bf16 products.
+//   warp 1   : S issuer     -- one thread issues S(u) = Q K_u^T as soon as its Q / K tiles have landed and a TMEM score
+//              buffer is free.
+//   warp 4   : PV issuer    -- one thread issues O (+)= P(u) V_u as soon as P(u) is published and V_u has landed.  Two
+//              issuing threads, not one: a tcgen05.mma issue blocks its thread until the tensor pipe accepts it, i.e.
+//              for about the execution time of the queue ahead; a single event-driven thread therefore serialised
+//              S(u+1) -> PV(u) -> S(u+2) ... with its polling latency exposed between any two (tensor pipe 61 % busy
+//              in the trace); with two, PV(u) is queued while S(u+1) still executes.  S goes to one of the TMEM score
+//              buffers, O to one of two TMEM output buffers (item parity), so neither the next item's PV nor the next S
+//              ever waits for the epilogue.  P is read from TENSOR MEMORY (TS form), V is consumed MN-major straight
+//              from its natural [keys x d] layout (no transpose pass); 3-term split-bf16 products.
 //   warp 2   : output store -- one thread issues the TMA stores of the O tile staged in shared memory.
 //   warp 3   : TMA producer of the V ring.
-//   warps 4.. : softmax     -- 4 * (BLOCK_KV/32) warps: TMEM lane == query row and every warp owns one 32-column
+//   warps 5.. : softmax     -- 4 * (BLOCK_KV/32) warps: TMEM lane == query row and every warp owns one 32-column
 //              chunk of the rows of its lane quarter.  Strided byte mask -> bit words via warp ballots, row max
 //              exchanged through smem, online max/sum across KV tiles with a LAZY rescale (the reference maximum only
 //              moves when it grew by more than 2^8, so the O accumulator is rarely touched and PV(u) does not
@@ -25,7 +30,12 @@
 //              PREVIOUS item (1/sum, hi/lo split) runs after the current unit's P is published; it writes the tile
 //              in the 128B-swizzled box layout into a staging buffer from which warp 2 stores it with TMA
 //              (coalesced, asynchronous, rows >= L clipped by the tensor map).
-// TMEM columns: S0/P0 [0,128) | S1/P1 [128,256) | O0 [256,384) | O1 [384,512).  P overwrites S in place: the warp
+// TMEM columns: S0/P0 [0,128) | S1/P1 [128,256) | O0 [256,384) | O1 [384,512).  64-key tiles (BLOCK_KV == 64: the
+// multi-tile label<-input / L = 983 shapes at d = 128) need only 64 score columns per buffer and use THREE of them,
+// S0/P0 [0,64) | S1/P1 [64,128) | S2/P2 [128,192): with two, S(u+2) had to wait until PV(u) had retired (P(u) lives in
+// its score buffer), which serialised the tensor pipe into S(u+1) -> PV(u) -> S(u+2) -> ... with the issue / completion
+// latencies exposed at every step (period 5.7 K clocks per unit for 3.6 K of tensor work); with three, S runs two
+// units ahead and the pipe only ever waits for operands.  P overwrites S in place: the warp
 // that owns a 32-column chunk of the scores holds them in registers and writes the chunk's hi (16 columns) and lo
 // (16 columns) bf16 pairs back over the same 32 columns.
 // Shared memory: Q tile | O staging tile (same shape) | ring of K/V slots; tile rows follow the label count
@@ -83,7 +93,7 @@ __device__ unsigned long long g_attn_trace[16 + 48][64];  // rows 16..: per soft
   } while (0)
 #define ATTN_TRACE_W(k, idx)                                                                              \
   do {                                                                                                    \
-    if (blockIdx.x == 0 && lane == 0 && (idx) < 64u) g_attn_trace[16 + (warp - 4) * 3 + (k)][idx] = clock64(); \
+    if (blockIdx.x == 0 && lane == 0 && (idx) < 64u) g_attn_trace[16 + (warp - LAMP_TRACE_SW0) * 3 + (k)][idx] = clock64(); \
   } while (0)
 #else
 #define ATTN_TRACE(ev, idx) do { } while (0)
@@ -98,8 +108,13 @@ constexpr float ATTN_RESCALE_LOG2 = 8.0f;  // lazy rescale: P stays below 2^8, h
 // row-statistics exchange between the column-warps of a row: max [2 units][NW][128] + sum [2 items][NW][128] floats
 constexpr uint32_t ATTN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
 constexpr uint32_t ATTN_BAR_BYTES = 256;
-// warps 0..3: Q/K TMA producer, MMA issuer, output store, V TMA producer; warps 4..: softmax (warp % 4 = TMEM lane quarter)
-__host__ __device__ constexpr int attn_threads(int block_kv) { return 128 + 128 * (block_kv / 32); }
+// warps 0..3(4): Q/K TMA producer, S (or S + PV) issuer, output store, V TMA producer, [PV issuer]; then the softmax
+// warps (warp % 4 = TMEM lane quarter)
+// 64-key tiles (multi-tile rows) run TWO issuing warps (S and PV) -> 5 control warps; 128-key tiles keep the single
+// event-driven issuer (their 16 softmax warps leave no register room for another warp: 672 threads would cap the kernel
+// at 80 registers and spill the softmax loop -- measured +22 % on the label<-label shape).
+__host__ __device__ constexpr int attn_ctrl_warps(int block_kv) { return block_kv == 64 ? 5 : 4; }
+__host__ __device__ constexpr int attn_threads(int block_kv) { return 32 * attn_ctrl_warps(block_kv) + 128 * (block_kv / 32); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -125,6 +140,13 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   constexpr int NPL = (NTERMS == 3) ? 2 : 1;
   constexpr int NW = BLOCK_KV / 32;        // 32-column score chunks per row == softmax warps per lane quarter
   constexpr int NSW = 4 * NW * 32;         // softmax threads
+  constexpr uint32_t NSB = (BLOCK_KV == 64) ? 3u : 2u;     // score / P buffers in TMEM (see the TMEM map above)
+  constexpr bool TWO_ISSUERS = (BLOCK_KV == 64);           // separate S / PV issuing warps (warp 1 / warp 4)
+  constexpr int SW0 = attn_ctrl_warps(BLOCK_KV);           // first softmax warp
+#ifdef LAMP_ATTN_TRACE
+  const int LAMP_TRACE_SW0 = SW0;
+#endif
+  constexpr uint32_t S_STRIDE = (BLOCK_KV == 64) ? 64u : 128u;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,16 +164,17 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red_max) + ATTN_RED_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* s_full = bars + 2;     // [2] S(u) complete (tcgen05.commit)
-  uint64_t* s_free = bars + 4;     // [2] score/P buffer released by the PV product that consumed it
-  uint64_t* p_full = bars + 6;     // [2] P(u) published by the NSW softmax threads
-  uint64_t* pv_done = bars + 8;    // [2] PV(u) complete, indexed by unit parity
-  uint64_t* o_free = bars + 10;    // [2] O buffer (item parity) drained by the epilogue, count NSW
-  uint64_t* ostage_full = bars + 12;   // staging tile written, count NSW
-  uint64_t* ostage_free = bars + 13;   // TMA store has read the staging tile
-  uint64_t* kv_full = bars + 14;   // [ATTN_MAX_SLOTS]
-  uint64_t* kv_empty = bars + 14 + ATTN_MAX_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * ATTN_MAX_SLOTS);
+  uint64_t* s_full = bars + 2;     // [NSB <= 3] S(u) complete (tcgen05.commit), buffer u % NSB
+  uint64_t* s_free = bars + 5;     // [NSB] score/P buffer released by the PV product that consumed it
+  uint64_t* p_full = bars + 8;     // [NSB] P(u) published by the NSW softmax threads
+  uint64_t* pv_done = bars + 11;   // [2] PV(u) complete, indexed by unit parity
+  uint64_t* o_free = bars + 13;    // [2] O buffer (item parity) drained by the epilogue, count NSW
+  uint64_t* ostage_full = bars + 15;   // staging tile written, count NSW
+  uint64_t* ostage_free = bars + 16;   // TMA store has read the staging tile
+  uint64_t* kv_full = bars + 17;   // [ATTN_MAX_SLOTS]
+  uint64_t* kv_empty = bars + 17 + ATTN_MAX_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17 + 2 * ATTN_MAX_SLOTS);
+  static_assert((17 + 2 * ATTN_MAX_SLOTS) * 8 + 4 <= ATTN_BAR_BYTES, "barrier area too small");
 
   // plane pl (0 = hi, 1 = lo), 64-column block kb
   auto q_tile = [&](int pl, int kb) { return sQ + (pl * kb64 + kb) * (p.qrows * 128); };
@@ -177,10 +200,12 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_free[i], 1);
       mbar_init(&p_full[i], NSW);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_free[i], NSW);
     }
@@ -275,8 +300,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer (event driven)
+  } else if (warp == 1 || (TWO_ISSUERS && warp == 4)) {
+    // ---------------------------------------------------------------- MMA issuers (warp 1: S [+ PV], warp 4: PV)
     if (lane == 0) {
       const uint32_t idesc_o = umma_idesc_bf16(ATTN_BLOCK_M, p.d, 0, 1);  // A = P from TMEM, B = V MN-major
       struct UnitIt {
@@ -316,13 +341,13 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       auto issue_s = [&](const UnitIt& x) {
         const uint32_t u = x.u;
         const int ks = u % RK;
-        const uint32_t sb = u & 1;
+        const uint32_t sb = u % NSB;
         int kvn = (min(BLOCK_KV, x.lk - x.j * BLOCK_KV) + 15) & ~15;
         if (kvn < 16) kvn = 16;
         const uint32_t idesc_s = umma_idesc_bf16(ATTN_BLOCK_M, kvn, 0, 0);
         ATTN_TRACE(4, u);
         tcgen05_fence_after();
-        const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128;
+        const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * S_STRIDE;
         const uint64_t dKs = dK0 + static_cast<uint32_t>(ks) * slot16;
         for (int t = 0; t < ksteps_d; ++t) {
           const uint32_t kb = t >> 2, koff16 = (t & 3) * 2;  // 16 bf16 = 32 B inside the swizzled 128 B row
@@ -344,13 +369,13 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       auto issue_pv = [&](const UnitIt& x) {
         const uint32_t u = x.u;
         const int vs = RK + u % RV;
-        const uint32_t sb = u & 1;
+        const uint32_t sb = u % NSB;
         ATTN_TRACE(6, u);
         tcgen05_fence_after();
         const int kv_valid = max(0, min(BLOCK_KV, x.lk - x.j * BLOCK_KV));
         const int ksteps_kv = max(1, (kv_valid + 15) >> 4);
         const uint32_t tO = tmem_base + ATTN_TMEM_O + (x.it & 1) * 128;
-        const uint32_t tP = tmem_base + ATTN_TMEM_S + sb * 128;  // P lives where S(u) was
+        const uint32_t tP = tmem_base + ATTN_TMEM_S + sb * S_STRIDE;  // P lives where S(u) was
         if (p.pv_split) {
           // two independent N = 64 chains (the two 64-wide d blocks of V, O columns [0,64) / [64,128)), interleaved
           const uint32_t idesc_h = umma_idesc_bf16(ATTN_BLOCK_M, 64, 0, 1);
@@ -387,46 +412,72 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             }
           }
         }
-        umma_commit(&pv_done[sb]);
+        umma_commit(&pv_done[u & 1]);
         umma_commit(&kv_empty[vs]);
-        umma_commit(&s_free[sb]);  // the score / P buffer may be overwritten by S(u + 2)
+        umma_commit(&s_free[sb]);  // the score / P buffer may be overwritten by S(u + NSB)
         ATTN_TRACE(5, u);
       };
 
-      UnitIt si{static_cast<int>(blockIdx.x), 0, 1, 0, 0u, 0u};
-      load_it(si);
-      UnitIt pi = si;
-      bool s_q = false, s_k = false, s_b = false;  // latched readiness of the next S: Q tile, K tile, score buffer
-      bool v_p = false, v_v = false, v_o = false;  // ... of the next PV: P published, V tile, O buffer
-      uint32_t idle = 0;
-      while (pi.item < num_items) {
-        bool progressed = false;
-        if (si.item < num_items) {
-          const uint32_t u = si.u;
-          if (!s_q) s_q = (si.j != 0) || mbar_test_wait(q_full, si.it & 1);
-          if (!s_k && (s_k = mbar_test_wait(&kv_full[u % RK], (u / RK) & 1))) ATTN_TRACE(14, u);
-          if (!s_b && (s_b = mbar_test_wait(&s_free[u & 1], ((u >> 1) & 1) ^ 1))) ATTN_TRACE(15, u);
-          if (s_q && s_k && s_b) {
-            issue_s(si);
-            advance(si);
-            s_q = s_k = s_b = false;
-            progressed = true;
+      UnitIt x{static_cast<int>(blockIdx.x), 0, 1, 0, 0u, 0u};
+      load_it(x);
+      if (!TWO_ISSUERS) {
+        // single event-driven issuer: polls (mbarrier.test_wait) the operands of the next S and of the next PV and
+        // issues whichever is ready
+        UnitIt si = x, pi = x;
+        bool s_q = false, s_k = false, s_b = false;  // latched readiness of the next S: Q tile, K tile, score buffer
+        bool v_p = false, v_v = false, v_o = false;  // ... of the next PV: P published, V tile, O buffer
+        uint32_t idle = 0;
+        while (pi.item < num_items) {
+          bool progressed = false;
+          if (si.item < num_items) {
+            const uint32_t u = si.u;
+            if (!s_q) s_q = (si.j != 0) || mbar_test_wait(q_full, si.it & 1);
+            if (!s_k && (s_k = mbar_test_wait(&kv_full[u % RK], (u / RK) & 1))) ATTN_TRACE(14, u);
+            if (!s_b && (s_b = mbar_test_wait(&s_free[u % NSB], ((u / NSB) & 1) ^ 1))) ATTN_TRACE(15, u);
+            if (s_q && s_k && s_b) {
+              issue_s(si);
+              advance(si);
+              s_q = s_k = s_b = false;
+              progressed = true;
+            }
           }
-        }
-        {
-          const uint32_t u = pi.u;
-          if (!v_p && (v_p = mbar_test_wait(&p_full[u & 1], (u >> 1) & 1))) ATTN_TRACE(12, u);
-          if (!v_v && (v_v = mbar_test_wait(&kv_full[RK + u % RV], (u / RV) & 1))) ATTN_TRACE(13, u);
-          if (!v_o) v_o = (pi.j != 0) || mbar_test_wait(&o_free[pi.it & 1], ((pi.it >> 1) & 1) ^ 1);
-          if (v_p && v_v && v_o) {
-            issue_pv(pi);
-            advance(pi);
-            v_p = v_v = v_o = false;
-            progressed = true;
+          {
+            const uint32_t u = pi.u;
+            if (!v_p && (v_p = mbar_test_wait(&p_full[u % NSB], (u / NSB) & 1))) ATTN_TRACE(12, u);
+            if (!v_v && (v_v = mbar_test_wait(&kv_full[RK + u % RV], (u / RV) & 1))) ATTN_TRACE(13, u);
+            if (!v_o) v_o = (pi.j != 0) || mbar_test_wait(&o_free[pi.it & 1], ((pi.it >> 1) & 1) ^ 1);
+            if (v_p && v_v && v_o) {
+              issue_pv(pi);
+              advance(pi);
+              v_p = v_v = v_o = false;
+              progressed = true;
+            }
           }
+          if (progressed) idle = 0;
+          else if (++idle > LAMP_WAIT_LIMIT) __trap();
         }
-        if (progressed) idle = 0;
-        else if (++idle > LAMP_WAIT_LIMIT) __trap();
+      } else if (warp == 1) {
+        // S(u): Q tile (first unit of an item), K tile, a free score buffer
+        for (; x.item < num_items; advance(x)) {
+          const uint32_t u = x.u;
+          if (x.j == 0) mbar_wait(q_full, x.it & 1);
+          mbar_wait(&kv_full[u % RK], (u / RK) & 1);
+          ATTN_TRACE(14, u);
+          mbar_wait(&s_free[u % NSB], ((u / NSB) & 1) ^ 1);
+          ATTN_TRACE(15, u);
+          issue_s(x);
+        }
+      } else {
+        // PV(u): P published, V tile, the item's O buffer drained by the epilogue of the item two back
+        for (; x.item < num_items; advance(x)) {
+          const uint32_t u = x.u;
+          mbar_wait(&p_full[u % NSB], (u / NSB) & 1);
+          ATTN_TRACE(12, u);
+          mbar_wait(&kv_full[RK + u % RV], (u / RV) & 1);
+          ATTN_TRACE(13, u);
+          if (x.j == 0) mbar_wait(&o_free[x.it & 1], ((x.it >> 1) & 1) ^ 1);
+          issue_pv(x);
+        }
       }
     }
   } else if (warp == 2) {
@@ -448,14 +499,14 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       }
       tma_store_wait_all0();  // global writes complete before the CTA exits
     }
-  } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax + epilogue (warps 4 .. 4+4*NW)
+  } else if (warp >= SW0) {
+    // ---------------------------------------------------------------- softmax + epilogue (warps SW0 .. SW0+4*NW)
     const int wq = warp & 3;           // TMEM lane quarter (hardware rule: warp_id % 4)
-    const int cw = (warp - 4) >> 2;    // 32-column chunk of the score tile owned by this warp
+    const int cw = (warp - SW0) >> 2;  // 32-column chunk of the score tile owned by this warp
     const int row = wq * 32 + lane;    // row inside the q tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
     const int ngroups = p.d >> 4;      // 16-column groups of O; group g belongs to column-warp g % NW
-    const bool tracer = (warp == 4 && lane == 0);
+    const bool tracer = (warp == SW0 && lane == 0);
     uint32_t mw = 0;                   // mask bits of (row, this warp's 32 columns); bit set = masked
     long long mkey = -1;               // (b, qt, j) combination the word was built for
 
@@ -547,8 +598,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       item_keys(b, lk, kbase, kbatch_unused, nkv);
       for (int j = 0; j < nkv; ++j, ++u) {
         const int k0 = j * BLOCK_KV + 32 * cw;  // first key column of this warp's chunk
-        const uint32_t sb = u & 1;
-        const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * 128 + lane_sel + 32 * cw;
+        const uint32_t sb = u % NSB;
+        const uint32_t tS = tmem_base + ATTN_TMEM_S + sb * S_STRIDE + lane_sel + 32 * cw;
         // ---- mask word for (row, this chunk); cached while the addressed mask region is unchanged.  For a
         //      key-padding mask (query stride 0: one byte per key, new every sample) the byte load is issued here and
         //      consumed after the score tile has arrived, so its latency hides behind the barrier wait.
@@ -590,7 +641,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
             }
           }
         }
-        mbar_wait(&s_full[sb], (u >> 1) & 1);
+        mbar_wait(&s_full[sb], (u / NSB) & 1);
         if (tracer) ATTN_TRACE(7, u);
         ATTN_TRACE_W(0, u);
         tcgen05_fence_after();

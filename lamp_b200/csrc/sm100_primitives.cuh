@@ -182,6 +182,13 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Shared memory -> tensor memory copy of one K = 16 step of a K-major operand tile: 128 rows x 256 bits (16 bf16), read
+// through the SAME shared-memory descriptor the SS-form tcgen05.mma would use for that step (128B swizzle included),
+// written to lane = row, 8 consecutive 32-bit columns -- exactly the TS-form A-operand layout.  Executes in issue order
+// with the tcgen05.mma of the same thread (validated bit for bit by scripts/probes/utccp_probe.cu).
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t dst_tmem, uint64_t smem_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(dst_tmem), "l"(smem_desc) : "memory");
+}
 // mbarrier arrives (count 1) once all previously issued UMMAs of this thread have completed.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

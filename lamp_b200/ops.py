@@ -322,20 +322,28 @@ def gemm(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, pre
                nbytes=lambda m: rows(m) * row_bytes + N * K * pl, rows_dev=m_dev)
 
 
-def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=False) -> Act:
-    """planes(x) @ W^T (+bias)(ReLU) -> planes only (operand for the next tensor-core stage)."""
-    hi, lo = _empty_planes(x.rows, N, prec, x.hi.device)
+def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=False, ld_pad: int = 0) -> Act:
+    """planes(x) @ W^T (+bias)(ReLU) -> planes only (operand for the next tensor-core stage).  ``ld_pad``: extra
+    (unused) columns in the row pitch of the result, see ``KV_LD_PAD``; the returned Act's ``cols`` is the pitch."""
+    ld = N + ld_pad
+    hi, lo = _empty_planes(x.rows, ld, prec, x.hi.device)
     gemm(x.hi, x.lo, x.cols, w_hi, w_lo, x.cols, x.rows, N, x.cols, prec, bias=bias, relu=relu, out_hi=hi, out_lo=lo,
-         ldp=N, m_dev=x.m_dev)
-    return Act(None, hi, lo, x.rows, N, x.bcast_rows, x.m_dev)
+         ldp=ld, m_dev=x.m_dev)
+    return Act(None, hi, lo, x.rows, ld, x.bcast_rows, x.m_dev)
 
 
-def project(x: Act, wp: WeightPlanes, key: str, params, N: int, prec: int, *, bias=None, relu=False) -> Act:
+# Row pitch padding (in bf16 columns) of the label<-input K|V plane matrix.  Its natural pitch, 2*H*d*n_layers columns =
+# 4096 B at the bench shape, is a power of two: the attention core's K/V tiles are 64 row segments of 128 B each exactly
+# one pitch apart, which aliases onto a few HBM channels.  A pitch that is not a power of two spreads them.
+KV_LD_PAD = int(os.environ.get('LAMP_KV_LD_PAD', '0'))
+
+
+def project(x: Act, wp: WeightPlanes, key: str, params, N: int, prec: int, *, bias=None, relu=False, ld_pad: int = 0) -> Act:
     """``x @ cat(params)^T (+bias)(ReLU)`` -> planes.  ``x`` may be a deferred LayerNorm: the normalisation is then
     folded into the weights and the epilogue of this GEMM (see :class:`DeferredLN`)."""
     if x.ln is None:
         w_hi, w_lo = wp.get(key, params, prec)
-        return linear_planes(x, w_hi, w_lo, N, prec, bias=bias, relu=relu)
+        return linear_planes(x, w_hi, w_lo, N, prec, bias=bias, relu=relu, ld_pad=ld_pad)
     ln = x.ln
     wg_hi, wg_lo, colsum, biasf = wp.get_folded(key, params, ln, bias, prec)
     hi, lo = _empty_planes(x.rows, N, prec, x.hi.device)

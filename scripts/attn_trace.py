@@ -113,7 +113,7 @@ def main():
         row = []
         for w in range(16):
             if t[16 + 3 * w][u]:
-                row.append('w%d:%d/%d/%d' % (w + 4, t[16 + 3 * w][u] - ref, t[17 + 3 * w][u] - ref, t[18 + 3 * w][u] - ref))
+                row.append('w%d:%d/%d/%d' % (w + 5, t[16 + 3 * w][u] - ref, t[17 + 3 * w][u] - ref, t[18 + 3 * w][u] - ref))
         print(f'  u{u}: ' + ' '.join(row))
     main_done = True
 
