@@ -12,7 +12,7 @@
 //              multi-tile rows (L = 983) the measured load-to-use latency is ~4400 clocks, i.e. 1.5 unit periods.
 //   warp 1   : S issuer     -- one thread issues S(u) = Q K_u^T as soon as its Q / K tiles have landed and a TMEM score
 //              buffer is free.
-//   warp 4   : PV issuer    -- one thread issues O (+)= P(u) V_u as soon as P(u) is published and V_u has landed.  Two
+//   warp 2   : PV issuer    -- one thread issues O (+)= P(u) V_u as soon as P(u) is published and V_u has landed.  Two
 //              issuing threads, not one: a tcgen05.mma issue blocks its thread until the tensor pipe accepts it, i.e.
 //              for about the execution time of the queue ahead; a single event-driven thread therefore serialised
 //              S(u+1) -> PV(u) -> S(u+2) ... with its polling latency exposed between any two (tensor pipe 61 % busy
@@ -20,7 +20,6 @@
 //              buffers, O to one of two TMEM output buffers (item parity), so neither the next item's PV nor the next S
 //              ever waits for the epilogue.  P is read from TENSOR MEMORY (TS form), V is consumed MN-major straight
 //              from its natural [keys x d] layout (no transpose pass); 3-term split-bf16 products.
-//   warp 2   : output store -- one thread issues the TMA stores of the O tile staged in shared memory.
 //   warp 3   : TMA producer of the V ring.
 //   warps 5.. : softmax     -- 4 * (BLOCK_KV/32) warps: TMEM lane == query row and every warp owns one 32-column
 //              chunk of the rows of its lane quarter.  Strided byte mask -> bit words via warp ballots, row max
@@ -28,8 +27,10 @@
 //              moves when it grew by more than 2^8, so the O accumulator is rarely touched and PV(u) does not
 //              serialise behind PV(u-1)), ex2, hi/lo split, P written back over S in TMEM.  The epilogue of the
 //              PREVIOUS item (1/sum, hi/lo split) runs after the current unit's P is published; it writes the tile
-//              in the 128B-swizzled box layout into a staging buffer from which warp 2 stores it with TMA
-//              (coalesced, asynchronous, rows >= L clipped by the tensor map).
+//              in the 128B-swizzled box layout into a staging buffer from which the first softmax thread stores it
+//              with TMA once a named barrier has collected the tile (coalesced, asynchronous, rows >= L clipped by
+//              the tensor map); the same thread waits for the store to have READ the tile before the next epilogue
+//              overwrites it.  (A dedicated store warp used to do this; its slot now belongs to the PV issuer.)
 // TMEM columns: S0/P0 [0,128) | S1/P1 [128,256) | O0 [256,384) | O1 [384,512).  64-key tiles (BLOCK_KV == 64: the
 // multi-tile label<-input / L = 983 shapes at d = 128) need only 64 score columns per buffer and use THREE of them,
 // S0/P0 [0,64) | S1/P1 [64,128) | S2/P2 [128,192): with two, S(u+2) had to wait until PV(u) had retired (P(u) lives in
@@ -108,12 +109,9 @@ constexpr float ATTN_RESCALE_LOG2 = 8.0f;  // lazy rescale: P stays below 2^8, h
 // row-statistics exchange between the column-warps of a row: max [2 units][NW][128] + sum [2 items][NW][128] floats
 constexpr uint32_t ATTN_RED_BYTES = 2 * 2 * 4 * 128 * 4;
 constexpr uint32_t ATTN_BAR_BYTES = 256;
-// warps 0..3(4): Q/K TMA producer, S (or S + PV) issuer, output store, V TMA producer, [PV issuer]; then the softmax
-// warps (warp % 4 = TMEM lane quarter)
-// 64-key tiles (multi-tile rows) run TWO issuing warps (S and PV) -> 5 control warps; 128-key tiles keep the single
-// event-driven issuer (their 16 softmax warps leave no register room for another warp: 672 threads would cap the kernel
-// at 80 registers and spill the softmax loop -- measured +22 % on the label<-label shape).
-__host__ __device__ constexpr int attn_ctrl_warps(int block_kv) { return block_kv == 64 ? 5 : 4; }
+// warps 0..3: Q/K TMA producer, S issuer, PV issuer, V TMA producer; warps 4..: softmax (warp % 4 = TMEM lane quarter)
+// 4 control warps (Q/K producer, S issuer, PV issuer, V producer) + the softmax warps.
+__host__ __device__ constexpr int attn_ctrl_warps(int) { return 4; }
 __host__ __device__ constexpr int attn_threads(int block_kv) { return 32 * attn_ctrl_warps(block_kv) + 128 * (block_kv / 32); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -141,7 +139,6 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
   constexpr int NW = BLOCK_KV / 32;        // 32-column score chunks per row == softmax warps per lane quarter
   constexpr int NSW = 4 * NW * 32;         // softmax threads
   constexpr uint32_t NSB = (BLOCK_KV == 64) ? 3u : 2u;     // score / P buffers in TMEM (see the TMEM map above)
-  constexpr bool TWO_ISSUERS = (BLOCK_KV == 64);           // separate S / PV issuing warps (warp 1 / warp 4)
   constexpr int SW0 = attn_ctrl_warps(BLOCK_KV);           // first softmax warp
 #ifdef LAMP_ATTN_TRACE
   const int LAMP_TRACE_SW0 = SW0;
@@ -300,8 +297,8 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
       }
     }
-  } else if (warp == 1 || (TWO_ISSUERS && warp == 4)) {
-    // ---------------------------------------------------------------- MMA issuers (warp 1: S [+ PV], warp 4: PV)
+  } else if (warp == 1 || warp == 2) {
+    // ---------------------------------------------------------------- MMA issuers (warp 1: S, warp 2: PV)
     if (lane == 0) {
       const uint32_t idesc_o = umma_idesc_bf16(ATTN_BLOCK_M, p.d, 0, 1);  // A = P from TMEM, B = V MN-major
       struct UnitIt {
@@ -420,43 +417,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
 
       UnitIt x{static_cast<int>(blockIdx.x), 0, 1, 0, 0u, 0u};
       load_it(x);
-      if (!TWO_ISSUERS) {
-        // single event-driven issuer: polls (mbarrier.test_wait) the operands of the next S and of the next PV and
-        // issues whichever is ready
-        UnitIt si = x, pi = x;
-        bool s_q = false, s_k = false, s_b = false;  // latched readiness of the next S: Q tile, K tile, score buffer
-        bool v_p = false, v_v = false, v_o = false;  // ... of the next PV: P published, V tile, O buffer
-        uint32_t idle = 0;
-        while (pi.item < num_items) {
-          bool progressed = false;
-          if (si.item < num_items) {
-            const uint32_t u = si.u;
-            if (!s_q) s_q = (si.j != 0) || mbar_test_wait(q_full, si.it & 1);
-            if (!s_k && (s_k = mbar_test_wait(&kv_full[u % RK], (u / RK) & 1))) ATTN_TRACE(14, u);
-            if (!s_b && (s_b = mbar_test_wait(&s_free[u % NSB], ((u / NSB) & 1) ^ 1))) ATTN_TRACE(15, u);
-            if (s_q && s_k && s_b) {
-              issue_s(si);
-              advance(si);
-              s_q = s_k = s_b = false;
-              progressed = true;
-            }
-          }
-          {
-            const uint32_t u = pi.u;
-            if (!v_p && (v_p = mbar_test_wait(&p_full[u % NSB], (u / NSB) & 1))) ATTN_TRACE(12, u);
-            if (!v_v && (v_v = mbar_test_wait(&kv_full[RK + u % RV], (u / RV) & 1))) ATTN_TRACE(13, u);
-            if (!v_o) v_o = (pi.j != 0) || mbar_test_wait(&o_free[pi.it & 1], ((pi.it >> 1) & 1) ^ 1);
-            if (v_p && v_v && v_o) {
-              issue_pv(pi);
-              advance(pi);
-              v_p = v_v = v_o = false;
-              progressed = true;
-            }
-          }
-          if (progressed) idle = 0;
-          else if (++idle > LAMP_WAIT_LIMIT) __trap();
-        }
-      } else if (warp == 1) {
+      if (warp == 1) {
         // S(u): Q tile (first unit of an item), K tile, a free score buffer
         for (; x.item < num_items; advance(x)) {
           const uint32_t u = x.u;
@@ -480,25 +441,6 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
         }
       }
     }
-  } else if (warp == 2) {
-    // ---------------------------------------------------------------- output store (TMA, from the staging tile)
-    if (lane == 0 && p.staged) {
-      uint32_t n = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++n) {
-        const int qt = item % num_qt;
-        const int h = (item / num_qt) % p.H;
-        const int b = item / (num_qt * p.H);
-        mbar_wait(ostage_full, n & 1);
-        for (int kb = 0; kb < kb64; ++kb) {
-          tma_store_3d(&tmO_hi, o_tile(0, kb), h * p.d + kb * 64, qt * ATTN_BLOCK_M, b);
-          if (NPL == 2 && p.o_lo != nullptr) tma_store_3d(&tmO_lo, o_tile(1, kb), h * p.d + kb * 64, qt * ATTN_BLOCK_M, b);
-        }
-        tma_store_commit();
-        tma_store_wait_read0();  // the staging tile may be overwritten
-        mbar_arrive(ostage_free);
-      }
-      tma_store_wait_all0();  // global writes complete before the CTA exits
-    }
   } else if (warp >= SW0) {
     // ---------------------------------------------------------------- softmax + epilogue (warps SW0 .. SW0+4*NW)
     const int wq = warp & 3;           // TMEM lane quarter (hardware rule: warp_id % 4)
@@ -506,7 +448,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
     const int row = wq * 32 + lane;    // row inside the q tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
     const int ngroups = p.d >> 4;      // 16-column groups of O; group g belongs to column-warp g % NW
-    const bool tracer = (warp == SW0 && lane == 0);
+    const bool tracer = (warp == SW0 && lane == 0);  // first softmax thread: trace stamps AND the TMA stores of the staged O tile
     uint32_t mw = 0;                   // mask bits of (row, this warp's 32 columns); bit set = masked
     long long mkey = -1;               // (b, qt, j) combination the word was built for
 
@@ -521,7 +463,11 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       const int qrow = qt * ATTN_BLOCK_M + row;
       const bool row_ok = qrow < p.Lq;
       const size_t grow = static_cast<size_t>(b) * p.Lq + qrow;
-      if (p.staged) mbar_wait(ostage_free, (pit & 1) ^ 1);  // the previous item's TMA store has read the tile
+      if (p.staged) {
+        // the previous item's TMA store must have READ the staging tile before anyone overwrites it
+        if (tracer) tma_store_wait_read0();
+        named_bar_sync(2, NSW);
+      }
       for (int g = cw; g < ngroups; g += NW) {
         uint32_t r[16];
         tmem_ld16(tO + 16 * g, r);
@@ -575,7 +521,14 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       mbar_arrive(&o_free[par]);  // this thread's part of the O buffer has been read
       if (p.staged) {
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
-        mbar_arrive(ostage_full);
+        named_bar_sync(2, NSW);    // the whole tile is staged
+        if (tracer) {
+          for (int kb = 0; kb < kb64; ++kb) {
+            tma_store_3d(&tmO_hi, o_tile(0, kb), h * p.d + kb * 64, qt * ATTN_BLOCK_M, b);
+            if (NPL == 2 && p.o_lo != nullptr) tma_store_3d(&tmO_lo, o_tile(1, kb), h * p.d + kb * 64, qt * ATTN_BLOCK_M, b);
+          }
+          tma_store_commit();
+        }
       }
       if (cw == 0 && row_ok && p.row_sum != nullptr) {
         const size_t si = (static_cast<size_t>(h) * p.B + b) * p.Lq + qrow;
@@ -731,6 +684,7 @@ attn_core_kernel(const __grid_constant__ CUtensorMap tmQ_hi, const __grid_consta
       tcgen05_fence_after();
       epilogue(pb, ph, pqt, it - 1, pm);
     }
+    if (tracer && p.staged) tma_store_wait_all0();  // global writes complete before the CTA exits
   }
 
   tcgen05_fence_before();
