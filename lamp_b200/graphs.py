@@ -14,6 +14,7 @@ to keep them).  The captured forward is the module's own fused path, so results 
 """
 from __future__ import annotations
 
+import gc
 import os
 from collections import OrderedDict
 
@@ -254,6 +255,10 @@ class GraphedTrainStep:
                 body()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        # an autograd graph of an earlier iteration that is still referenced (a kept loss, a reference cycle waiting
+        # for the collector) keeps its AccumulateGrad nodes and THEIR streams alive; the engine would then make that
+        # stream wait on the capturing one, which invalidates the capture.  Collect what can be collected first.
+        gc.collect()
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.STATS.launches
         with torch.cuda.graph(self.graph):

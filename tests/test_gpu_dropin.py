@@ -265,7 +265,8 @@ def test_bce_with_logits_kernel_matches_torch_value_and_gradient():
         for _ in range(2):   # second call: the ticket counter was re-armed by the kernel
             got = ops.bce_with_logits(x, y)
             (gg,) = torch.autograd.grad(got * 3.0, x)
-            assert abs(float(got) - float(want)) < 1e-6 * max(1.0, abs(float(want))), shape
+            g_val, w_val = float(got.detach()), float(want.detach())
+            assert abs(g_val - w_val) < 1e-6 * max(1.0, abs(w_val)), shape
             assert rel_err(gg, gw * 3.0) < 1e-5, shape
 
 
