@@ -193,6 +193,13 @@ int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, co
                int D, float* out, void* out_hi, void* out_lo, const int64_t* row_index, const int32_t* m_dev,
                void* stream);
 
+/* Backward of lamp_embed without row_index (autograd of lamp/Encoders.py:66,75; torch.nn.Embedding(padding_idx)):
+ * dword[seq[r],:] += g[r,:] unless seq[r] == pad_word, dpos[pos[r],:] += g[r,:] unless pos[r] == pad_pos (pass -1
+ * for "no padding row").  Accumulates with vector reductions into the caller-zeroed tables; either table may be NULL.
+ * The order of the additions is not fixed. */
+int lamp_embed_bwd(const float* g, const int64_t* seq, const int64_t* pos, int64_t rows, int D, int64_t pad_word,
+                   int64_t pad_pos, float* dword, float* dpos, void* stream);
+
 /* out[r,:] = src[index[r],:] (fp32): un-packs a packed activation into the dense [B*T, D] API tensor. */
 int lamp_gather_rows(const float* src, const int64_t* index, int64_t rows, int D, float* out, void* stream);
 

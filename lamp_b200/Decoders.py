@@ -69,7 +69,9 @@ class GraphDecoder(nn.Module):
         dev = enc_output.device
         L = self.n_tgt_vocab
         tgt_seq = torch.arange(L, device=dev).unsqueeze(0).expand(B, L)
-        dec_input = self.tgt_word_emb(tgt_seq)
+        # every sample embeds the same ids 0..L-1 (lamp/Decoders.py:131-134): the table itself, broadcast over the
+        # batch -- its gradient is then a sum over the batch dimension instead of a sort-based embedding backward
+        dec_input = self.tgt_word_emb.weight[:L].unsqueeze(0).expand(B, L, self.tgt_word_emb.weight.shape[1])
         pad_mask = None
         if not self.enc_vec:
             pad_mask = utils.get_attn_padding_mask(tgt_seq, src_seq[:, 0:enc_output.size(1)])

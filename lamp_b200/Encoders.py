@@ -116,10 +116,11 @@ class GraphEncoder(nn.Module):
         src_row = torch.where(keep, torch.cumsum(keep.to(torch.int64), 0) - 1, torch.full_like(seq_flat, n))
         pad_tok = torch.zeros((1,), dtype=seq_flat.dtype, device=seq_flat.device)  # (PAD, position 0): the representative
         seq_p = torch.cat((seq_flat.index_select(0, idx), pad_tok))
-        x = self.src_word_emb(seq_p)
-        if hasattr(self, 'position_enc'):
-            x = x + self.position_enc(torch.cat((pos_flat.index_select(0, idx), pad_tok)))
+        pos_emb = self.position_enc if hasattr(self, 'position_enc') else None
+        pos_p = torch.cat((pos_flat.index_select(0, idx), pad_tok)) if pos_emb is not None else None
+        x = ops.embed_train(seq_p, pos_p, self.src_word_emb, pos_emb)   # lamp_embed / lamp_embed_bwd, planes stashed
         out = x.unsqueeze(0)                                      # [1, n + 1, D]
+        out._lamp_planes = x._lamp_planes[:2] + (out._version,) + x._lamp_planes[3:]
         for layer in self.layer_stack:
             out = layer.pos_ffn(out)                              # ops.FFNTrainFunction, planes stashed on the result
         dense = out[0].index_select(0, src_row).view(B, T, self.d_model)   # API tensor (PAD rows = the representative)

@@ -66,6 +66,7 @@ _SIGNATURES = {
     'lamp_bce_logits': ([_vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp], _i),
     'lamp_layernorm': ([_vp, _vp, _i, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp, _vp], _i),
     'lamp_embed': ([_vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    'lamp_embed_bwd': ([_vp, _vp, _vp, _i64, _i, _i64, _i64, _vp, _vp, _vp], _i),
     'lamp_gather_rows': ([_vp, _vp, _i64, _i, _vp, _vp], _i),
     'lamp_zero_guard_rows': ([_vp, _vp, _i64, _i, _vp, _i64, _i, _vp], _i),
     'lamp_diag_proj': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp], _i),

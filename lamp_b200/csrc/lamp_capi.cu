@@ -969,6 +969,18 @@ int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, floa
   return launch_check();
 }
 
+// bias gradient next to a weight gradient: column sums of the dY planes into the (zeroed or accumulating) db
+static int launch_colsum(const void* dy_hi, const void* dy_lo, int64_t ldy, int64_t M, int N, float* db, cudaStream_t st) {
+  const unsigned slabs = (unsigned)((N + 255) / 256);
+  long long rb = (4LL * sm_count_cached() + slabs - 1) / slabs;   // ~4 blocks per SM
+  long long chunk = ((M + rb - 1) / rb + 31) / 32 * 32;           // whole 32-row steps of the unrolled loop
+  if (chunk < 32) chunk = 32;
+  rb = (M + chunk - 1) / chunk;
+  colsum_planes_kernel<<<dim3((unsigned)rb, slabs), COLSUM_THREADS, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(dy_hi), static_cast<const __nv_bfloat16*>(dy_lo), ldy, M, N, chunk, db);
+  return launch_check();
+}
+
 int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const void* x_hi, const void* x_lo, int64_t ldx,
                      int64_t M, int N, int K, float* dW, float* db, void* stream) {
   if (int rc = arch_check()) return rc;
@@ -1008,13 +1020,7 @@ int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const vo
     else
       gemm_tn_tc_kernel<1><<<(unsigned)(tiles * splits), TNC_THREADS, tnc_smem_bytes(1), st>>>(ty_hi, ty_lo, tx_hi, tx_lo, gp);
     if (int rc = launch_check()) return rc;
-    if (db != nullptr) {
-      long long rb = (M + 511) / 512;
-      dim3 grid((unsigned)rb, (unsigned)((N + 127) / 128));
-      colsum_planes_kernel<<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(dy_hi),
-                                                 static_cast<const __nv_bfloat16*>(dy_lo), ldy, M, N, 512, db);
-      return launch_check();
-    }
+    if (db != nullptr) return launch_colsum(dy_hi, dy_lo, ldy, M, N, db, st);
     return LAMP_OK;
   }
   static PerDeviceOnce once;
@@ -1032,13 +1038,7 @@ int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const vo
       static_cast<const __nv_bfloat16*>(dy_hi), static_cast<const __nv_bfloat16*>(dy_lo), ldy,
       static_cast<const __nv_bfloat16*>(x_hi), static_cast<const __nv_bfloat16*>(x_lo), ldx, M, N, K, chunk, dW);
   if (int rc = launch_check()) return rc;
-  if (db != nullptr) {
-    long long rb = (M + 511) / 512;
-    dim3 grid((unsigned)rb, (unsigned)((N + 127) / 128));
-    colsum_planes_kernel<<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(dy_hi),
-                                               static_cast<const __nv_bfloat16*>(dy_lo), ldy, M, N, 512, db);
-    return launch_check();
-  }
+  if (db != nullptr) return launch_colsum(dy_hi, dy_lo, ldy, M, N, db, st);
   return LAMP_OK;
 }
 
@@ -1056,7 +1056,17 @@ int lamp_diag_proj_bwd(const float* g, const float* x, const float* W, int64_t B
     if (int rc = launch_check()) return rc;
   }
   if (dW != nullptr) {
-    diag_proj_bwd_dw_kernel<<<(unsigned)L, 256, 0, st>>>(g, x, B, L, D, dW, dbias);
+    REQUIRE(aligned16(x) && aligned16(dW), "diag_proj_bwd: x and dW must be 16-byte aligned");
+    // ~4 blocks per SM: labels x batch slices, partial sums reduced into the zeroed outputs
+    long long slices = (4LL * sm_count_cached() + L - 1) / L;
+    if (slices > (B + 7) / 8) slices = (B + 7) / 8;
+    if (slices < 1) slices = 1;
+    const long long bchunk = (B + slices - 1) / slices;
+    slices = (B + bchunk - 1) / bchunk;
+    if (cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)L * D, st) != cudaSuccess) return launch_check();
+    if (dbias != nullptr && cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)L, st) != cudaSuccess) return launch_check();
+    const int threads = D / 4 >= 256 ? 256 : (D / 4 >= 128 ? 128 : 64);
+    diag_proj_bwd_dw_kernel<<<dim3((unsigned)L, (unsigned)slices), threads, 0, st>>>(g, x, B, L, D, bchunk, dW, dbias);
     return launch_check();
   }
   return LAMP_OK;
@@ -1192,6 +1202,21 @@ int lamp_embed(const int64_t* seq, const int64_t* pos, const float* word_emb, co
                            (long long)rows, D, out, static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo),
                            reinterpret_cast<const long long*>(row_index), m_dev);
   if (e != cudaSuccess) return fail(LAMP_ECUDA, "embed launch: %s", cudaGetErrorString(e));
+  return launch_check();
+}
+
+int lamp_embed_bwd(const float* g, const int64_t* seq, const int64_t* pos, int64_t rows, int D, int64_t pad_word,
+                   int64_t pad_pos, float* dword, float* dpos, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(g && (dword || dpos), "embed_bwd: null pointer");
+  REQUIRE((!dword || seq) && (!dpos || pos), "embed_bwd: a gradient table without its ids");
+  REQUIRE(D % 4 == 0 && aligned16(g) && (!dword || aligned16(dword)) && (!dpos || aligned16(dpos)),
+          "embed_bwd: D multiple of 4 and 16-byte alignment required");
+  if (rows == 0) return LAMP_OK;
+  const long long blocks = (rows * 32 + 255) / 256;
+  embed_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      g, reinterpret_cast<const long long*>(seq), reinterpret_cast<const long long*>(pos), (long long)rows, D,
+      (long long)pad_word, (long long)pad_pos, dword, dpos);
   return launch_check();
 }
 

@@ -190,23 +190,70 @@ __global__ void __launch_bounds__(BWD_THREADS) gemm_tn_kernel(const __nv_bfloat1
   }
 }
 
-// db[n] += sum_m dY[m, n] (dY given as planes): thread per column, `chunk` rows per block, one atomic per thread.
-__global__ void colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                     long long ldy, long long M, int N, long long chunk, float* __restrict__ db) {
-  const int n = blockIdx.y * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const long long m_begin = blockIdx.x * chunk, m_end = min(M, m_begin + chunk);
-  float s = 0.f;
-  for (long long m = m_begin; m < m_end; ++m) {
-    s += __bfloat162float(hi[m * ldy + n]);
-    if (lo != nullptr) s += __bfloat162float(lo[m * ldy + n]);
+// db[n] += sum_m dY[m, n] (dY given as planes; N and ldy multiples of 8, planes 16-byte aligned -- what
+// lamp_gemm_tn_acc requires anyway).  HBM-bound: 4 B per element, read once.  256 threads = 8 row lanes (warps) x 32 column groups of 8
+// columns: a warp reads 512 contiguous bytes of a row per plane with one 16-byte load per thread, four rows in flight
+// per thread.  blockIdx.y selects the 256-column slab, blockIdx.x the `chunk` rows; the 8 row lanes are combined in
+// shared memory and each column costs one atomic per block.
+constexpr int COLSUM_THREADS = 256;
+__device__ __forceinline__ void colsum_acc8(float (&s)[8], const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s[2 * j] += __uint_as_float(w[j] << 16);
+    s[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
   }
-  atomicAdd(db + n, s);
+}
+__global__ void __launch_bounds__(COLSUM_THREADS) colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi,
+                                                                       const __nv_bfloat16* __restrict__ lo, long long ldy,
+                                                                       long long M, int N, long long chunk,
+                                                                       float* __restrict__ db) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n0 = (blockIdx.y * 32 + cg) * 8;
+  const long long m_begin = blockIdx.x * chunk, m_end = min(M, m_begin + chunk);
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (n0 < N) {
+    const __nv_bfloat16* ph = hi + n0;
+    const __nv_bfloat16* pl = lo != nullptr ? lo + n0 : nullptr;
+    long long m = m_begin + rl;
+    for (; m + 24 < m_end; m += 32) {   // rows m, m + 8, m + 16, m + 24 of this row lane
+      uint4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = __ldg(reinterpret_cast<const uint4*>(ph + (m + 8 * u) * ldy));
+      if (pl != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) b[u] = __ldg(reinterpret_cast<const uint4*>(pl + (m + 8 * u) * ldy));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) colsum_acc8(s, a[u]);
+      if (pl != nullptr) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) colsum_acc8(s, b[u]);
+      }
+    }
+    for (; m < m_end; m += 8) {
+      colsum_acc8(s, __ldg(reinterpret_cast<const uint4*>(ph + m * ldy)));
+      if (pl != nullptr) colsum_acc8(s, __ldg(reinterpret_cast<const uint4*>(pl + m * ldy)));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = s[j];
+  __syncthreads();
+  const int n = blockIdx.y * 256 + threadIdx.x;
+  if (n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+    atomicAdd(db + n, t);
+  }
 }
 
 // Backward of the diagonal label projection logits[b, l] = <x[b, l, :], W[l, :]> (+ bias[l]) (lamp/Models.py:124-126):
 //   dx[b, l, :] = g[b, l] * W[l, :]                       (one warp per (b, l) row)
-//   dW[l, :]    = sum_b g[b, l] * x[b, l, :],  dbias[l] = sum_b g[b, l]   (one block per label, threads over D)
+//   dW[l, :]    = sum_b g[b, l] * x[b, l, :],  dbias[l] = sum_b g[b, l]   (blocks over labels x batch slices)
 __global__ void diag_proj_bwd_dx_kernel(const float* __restrict__ g, const float* __restrict__ W, long long rows, int L,
                                         int D, float* __restrict__ dx) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -220,21 +267,77 @@ __global__ void diag_proj_bwd_dx_kernel(const float* __restrict__ g, const float
     o[idx] = make_float4(gv * w.x, gv * w.y, gv * w.z, gv * w.w);
   }
 }
+// dW / dbias: blockIdx.x = label, blockIdx.y = slice of the batch (`bchunk` samples); threads own 4 consecutive columns
+// (one 16-byte load per sample row), four samples in flight; partial sums leave with one vector reduction per thread
+// into the ZEROED dW (and one atomic per block into the zeroed dbias).
 __global__ void diag_proj_bwd_dw_kernel(const float* __restrict__ g, const float* __restrict__ x, long long B, int L,
-                                        int D, float* __restrict__ dW, float* __restrict__ dbias) {
+                                        int D, long long bchunk, float* __restrict__ dW, float* __restrict__ dbias) {
   const int l = blockIdx.x;
+  const long long b0 = blockIdx.y * bchunk, b1 = min(B, b0 + bchunk);
+  const long long rs = static_cast<long long>(L) * D;   // distance between the rows of label l of consecutive samples
   float gs = 0.f;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float s = 0.f;
+  for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* xp = x + static_cast<long long>(l) * D + c;
     gs = 0.f;
-    for (long long b = 0; b < B; ++b) {
-      const float gv = g[b * L + l];
-      s = fmaf(gv, x[(b * L + l) * D + c], s);
+    long long b = b0;
+    for (; b + 3 < b1; b += 4) {
+      float4 v[4];
+      float gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = __ldg(reinterpret_cast<const float4*>(xp + (b + u) * rs));
+        gv[u] = __ldg(g + (b + u) * L + l);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s.x = fmaf(gv[u], v[u].x, s.x); s.y = fmaf(gv[u], v[u].y, s.y);
+        s.z = fmaf(gv[u], v[u].z, s.z); s.w = fmaf(gv[u], v[u].w, s.w);
+        gs += gv[u];
+      }
+    }
+    for (; b < b1; ++b) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xp + b * rs));
+      const float gv = __ldg(g + b * L + l);
+      s.x = fmaf(gv, v.x, s.x); s.y = fmaf(gv, v.y, s.y); s.z = fmaf(gv, v.z, s.z); s.w = fmaf(gv, v.w, s.w);
       gs += gv;
     }
-    dW[static_cast<long long>(l) * D + c] = s;
+    float* o = dW + static_cast<long long>(l) * D + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
   }
-  if (dbias != nullptr && threadIdx.x == 0) dbias[l] = gs;  // thread 0 always owns column 0: its gs is the full sum
+  if (dbias != nullptr && threadIdx.x == 0) atomicAdd(dbias + l, gs);  // thread 0 always owns columns 0..3
+}
+
+// Backward of the token + position embedding sum (lamp/Encoders.py:66,75; torch.nn.Embedding with padding_idx):
+//   dword[seq[r], :] += g[r, :] unless seq[r] == pad_word;   dpos[pos[r], :] += g[r, :] unless pos[r] == pad_pos.
+// One warp per gradient row, one 16-byte vector reduction per lane and table: rows of the same token / position meet
+// in L2 (order of the additions is not fixed: fp32 sums differ in the last bits from run to run).  dword / dpos are
+// accumulated into (the caller zeroes them); either may be NULL.
+__global__ void embed_bwd_kernel(const float* __restrict__ g, const long long* __restrict__ seq,
+                                 const long long* __restrict__ pos, long long rows, int D, long long pad_word,
+                                 long long pad_pos, float* __restrict__ dword, float* __restrict__ dpos) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* w = nullptr;
+  float* q = nullptr;
+  if (dword != nullptr) {
+    const long long id = seq[row];
+    if (id != pad_word) w = dword + id * D;
+  }
+  if (dpos != nullptr) {
+    const long long id = pos[row];
+    if (id != pad_pos) q = dpos + id * D;
+  }
+  if (w == nullptr && q == nullptr) return;
+  const float4* gr = reinterpret_cast<const float4*>(g + row * D);
+  for (int idx = lane; idx < (D >> 2); idx += 32) {
+    const float4 v = __ldg(gr + idx);
+    if (w != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(w + 4 * idx), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    if (q != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 4 * idx), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
 }
 
 // ---- device-side training targets and loss (train.py:34-38; utils/utils.py:205-216) --------------------------------

@@ -830,21 +830,45 @@ def dropout_split(dy: torch.Tensor, p: float, seed: int):
     return hi, lo
 
 
-def _layernorm_bwd(y: torch.Tensor, g: torch.Tensor, gamma: torch.Tensor, eps: float):
+class _ZeroPool:
+    """The zero-initialised gradient accumulators of one backward node (dW / db of the split-K weight-gradient
+    kernels, dgamma / dbeta of the LayerNorm backward) carved out of ONE ``torch.zeros`` -- one fill launch per node
+    instead of one per tensor.  Slices start on 16-byte boundaries."""
+
+    def __init__(self, device, *shapes):
+        self._sizes = [(math.prod(sh) + 3) // 4 * 4 for sh in shapes]
+        self._buf = torch.zeros((sum(self._sizes),), dtype=torch.float32, device=device)
+        self._shapes, self._next, self._off = list(shapes), 0, 0
+
+    def take(self, shape) -> torch.Tensor:
+        want = self._shapes[self._next]
+        assert tuple(shape) == tuple(want), (shape, want)
+        n = math.prod(want)
+        out = self._buf[self._off:self._off + n].view(want)
+        self._off += self._sizes[self._next]
+        self._next += 1
+        return out
+
+
+def _zeros(zp: Optional[_ZeroPool], shape, device) -> torch.Tensor:
+    return zp.take(shape) if zp is not None else torch.zeros(shape, dtype=torch.float32, device=device)
+
+
+def _layernorm_bwd(y: torch.Tensor, g: torch.Tensor, gamma: torch.Tensor, eps: float, zp: Optional[_ZeroPool] = None):
     rows, D = y.shape
     dy = torch.empty_like(y)
-    dg = torch.zeros((D,), dtype=torch.float32, device=y.device)
-    db = torch.zeros_like(dg)
+    dg = _zeros(zp, (D,), y.device)
+    db = _zeros(zp, (D,), y.device)
     STATS.call('layernorm_bwd', 1, nat.lib().lamp_layernorm_bwd,
                (y.data_ptr(), g.data_ptr(), gamma.detach().float().contiguous().data_ptr(), float(eps), rows, D,
                 dy.data_ptr(), dg.data_ptr(), db.data_ptr(), nat.stream()), nbytes=rows * D * 12)
     return dy, dg, db
 
 
-def _gemm_tn(d_hi, d_lo, N: int, a_hi, a_lo, K: int, M: int, want_bias: bool):
+def _gemm_tn(d_hi, d_lo, N: int, a_hi, a_lo, K: int, M: int, want_bias: bool, zp: Optional[_ZeroPool] = None):
     """dW [N, K] = dy^T x and db [N] = column sums of dy, both from operand planes."""
-    dW = torch.zeros((N, K), dtype=torch.float32, device=d_hi.device)
-    db = torch.zeros((N,), dtype=torch.float32, device=d_hi.device) if want_bias else None
+    dW = _zeros(zp, (N, K), d_hi.device)
+    db = _zeros(zp, (N,), d_hi.device) if want_bias else None
     STATS.call('gemm_tn', 2 if want_bias else 1, nat.lib().lamp_gemm_tn_acc,
                (d_hi.data_ptr(), nat.ptr(d_lo), N, a_hi.data_ptr(), nat.ptr(a_lo), K, M, N, K, dW.data_ptr(), nat.ptr(db),
                 nat.stream()), flops=2.0 * M * N * K)
@@ -881,6 +905,7 @@ class FFNTrainFunction(torch.autograd.Function):
         ctx.save_for_backward(x_hi, x_lo, h_hi, h_lo, y, W1, W2, gamma)
         ctx.eps, ctx.p_drop, ctx.seed, ctx.x_shape = eps, p_drop, seed, tuple(x.shape)
         ctx.mark_non_differentiable(out.hi, out.lo)
+        ctx.set_materialize_grads(False)   # no zero tensors for the plane outputs' (never defined) gradients
         return out.f32.view(x.shape), out.hi, out.lo
 
     @staticmethod
@@ -889,15 +914,18 @@ class FFNTrainFunction(torch.autograd.Function):
         prec = nat.PREC_FP32
         M, D = y.shape
         dh = W1.shape[0]
-        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(M, D).float().contiguous(), gamma, ctx.eps)
+        if g is None:
+            g = torch.zeros_like(y)
+        zp = _ZeroPool(y.device, (D,), (D,), (D, dh), (D,), (dh, D), (dh,))
+        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(M, D).float().contiguous(), gamma, ctx.eps, zp)
         d_hi, d_lo = dropout_split(dy, ctx.p_drop, ctx.seed)
-        dW2, db2 = _gemm_tn(d_hi, d_lo, D, h_hi, h_lo, dh, M, True)
+        dW2, db2 = _gemm_tn(d_hi, d_lo, D, h_hi, h_lo, dh, M, True, zp)
         w2t_hi, w2t_lo = _wplanes(W2, prec, transpose=True)          # [dh, D]: dh = d W2
         g_hi, g_lo = _empty_planes(M, dh, prec, y.device)
         gemm(d_hi, d_lo, D, w2t_hi, w2t_lo, D, M, dh, D, prec, out_hi=g_hi, out_lo=g_lo, ldp=dh)
         STATS.call('relu_mask', 1, nat.lib().lamp_relu_mask_planes,
                    (g_hi.data_ptr(), g_lo.data_ptr(), h_hi.data_ptr(), M * dh, nat.stream()), nbytes=M * dh * 10)
-        dW1, db1 = _gemm_tn(g_hi, g_lo, dh, x_hi, x_lo, D, M, True)
+        dW1, db1 = _gemm_tn(g_hi, g_lo, dh, x_hi, x_lo, D, M, True, zp)
         w1t_hi, w1t_lo = _wplanes(W1, prec, transpose=True)          # [D, dh]: dx = dh W1 (+ the residual branch)
         dx = torch.empty((M, D), dtype=torch.float32, device=y.device)
         gemm(g_hi, g_lo, dh, w1t_hi, w1t_lo, dh, M, D, dh, prec, residual=dy, ldr=D, out_f32=dx, ldo=D)
@@ -985,6 +1013,7 @@ class MHATrainFunction(torch.autograd.Function):
         else:
             attn = emptyf
             ctx.mark_non_differentiable(out.hi, out.lo, attn)
+        ctx.set_materialize_grads(False)
         return out.f32.view(B, Lq, D), out.hi, out.lo, attn
 
     @staticmethod
@@ -998,9 +1027,12 @@ class MHATrainFunction(torch.autograd.Function):
         hd = H * d
         Mq, Mk = B * Lq, B * Lk
         dev = y.device
-        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(Mq, D).float().contiguous(), gamma, eps)
+        if g is None:
+            g = torch.zeros_like(y)
+        zp = _ZeroPool(dev, (D,), (D,), (D, hd), *(((3 * hd, D),) if self_attn else ((hd, D), (2 * hd, D))))
+        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(Mq, D).float().contiguous(), gamma, eps, zp)
         d_hi, d_lo = dropout_split(dy, p_out, seed_out)
-        dWfc, _ = _gemm_tn(d_hi, d_lo, D, o_hi, o_lo, hd, Mq, False)
+        dWfc, _ = _gemm_tn(d_hi, d_lo, D, o_hi, o_lo, hd, Mq, False, zp)
         wfct_hi, wfct_lo = _wplanes(Wfc, prec, transpose=True)       # [hd, D]: dO = d Wfc
         do_hi, do_lo = _empty_planes(Mq, hd, prec, dev)
         gemm(d_hi, d_lo, D, wfct_hi, wfct_lo, D, Mq, hd, D, prec, out_hi=do_hi, out_lo=do_lo, ldp=hd)
@@ -1026,12 +1058,12 @@ class MHATrainFunction(torch.autograd.Function):
         dxq = torch.empty((Mq, D), dtype=torch.float32, device=dev)
         dxkv = None
         if self_attn:
-            dW, _ = _gemm_tn(dq[0], dq[1], 3 * hd, xq_hi, xq_lo, D, Mq, False)
+            dW, _ = _gemm_tn(dq[0], dq[1], 3 * hd, xq_hi, xq_lo, D, Mq, False, zp)
             dWq, dWk, dWv = dW[:hd], dW[hd:2 * hd], dW[2 * hd:]
             wt_hi, wt_lo = _wplanes(torch.cat((Wq.detach(), Wk.detach(), Wv.detach()), dim=0), prec, transpose=True)  # [D, 3hd]
             gemm(dq[0], dq[1], 3 * hd, wt_hi, wt_lo, 3 * hd, Mq, D, 3 * hd, prec, residual=dy, ldr=D, out_f32=dxq, ldo=D)
         else:
-            dWq, _ = _gemm_tn(dq[0], dq[1], hd, xq_hi, xq_lo, D, Mq, False)
+            dWq, _ = _gemm_tn(dq[0], dq[1], hd, xq_hi, xq_lo, D, Mq, False, zp)
             wqt_hi, wqt_lo = _wplanes(Wq, prec, transpose=True)      # [D, hd]
             gemm(dq[0], dq[1], hd, wqt_hi, wqt_lo, hd, Mq, D, hd, prec, residual=dy, ldr=D, out_f32=dxq, ldo=D)
             if kv_idx is not None:
@@ -1040,7 +1072,7 @@ class MHATrainFunction(torch.autograd.Function):
                 zrow = dkv[0].new_zeros((1, 2 * hd))
                 dkv = (torch.cat((dkv[0].index_select(0, kv_idx), zrow)), torch.cat((dkv[1].index_select(0, kv_idx), zrow)))
                 Mk = dkv[0].shape[0]
-            dWkv, _ = _gemm_tn(dkv[0], dkv[1], 2 * hd, xkv_hi, xkv_lo, D, Mk, False)
+            dWkv, _ = _gemm_tn(dkv[0], dkv[1], 2 * hd, xkv_hi, xkv_lo, D, Mk, False, zp)
             dWk, dWv = dWkv[:hd], dWkv[hd:]
             wkvt_hi, wkvt_lo = _wplanes(torch.cat((Wk.detach(), Wv.detach()), dim=0), prec, transpose=True)  # [D, 2hd]
             dxkv = torch.empty((Mk, D), dtype=torch.float32, device=dev)
@@ -1048,6 +1080,53 @@ class MHATrainFunction(torch.autograd.Function):
             dxkv = dxkv.view(kv_shape)
         return (dxq.view(B, Lq, D), None, None, dxkv, None, None, dWq.to(Wq.dtype), dWk.to(Wk.dtype), dWv.to(Wv.dtype),
                 dWfc.to(Wfc.dtype), dgamma, dbeta, None, None, None, None, None, None, None, None, None, None, None)
+
+
+class EmbedTrainFunction(torch.autograd.Function):
+    """Token (+ position) embedding of the training path (lamp/Encoders.py:66,75) as one autograd node: forward =
+    ``lamp_embed`` (fp32 + operand planes for the first FFN), backward = ``lamp_embed_bwd`` -- vector reductions into
+    dense gradient tables instead of torch's sort-based embedding backward; the ``padding_idx`` rows get no gradient,
+    as with ``nn.Embedding``."""
+
+    @staticmethod
+    def forward(ctx, seq, pos, word_w, pos_w, pad_word, pad_pos):
+        prec = nat.PREC_FP32
+        act = embed(seq, pos, word_w.detach(), None if pos_w is None else pos_w.detach(), prec, want_f32=True)
+        ctx.save_for_backward(seq, pos if pos_w is not None else seq)
+        ctx.cfg = (tuple(word_w.shape), None if pos_w is None else tuple(pos_w.shape), int(pad_word), int(pad_pos))
+        ctx.mark_non_differentiable(act.hi, act.lo)
+        ctx.set_materialize_grads(False)
+        return act.f32, act.hi, act.lo
+
+    @staticmethod
+    def backward(ctx, g, _ghi, _glo):
+        seq, pos = ctx.saved_tensors
+        wshape, pshape, pad_word, pad_pos = ctx.cfg
+        want_w, want_p = ctx.needs_input_grad[2], (pshape is not None and ctx.needs_input_grad[3])
+        if g is None or not (want_w or want_p):
+            return None, None, None, None, None, None
+        g = g.float().contiguous()
+        rows, D = g.shape
+        dword = torch.zeros(wshape, dtype=torch.float32, device=g.device) if want_w else None
+        dpos = torch.zeros(pshape, dtype=torch.float32, device=g.device) if want_p else None
+        STATS.call('embed_bwd', 1, nat.lib().lamp_embed_bwd,
+                   (g.data_ptr(), seq.data_ptr(), pos.data_ptr(), rows, D, pad_word, pad_pos, nat.ptr(dword), nat.ptr(dpos),
+                    nat.stream()), nbytes=rows * D * 4 * (1 + int(want_w) + int(want_p)))
+        return None, None, dword, dpos, None, None
+
+
+def embed_train(seq: torch.Tensor, pos: Optional[torch.Tensor], word_emb, pos_emb) -> torch.Tensor:
+    """``word_emb(seq) (+ pos_emb(pos))`` for flat int64 id vectors through :class:`EmbedTrainFunction`
+    (``word_emb`` / ``pos_emb``: ``nn.Embedding`` modules, fp32 tables); the operand planes of the result are stashed
+    on the returned [rows, D] tensor."""
+    def pad_of(m):
+        return -1 if m is None or m.padding_idx is None else int(m.padding_idx)
+    seq = seq.contiguous().long()
+    pos = None if pos_emb is None else pos.contiguous().long()
+    out, hi, lo = EmbedTrainFunction.apply(seq, pos, word_emb.weight, None if pos_emb is None else pos_emb.weight,
+                                           pad_of(word_emb), pad_of(pos_emb))
+    out._lamp_planes = (hi, lo, out._version, nat.PREC_FP32)
+    return out
 
 
 def _train_seed() -> int:

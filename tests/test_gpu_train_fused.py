@@ -192,3 +192,65 @@ def test_mha_train_recompute_form_matches_fp64_autograd_and_the_stored_form(case
     assert rel_err(out_b, out_a) < 1e-6
     for name in g_a:
         assert rel_err(g_b[name], g_a[name]) < 2e-5, name
+
+
+@pytest.mark.parametrize('rows,V,P,D,with_pos', [(4000, 500, 61, 128, True), (777, 50, 301, 512, True),
+                                                  (1000, 20, 0, 64, False)])
+def test_embed_train_matches_torch_embedding_forward_and_backward(rows, V, P, D, with_pos):
+    """``ops.embed_train`` (lamp_embed + lamp_embed_bwd) against ``nn.Embedding(padding_idx=0)`` sums in fp64: heavy id
+    collisions (V << rows), PAD ids present, the padding rows of both tables get no gradient."""
+    g = torch.Generator().manual_seed(rows)
+    word = torch.nn.Embedding(V, D, padding_idx=0)
+    posm = torch.nn.Embedding(P, D, padding_idx=0) if with_pos else None
+    with torch.no_grad():
+        word.weight[0].normal_()          # a state dict may hold a non-zero padding row: it is read, never updated
+    seq = torch.randint(0, V, (rows,), generator=g)
+    pos = torch.randint(0, P, (rows,), generator=g) if with_pos else None
+    w = torch.randn(rows, D, generator=g)
+    ref = word.weight.double()[seq] + (posm.weight.double()[pos] if with_pos else 0)
+    gw = torch.zeros(V, D, dtype=torch.float64).index_add_(0, seq, w.double())
+    gw[0] = 0
+    if with_pos:
+        gp = torch.zeros(P, D, dtype=torch.float64).index_add_(0, pos, w.double())
+        gp[0] = 0
+    word, posm = word.to(DEV), (posm.to(DEV) if with_pos else None)
+    ops.STATS.reset()
+    out = ops.embed_train(seq.to(DEV), pos.to(DEV) if with_pos else None, word, posm)
+    assert out.shape == (rows, D) and getattr(out, '_lamp_planes', None) is not None
+    hi, lo = out._lamp_planes[:2]
+    assert rel_err(hi.float() + lo.float(), ref) < 2e-5
+    assert rel_err(out, ref) < 1e-6
+    (out * w.to(DEV)).sum().backward()
+    assert ops.STATS.by_kernel.get('embed', 0) == 1 and ops.STATS.by_kernel.get('embed_bwd', 0) == 1
+    assert rel_err(word.weight.grad, gw) < 1e-5 and float(word.weight.grad[0].abs().max()) == 0.0
+    if with_pos:
+        assert rel_err(posm.weight.grad, gp) < 1e-5 and float(posm.weight.grad[0].abs().max()) == 0.0
+
+
+def test_weight_and_bias_gradient_kernels_on_ragged_row_counts():
+    """``lamp_gemm_tn_acc`` with the vectorised column-sum kernel: row counts that are not multiples of the 32-row
+    step, N = 8 ... 1024, accumulation into a pre-loaded db."""
+    rs = np.random.RandomState(11)
+    for M, N, K in ((1, 8, 8), (31, 264, 64), (33, 512, 128), (26368, 512, 512), (4191, 1024, 64)):
+        dy = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(DEV)
+        x = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).to(DEV)
+        d_hi, d_lo = ops.split(dy, nat.PREC_FP32)
+        x_hi, x_lo = ops.split(x, nat.PREC_FP32)
+        dW, db = ops._gemm_tn(d_hi, d_lo, N, x_hi, x_lo, K, M, True)
+        assert rel_err(db, dy.double().sum(0)) < 2e-5, (M, N, K)
+        assert rel_err(dW, dy.double().t() @ x.double()) < 2e-5, (M, N, K)
+
+
+def test_diag_proj_backward_batch_slices():
+    """dW / dbias of the diagonal label projection are reduced over batch slices: ragged batch sizes."""
+    rs = np.random.RandomState(12)
+    for B, L, D in ((1, 5, 64), (7, 103, 512), (256, 103, 512), (33, 983, 128)):
+        g = torch.from_numpy(rs.standard_normal((B, L)).astype(np.float32)).to(DEV)
+        x = torch.from_numpy(rs.standard_normal((B, L, D)).astype(np.float32)).to(DEV)
+        W = torch.from_numpy(rs.standard_normal((L, D)).astype(np.float32)).to(DEV)
+        dx, dW, dbias = (torch.empty_like(x), torch.full((L, D), 7.0, device=DEV), torch.full((L,), 7.0, device=DEV))
+        nat.check(nat.lib().lamp_diag_proj_bwd(g.data_ptr(), x.data_ptr(), W.data_ptr(), B, L, D, dx.data_ptr(),
+                                               dW.data_ptr(), dbias.data_ptr(), nat.stream()), 'diag_proj_bwd')
+        assert rel_err(dW, torch.einsum('bl,bld->ld', g.double(), x.double())) < 1e-5, (B, L, D)
+        assert rel_err(dbias, g.double().sum(0)) < 1e-5
+        assert rel_err(dx, g.double().unsqueeze(-1) * W.double().unsqueeze(0)) < 1e-6
