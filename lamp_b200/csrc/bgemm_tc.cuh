@@ -10,9 +10,12 @@
 //     dV = A^T dO     (A: A  MN-major, B: dO MN-major)        dK = dS^T Q    (A: dS MN-major, B: Q  MN-major)
 // Persistent: one CTA per SM walks (batch, 128-row m tile, TN-column n tile) work items; contraction in 64-wide chunks
 // through a TMA ring that keeps running across items; 3-term split-bf16 products into one of two TMEM accumulators,
-// so the epilogue of an item (tcgen05.ld, lane == output row, scaled fp32 stores) overlaps the MMAs of the next one.
-// (The first version launched one CTA per item: with 2 chunks of work each, TMEM allocation and barrier set-up
-// dominated -- tensor pipe 7-8 % active.)
+// so the epilogue of an item overlaps the MMAs of the next one.  Epilogue: tcgen05.ld (lane == output row) -> scale ->
+// fp32 or split-bf16 -> the warp's 128B-swizzled staging boxes in shared memory -> 4-D TMA stores through output maps
+// with the same {cols, rows, head, sample} indexing (rows / columns outside one (sample, head) matrix are clipped by
+// the hardware).  (History: one CTA per item -- TMEM allocation and barrier set-up dominated, tensor pipe 7-8 % active;
+// then persistent CTAs with per-row scalar stores -- the four epilogue warps executed ~1000 instructions per tile, most
+// of them 2- and 4-byte stores with 64-bit address arithmetic, and were the critical path at ~10 K clocks per tile.)
 #pragma once
 #include "sm100_primitives.cuh"
 
@@ -22,7 +25,8 @@ constexpr int BG_THREADS = 192;
 constexpr int BG_KC = 64;  // contraction chunk
 __host__ __device__ constexpr uint32_t bg_stage_bytes(int npl, int tn) { return npl * (128 + tn) * BG_KC * 2; }
 __host__ __device__ constexpr int bg_stages(int npl, int tn) { return (192 * 1024) / bg_stage_bytes(npl, tn); }
-constexpr uint32_t BG_EPI_STAGING = 4 * 32 * 33 * 4;  // per epilogue warp: a [32 x 32] fp32 chunk, row pitch 33 words
+constexpr uint32_t BG_EPI_WARP = 8192;                  // per epilogue warp: two [32 rows x 128 B] swizzled boxes
+constexpr uint32_t BG_EPI_STAGING = 4 * BG_EPI_WARP;
 __host__ __device__ constexpr uint32_t bg_smem_bytes(int npl, int tn) {
   return (bg_stages(npl, tn) > 4 ? 4 : bg_stages(npl, tn)) * bg_stage_bytes(npl, tn) + BG_EPI_STAGING + 1024 + 256;
 }
@@ -30,17 +34,15 @@ __host__ __device__ constexpr uint32_t bg_smem_bytes(int npl, int tn) {
 struct BgemmParams {
   int batch, H, M, N, Kc;   // batch = samples * H; item -> (sample = batch / H, head = batch % H)
   float scale;              // C = scale * (A B)
-  float* C;                 // fp32 output (nullable): element (sample, head, m, n) at C[sample*stride_c + head*stride_ch + m*ldc + n]
-  __nv_bfloat16* C_hi;      // split-bf16 plane output (nullable), same indexing
-  __nv_bfloat16* C_lo;
-  long long ldc, stride_c, stride_ch;
+  int out_f32;              // 1: tmC0 is an fp32 map (box {32 cols, 32 rows}); 0: tmC0 / tmC1 are the hi / lo plane maps
+  int out_lo;               // planes: the lo plane is written as well
 };
 
 template <bool A_MN, bool B_MN, int NTERMS, int TN>
 __global__ void __launch_bounds__(BG_THREADS, 1)
 bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                const BgemmParams p) {
+                const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1, const BgemmParams p) {
   constexpr int NPL = (NTERMS == 3) ? 2 : 1;
   constexpr int STAGES = bg_stages(NPL, TN) > 4 ? 4 : bg_stages(NPL, TN);
   constexpr uint32_t A_BYTES = 128 * BG_KC * 2, B_BYTES = TN * BG_KC * 2;
@@ -49,7 +51,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   static_assert(STAGES >= 2, "ring too shallow");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BG_EPI_STAGING);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -68,6 +70,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmB_hi);
+    tma_prefetch_desc(&tmC0);
     if (NPL == 2) {
       tma_prefetch_desc(&tmA_lo);
       tma_prefetch_desc(&tmB_lo);
@@ -157,6 +160,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     }
   } else {
     const int wq = warp & 3;
+    const uint32_t stg = smem_u32(epi_stage) + (warp - 2) * BG_EPI_WARP;
+    const uint32_t srow = stg + lane * 128, sx = lane & 7;   // this lane's row in a box; chunk c sits at c ^ (row & 7)
     uint32_t t = 0;
     for (long long item = blockIdx.x; item < num_items; item += gridDim.x, ++t) {
       const int bh = static_cast<int>(item / per_batch), tile = static_cast<int>(item % per_batch);
@@ -165,41 +170,61 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       const uint32_t acc = t & 1, use = t >> 1;
       mbar_wait(&acc_full[acc], use & 1);
       tcgen05_fence_after();
-      // registers (lane == row) -> per-warp smem chunk -> row-contiguous global stores: every store instruction writes
-      // one contiguous segment of one output row (lane == column) instead of 32 scattered words
-      float* stg = epi_stage + (warp - 2) * (32 * 33);
-      const long long off0 = static_cast<long long>(b) * p.stride_c + static_cast<long long>(h) * p.stride_ch +
-                             static_cast<long long>(m0 + wq * 32) * p.ldc + n0;
-      const int rows_valid = p.M - (m0 + wq * 32);  // rows of this warp's 32 that exist
-      for (int c0 = 0; c0 < TN; c0 += 32) {
+      const int r0 = m0 + wq * 32;          // first output row of this warp
+      const bool store = r0 < p.M;          // (rows of the box beyond M are clipped by the TMA unit)
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 64) {
         if (n0 + c0 >= p.N) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + acc * TN + (static_cast<uint32_t>(wq * 32) << 16) + c0, r);
+        uint32_t ra[32], rb[32];
+        const uint32_t taddr = tmem_base + acc * TN + (static_cast<uint32_t>(wq * 32) << 16) + c0;
+        tmem_ld32(taddr, ra);
+        tmem_ld32(taddr + 32, rb);
         tmem_wait_ld();
+        if (c0 + 64 >= TN || n0 + c0 + 64 >= p.N) {   // last read of this accumulator: hand it back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(&acc_empty[acc]);
+        }
+        if (lane == 0) tma_store_wait_read0();        // the previous stores have read the staging boxes
+        __syncwarp();
+        if (p.out_f32) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) stg[lane * 33 + e] = __uint_as_float(r[e]) * p.scale;
-        __syncwarp();
-        const bool col_ok = n0 + c0 + lane < p.N;
-        if (p.C != nullptr) {
-          float* base = p.C + off0;
-          for (int rr = 0; rr < 32; ++rr)
-            if (rr < rows_valid && col_ok) base[static_cast<long long>(rr) * p.ldc + c0 + lane] = stg[rr * 33 + lane];
+          for (int c = 0; c < 8; ++c) {
+            uint4 v0, v1;
+            v0.x = __float_as_uint(__uint_as_float(ra[4 * c]) * p.scale);     v0.y = __float_as_uint(__uint_as_float(ra[4 * c + 1]) * p.scale);
+            v0.z = __float_as_uint(__uint_as_float(ra[4 * c + 2]) * p.scale); v0.w = __float_as_uint(__uint_as_float(ra[4 * c + 3]) * p.scale);
+            v1.x = __float_as_uint(__uint_as_float(rb[4 * c]) * p.scale);     v1.y = __float_as_uint(__uint_as_float(rb[4 * c + 1]) * p.scale);
+            v1.z = __float_as_uint(__uint_as_float(rb[4 * c + 2]) * p.scale); v1.w = __float_as_uint(__uint_as_float(rb[4 * c + 3]) * p.scale);
+            sts128(srow + ((c ^ sx) << 4), v0);           // box 0: columns c0 .. c0 + 31
+            sts128(srow + 4096 + ((c ^ sx) << 4), v1);    // box 1: columns c0 + 32 .. c0 + 63
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {   // 8 columns = one 16-byte chunk of a plane row; columns 8c .. 8c + 7 of the 64
+            const uint32_t* src = c < 4 ? ra + 8 * c : rb + 8 * (c - 4);
+            uint4 hv, lv;
+            split_bf16x2(__uint_as_float(src[0]) * p.scale, __uint_as_float(src[1]) * p.scale, hv.x, lv.x);
+            split_bf16x2(__uint_as_float(src[2]) * p.scale, __uint_as_float(src[3]) * p.scale, hv.y, lv.y);
+            split_bf16x2(__uint_as_float(src[4]) * p.scale, __uint_as_float(src[5]) * p.scale, hv.z, lv.z);
+            split_bf16x2(__uint_as_float(src[6]) * p.scale, __uint_as_float(src[7]) * p.scale, hv.w, lv.w);
+            sts128(srow + ((c ^ sx) << 4), hv);
+            if (p.out_lo) sts128(srow + 4096 + ((c ^ sx) << 4), lv);
+          }
         }
-        if (p.C_hi != nullptr) {
-          for (int rr = 0; rr < 32; ++rr)
-            if (rr < rows_valid && col_ok) {
-              const float v = stg[rr * 33 + lane];
-              const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-              const long long o = off0 + static_cast<long long>(rr) * p.ldc + c0 + lane;
-              p.C_hi[o] = hi;
-              if (p.C_lo != nullptr) p.C_lo[o] = __float2bfloat16_rn(v - __bfloat162float(hi));
-            }
-        }
+        fence_proxy_async_smem();
         __syncwarp();
+        if (lane == 0 && store) {
+          if (p.out_f32) {
+            tma_store_4d(&tmC0, stg, n0 + c0, r0, h, b);
+            if (n0 + c0 + 32 < p.N) tma_store_4d(&tmC0, stg + 4096, n0 + c0 + 32, r0, h, b);
+          } else {
+            tma_store_4d(&tmC0, stg, n0 + c0, r0, h, b);
+            if (p.out_lo) tma_store_4d(&tmC1, stg + 4096, n0 + c0, r0, h, b);
+          }
+          tma_store_commit();
+        }
       }
-      tcgen05_fence_before();
-      mbar_arrive(&acc_empty[acc]);
     }
+    if (lane == 0) tma_store_wait_all0();   // global writes performed before the CTA (and its shared memory) goes away
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -211,6 +236,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
 // dS = P o (dA * keep / (1 - p) - delta) / temperature  ->  split-bf16 planes [N*Lq, ld] (ld = Lk rounded up to 8; the
 // pad columns are written as 0), and A (attn after dropout) -> planes, both operands of the dQ / dK / dV products.
+// dA (and S in the recompute form) are workspace tensors with row pitch ld as well (TMA-stored by the batched product:
+// the pitch must be a multiple of 16 bytes); P and A are the caller's dense [N, Lq, Lk] tensors.
 // delta_i = <dO_i, O_i> is computed by the same block (one warp per row) before the row is swept.
 __global__ void attn_bwd_ds_kernel(const float* __restrict__ dA, const float* __restrict__ P, const float* __restrict__ A,
                                    const float* __restrict__ dO, const float* __restrict__ O, long long rows, int Lk,
@@ -230,7 +257,7 @@ __global__ void attn_bwd_ds_kernel(const float* __restrict__ dA, const float* __
       const long long g = row * Lk + c;
       a = A[g];
       const float keep = (a != 0.0f) ? drop_scale : 0.0f;
-      ds = P[g] * (dA[g] * keep - delta) * inv_temp;
+      ds = P[g] * (dA[row * ld + c] * keep - delta) * inv_temp;
     }
     const __nv_bfloat16 h = __float2bfloat16_rn(ds);
     dS_hi[row * ld + c] = h;
@@ -274,7 +301,7 @@ __global__ void attn_bwd_ds_planes_kernel(const float* __restrict__ dA, const fl
       const long long g = row * Lk + c;
       a = A[g];
       const float keep = (a != 0.0f) ? drop_scale : 0.0f;
-      ds = P[g] * (dA[g] * keep - delta) * inv_temp;
+      ds = P[g] * (dA[row * ld + c] * keep - delta) * inv_temp;
     }
     const __nv_bfloat16 hh = __float2bfloat16_rn(ds);
     dS_hi[row * ld + c] = hh;
@@ -304,7 +331,10 @@ struct DsRecomputeParams {
   int B, H, Lq, Lk, d, ld;
   __nv_bfloat16 *dS_hi, *dS_lo, *A_hi, *A_lo;
 };
-__global__ void attn_bwd_ds_recompute_kernel(const DsRecomputeParams p) {
+// One warp per (head, sample, query) row, four consecutive keys per lane and step: 16-byte loads of S and dA, 8-byte
+// stores of the four plane rows.  (The scalar version executed ~107 thread instructions per element -- 2-byte stores
+// and 64-bit address arithmetic per array -- and was instruction-bound at 32 % of DRAM.)
+__global__ void __launch_bounds__(256) attn_bwd_ds_recompute_kernel(const DsRecomputeParams p) {
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long rows = static_cast<long long>(p.H) * p.B * p.Lq;
@@ -314,10 +344,19 @@ __global__ void attn_bwd_ds_recompute_kernel(const DsRecomputeParams p) {
   const int b = static_cast<int>(n % p.B), h = static_cast<int>(n / p.B);
   const long long orow = (static_cast<long long>(b) * p.Lq + i) * p.ld_o + static_cast<long long>(h) * p.d;
   float delta = 0.f;
-  for (int c = lane; c < p.d; c += 32) {
-    const float g = __bfloat162float(p.dO_hi[orow + c]) + __bfloat162float(p.dO_lo[orow + c]);
-    const float o = __bfloat162float(p.O_hi[orow + c]) + __bfloat162float(p.O_lo[orow + c]);
-    delta = fmaf(g, o, delta);
+  for (int c = lane * 4; c < p.d; c += 128) {   // d is a multiple of 16, the planes are 16-byte aligned per head slice
+    const uint2 gh = __ldg(reinterpret_cast<const uint2*>(p.dO_hi + orow + c)), gl = __ldg(reinterpret_cast<const uint2*>(p.dO_lo + orow + c));
+    const uint2 oh = __ldg(reinterpret_cast<const uint2*>(p.O_hi + orow + c)), ol = __ldg(reinterpret_cast<const uint2*>(p.O_lo + orow + c));
+    const uint32_t g4[4] = {gh.x, gh.y, gl.x, gl.y}, o4[4] = {oh.x, oh.y, ol.x, ol.y};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float g0 = __uint_as_float(g4[j] << 16) + __uint_as_float(g4[j + 2] << 16);
+      const float g1 = __uint_as_float(g4[j] & 0xFFFF0000u) + __uint_as_float(g4[j + 2] & 0xFFFF0000u);
+      const float o0 = __uint_as_float(o4[j] << 16) + __uint_as_float(o4[j + 2] << 16);
+      const float o1 = __uint_as_float(o4[j] & 0xFFFF0000u) + __uint_as_float(o4[j + 2] & 0xFFFF0000u);
+      delta = fmaf(g0, o0, delta);
+      delta = fmaf(g1, o1, delta);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xFFFFFFFFu, delta, o);
@@ -326,22 +365,39 @@ __global__ void attn_bwd_ds_recompute_kernel(const DsRecomputeParams p) {
                                                    static_cast<unsigned long long>(row))
                                     : 0u;
   const uint8_t* mrow = p.mask ? p.mask + static_cast<long long>(b) * p.msb + static_cast<long long>(i) * p.msq : nullptr;
-  for (int c = lane; c < p.ld; c += 32) {
-    float ds = 0.f, a = 0.f;
+  const float* Srow = p.S + row * p.ld;
+  const float* dArow = p.dA + row * p.ld;
+  __nv_bfloat16* o_dsh = p.dS_hi + row * p.ld;
+  __nv_bfloat16* o_dsl = p.dS_lo + row * p.ld;
+  __nv_bfloat16* o_ah = p.A_hi + row * p.ld;
+  __nv_bfloat16* o_al = p.A_lo + row * p.ld;
+  for (int c = lane * 4; c < p.ld; c += 128) {
+    float ds[4] = {0.f, 0.f, 0.f, 0.f}, a[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < p.Lk) {
-      const long long g = row * p.Lk + c;
-      const bool masked = mrow != nullptr && mrow[static_cast<long long>(c) * p.msk] != 0;
-      const float pr = masked ? (0.0f * rinv) : exp2f(p.S[g] * p.scale_log2 - rmx) * rinv;
-      const float keep = (!p.drop_thresh || drop_keep(rh, static_cast<uint32_t>(c), p.drop_thresh)) ? p.drop_scale : 0.0f;
-      a = pr * keep;
-      ds = pr * (p.dA[g] * keep - delta) * p.inv_temp;
+      const float4 s4 = *reinterpret_cast<const float4*>(Srow + c), d4 = *reinterpret_cast<const float4*>(dArow + c);
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c + j < p.Lk) {   // (columns Lk .. ld-1 of S / dA were clipped by the store: never read)
+          const bool masked = mrow != nullptr && mrow[static_cast<long long>(c + j) * p.msk] != 0;
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(sv[j], p.scale_log2, -rmx)));
+          const float pr = masked ? (0.0f * rinv) : e * rinv;
+          const float keep = (!p.drop_thresh || drop_keep(rh, static_cast<uint32_t>(c + j), p.drop_thresh)) ? p.drop_scale : 0.0f;
+          a[j] = pr * keep;
+          ds[j] = pr * (dv[j] * keep - delta) * p.inv_temp;
+        }
+      }
     }
-    const __nv_bfloat16 hh = __float2bfloat16_rn(ds);
-    p.dS_hi[row * p.ld + c] = hh;
-    p.dS_lo[row * p.ld + c] = __float2bfloat16_rn(ds - __bfloat162float(hh));
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a);
-    p.A_hi[row * p.ld + c] = ah;
-    p.A_lo[row * p.ld + c] = __float2bfloat16_rn(a - __bfloat162float(ah));
+    uint2 dh, dl, ah, al;
+    split_bf16x2(ds[0], ds[1], dh.x, dl.x);
+    split_bf16x2(ds[2], ds[3], dh.y, dl.y);
+    split_bf16x2(a[0], a[1], ah.x, al.x);
+    split_bf16x2(a[2], a[3], ah.y, al.y);
+    *reinterpret_cast<uint2*>(o_dsh + c) = dh;
+    *reinterpret_cast<uint2*>(o_dsl + c) = dl;
+    *reinterpret_cast<uint2*>(o_ah + c) = ah;
+    *reinterpret_cast<uint2*>(o_al + c) = al;
   }
 }
 

@@ -101,20 +101,23 @@ inline int current_device() {
 // box = {64 cols, box_rows, 1, 1}, 128B swizzle, zero OOB fill.  Used by the batched attention-backward products, whose
 // operands are either head-major [H*B, L, d] tensors or head column slices of [B*L, H*d] plane matrices.
 int make_tmap4(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t heads, uint64_t samples,
-               uint64_t ld_elems, uint64_t head_stride, uint64_t sample_stride, uint32_t box_rows) {
+               uint64_t ld_elems, uint64_t head_stride, uint64_t sample_stride, uint32_t box_rows, bool f32 = false) {
+  // f32 = true: the same view of an fp32 tensor, box = {32 cols (128 B), box_rows, 1, 1} (the fp32 outputs of the
+  // batched products are stored through such maps)
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (!aligned16(base)) return fail(LAMP_EINVAL, "TMA base pointer not 16-byte aligned");
-  if ((ld_elems * 2) % 16 != 0 || (head_stride * 2) % 16 != 0 || (sample_stride * 2) % 16 != 0)
-    return fail(LAMP_EINVAL, "TMA strides (%llu, %llu, %llu elements) must be multiples of 8 elements",
+  const uint64_t eb = f32 ? 4 : 2;
+  if ((ld_elems * eb) % 16 != 0 || (head_stride * eb) % 16 != 0 || (sample_stride * eb) % 16 != 0)
+    return fail(LAMP_EINVAL, "TMA strides (%llu, %llu, %llu elements) must be multiples of 16 bytes",
                 (unsigned long long)ld_elems, (unsigned long long)head_stride, (unsigned long long)sample_stride);
   cuuint64_t dims[4] = {cols, rows, heads, samples};
-  cuuint64_t strides[3] = {ld_elems * 2, head_stride * 2, sample_stride * 2};
-  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint64_t strides[3] = {ld_elems * eb, head_stride * eb, sample_stride * eb};
+  cuuint32_t box[4] = {f32 ? 32u : 64u, box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LAMP_ECUDA, "cuTensorMapEncodeTiled (4-D) failed with CUresult %d", (int)r);
   return LAMP_OK;
 }
@@ -737,7 +740,7 @@ AttnBwdPlan attn_bwd_plan(int N, int Lq, int Lk, int d) {
   pl.kp = c.off;  c.take(nk * d * 4);
   pl.vp = c.off;  c.take(nk * d * 4);
   pl.dop = c.off; c.take(nq * d * 4);
-  pl.dA = c.off;  c.take(nq * Lk * 4);
+  pl.dA = c.off;  c.take(nq * pl.ld * 4);   // fp32, row pitch ld (TMA-stored)
   pl.dSp = c.off; c.take(nq * pl.ld * 4);
   pl.Ap = c.off;  c.take(nq * pl.ld * 4);
   pl.total = c.off;
@@ -772,7 +775,7 @@ struct BgOutput {
 
 template <bool A_MN, bool B_MN>
 int launch_bgemm(const BgOperand& a, const BgOperand& b, int samples, int H, int M, int N, int Kc, float scale,
-                 const BgOutput& c, cudaStream_t st) {
+                 const BgOutput& c_in, cudaStream_t st) {
   constexpr int TN = 128;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   const uint32_t a_box_rows = A_MN ? 64 : 128, b_box_rows = B_MN ? 64 : TN;
@@ -783,16 +786,34 @@ int launch_bgemm(const BgOperand& a, const BgOperand& b, int samples, int H, int
   if (int rc = mk(&ta_lo, a.lo ? a.lo : a.hi, a, a_box_rows)) return rc;
   if (int rc = mk(&tb_hi, b.hi, b, b_box_rows)) return rc;
   if (int rc = mk(&tb_lo, b.lo ? b.lo : b.hi, b, b_box_rows)) return rc;
+  // output maps: the same {cols, rows, head, sample} indexing, boxes of 32 rows x 128 B (one per epilogue warp)
+  CUtensorMap tc0, tc1;
+  BgOutput c = c_in;
+  if (H == 1 && c.stride_ch == 0) c.stride_ch = c.stride_c;   // a size-1 dimension still needs a valid stride
+  if (c.f32 != nullptr) {
+    if (c.hi != nullptr) return fail(LAMP_EINVAL, "bgemm: give an fp32 output or plane outputs, not both");
+    if (int rc = make_tmap4(&tc0, c.f32, (uint64_t)N, (uint64_t)M, (uint64_t)H, (uint64_t)samples, (uint64_t)c.ldc,
+                            (uint64_t)c.stride_ch, (uint64_t)c.stride_c, 32, true)) return rc;
+    tc1 = tc0;
+  } else {
+    if (int rc = make_tmap4(&tc0, c.hi, (uint64_t)N, (uint64_t)M, (uint64_t)H, (uint64_t)samples, (uint64_t)c.ldc,
+                            (uint64_t)c.stride_ch, (uint64_t)c.stride_c, 32)) return rc;
+    if (c.lo != nullptr) {
+      if (int rc = make_tmap4(&tc1, c.lo, (uint64_t)N, (uint64_t)M, (uint64_t)H, (uint64_t)samples, (uint64_t)c.ldc,
+                              (uint64_t)c.stride_ch, (uint64_t)c.stride_c, 32)) return rc;
+    } else {
+      tc1 = tc0;
+    }
+  }
   auto kernel = bgemm_tc_kernel<A_MN, B_MN, 3, TN>;
   static PerDeviceOnce once;
   if (int once_rc = per_device_once(once, [kernel] { int rc_ = set_smem(kernel, bg_smem_bytes(2, TN)); return rc_; })) return once_rc;
   BgemmParams p;
   p.batch = samples * H; p.H = H; p.M = M; p.N = N; p.Kc = Kc; p.scale = scale;
-  p.C = c.f32; p.C_hi = static_cast<__nv_bfloat16*>(c.hi); p.C_lo = static_cast<__nv_bfloat16*>(c.lo);
-  p.ldc = c.ldc; p.stride_c = c.stride_c; p.stride_ch = c.stride_ch;
+  p.out_f32 = c.f32 != nullptr ? 1 : 0; p.out_lo = c.lo != nullptr ? 1 : 0;
   const long long items = (long long)p.batch * ((M + 127) / 128) * ((N + TN - 1) / TN);
   const long long grid = items < sm_count_cached() ? items : sm_count_cached();  // persistent: one CTA per SM
-  kernel<<<(unsigned)grid, BG_THREADS, bg_smem_bytes(2, TN), st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  kernel<<<(unsigned)grid, BG_THREADS, bg_smem_bytes(2, TN), st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tc0, tc1, p);
   return launch_check();
 }
 }  // namespace
@@ -847,7 +868,7 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
   if (int rc = lamp_split_planes(dO, (int64_t)nq, d, d, gh, gl, d, stream)) return rc;
   // dA = dO V^T  [N, Lq, Lk]
   if (int rc = launch_bgemm<false, false>(bg_headmajor(gh, gl, d, Lq, d), bg_headmajor(vh, vl, d, Lk, d), N, 1, Lq, Lk, d, 1.0f,
-                                          BgOutput{dA, nullptr, nullptr, Lk, (long long)Lq * Lk, 0}, st)) return rc;
+                                          BgOutput{dA, nullptr, nullptr, pl.ld, (long long)Lq * pl.ld, 0}, st)) return rc;
   // dS (scaled by 1/temperature) and A as planes [N*Lq, ld]
   {
     const long long blocks = ((long long)nq * 32 + 255) / 256;
@@ -871,7 +892,7 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
  * [H*B, Lq, Lk] tensors the training forward wrote.  dQ / dK / dV leave as planes in the same slice layout. */
 size_t lamp_attn_bwd_planes_workspace_bytes(int B, int H, int Lq, int Lk) {
   const size_t nq = (size_t)B * H * Lq, ld = (size_t)(Lk + 7) / 8 * 8;
-  return 2 * align_up(nq * Lk * 4) + 2 * align_up(nq * ld * 4);  // dA, S (recompute form), dS planes, A planes
+  return 4 * align_up(nq * ld * 4);  // dA, S (recompute form; fp32 with row pitch ld), dS planes, A planes
 }
 
 int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, const void* kv_hi, const void* kv_lo,
@@ -897,8 +918,8 @@ int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_
   const size_t nq = (size_t)B * H * Lq;
   const int ld = (Lk + 7) / 8 * 8;
   Carver cv(workspace);
-  float* dA = static_cast<float*>(cv.take(nq * Lk * 4));
-  float* S = static_cast<float*>(cv.take(nq * Lk * 4));
+  float* dA = static_cast<float*>(cv.take(nq * ld * 4));
+  float* S = static_cast<float*>(cv.take(nq * ld * 4));
   __nv_bfloat16* sh = static_cast<__nv_bfloat16*>(cv.take(nq * ld * 4));
   __nv_bfloat16* sl = sh + nq * ld;
   __nv_bfloat16* ah = static_cast<__nv_bfloat16*>(cv.take(nq * ld * 4));
@@ -911,7 +932,7 @@ int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_
   };
   // dA = dO V^T   [H*B, Lq, Lk] fp32
   if (int rc = launch_bgemm<false, false>(G, V, B, H, Lq, Lk, d, 1.0f,
-                                          BgOutput{dA, nullptr, nullptr, Lk, (long long)Lq * Lk, (long long)B * Lq * Lk}, st)) return rc;
+                                          BgOutput{dA, nullptr, nullptr, ld, (long long)Lq * ld, (long long)B * Lq * ld}, st)) return rc;
   const long long ds_blocks = ((long long)nq * 32 + 255) / 256;
   if (P != nullptr) {
     attn_bwd_ds_planes_kernel<<<(unsigned)ds_blocks, 256, 0, st>>>(
@@ -922,7 +943,7 @@ int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_
   } else {
     // recompute form: S = Q K^T once more, P rebuilt inside the element-wise kernel
     if (int rc = launch_bgemm<false, false>(Q, K, B, H, Lq, Lk, d, 1.0f,
-                                            BgOutput{S, nullptr, nullptr, Lk, (long long)Lq * Lk, (long long)B * Lq * Lk}, st)) return rc;
+                                            BgOutput{S, nullptr, nullptr, ld, (long long)Lq * ld, (long long)B * Lq * ld}, st)) return rc;
     DsRecomputeParams rp;
     rp.S = S; rp.dA = dA; rp.row_max = row_max; rp.row_sum = row_sum;
     rp.mask = mask; rp.msb = msb; rp.msq = msq; rp.msk = msk;
