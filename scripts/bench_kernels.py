@@ -146,12 +146,14 @@ def bench_attn(prec=0):
 
 
 def bench_ln(prec=0):
-    for rows in (1024 * 300, 1024 * 103):
+    for rows in (1100 * 160, 1100 * 103):
         y = torch.randn(rows, 512, device=DEV)
         g = torch.ones(512, device=DEV)
         b = torch.zeros(512, device=DEV)
-        t = timeit(lambda: ops.layernorm(y, g, b, 1e-5, prec))
-        print(f'layernorm rows={rows}: {t * 1e6:8.1f} us  {rows * 512 * 12 / t / 1e9:7.1f} GB/s', flush=True)
+        for want_f32 in (True, False):
+            t = timeit(lambda: ops.layernorm(y, g, b, 1e-5, prec, want_f32=want_f32))
+            nb = rows * 512 * (12 if want_f32 else 8)
+            print(f'layernorm rows={rows} f32_out={int(want_f32)}: {t * 1e6:8.1f} us  {nb / t / 1e9:7.1f} GB/s', flush=True)
 
 
 if __name__ == '__main__':
