@@ -63,6 +63,20 @@ int lamp_set_tuning(int key, int value);
 int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* hi, void* lo, int64_t ldp,
                       void* stream);
 
+/* Many small splits in one launch (training: the planes of every projection weight, W and W^T, once per step).
+ * Job: fp32 src [rows, cols] (leading dim ld) -> planes [rows, cols], or [cols, rows] with transpose != 0 (leading dim
+ * ldp; hi / lo may point into a wider matrix, e.g. the Wq | Wk | Wv row blocks of one [3*H*d, D] operand).  lo may be
+ * NULL.  No alignment requirements beyond the element types. */
+typedef struct LampSplitJob {
+  const float* src;
+  void* hi;
+  void* lo;
+  int rows, cols;
+  int64_t ld, ldp;
+  int transpose;
+} LampSplitJob;
+int lamp_split_planes_multi(const LampSplitJob* jobs, int n_jobs, void* stream);
+
 /* C[M,N] = A[M,K] * W[N,K]^T, then (+bias[N]) (ReLU) (+residual[row % resid_mod or row, :]) and store as fp32
  * and/or planes.  Replaces the nn.Linear / Conv1d(k=1) contractions of lamp/SubLayers.py:91-93 (w_qs,w_ks,w_vs),
  * :110 (fc) and :133 (w_1, w_2).  K % 8 == 0, N % 8 == 0.  m_dev (nullable, device int32): process only

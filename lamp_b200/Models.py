@@ -102,6 +102,10 @@ class LAMP(nn.Module):
         src_seq, src_pos = src
         batch_size = src_seq.size(0)
         fused = not _needs_autograd(self)
+        if not fused and ops.NATIVE_TRAINING and src_seq.is_cuda and not getattr(self, '_is_replica', False):
+            # training step: the operand planes (W and W^T) of every projection weight the fused sub-layers used in
+            # an earlier step are rebuilt by one launch, now that the optimizer has changed the weights
+            ops.TRAIN_WEIGHTS.refresh_all(src_seq.device)
         enc_output, *enc_self_attns = self.encoder(src_seq, adj, src_pos, return_attns=return_attns)
         # fused inference: the decoder may hand over its output with the last LayerNorm still pending; it is then
         # applied inside the diagonal label-projection kernel (dec_output itself is not part of LAMP's return value)

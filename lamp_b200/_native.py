@@ -22,6 +22,12 @@ _lib = None
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 
+class LampSplitJob(C.Structure):
+    """``LampSplitJob`` of include/lamp_b200.h (one matrix of a ``lamp_split_planes_multi`` launch)."""
+    _fields_ = [('src', C.c_void_p), ('hi', C.c_void_p), ('lo', C.c_void_p), ('rows', C.c_int), ('cols', C.c_int),
+                ('ld', C.c_int64), ('ldp', C.c_int64), ('transpose', C.c_int)]
+
+
 _SIGNATURES = {
     'lamp_version': ([], _i),
     'lamp_last_error': ([], C.c_char_p),
@@ -29,6 +35,7 @@ _SIGNATURES = {
     'lamp_sm_count': ([], _i),
     'lamp_set_tuning': ([_i, _i], _i),
     'lamp_split_planes': ([_vp, _i64, _i, _i64, _vp, _vp, _i64, _vp], _i),
+    'lamp_split_planes_multi': ([_vp, _i, _vp], _i),
     'lamp_gemm_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp,
                           _i64, _vp, _vp], _i),
     'lamp_gemm_planes_pres': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp,

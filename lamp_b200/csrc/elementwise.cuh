@@ -23,6 +23,59 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long rows,
   }
 }
 
+// Many small splits in ONE launch (the weight matrices of a training step: every projection weight is needed as
+// planes, W for the forward products and W^T for the input-gradient products, and changes every step).  Job j:
+// fp32 src [rows, cols] (leading dim ld) -> planes dst [rows, cols] or, with `transpose`, dst [cols, rows] (leading dim
+// ldp; dst may be a row / column slice of a wider matrix: that is how Wq | Wk | Wv land in one [3*H*d, D] operand without
+// a concatenation).  blockIdx.y = job, blockIdx.x = 32 x 32 tile; 256 threads, tile transposed through shared memory.
+struct SplitJob {
+  const float* src;
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;   // nullable
+  int rows, cols;
+  long long ld, ldp;
+  int transpose;
+};
+constexpr int SPLIT_MULTI_MAX_JOBS = 56;   // 56 x 56 B of kernel parameters
+struct SplitJobs {
+  SplitJob job[SPLIT_MULTI_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) split_planes_multi_kernel(const __grid_constant__ SplitJobs jobs) {
+  __shared__ float tile[32][33];
+  const SplitJob& jb = jobs.job[blockIdx.y];
+  const int tiles_c = (jb.cols + 31) >> 5, tiles_r = (jb.rows + 31) >> 5;
+  if (static_cast<int>(blockIdx.x) >= tiles_c * tiles_r) return;
+  const int r0 = (blockIdx.x / tiles_c) << 5, c0 = (blockIdx.x % tiles_c) << 5;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 row lanes
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < jb.rows && c < jb.cols) ? jb.src[static_cast<long long>(r) * jb.ld + c] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = ty + 8 * i;   // row of the OUTPUT tile handled by this thread, column tx
+    float v;
+    long long off;
+    bool ok;
+    if (jb.transpose) {
+      v = tile[tx][a];          // out[c0 + a][r0 + tx] = src[r0 + tx][c0 + a]
+      ok = (c0 + a < jb.cols) && (r0 + tx < jb.rows);
+      off = static_cast<long long>(c0 + a) * jb.ldp + r0 + tx;
+    } else {
+      v = tile[a][tx];
+      ok = (r0 + a < jb.rows) && (c0 + tx < jb.cols);
+      off = static_cast<long long>(r0 + a) * jb.ldp + c0 + tx;
+    }
+    if (ok) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      jb.hi[off] = h;
+      if (jb.lo != nullptr) jb.lo[off] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
 // out = LayerNorm(y (+ add)) * gamma + beta  (biased variance, eps inside the sqrt: torch.nn.LayerNorm, used at
 // lamp/SubLayers.py:117,141).  One warp per row, the row lives in registers (D <= 32*4*MAXV), two-pass variance.
 // `add` rows are indexed modulo add_mod when add_mod > 0 (label embeddings shared by every sample).

@@ -394,6 +394,32 @@ int lamp_split_planes(const float* x, int64_t rows, int cols, int64_t ld, void* 
   return launch_check();
 }
 
+int lamp_split_planes_multi(const LampSplitJob* jobs, int n_jobs, void* stream) {
+  if (int rc = arch_check()) return rc;
+  REQUIRE(n_jobs >= 0 && (jobs || n_jobs == 0), "split_planes_multi: null job list");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int j0 = 0; j0 < n_jobs; j0 += SPLIT_MULTI_MAX_JOBS) {
+    SplitJobs pack;
+    const int n = n_jobs - j0 < SPLIT_MULTI_MAX_JOBS ? n_jobs - j0 : SPLIT_MULTI_MAX_JOBS;
+    long long max_tiles = 0;
+    for (int j = 0; j < n; ++j) {
+      const LampSplitJob& in = jobs[j0 + j];
+      REQUIRE(in.src && in.hi && in.rows > 0 && in.cols > 0, "split_planes_multi: job %d: null pointer or empty shape", j0 + j);
+      REQUIRE(in.ld >= in.cols && in.ldp >= (in.transpose ? in.rows : in.cols), "split_planes_multi: job %d: leading dimension too small", j0 + j);
+      SplitJob& o = pack.job[j];
+      o.src = in.src; o.hi = static_cast<__nv_bfloat16*>(in.hi); o.lo = static_cast<__nv_bfloat16*>(in.lo);
+      o.rows = in.rows; o.cols = in.cols; o.ld = in.ld; o.ldp = in.ldp; o.transpose = in.transpose;
+      const long long tiles = (long long)((in.rows + 31) / 32) * ((in.cols + 31) / 32);
+      if (tiles > max_tiles) max_tiles = tiles;
+    }
+    for (int j = n; j < SPLIT_MULTI_MAX_JOBS; ++j) pack.job[j] = SplitJob{nullptr, nullptr, nullptr, 0, 0, 0, 0, 0};
+    REQUIRE(max_tiles < (1LL << 31), "split_planes_multi: matrix too large");
+    split_planes_multi_kernel<<<dim3((unsigned)max_tiles, (unsigned)n), 256, 0, st>>>(pack);
+    if (int rc = launch_check()) return rc;
+  }
+  return LAMP_OK;
+}
+
 namespace {
 struct DlnArgs {  // deferred-LayerNorm extras of a GEMM launch (all null / 0: none)
   const float* a_stats = nullptr; int a_nparts = 0; float a_eps = 0.f; const float* a_colsum = nullptr;

@@ -11,9 +11,11 @@ The training path lives here as autograd Functions over the s
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import os
 import threading
+import weakref
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -801,8 +803,103 @@ def planes_of(x: torch.Tensor, prec: int) -> Tuple[torch.Tensor, Optional[torch.
     return split(x.detach().reshape(rows, cols).float(), prec)
 
 
-def _wplanes(W: torch.Tensor, prec: int, transpose: bool = False):
-    w2 = W.detach().reshape(W.shape[0], -1).float()
+class _TrainWeightCache:
+    """Operand planes of the projection weights of the training path, W (forward products) and W^T (input-gradient
+    products), row blocks of several parameters side by side where one GEMM consumes them together (Wq | Wk | Wv).
+    Weights change every optimizer step, so every entry is rebuilt once per step -- all stale entries of all live
+    models by ONE ``lamp_split_planes_multi`` launch at the start of the training forward (``refresh_all``), instead
+    of a concatenation, a transposed copy and a split per weight and use.  An entry is validated by the parameters'
+    identity (weak references), tensor versions and addresses; a miss or a stale entry met outside ``refresh_all`` is
+    (re)built on the spot with its own launch.  Buffers persist (CUDA-graph safe: same addresses every step)."""
+
+    class Entry:
+        __slots__ = ('refs', 'transpose', 'hi', 'lo', 'stamp', 'rows', 'cols')
+
+    def __init__(self):
+        self.entries = {}
+        self.lock = threading.Lock()
+
+    @staticmethod
+    def _stamp(ws):
+        return tuple((w._version, w.data_ptr()) for w in ws)
+
+    def _jobs(self, e, ws):
+        jobs, r0 = [], 0
+        for w in ws:
+            n, k = w.shape[0], w[0].numel()
+            j = nat.LampSplitJob()
+            j.src, j.rows, j.cols, j.ld, j.transpose = w.data_ptr(), n, k, k, int(e.transpose)
+            if e.transpose:      # dst [K, sum N]: this parameter's block is the column slice r0 .. r0 + n
+                j.hi, j.lo, j.ldp = e.hi.data_ptr() + 2 * r0, e.lo.data_ptr() + 2 * r0, e.rows
+            else:                # dst [sum N, K]: row block r0 .. r0 + n
+                j.hi, j.lo, j.ldp = e.hi.data_ptr() + 2 * r0 * k, e.lo.data_ptr() + 2 * r0 * k, k
+            jobs.append(j)
+            r0 += n
+        return jobs
+
+    @staticmethod
+    def _launch(jobs):
+        if not jobs:
+            return
+        arr = (nat.LampSplitJob * len(jobs))(*jobs)
+        STATS.call('split_planes', (len(jobs) + 55) // 56, nat.lib().lamp_split_planes_multi,
+                   (C.addressof(arr), len(jobs), nat.stream()))
+
+    def get(self, ws, transpose: bool):
+        key = tuple(id(w) for w in ws) + (bool(transpose),)
+        with self.lock:
+            e = self.entries.get(key)
+            if e is not None and not all(r() is w for r, w in zip(e.refs, ws)):
+                e = None                                  # an id was recycled by another tensor
+            if e is None:
+                e = self.Entry()
+                e.refs, e.transpose = tuple(weakref.ref(w) for w in ws), bool(transpose)
+                e.rows, e.cols = sum(w.shape[0] for w in ws), ws[0][0].numel()
+                shape = (e.cols, e.rows) if transpose else (e.rows, e.cols)
+                e.hi = torch.empty(shape, dtype=torch.bfloat16, device=ws[0].device)
+                e.lo = torch.empty(shape, dtype=torch.bfloat16, device=ws[0].device)
+                e.stamp = None
+                self.entries[key] = e
+            stamp = self._stamp(ws)
+            if e.stamp != stamp:
+                self._launch(self._jobs(e, ws))
+                e.stamp = stamp
+            return e.hi, e.lo
+
+    def refresh_all(self, device):
+        """Rebuild every stale entry whose parameters live on ``device`` with one launch; forget dead entries."""
+        with self.lock:
+            jobs, fresh = [], []
+            for key, e in list(self.entries.items()):
+                ws = tuple(r() for r in e.refs)
+                if any(w is None for w in ws):
+                    del self.entries[key]
+                    continue
+                if ws[0].device != device:
+                    continue
+                stamp = self._stamp(ws)
+                if e.stamp != stamp:
+                    jobs += self._jobs(e, ws)
+                    fresh.append((e, stamp))
+            self._launch(jobs)
+            for e, stamp in fresh:
+                e.stamp = stamp
+
+
+TRAIN_WEIGHTS = _TrainWeightCache()
+
+
+def _wplanes(W, prec: int, transpose: bool = False):
+    """Operand planes of a projection weight -- or of several weights stacked along their output dimension (``W`` a
+    tuple: Wq | Wk | Wv) -- for the training path: [sum N, K], or [K, sum N] with ``transpose``.  Leaf fp32 CUDA
+    parameters go through :data:`TRAIN_WEIGHTS`; anything else (DataParallel replicas hold non-leaf views that are
+    re-created every forward, other dtypes) is concatenated / transposed / split on the spot."""
+    ws = W if isinstance(W, tuple) else (W,)
+    if prec == nat.PREC_FP32 and all(w.is_leaf and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+                                     for w in ws):
+        return TRAIN_WEIGHTS.get(ws, transpose)
+    w2 = ws[0].detach() if len(ws) == 1 else torch.cat([w.detach() for w in ws], dim=0)
+    w2 = w2.reshape(w2.shape[0], -1).float()
     return split(w2.t().contiguous() if transpose else w2.contiguous(), prec)
 
 
@@ -957,7 +1054,7 @@ class MHATrainFunction(torch.autograd.Function):
         if xq_hi is None:
             xq_hi, xq_lo = split(x2, prec)
         if self_attn:
-            w_hi, w_lo = _wplanes(torch.cat((Wq.detach(), Wk.detach(), Wv.detach()), dim=0), prec)
+            w_hi, w_lo = _wplanes((Wq, Wk, Wv), prec)
             qp = _empty_planes(Mq, 3 * hd, prec, dev)
             gemm(xq_hi, xq_lo, D, w_hi, w_lo, D, Mq, 3 * hd, D, prec, out_hi=qp[0], out_lo=qp[1], ldp=3 * hd)
             kvp, ldq, ldkv, k_col0, v_col0 = qp, 3 * hd, 3 * hd, hd, 2 * hd
@@ -965,7 +1062,7 @@ class MHATrainFunction(torch.autograd.Function):
             if xkv_hi is None:
                 xkv_hi, xkv_lo = split(xkv.detach().reshape(-1, D).float().contiguous(), prec)
             wq_hi, wq_lo = _wplanes(Wq, prec)
-            wkv_hi, wkv_lo = _wplanes(torch.cat((Wk.detach(), Wv.detach()), dim=0), prec)
+            wkv_hi, wkv_lo = _wplanes((Wk, Wv), prec)
             qp = _empty_planes(Mq, hd, prec, dev)
             gemm(xq_hi, xq_lo, D, wq_hi, wq_lo, D, Mq, hd, D, prec, out_hi=qp[0], out_lo=qp[1], ldp=hd)
             if kv_map is None:
@@ -1060,7 +1157,7 @@ class MHATrainFunction(torch.autograd.Function):
         if self_attn:
             dW, _ = _gemm_tn(dq[0], dq[1], 3 * hd, xq_hi, xq_lo, D, Mq, False, zp)
             dWq, dWk, dWv = dW[:hd], dW[hd:2 * hd], dW[2 * hd:]
-            wt_hi, wt_lo = _wplanes(torch.cat((Wq.detach(), Wk.detach(), Wv.detach()), dim=0), prec, transpose=True)  # [D, 3hd]
+            wt_hi, wt_lo = _wplanes((Wq, Wk, Wv), prec, transpose=True)  # [D, 3hd]
             gemm(dq[0], dq[1], 3 * hd, wt_hi, wt_lo, 3 * hd, Mq, D, 3 * hd, prec, residual=dy, ldr=D, out_f32=dxq, ldo=D)
         else:
             dWq, _ = _gemm_tn(dq[0], dq[1], hd, xq_hi, xq_lo, D, Mq, False, zp)
@@ -1074,7 +1171,7 @@ class MHATrainFunction(torch.autograd.Function):
                 Mk = dkv[0].shape[0]
             dWkv, _ = _gemm_tn(dkv[0], dkv[1], 2 * hd, xkv_hi, xkv_lo, D, Mk, False, zp)
             dWk, dWv = dWkv[:hd], dWkv[hd:]
-            wkvt_hi, wkvt_lo = _wplanes(torch.cat((Wk.detach(), Wv.detach()), dim=0), prec, transpose=True)  # [D, 2hd]
+            wkvt_hi, wkvt_lo = _wplanes((Wk, Wv), prec, transpose=True)  # [D, 2hd]
             dxkv = torch.empty((Mk, D), dtype=torch.float32, device=dev)
             gemm(dkv[0], dkv[1], 2 * hd, wkvt_hi, wkvt_lo, 2 * hd, Mk, D, 2 * hd, prec, out_f32=dxkv, ldo=D)
             dxkv = dxkv.view(kv_shape)

@@ -254,3 +254,41 @@ def test_diag_proj_backward_batch_slices():
         assert rel_err(dW, torch.einsum('bl,bld->ld', g.double(), x.double())) < 1e-5, (B, L, D)
         assert rel_err(dbias, g.double().sum(0)) < 1e-5
         assert rel_err(dx, g.double().unsqueeze(-1) * W.double().unsqueeze(0)) < 1e-6
+
+
+def test_training_weight_planes_cache_builds_w_and_wt_and_follows_updates():
+    """``ops._wplanes`` through ``TRAIN_WEIGHTS`` (``lamp_split_planes_multi``): stacked parameters, transposed form,
+    Conv1d-shaped weights, ragged shapes, in-place updates (optimizer steps) and ``refresh_all``."""
+    g = torch.Generator().manual_seed(21)
+    mk = lambda *shape: torch.nn.Parameter(torch.randn(*shape, generator=g).to(DEV))
+    Wq, Wk, Wv, Wc, Wr = mk(96, 200), mk(96, 200), mk(40, 200), mk(72, 136, 1), mk(33, 50)
+
+    def check(ws, transpose):
+        hi, lo = ops._wplanes(ws if len(ws) > 1 else ws[0], nat.PREC_FP32, transpose=transpose)
+        want = torch.cat([w.detach().reshape(w.shape[0], -1) for w in ws], dim=0)
+        want = want.t() if transpose else want
+        assert hi.shape == want.shape and hi.dtype == torch.bfloat16
+        assert torch.equal(hi, want.to(torch.bfloat16))                       # hi = bf16_rn(w)
+        assert rel_err(hi.float() + lo.float(), want) < 2e-5
+        return hi
+
+    for tr in (False, True):
+        for ws in ((Wq, Wk, Wv), (Wq,), (Wk, Wv), (Wc,), (Wr,)):
+            check(ws, tr)
+    ops.STATS.reset()
+    h1 = check((Wq, Wk, Wv), True)
+    assert ops.STATS.launches == 0                                           # unchanged weights: cache hit
+    with torch.no_grad():
+        Wk.mul_(1.5)
+        Wr.add_(1.0)
+    ops.TRAIN_WEIGHTS.refresh_all(torch.device(DEV, torch.cuda.current_device()))
+    n = ops.STATS.launches
+    assert n >= 1
+    h2 = check((Wq, Wk, Wv), True)
+    check((Wk, Wv), False)
+    check((Wr,), True)
+    assert ops.STATS.launches == n                                           # all refreshed by the one call
+    assert h2.data_ptr() == h1.data_ptr()                                    # same buffers (CUDA-graph safe)
+    # non-leaf weights (DataParallel replicas) take the direct path
+    hi, lo = ops._wplanes((Wq * 1.0, Wk * 1.0), nat.PREC_FP32)
+    assert rel_err(hi.float() + lo.float(), torch.cat((Wq, Wk)).detach()) < 2e-5
