@@ -17,6 +17,7 @@ L=103 labels, T=300 tokens, d_model=512, n_head=4, 2+2 layers, d_inner=512, prio
   roofline      : dominant kernel (projection GEMM, tensor-bound) -- algorithmic FLOPs / measured kernel time.  The
                   per-kernel durations come from a second timed region of the same K steps, launched eagerly with a
                   CUDA-event pair around every native call (`eager_ms_per_step` is that region's step time)
+  roofline_layernorm : the standalone LayerNorm launches of the step (streaming, 8 B/element): in-step HBM yardstick
   roofline_attn : masked label<-label attention core kernel under the label-graph mask (HBM-bound) -- algorithmic
                   bytes / measured kernel time; roofline_attn_enc: the same kernel on the label<-input shape (T=300)
   train         : the training step north_star's multi-GPU clause names -- forward + BCE + backward + bucketed,
@@ -521,6 +522,8 @@ def main():
                             max=max(b - a for a, b in zip(host_t, host_t[1:])) * 1e3),
         roofline=roof('gemm_planes', 'tensor'), roofline_attn=roof('attn_core_self', 'hbm'),
         roofline_attn_enc=roof('attn_core_enc', 'hbm'),
+        roofline_layernorm=roof('layernorm', 'hbm'),   # pure streaming kernel (0.92-1.0 of the peak when timed alone): the
+                                                       # HBM fraction a kernel can reach INSIDE this power-capped step
         kernels={k: dict(calls=v['calls'], ms=round(v['ms'], 3)) for k, v in per_kernel.items()},
         lib_source_hash=lib_source_hash())
     if args.precision != 'fp32':
