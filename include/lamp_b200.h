@@ -87,6 +87,16 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
                      const float* residual, int64_t ldr, int resid_mod, float* out_f32, int64_t ldo, void* out_hi,
                      void* out_lo, int64_t ldp, const int32_t* m_dev, void* stream);
 
+/* Training variant of lamp_gemm_planes (3-term products): out_f32 = dropout(A W^T + bias) + residual, the dropout
+ * being the counter hash of lamp_dropout_add / lamp_dropout_split (keep(row, col) is a pure function of
+ * (seed + *seed_dev, row, col); seed_dev nullable) -- fc / w_2 followed by nn.Dropout and the residual add
+ * (lamp/SubLayers.py:113-117, 136-141) without a separate element-wise pass.  p_drop == 0 degenerates to
+ * lamp_gemm_planes with a residual. */
+int lamp_gemm_planes_drop(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                          int64_t ldw, int M, int N, int K, const float* bias, float p_drop, uint64_t seed,
+                          const uint64_t* seed_dev, const float* residual, int64_t ldr, int resid_mod, float* out_f32,
+                          int64_t ldo, void* stream);
+
 /* lamp_gemm_planes with the residual given as split-bf16 planes (hi + lo reconstructs it to 2^-17 relative): lets a
  * layer keep its activations in operand form only, without an fp32 copy in HBM.  res_lo may be NULL. */
 int lamp_gemm_planes_pres(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,

@@ -38,6 +38,8 @@ _SIGNATURES = {
     'lamp_split_planes_multi': ([_vp, _i, _vp], _i),
     'lamp_gemm_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp,
                           _i64, _vp, _vp], _i),
+    'lamp_gemm_planes_drop': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _f, C.c_uint64, _vp, _vp, _i64, _i, _vp,
+                               _i64, _vp], _i),
     'lamp_gemm_planes_pres': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp,
                                _vp, _i64, _vp, _vp], _i),
     'lamp_gemm_ln_planes': ([_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _f, _vp, _i64,

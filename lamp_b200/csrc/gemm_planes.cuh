@@ -59,6 +59,12 @@ struct GemmParams {
   const float* r_gamma;   // [N]
   const float* r_beta;    // [N]
   float2* stats_out;      // [M][2 * num_n]
+  // ---- EPI_F32_DROP (training): out = dropout(acc + bias) + residual with the counter hash of the element-wise
+  // dropout kernels (keep(row, col) is a pure function of (seed, row, col): the backward recomputes the mask)
+  uint32_t drop_thresh;
+  float drop_scale;
+  unsigned long long drop_seed;
+  const unsigned long long* drop_seed_dev;  // nullable: device-side addend of the seed (advanced inside CUDA graphs)
 };
 
 // Residual values of the 8 rows (m_base + 4 i, i = 0..7) x 4 consecutive columns handled by one lane of the coalesced
@@ -115,6 +121,7 @@ constexpr int EPI_LN = 3;      // (+bias)(+residual) -> LayerNorm over the whole
                                // row statistics are complete on chip and the pre-norm tensor never touches HBM.
 constexpr int EPI_DLN_A = 4;   // A operand is a deferred LayerNorm: rstd*(acc - mean*colsum) + bias' (ReLU) -> planes
 constexpr int EPI_RSTATS = 5;  // (+bias) + residual (fp32 | planes | deferred-LayerNorm planes) -> planes + row stats
+constexpr int EPI_F32_DROP = 6;  // dropout(acc + bias) + residual -> fp32 (training: fc / w_2 of lamp/SubLayers.py:113-117,136-141)
 
 template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP = 1>
 struct GemmCfg {
@@ -322,12 +329,13 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int sub_c = lane & 7;   // 16-byte chunk (4 fp32) inside the 128 B row segment
     constexpr bool DLN_A = (EPI == EPI_DLN_A);
     constexpr bool RSTATS = (EPI == EPI_RSTATS);
-    const bool want_f32 = (EPI == EPI_F32) || (EPI == EPI_ANY && p.out_f32 != nullptr);
+    constexpr bool DROP = (EPI == EPI_F32_DROP);
+    const bool want_f32 = (EPI == EPI_F32) || DROP || (EPI == EPI_ANY && p.out_f32 != nullptr);
     const bool want_pl = (EPI == EPI_PLANES) || DLN_A || RSTATS || (EPI == EPI_ANY && p.out_hi != nullptr);
     const bool want_lo = want_pl && p.out_lo != nullptr;
     const bool has_res = (EPI != EPI_PLANES) && !DLN_A && (p.residual != nullptr || p.res_hi != nullptr);
     const bool has_bias = p.bias != nullptr;
-    const bool relu = (EPI != EPI_F32) && !RSTATS && p.relu;
+    const bool relu = (EPI != EPI_F32) && !DROP && !RSTATS && p.relu;
     const bool res_dln = RSTATS && p.r_stats != nullptr;  // the residual is a deferred LayerNorm
     const uint32_t te_addr[2] = {mapa_shared(&tmem_empty[0], 0), mapa_shared(&tmem_empty[1], 0)};  // leader's copies
     if constexpr (EPI == EPI_LN) {
@@ -489,6 +497,12 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           roff[i] = (p.resid_mod ? (row % p.resid_mod) : row) * p.ldr;
         }
       }
+      uint32_t rh[8];  // EPI_F32_DROP: dropout row hashes of this lane's 8 rows
+      if (DROP) {
+        const unsigned long long sd = p.drop_seed + (p.drop_seed_dev != nullptr ? __ldg(p.drop_seed_dev) : 0ull);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rh[i] = drop_rowhash(sd, static_cast<unsigned long long>(m0 + sub_r + 4 * i));
+      }
       auto load_res = [&](int c0, ResBuf& d) {
         if (!has_res || c0 >= BLOCK_N) return;
         const int col = n0 + c0 + sub_c * 4;
@@ -578,6 +592,13 @@ gemm_planes_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           if (has_bias) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
           if (relu) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+          if (DROP) {
+            const uint32_t cb = static_cast<uint32_t>(col);
+            v.x = drop_keep(rh[i], cb, p.drop_thresh) ? v.x * p.drop_scale : 0.f;
+            v.y = drop_keep(rh[i], cb + 1, p.drop_thresh) ? v.y * p.drop_scale : 0.f;
+            v.z = drop_keep(rh[i], cb + 2, p.drop_thresh) ? v.z * p.drop_scale : 0.f;
+            v.w = drop_keep(rh[i], cb + 3, p.drop_thresh) ? v.w * p.drop_scale : 0.f;
           }
           if (has_res) {
             const uint4 q = cur.raw[i];

@@ -228,6 +228,12 @@ int launch_gemm_epi(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUte
 template <int BLOCK_N, int NTERMS, int BLOCK_K, int CTA_GROUP>
 int launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi, const CUtensorMap& w_lo,
                 const GemmParams& p, cudaStream_t st) {
+  if (p.drop_thresh != 0) {
+    if constexpr (NTERMS == 3)   // training runs on 3-term products only
+      return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_F32_DROP, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
+    else
+      return fail(LAMP_EINVAL, "gemm: the dropout epilogue exists for LAMP_PREC_FP32 only");
+  }
   if (p.a_stats != nullptr)
     return launch_gemm_epi<BLOCK_N, NTERMS, BLOCK_K, EPI_DLN_A, CTA_GROUP>(a_hi, a_lo, w_hi, w_lo, p, st);
   if (p.stats_out != nullptr)
@@ -425,6 +431,8 @@ struct DlnArgs {  // deferred-LayerNorm extras of a GEMM launch (all null / 0: n
   const float* a_stats = nullptr; int a_nparts = 0; float a_eps = 0.f; const float* a_colsum = nullptr;
   const float* r_stats = nullptr; int r_nparts = 0; float r_eps = 0.f; const float* r_gamma = nullptr;
   const float* r_beta = nullptr; float* stats_out = nullptr;
+  uint32_t drop_thresh = 0; float drop_scale = 1.0f; unsigned long long drop_seed = 0;   // EPI_F32_DROP
+  const unsigned long long* drop_seed_dev = nullptr;
 };
 }  // namespace
 
@@ -488,6 +496,8 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int64_t lda, const void
   p.r_stats = reinterpret_cast<const float2*>(dln.r_stats); p.r_nparts = dln.r_nparts; p.r_eps = dln.r_eps;
   p.r_gamma = dln.r_gamma; p.r_beta = dln.r_beta;
   p.stats_out = reinterpret_cast<float2*>(dln.stats_out);
+  p.drop_thresh = dln.drop_thresh; p.drop_scale = dln.drop_scale; p.drop_seed = dln.drop_seed;
+  p.drop_seed_dev = dln.drop_seed_dev;
   cudaStream_t st = (cudaStream_t)stream;
 #define LAMP_GEMM_DISPATCH(BK)                                                                                      \
   do {                                                                                                             \
@@ -511,6 +521,21 @@ int lamp_gemm_planes(const void* a_hi, const void* a_lo, int64_t lda, const void
                      void* out_lo, int64_t ldp, const int32_t* m_dev, void* stream) {
   return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, precision, bias, relu, residual, nullptr, nullptr, ldr,
                    resid_mod, out_f32, ldo, out_hi, out_lo, ldp, nullptr, nullptr, 0.0f, m_dev, stream);
+}
+
+int lamp_gemm_planes_drop(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,
+                          int64_t ldw, int M, int N, int K, const float* bias, float p_drop, uint64_t seed,
+                          const uint64_t* seed_dev, const float* residual, int64_t ldr, int resid_mod, float* out_f32,
+                          int64_t ldo, void* stream) {
+  REQUIRE(out_f32 != nullptr, "gemm_planes_drop: fp32 output required");
+  REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "gemm_planes_drop: rate outside [0, 1)");
+  DlnArgs d;
+  d.drop_thresh = drop_threshold(p_drop);
+  d.drop_scale = 1.0f / (1.0f - p_drop);
+  d.drop_seed = seed;
+  d.drop_seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  return gemm_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, M, N, K, LAMP_PREC_FP32, bias, 0, residual, nullptr, nullptr, ldr,
+                   resid_mod, out_f32, ldo, nullptr, nullptr, 0, nullptr, nullptr, 0.0f, nullptr, stream, d);
 }
 
 int lamp_gemm_planes_pres(const void* a_hi, const void* a_lo, int64_t lda, const void* w_hi, const void* w_lo,

@@ -324,6 +324,16 @@ def gemm(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, pre
                nbytes=lambda m: rows(m) * row_bytes + N * K * pl, rows_dev=m_dev)
 
 
+def gemm_drop(a_hi, a_lo, lda: int, w_hi, w_lo, ldw: int, M: int, N: int, K: int, *, bias, p_drop: float, seed: int,
+              residual, ldr: int, out_f32, ldo: int) -> None:
+    """Training epilogue (3-term products): ``out_f32 = dropout(A W^T + bias) + residual`` in ONE kernel, with the
+    counter-hash mask of ``dropout_add`` / ``dropout_split`` (``lamp_gemm_planes_drop``)."""
+    STATS.call('gemm_planes', 1, nat.lib().lamp_gemm_planes_drop,
+               (nat.ptr(a_hi), nat.ptr(a_lo), lda, nat.ptr(w_hi), nat.ptr(w_lo), ldw, M, N, K, nat.ptr(bias), float(p_drop),
+                int(seed), _seed_dev_ptr(), nat.ptr(residual), ldr, 0, nat.ptr(out_f32), ldo, nat.stream()),
+               flops=2.0 * M * N * K, nbytes=M * (K * 4 + N * 8) + N * K * 4)
+
+
 def linear_planes(x: Act, w_hi, w_lo, N: int, prec: int, *, bias=None, relu=False, ld_pad: int = 0) -> Act:
     """planes(x) @ W^T (+bias)(ReLU) -> planes only (operand for the next tensor-core stage).  ``ld_pad``: extra
     (unused) columns in the row pitch of the result, see ``KV_LD_PAD``; the returned Act's ``cols`` is the pitch."""
@@ -787,6 +797,8 @@ class DiagProjFunction(torch.autograd.Function):
 # stored dropout masks (counter-hash masks are recomputed in the backward), ReLU / bias / residual in GEMM epilogues.
 FUSED_TRAINING = os.environ.get('LAMP_FUSED_TRAIN', '1') != '0'
 # training encoder on the packed non-PAD token rows (one host read of the row count per step; dense inside graph captures)
+# dropout + residual inside the fc / w_2 GEMM epilogue (0: separate dropout_add kernel, the round-2 first version)
+FUSED_DROPOUT_EPILOGUE = os.environ.get('LAMP_FUSED_DROPOUT', '1') != '0'
 PACKED_TRAINING = os.environ.get('LAMP_PACKED_TRAIN', '1') != '0'
 
 
@@ -992,7 +1004,10 @@ class FFNTrainFunction(torch.autograd.Function):
              out_lo=h_lo, ldp=dh)
         y = torch.empty((M, D), dtype=torch.float32, device=x.device)
         b2f = b2.detach().float().contiguous()
-        if p_drop > 0:
+        if p_drop > 0 and FUSED_DROPOUT_EPILOGUE:
+            gemm_drop(h_hi, h_lo, dh, w2h, w2l, dh, M, D, dh, bias=b2f, p_drop=p_drop, seed=seed, residual=x2, ldr=D,
+                      out_f32=y, ldo=D)
+        elif p_drop > 0:
             y0 = torch.empty_like(y)
             gemm(h_hi, h_lo, dh, w2h, w2l, dh, M, D, dh, prec, bias=b2f, out_f32=y0, ldo=D)
             y = dropout_add(y0, x2, p_drop, seed)
@@ -1089,7 +1104,10 @@ class MHATrainFunction(torch.autograd.Function):
                     _seed_dev_ptr(), nat.stream()), flops=4.0 * H * Lq * d * B * Lk)
         wfc_hi, wfc_lo = _wplanes(Wfc, prec)
         y = torch.empty((Mq, D), dtype=torch.float32, device=dev)
-        if p_out > 0:
+        if p_out > 0 and FUSED_DROPOUT_EPILOGUE:
+            gemm_drop(o_hi, o_lo, hd, wfc_hi, wfc_lo, hd, Mq, D, hd, bias=None, p_drop=p_out, seed=seed_out, residual=x2,
+                      ldr=D, out_f32=y, ldo=D)
+        elif p_out > 0:
             y0 = torch.empty_like(y)
             gemm(o_hi, o_lo, hd, wfc_hi, wfc_lo, hd, Mq, D, hd, prec, out_f32=y0, ldo=D)
             y = dropout_add(y0, x2, p_out, seed_out)

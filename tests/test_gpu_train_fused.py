@@ -292,3 +292,32 @@ def test_training_weight_planes_cache_builds_w_and_wt_and_follows_updates():
     # non-leaf weights (DataParallel replicas) take the direct path
     hi, lo = ops._wplanes((Wq * 1.0, Wk * 1.0), nat.PREC_FP32)
     assert rel_err(hi.float() + lo.float(), torch.cat((Wq, Wk)).detach()) < 2e-5
+
+
+@pytest.mark.parametrize('M,N,K,bias', [(300, 512, 512, True), (26368, 512, 512, False), (1000, 128, 256, True),
+                                        (77, 264, 64, True)])
+def test_gemm_dropout_epilogue_equals_gemm_then_dropout_add(M, N, K, bias):
+    """``lamp_gemm_planes_drop`` (dropout + residual inside the GEMM epilogue) against the two-kernel sequence
+    ``lamp_gemm_planes`` -> ``lamp_dropout_add`` with the same seed: the same elements are dropped (they equal the
+    residual exactly), the kept ones agree to the last bits."""
+    rs = np.random.RandomState(M + N)
+    a = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).to(DEV)
+    w = torch.from_numpy((rs.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).to(DEV)
+    x = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).to(DEV)
+    b = torch.from_numpy(rs.standard_normal((N,)).astype(np.float32)).to(DEV) if bias else None
+    a_hi, a_lo = ops.split(a, nat.PREC_FP32)
+    w_hi, w_lo = ops.split(w, nat.PREC_FP32)
+    p, seed = 0.3, 123456789
+    y0 = torch.empty((M, N), dtype=torch.float32, device=DEV)
+    ops.gemm(a_hi, a_lo, K, w_hi, w_lo, K, M, N, K, nat.PREC_FP32, bias=b, out_f32=y0, ldo=N)
+    want = ops.dropout_add(y0, x, p, seed)
+    got = torch.empty_like(want)
+    ops.gemm_drop(a_hi, a_lo, K, w_hi, w_lo, K, M, N, K, bias=b, p_drop=p, seed=seed, residual=x, ldr=N, out_f32=got, ldo=N)
+    dropped_want, dropped_got = (want == x), (got == x)
+    assert torch.equal(dropped_want, dropped_got)
+    frac = float(dropped_got.float().mean())
+    assert abs(frac - p) < 0.02, frac
+    assert rel_err(got, want) < 1e-6
+    ref = (a.double() @ w.double().t() + (b.double() if bias else 0)) / (1 - p)
+    kept = ~dropped_got
+    assert rel_err((got.double() - x.double())[kept], ref[kept]) < 2e-5
