@@ -199,6 +199,14 @@ int lamp_attn_core_bwd(const float* q, const float* k, const float* v, const flo
 int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
                        float* dgamma, float* dbeta, void* stream);
 
+/* lamp_layernorm_bwd that ALSO writes planes(dropout-backward(dx)) = planes(keep(row, col) * dx / (1 - p)) with the
+ * counter hash of lamp_dropout_add / lamp_gemm_planes_drop: the gradient of the sub-layer's dropped branch, directly as
+ * the operand of its dW / input-gradient products (replaces a lamp_dropout_split pass over dx).  p_drop == 0: a plain
+ * split of dx. */
+int lamp_layernorm_bwd_drop(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
+                            float* dgamma, float* dbeta, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* dx_hi,
+                            void* dx_lo, void* stream);
+
 /* Weight / bias gradient of Y = X W^T (+ b): dW[N,K] += dY[M,N]^T X[M,K], db[N] += column sums of dY (db may be
  * NULL).  dY and X are given as split-bf16 planes (lo planes NULL in bf16 mode).  Accumulating (fp32 atomics over row
  * chunks): zero or pre-load dW / db.  N % 8 == 0, K % 8 == 0.  The input gradient dX = dY W is lamp_gemm_planes on

@@ -59,6 +59,7 @@ _SIGNATURES = {
     'lamp_attn_core_bwd_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'lamp_attn_core_bwd': ([_vp] * 10 + [_i, _i, _i, _i, _f, _f, _vp, _sz, _vp], _i),
     'lamp_layernorm_bwd': ([_vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _vp], _i),
+    'lamp_layernorm_bwd_drop': ([_vp, _vp, _vp, _f, _i64, _i, _vp, _vp, _vp, _f, C.c_uint64, _vp, _vp, _vp, _vp], _i),
     'lamp_gemm_tn_acc': ([_vp, _vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _vp, _vp, _vp], _i),
     'lamp_diag_proj_bwd': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp], _i),
     'lamp_attn_core_planes_train': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,

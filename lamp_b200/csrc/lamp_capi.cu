@@ -1020,25 +1020,46 @@ int lamp_attn_bwd_planes(const void* q_hi, const void* q_lo, int64_t ldq, int q_
   return launch_bgemm<true, true>(dS, Q, B, H, Lk, d, Lq, 1.0f, out(dkv_hi, dkv_lo, dk_col0, lddkv, Lk), st);
 }
 
-int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
-                       float* dgamma, float* dbeta, void* stream) {
+static int layernorm_bwd_impl(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
+                              float* dgamma, float* dbeta, const LnBwdDrop& dp, void* stream) {
   if (int rc = arch_check()) return rc;
   REQUIRE(x && dy && gamma && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
   REQUIRE(D % 4 == 0 && D > 0 && D <= 4096, "layernorm_bwd: D=%d must be a multiple of 4, <= 4096", D);
   REQUIRE(aligned16(x) && aligned16(dy) && aligned16(gamma) && aligned16(dx), "layernorm_bwd: alignment");
+  REQUIRE(!dp.hi || (dp.lo && aligned16(dp.hi) && aligned16(dp.lo)), "layernorm_bwd: plane outputs need hi and lo, 16-byte aligned");
   if (rows == 0) return LAMP_OK;
   long long blocks = (rows * 32 + 255) / 256;
   const long long cap = 4LL * sm_count_cached();  // grid-stride: few, long-lived blocks keep the atomic count low
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t red = (size_t)2 * D * sizeof(float);
-  if (D <= 512)
-    layernorm_bwd_kernel<4><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta);
-  else if (D <= 1024)
-    layernorm_bwd_kernel<8><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta);
-  else
-    layernorm_bwd_kernel<32><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta);
+#define LAMP_LNB(MAXV)                                                                                                  \
+  do {                                                                                                                  \
+    if (dp.hi != nullptr)                                                                                               \
+      layernorm_bwd_kernel<MAXV, true><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta, dp); \
+    else                                                                                                                \
+      layernorm_bwd_kernel<MAXV, false><<<(unsigned)blocks, 256, red, st>>>(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta, dp); \
+  } while (0)
+  if (D <= 512) LAMP_LNB(4);
+  else if (D <= 1024) LAMP_LNB(8);
+  else LAMP_LNB(32);
+#undef LAMP_LNB
   return launch_check();
+}
+
+int lamp_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
+                       float* dgamma, float* dbeta, void* stream) {
+  return layernorm_bwd_impl(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta, LnBwdDrop{nullptr, nullptr, 0u, 1.0f, 0ull, nullptr}, stream);
+}
+
+int lamp_layernorm_bwd_drop(const float* x, const float* dy, const float* gamma, float eps, int64_t rows, int D, float* dx,
+                            float* dgamma, float* dbeta, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* dx_hi,
+                            void* dx_lo, void* stream) {
+  REQUIRE(dx_hi && dx_lo, "layernorm_bwd_drop: plane outputs required");
+  REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "layernorm_bwd_drop: rate outside [0, 1)");
+  LnBwdDrop dp{static_cast<__nv_bfloat16*>(dx_hi), static_cast<__nv_bfloat16*>(dx_lo), drop_threshold(p_drop),
+               1.0f / (1.0f - p_drop), seed, reinterpret_cast<const unsigned long long*>(seed_dev)};
+  return layernorm_bwd_impl(x, dy, gamma, eps, rows, D, dx, dgamma, dbeta, dp, stream);
 }
 
 // bias gradient next to a weight gradient: column sums of the dY planes into the (zeroed or accumulating) db

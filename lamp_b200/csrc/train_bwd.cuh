@@ -11,10 +11,22 @@ namespace lamp {
 //   xhat = (x - mean) * rstd;  g = dy * gamma;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat));
 //   dgamma += sum_rows dy * xhat;  dbeta += sum_rows dy   (accumulated with fp32 atomics: zero them first).
 // One warp per row (grid-stride), the row and the warp's dgamma / dbeta partials live in registers (D <= 128 * MAXV).
-template <int MAXV>
+// PLANES: dx is ALSO written as the split-bf16 planes of dropout-backward(dx) = keep(row, col) * dx / (1 - p) -- the
+// operand of the dW / input-gradient products of the sub-layer's last projection (thresh == 0: a plain split), which
+// saves the separate dropout_split pass over dx.
+struct LnBwdDrop {
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  uint32_t thresh;
+  float scale;
+  unsigned long long seed;
+  const unsigned long long* seed_dev;
+};
+template <int MAXV, bool PLANES>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                      const float* __restrict__ gamma, float eps, long long rows, int D,
-                                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     const LnBwdDrop dp) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -80,6 +92,9 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
     c1 /= D;
     c2 /= D;
     float4* outr = reinterpret_cast<float4*>(dx + row * D);
+    uint32_t rh = 0u;
+    if (PLANES && dp.thresh)
+      rh = drop_rowhash(dp.seed + (dp.seed_dev ? __ldg(dp.seed_dev) : 0ull), static_cast<unsigned long long>(row));
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int idx = lane + 32 * i;
@@ -90,6 +105,19 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, const float* _
         o.z = rstd * (dv[i].z * gam[i].z - c1 - xv[i].z * c2);
         o.w = rstd * (dv[i].w * gam[i].w - c1 - xv[i].w * c2);
         outr[idx] = o;
+        if (PLANES) {
+          const uint32_t col = 4u * idx;
+          float4 v;
+          v.x = (dp.thresh && !drop_keep(rh, col, dp.thresh)) ? 0.f : o.x * dp.scale;
+          v.y = (dp.thresh && !drop_keep(rh, col + 1, dp.thresh)) ? 0.f : o.y * dp.scale;
+          v.z = (dp.thresh && !drop_keep(rh, col + 2, dp.thresh)) ? 0.f : o.z * dp.scale;
+          v.w = (dp.thresh && !drop_keep(rh, col + 3, dp.thresh)) ? 0.f : o.w * dp.scale;
+          uint2 h, l;
+          split_bf16x2(v.x, v.y, h.x, l.x);
+          split_bf16x2(v.z, v.w, h.y, l.y);
+          reinterpret_cast<uint2*>(dp.hi + row * D)[idx] = h;
+          reinterpret_cast<uint2*>(dp.lo + row * D)[idx] = l;
+        }
       }
     }
   }

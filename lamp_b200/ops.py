@@ -963,15 +963,29 @@ def _zeros(zp: Optional[_ZeroPool], shape, device) -> torch.Tensor:
     return zp.take(shape) if zp is not None else torch.zeros(shape, dtype=torch.float32, device=device)
 
 
-def _layernorm_bwd(y: torch.Tensor, g: torch.Tensor, gamma: torch.Tensor, eps: float, zp: Optional[_ZeroPool] = None):
+def _layernorm_bwd(y: torch.Tensor, g: torch.Tensor, gamma: torch.Tensor, eps: float, zp: Optional[_ZeroPool] = None,
+                   drop=None):
+    """LayerNorm backward -> (dy, dgamma, dbeta[, (d_hi, d_lo)]).  ``drop = (p, seed)``: the same kernel also writes
+    planes(dropout-backward(dy)) (``lamp_layernorm_bwd_drop``), the operand of the sub-layer's dW / input-gradient
+    products -- otherwise that is a separate ``dropout_split`` pass."""
     rows, D = y.shape
     dy = torch.empty_like(y)
     dg = _zeros(zp, (D,), y.device)
     db = _zeros(zp, (D,), y.device)
-    STATS.call('layernorm_bwd', 1, nat.lib().lamp_layernorm_bwd,
-               (y.data_ptr(), g.data_ptr(), gamma.detach().float().contiguous().data_ptr(), float(eps), rows, D,
-                dy.data_ptr(), dg.data_ptr(), db.data_ptr(), nat.stream()), nbytes=rows * D * 12)
-    return dy, dg, db
+    gam = gamma.detach().float().contiguous()
+    if drop is None or not FUSED_DROPOUT_EPILOGUE:
+        STATS.call('layernorm_bwd', 1, nat.lib().lamp_layernorm_bwd,
+                   (y.data_ptr(), g.data_ptr(), gam.data_ptr(), float(eps), rows, D, dy.data_ptr(), dg.data_ptr(),
+                    db.data_ptr(), nat.stream()), nbytes=rows * D * 12)
+        if drop is None:
+            return dy, dg, db
+        return dy, dg, db, dropout_split(dy, drop[0], drop[1])
+    hi, lo = _empty_planes(rows, D, nat.PREC_FP32, y.device)
+    STATS.call('layernorm_bwd', 1, nat.lib().lamp_layernorm_bwd_drop,
+               (y.data_ptr(), g.data_ptr(), gam.data_ptr(), float(eps), rows, D, dy.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                float(drop[0]), int(drop[1]), _seed_dev_ptr(), hi.data_ptr(), lo.data_ptr(), nat.stream()),
+               nbytes=rows * D * 16)
+    return dy, dg, db, (hi, lo)
 
 
 def _gemm_tn(d_hi, d_lo, N: int, a_hi, a_lo, K: int, M: int, want_bias: bool, zp: Optional[_ZeroPool] = None):
@@ -1029,8 +1043,8 @@ class FFNTrainFunction(torch.autograd.Function):
         if g is None:
             g = torch.zeros_like(y)
         zp = _ZeroPool(y.device, (D,), (D,), (D, dh), (D,), (dh, D), (dh,))
-        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(M, D).float().contiguous(), gamma, ctx.eps, zp)
-        d_hi, d_lo = dropout_split(dy, ctx.p_drop, ctx.seed)
+        dy, dgamma, dbeta, (d_hi, d_lo) = _layernorm_bwd(y, g.reshape(M, D).float().contiguous(), gamma, ctx.eps, zp,
+                                                         drop=(ctx.p_drop, ctx.seed))
         dW2, db2 = _gemm_tn(d_hi, d_lo, D, h_hi, h_lo, dh, M, True, zp)
         w2t_hi, w2t_lo = _wplanes(W2, prec, transpose=True)          # [dh, D]: dh = d W2
         g_hi, g_lo = _empty_planes(M, dh, prec, y.device)
@@ -1145,8 +1159,8 @@ class MHATrainFunction(torch.autograd.Function):
         if g is None:
             g = torch.zeros_like(y)
         zp = _ZeroPool(dev, (D,), (D,), (D, hd), *(((3 * hd, D),) if self_attn else ((hd, D), (2 * hd, D))))
-        dy, dgamma, dbeta = _layernorm_bwd(y, g.reshape(Mq, D).float().contiguous(), gamma, eps, zp)
-        d_hi, d_lo = dropout_split(dy, p_out, seed_out)
+        dy, dgamma, dbeta, (d_hi, d_lo) = _layernorm_bwd(y, g.reshape(Mq, D).float().contiguous(), gamma, eps, zp,
+                                                         drop=(p_out, seed_out))
         dWfc, _ = _gemm_tn(d_hi, d_lo, D, o_hi, o_lo, hd, Mq, False, zp)
         wfct_hi, wfct_lo = _wplanes(Wfc, prec, transpose=True)       # [hd, D]: dO = d Wfc
         do_hi, do_lo = _empty_planes(Mq, hd, prec, dev)

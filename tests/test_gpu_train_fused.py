@@ -321,3 +321,20 @@ def test_gemm_dropout_epilogue_equals_gemm_then_dropout_add(M, N, K, bias):
     ref = (a.double() @ w.double().t() + (b.double() if bias else 0)) / (1 - p)
     kept = ~dropped_got
     assert rel_err((got.double() - x.double())[kept], ref[kept]) < 2e-5
+
+
+@pytest.mark.parametrize('rows,D,p', [(1000, 512, 0.2), (333, 128, 0.0), (26368, 512, 0.5), (50, 1024, 0.1)])
+def test_layernorm_backward_with_fused_dropout_planes(rows, D, p):
+    """``lamp_layernorm_bwd_drop``: same dx / dgamma / dbeta as ``lamp_layernorm_bwd`` and bit-identical planes to a
+    ``lamp_dropout_split`` pass over dx with the same seed."""
+    g = torch.Generator().manual_seed(rows)
+    y = torch.randn(rows, D, generator=g).to(DEV)
+    gy = torch.randn(rows, D, generator=g).to(DEV)
+    gamma = (torch.rand(D, generator=g) + 0.5).to(DEV)
+    seed = 987654321
+    dy0, dg0, db0 = ops._layernorm_bwd(y, gy, gamma, 1e-5)
+    dy1, dg1, db1, (hi, lo) = ops._layernorm_bwd(y, gy, gamma, 1e-5, drop=(p, seed))
+    assert torch.equal(dy0, dy1)
+    assert rel_err(dg1, dg0) < 1e-5 and rel_err(db1, db0) < 1e-5      # (atomics: order of the partial sums differs)
+    h2, l2 = ops.dropout_split(dy0, p, seed)
+    assert torch.equal(hi, h2) and torch.equal(lo, l2)
