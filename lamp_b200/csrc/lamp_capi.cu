@@ -1099,7 +1099,10 @@ int lamp_gemm_tn_acc(const void* dy_hi, const void* dy_lo, int64_t ldy, const vo
     if (int once_tc_rc = per_device_once(once_tc, [] { int rc_ = set_smem(gemm_tn_tc_kernel<3>, tnc_smem_bytes(2));
       if (rc_ == LAMP_OK) rc_ = set_smem(gemm_tn_tc_kernel<1>, tnc_smem_bytes(1)); return rc_; })) return once_tc_rc;
     const long long tiles = (long long)((N + TNC_TILE_N - 1) / TNC_TILE_N) * ((K + TNC_TILE_K - 1) / TNC_TILE_K);
-    long long splits = (sm_count_cached() + tiles - 1) / tiles;  // one CTA per SM (192 KB of smem each)
+    // one CTA per SM (192 KB of shared memory each) and ONE wave: tiles * splits <= #SMs.  (Rounding the split count
+    // up gave 152 / 160 / 168 CTAs on 148 SMs: the 4-20 CTAs of the second wave doubled the kernel's duration -- ncu
+    // showed the tensor pipe at 74-89 % of the active but only 40-45 % of the elapsed cycles.)
+    long long splits = sm_count_cached() / tiles;
     const long long max_splits = (M + TNC_BM - 1) / TNC_BM;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
