@@ -1198,9 +1198,15 @@ class MHATrainFunction(torch.autograd.Function):
             if kv_idx is not None:
                 # packed encoder rows: gather the key/value gradients of the non-PAD positions; the PAD representative
                 # (last packed row) gets exactly zero -- PAD keys are masked, their dK / dV are 0
-                zrow = dkv[0].new_zeros((1, 2 * hd))
-                dkv = (torch.cat((dkv[0].index_select(0, kv_idx), zrow)), torch.cat((dkv[1].index_select(0, kv_idx), zrow)))
-                Mk = dkv[0].shape[0]
+                n_pk = kv_idx.numel()
+                packed = []
+                for plane in dkv:   # gather straight into the [n + 1, 2hd] operand (no concatenation pass)
+                    buf = torch.empty((n_pk + 1, 2 * hd), dtype=plane.dtype, device=dev)
+                    torch.index_select(plane, 0, kv_idx, out=buf[:n_pk])
+                    buf[n_pk:].zero_()
+                    packed.append(buf)
+                dkv = tuple(packed)
+                Mk = n_pk + 1
             dWkv, _ = _gemm_tn(dkv[0], dkv[1], 2 * hd, xkv_hi, xkv_lo, D, Mk, False, zp)
             dWk, dWv = dWkv[:hd], dWkv[hd:]
             wkvt_hi, wkvt_lo = _wplanes((Wk, Wv), prec, transpose=True)  # [D, 2hd]
