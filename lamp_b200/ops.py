@@ -875,11 +875,16 @@ class _TrainWeightCache:
             stamp = self._stamp(ws)
             if e.stamp != stamp:
                 self._launch(self._jobs(e, ws))
+                # a build recorded into a CUDA graph proves nothing about later replays: the stamp of an entry that was
+                # built under capture only becomes valid through refresh_all, which rebuilds everything under capture
                 e.stamp = stamp
             return e.hi, e.lo
 
     def refresh_all(self, device):
         """Rebuild every stale entry whose parameters live on ``device`` with one launch; forget dead entries."""
+        # Under stream capture EVERY entry is rebuilt: the recorded launch is what refreshes the planes on each replay
+        # (an optimizer step between replays changes the weights without any host-side check running again).
+        capturing = torch.cuda.is_current_stream_capturing()
         with self.lock:
             jobs, fresh = [], []
             for key, e in list(self.entries.items()):
@@ -890,7 +895,7 @@ class _TrainWeightCache:
                 if ws[0].device != device:
                     continue
                 stamp = self._stamp(ws)
-                if e.stamp != stamp:
+                if capturing or e.stamp != stamp:
                     jobs += self._jobs(e, ws)
                     fresh.append((e, stamp))
             self._launch(jobs)

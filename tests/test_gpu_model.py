@@ -499,3 +499,44 @@ def test_graphed_forward_replays_equal_eager_for_new_batches():
         assert torch.equal(enc, ref_enc), trial
     with pytest.raises(RuntimeError):
         runner(src_seq[:2].to(DEV), src_pos[:2].to(DEV))
+
+
+def test_graphed_train_step_follows_eager_optimizer_steps_between_replays():
+    """The documented loop ``loss = step(...); optimizer.step()``: the weights change BETWEEN replays, on the host
+    side, so the replay itself must rebuild the weight operand planes (W and W^T of ``ops.TRAIN_WEIGHTS``): its loss
+    and gradients equal an eager step on the updated weights."""
+    from lamp_b200 import ops
+    c = dict(cases.MODEL_CASES['lamp_L37_none'])
+    p, cfg, src_seq, src_pos, adj = cases.model_inputs(c)
+    B, T = src_seq.shape
+    tgt = (torch.arange(B * c['L']).view(B, c['L']) % 3 == 0).float()
+    loss_fn = torch.nn.functional.binary_cross_entropy_with_logits
+    try:
+        model = build_model(c, p, adj)
+        model.train()
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        # an eager step first, so that the cache entries exist (and are fresh) when the capture starts
+        loss_fn(model((src_seq.to(DEV), src_pos.to(DEV)), None, None, None)[0], tgt.to(DEV)).backward()
+        step = lamp_b200.GraphedTrainStep(model, loss_fn, B, T, example=(src_seq, src_pos, tgt))
+        opt = torch.optim.SGD(model.get_trainable_parameters(), lr=0.5)
+        seen = []
+        for _ in range(3):
+            loss = float(step(src_seq, src_pos, tgt))
+            g_graph = {n: q.grad.clone() for n, q in model.named_parameters() if q.grad is not None}
+            opt.step()                                   # eager, outside the graph
+            seen.append(loss)
+        assert seen[2] < seen[1] < seen[0], seen         # the replays saw the new weights
+        loss = float(step(src_seq, src_pos, tgt))
+        g_graph = {n: q.grad.clone() for n, q in model.named_parameters() if q.grad is not None}
+        ops.TRAIN_SEED_DEV = None
+        model.zero_grad(set_to_none=True)
+        l2 = loss_fn(model((src_seq.to(DEV), src_pos.to(DEV)), None, None, None)[0], tgt.to(DEV))
+        l2.backward()
+        assert abs(loss - float(l2)) < 1e-6 * max(1.0, abs(loss))
+        for n, q in model.named_parameters():
+            if q.grad is not None:
+                assert rel_err(g_graph[n], q.grad) < 1e-5, n
+    finally:
+        ops.TRAIN_SEED_DEV = None
