@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel CUDA-event breakdown of one training step (fwd + BCE + bwd) at the bench's cfg-1 or cfg-4 dims.
-usage: python scripts/train_step_breakdown.py [cfg1|cfg4] [batch]"""
+usage: python scripts/train_step_breakdown.py [cfg1|cfg4] [batch] [dropout rate override]"""
 import json
 import os
 import sys
@@ -19,6 +19,10 @@ dev = torch.device('cuda', 0)
 params, adj, src_seq, src_pos = bench.synth(batch, 500, c)
 model = bench.build_model(c, params, adj, dev).train()
 seq, pos = src_seq.to(dev), src_pos.to(dev)
+if len(sys.argv) > 3:
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = float(sys.argv[3])
 gold = (torch.rand(batch, c['L'], device=dev) < 0.05).float()
 
 
@@ -43,6 +47,6 @@ ms = e0.elapsed_time(e1) / 5
 with ops.STATS.timed():
     step()
     per = ops.STATS.stop_timing()
-print(json.dumps(dict(workload=which, batch=batch, ms_per_step=ms,
+print(json.dumps(dict(workload=which, batch=batch, dropout=(sys.argv[3] if len(sys.argv) > 3 else 'model default'), ms_per_step=ms,
                       native_kernel_ms={k: round(v['ms'], 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1]['ms'])},
                       native_calls={k: v['calls'] for k, v in per.items()})))
