@@ -363,3 +363,25 @@ def test_model_deepcopy_and_pickle_drop_runtime_caches():
     buf.seek(0)
     r = torch.load(buf, weights_only=False)
     assert list(r.state_dict()) == list(m.state_dict())
+
+
+def test_zero_pool_hands_out_aligned_disjoint_zero_views():
+    """ops._ZeroPool (one zero fill per backward node): views have the requested shapes, start on 16-byte boundaries,
+    do not overlap, and must be taken in the declared order."""
+    from lamp_b200 import ops
+    shapes = [(5,), (5,), (3, 7), (3,), (7, 3), (1,)]
+    zp = ops._ZeroPool(torch.device('cpu'), *shapes)
+    views = [zp.take(sh) for sh in shapes]
+    base = views[0].data_ptr()
+    spans = []
+    for v, sh in zip(views, shapes):
+        assert tuple(v.shape) == sh and v.dtype == torch.float32 and float(v.abs().sum()) == 0.0
+        assert (v.data_ptr() - base) % 16 == 0
+        spans.append((v.data_ptr(), v.data_ptr() + v.numel() * 4))
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    views[2].fill_(1.0)
+    assert float(views[1].sum()) == 0.0 and float(views[3].sum()) == 0.0
+    zp2 = ops._ZeroPool(torch.device('cpu'), (4,), (2, 2))
+    with pytest.raises(AssertionError):
+        zp2.take((2, 2))
