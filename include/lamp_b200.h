@@ -263,6 +263,17 @@ int lamp_attn_core_planes_train(const void* q_hi, const void* q_lo, int64_t ldq,
                                 float* attn, float* probs_pre, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                                 void* stream);
 
+/* lamp_attn_core_planes_train with the mask given as packed bits (lamp_pack_mask_bits; one 4-byte load per thread and
+ * key tile instead of 32 byte loads + ballots -- the label-graph mask of a multi-tile problem, L > 128) and without
+ * the probability outputs (recompute-form training: the backward rebuilds P from the row statistics and the BYTE
+ * mask). */
+int lamp_attn_core_planes_train_mbits(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                                      const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B,
+                                      int H, int Lq, int Lk, int d, float temperature, int precision,
+                                      const uint32_t* mask_bits, int64_t mbb, int64_t mbq, void* o_hi, void* o_lo,
+                                      int64_t ldo, float* row_max, float* row_sum, float p_drop, uint64_t seed,
+                                      const uint64_t* seed_dev, void* stream);
+
 /* Backward of the attention core with every operand in place: Q / K / V / dO / O are split-bf16 planes, head h = column
  * slice [col0 + h*d, col0 + (h+1)*d) of a [B*L, ld] matrix (dO and O: [B*Lq, ldo], col0 = 0); P / A: the fp32 head-major
  * [H*B, Lq, Lk] tensors of the training forward (A may be NULL or == P without dropout).  dQ -> planes [B*Lq, lddq] at

@@ -64,6 +64,8 @@ _SIGNATURES = {
     'lamp_diag_proj_bwd': ([_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp], _i),
     'lamp_attn_core_planes_train': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp, _i64,
                                      _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _f, C.c_uint64, _vp, _vp], _i),
+    'lamp_attn_core_planes_train_mbits': ([_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp,
+                                           _i64, _i64, _vp, _vp, _i64, _vp, _vp, _f, C.c_uint64, _vp, _vp], _i),
     'lamp_attn_bwd_planes_workspace_bytes': ([_i, _i, _i, _i], _sz),
     'lamp_attn_bwd_planes': ([_vp, _vp, _i64, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
                               _i64, _i, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _i64, _i64, _i64,

@@ -676,7 +676,8 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
                      float* probs_pre, const uint64_t* seed_dev) {
   if (int rc = arch_check()) return rc;
   REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "attn: dropout rate %f outside [0, 1)", (double)p_drop);
-  REQUIRE(p_drop == 0.0f || (!kv_len && !mask_bits), "attn: dropout is a training-path feature (dense keys, byte mask)");
+  REQUIRE(p_drop == 0.0f || !kv_len, "attn: dropout is a training-path feature (dense keys)");
+  REQUIRE(!mask_bits || !probs, "attn: the probability output needs the byte mask");
   REQUIRE(!probs_pre || probs, "attn: probs_pre goes with probs");
   REQUIRE((kv_start == nullptr) == (kv_len == nullptr), "attn: kv_start and kv_len go together");
   REQUIRE(!kv_len || (!probs && kv_rows > 0), "attn: packed keys exclude the probability output");
@@ -1184,6 +1185,19 @@ int lamp_attn_core_planes_train(const void* q_hi, const void* q_lo, int64_t ldq,
   return attn_impl(q_hi, q_lo, ldq, q_col0, q_bcast, kv_hi, kv_lo, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature,
                    precision, mask, msb, msq, msk, nullptr, 0, 0, o_hi, o_lo, ldo, nullptr, 0, row_max, row_sum, attn,
                    nullptr, nullptr, 0, stream, p_drop, seed, probs_pre, seed_dev);
+}
+
+int lamp_attn_core_planes_train_mbits(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0, int q_bcast,
+                                      const void* kv_hi, const void* kv_lo, int64_t ldkv, int k_col0, int v_col0, int B,
+                                      int H, int Lq, int Lk, int d, float temperature, int precision,
+                                      const uint32_t* mask_bits, int64_t mbb, int64_t mbq, void* o_hi, void* o_lo,
+                                      int64_t ldo, float* row_max, float* row_sum, float p_drop, uint64_t seed,
+                                      const uint64_t* seed_dev, void* stream) {
+  REQUIRE(row_max && row_sum, "attn_train: the row statistics buffers are required");
+  REQUIRE(mask_bits != nullptr && mbq >= (Lk + 31) / 32, "attn_train_mbits: packed mask missing or row stride too small");
+  return attn_impl(q_hi, q_lo, ldq, q_col0, q_bcast, kv_hi, kv_lo, ldkv, k_col0, v_col0, B, H, Lq, Lk, d, temperature,
+                   precision, nullptr, 0, 0, 0, mask_bits, mbb, mbq, o_hi, o_lo, ldo, nullptr, 0, row_max, row_sum, nullptr,
+                   nullptr, nullptr, 0, stream, p_drop, seed, nullptr, seed_dev);
 }
 
 int lamp_dropout_add(const float* y0, const float* x, int64_t rows, int D, int x_mod, float p_drop, uint64_t seed,

@@ -1116,11 +1116,21 @@ class MHATrainFunction(torch.autograd.Function):
         pre = torch.empty_like(attn) if (want_attn and p_attn > 0) else None
         stats = torch.empty((2, H * B * Lq), dtype=torch.float32, device=dev)
         keep, mptr, sb, sq, sk = mask_args(mask, B, Lq, Lk)
-        STATS.call('attn_core_train', 2 if want_attn else 1, L.lamp_attn_core_planes_train,
-                   (qp[0].data_ptr(), qp[1].data_ptr(), ldq, 0, 0, kvp[0].data_ptr(), kvp[1].data_ptr(), ldkv, k_col0, v_col0,
-                    B, H, Lq, Lk, d, float(temperature), prec, mptr, sb, sq, sk, o_hi.data_ptr(), o_lo.data_ptr(), hd,
-                    stats[0].data_ptr(), stats[1].data_ptr(), nat.ptr(attn), nat.ptr(pre), float(p_attn), int(seed_attn),
-                    _seed_dev_ptr(), nat.stream()), flops=4.0 * H * Lq * d * B * Lk)
+        if keep is not None and not want_attn and sq != 0 and (Lk > 128 or sb != 0):
+            # per-(query, key) mask of a multi-tile problem: packed bits for the forward core (the label-graph mask is
+            # packed once and cached); the backward's recompute kernel reads the byte mask
+            words, mbb, mbq = mask_bits(keep, B, Lq, Lk)
+            STATS.call('attn_core_train', 1, L.lamp_attn_core_planes_train_mbits,
+                       (qp[0].data_ptr(), qp[1].data_ptr(), ldq, 0, 0, kvp[0].data_ptr(), kvp[1].data_ptr(), ldkv, k_col0,
+                        v_col0, B, H, Lq, Lk, d, float(temperature), prec, words.data_ptr(), mbb, mbq, o_hi.data_ptr(),
+                        o_lo.data_ptr(), hd, stats[0].data_ptr(), stats[1].data_ptr(), float(p_attn), int(seed_attn),
+                        _seed_dev_ptr(), nat.stream()), flops=4.0 * H * Lq * d * B * Lk)
+        else:
+            STATS.call('attn_core_train', 2 if want_attn else 1, L.lamp_attn_core_planes_train,
+                       (qp[0].data_ptr(), qp[1].data_ptr(), ldq, 0, 0, kvp[0].data_ptr(), kvp[1].data_ptr(), ldkv, k_col0,
+                        v_col0, B, H, Lq, Lk, d, float(temperature), prec, mptr, sb, sq, sk, o_hi.data_ptr(), o_lo.data_ptr(),
+                        hd, stats[0].data_ptr(), stats[1].data_ptr(), nat.ptr(attn), nat.ptr(pre), float(p_attn),
+                        int(seed_attn), _seed_dev_ptr(), nat.stream()), flops=4.0 * H * Lq * d * B * Lk)
         wfc_hi, wfc_lo = _wplanes(Wfc, prec)
         y = torch.empty((Mq, D), dtype=torch.float32, device=dev)
         if p_out > 0 and FUSED_DROPOUT_EPILOGUE:

@@ -145,13 +145,16 @@ def test_fused_sublayers_with_dropout_are_consistent_between_forward_and_backwar
         assert rel_err(q.grad, p64[name].grad) < 5e-5, name
 
 
-@pytest.mark.parametrize('case', ['self_prior', 'enc_pad'])
+@pytest.mark.parametrize('case', ['self_prior', 'enc_pad', 'self_L300_prior'])
 def test_mha_train_recompute_form_matches_fp64_autograd_and_the_stored_form(case):
     """return_attn=False in training: the forward writes no probability tensor, the backward rebuilds P from the saved
     row statistics, the mask and the dropout hash (lamp_attn_bwd_planes, recompute form).  (i) without dropout: fp64
     autograd of the oracle; (ii) with attention dropout 0.2 and the same seeds: identical to the stored-P form."""
     cfg = dict(self_prior=dict(B=2, Lq=103, Lk=103, D=512, H=4, mask='prior', self_attn=True, seed=201),
-               enc_pad=dict(B=3, Lq=53, Lk=90, D=256, H=4, mask='pad', self_attn=False, seed=203))[case]
+               enc_pad=dict(B=3, Lq=53, Lk=90, D=256, H=4, mask='pad', self_attn=False, seed=203),
+               # multi-tile label graph (L > 128): the forward core reads the mask as packed bits, the recompute
+               # backward as bytes
+               self_L300_prior=dict(B=2, Lq=300, Lk=300, D=256, H=2, mask='prior', self_attn=True, seed=205))[case]
     c = dict(cfg)
     p, q, kv, mask = cases.mha_inputs(c)
     d = c['D'] // c['H']
