@@ -54,6 +54,7 @@ int lamp_sm_count(void);
 #define LAMP_TUNE_GEMM_TN_TC 6     /* 1 (default): weight gradient dY^T X on tcgen05 (MN-major operands), 0: warp-MMA version */
 #define LAMP_TUNE_ATTN_BWD_TC 7    /* 1 (default): attention backward as batched tcgen05 products, 0: warp-MMA kernels */
 #define LAMP_TUNE_PDL 8            /* programmatic dependent launch: 2 (default: launches of <= 16384 rows), 1 (always), 0 (never) */
+#define LAMP_TUNE_ATTN_KV128_MIN_LK 9 /* L (default 512): 128-key tiles (one K, one V slot) for d > 64 when Lk >= L; 0: always 64-key tiles there */
 #define LAMP_TUNE_GEMM_CTA_PAIR 2 /* 1 (default: tcgen05 cta_group::2 pairs for 256-wide tiles) or 0 (single CTAs) */
 int lamp_set_tuning(int key, int value);
 

@@ -258,6 +258,7 @@ std::atomic<int> g_attn_stage{1};     // tuning knob: 1 -> O planes leave throug
 std::atomic<int> g_attn_pv_split{0};  // tuning knob: 1 -> PV product as two interleaved N = 64 chains when d == 128
 std::atomic<int> g_gemm_tn_tc{1};     // tuning knob: 1 -> weight gradient on tcgen05 (gemm_tn_tc.cuh), 0 -> warp-MMA version
 std::atomic<int> g_attn_bwd_tc{1};    // tuning knob: 1 -> attention backward as batched tcgen05 products, 0 -> warp-MMA kernels
+std::atomic<int> g_attn_kv128_min_lk{512};  // tuning knob: > 0 -> 128-key tiles for d > 64 when Lk >= this (dense keys); 0 -> always 64-key tiles there
 std::atomic<int> g_gemm_pair{1};      // tuning knob: 1 -> CTA pairs (cta_group::2) for the 256-wide tiles, 0 -> single CTAs
 
 constexpr uint32_t kMaxDynSmem = 232448;  // 227 KB: the sm_100 per-CTA opt-in maximum
@@ -375,6 +376,10 @@ int lamp_set_tuning(int key, int value) {
   }
   if (key == LAMP_TUNE_PDL && (value == 0 || value == 1 || value == 2)) {
     g_pdl.store(value);
+    return LAMP_OK;
+  }
+  if (key == LAMP_TUNE_ATTN_KV128_MIN_LK && value >= 0) {
+    g_attn_kv128_min_lk.store(value);
     return LAMP_OK;
   }
   if (key == LAMP_TUNE_GEMM_CTA_PAIR && (value == 0 || value == 1)) {
@@ -695,7 +700,12 @@ static int attn_impl(const void* q_hi, const void* q_lo, int64_t ldq, int q_col0
   REQUIRE(q_col0 % 8 == 0 && k_col0 % 8 == 0 && v_col0 % 8 == 0, "attn: column offsets must be multiples of 8");
   if (B == 0) return LAMP_OK;
   const bool multi = Lk > 128;
-  const int block_kv = (d > 64 && multi) ? 64 : 128;
+  // 64-key tiles for wide heads on multi-tile rows: K and V rings of >= 2 slots each fit next to Q.  Long rows (knob
+  // LAMP_TUNE_ATTN_KV128_MIN_LK, default 512) use 128-key tiles with ONE K and ONE V slot: an N = 64 score MMA
+  // costs 55 clocks for 32 clocks of work, an N = 128 one 64 for 64, and a 128-key unit is long enough (~3 K clocks of
+  // MMAs) to cover the load of the next tile.
+  const int kv128_min = g_attn_kv128_min_lk.load();
+  const int block_kv = (d > 64 && multi && !(kv128_min > 0 && Lk >= kv128_min && !kv_len)) ? 64 : 128;
   auto round_up = [](int x, int m) { return (x + m - 1) / m * m; };
   // TMA box rows follow the label count: a single-tile problem (Lk <= 128) only stages the rows that exist
   const bool compact = g_attn_compact.load() != 0;
